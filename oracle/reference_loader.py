@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference (oscarknagg/wurm) for pinning the oracle.
+
+This module is used only by `oracle/gen_golden.py` and `oracle/validate_vs_reference.py`, in the
+build container where the read-only reference tree exists (default `/root/reference`, override
+with `WURM_REFERENCE_PATH`).  It never runs on the GPU box and nothing in `wurm_b200/` imports it.
+
+The reference was written for torch 1.1 / python 3.6.  It is imported *unmodified*; what is patched
+is the interpreter around it, restoring the semantics the reference was written against
+(SURVEY.md Appendix B.1):
+
+  1. `gym` / `matplotlib` are absent          -> empty stub modules (rendering is never exercised)
+  2. `collections.Iterable` moved             -> alias to `collections.abc.Iterable`
+  3. `config.DEFAULT_DEVICE == 'cuda'`        -> patched to 'cpu' *before* `wurm.*` binds ctor defaults
+  4. uint8 masks: `~mask` was logical-not     -> `torch.uint8 = torch.bool`, `Tensor.byte() -> .bool()`
+  5. integer `/` was floor/trunc division     -> `Tensor.__truediv__` truncates for integer tensors
+
+Because (4) and (5) monkey-patch torch process-wide, import this module only from a dedicated
+process (the two scripts above do that).
+
+Draw recording: the names `drop_duplicates` and `torch` in the namespaces of
+`wurm.envs.single_snake` / `wurm.envs.multi_snake` are wrapped so that every random draw the
+reference makes is appended to `TAPE` tagged with its call-site line number.
+"""
+import collections
+import collections.abc
+import inspect
+import os
+import sys
+import types
+
+import torch
+
+REFERENCE_PATH = os.environ.get('WURM_REFERENCE_PATH', '/root/reference')
+
+TAPE = []          # list of (kind, lineno, payload) appended by the recording proxies
+_loaded = {}
+
+
+def _stub(name):
+    mod = types.ModuleType(name)
+    mod.__path__ = []
+    sys.modules[name] = mod
+    return mod
+
+
+def _install_shims():
+    # (1) absent packages
+    for name in ['gym', 'gym.envs', 'gym.envs.classic_control', 'gym.envs.classic_control.rendering',
+                 'gym.wrappers', 'gym.wrappers.monitoring', 'gym.wrappers.monitoring.video_recorder',
+                 'matplotlib', 'matplotlib.pyplot']:
+        if name not in sys.modules:
+            _stub(name)
+    sys.modules['gym.envs.classic_control'].rendering = sys.modules['gym.envs.classic_control.rendering']
+    sys.modules['gym.wrappers.monitoring.video_recorder'].VideoRecorder = type('VideoRecorder', (), {})
+    # (2)
+    if not hasattr(collections, 'Iterable'):
+        collections.Iterable = collections.abc.Iterable
+    # (4) torch-1.1 mask semantics
+    torch.uint8 = torch.bool
+    torch.Tensor.byte = lambda t: t.bool()
+    # (5) torch-1.1 integer division
+    _truediv = torch.Tensor.__truediv__
+
+    def _int_truediv(self, other):
+        if not self.is_floating_point() and isinstance(other, int):
+            return torch.div(self, other, rounding_mode='trunc')
+        return _truediv(self, other)
+    torch.Tensor.__truediv__ = _int_truediv
+
+
+class _TorchProxy(object):
+    """Stands in for the name `torch` inside a reference module; records random draws."""
+
+    def __init__(self, tag):
+        self._tag = tag
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def _line():
+        return inspect.stack()[2].lineno
+
+    def rand(self, *a, **k):
+        out = torch.rand(*a, **k)
+        TAPE.append(('rand', self._line(), out.clone()))
+        return out
+
+    def rand_like(self, *a, **k):
+        out = torch.rand_like(*a, **k)
+        TAPE.append(('rand_like', self._line(), out.clone()))
+        return out
+
+    def randint(self, *a, **k):
+        out = torch.randint(*a, **k)
+        TAPE.append(('randint', self._line(), out.clone()))
+        return out
+
+
+def load():
+    """Returns a namespace with the reference's SingleSnake, MultiSnake, utils and config modules."""
+    if _loaded:
+        return types.SimpleNamespace(**_loaded)
+    if not os.path.isdir(REFERENCE_PATH):
+        raise RuntimeError(f'reference tree not found at {REFERENCE_PATH} (container-only tooling)')
+    _install_shims()
+    sys.path.insert(0, REFERENCE_PATH)
+    import config as ref_config                      # (3) patch before wurm.* is imported
+    assert os.path.realpath(ref_config.__file__).startswith(os.path.realpath(REFERENCE_PATH))
+    ref_config.DEFAULT_DEVICE = 'cpu'
+    import wurm.utils as ref_utils
+    import wurm.envs.single_snake as ref_single
+    import wurm.envs.multi_snake as ref_multi
+
+    for mod in (ref_single, ref_multi):
+        orig = mod.drop_duplicates
+
+        def recording_drop_duplicates(tensor, column, random=True, _orig=orig):
+            out = _orig(tensor, column, random)
+            TAPE.append(('drop_duplicates', inspect.stack()[1].lineno, out.clone()))
+            return out
+        mod.drop_duplicates = recording_drop_duplicates
+        mod.torch = _TorchProxy(mod.__name__)
+
+    _loaded.update(dict(config=ref_config, utils=ref_utils, single=ref_single, multi=ref_multi,
+                        SingleSnake=ref_single.SingleSnake, MultiSnake=ref_multi.MultiSnake))
+    return types.SimpleNamespace(**_loaded)
+
+
+def take_tape():
+    """Returns and clears the draws recorded since the last call."""
+    out = list(TAPE)
+    del TAPE[:]
+    return out
