@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the unmodified reference.
+
+    python oracle/gen_golden.py            (container-only: needs the reference tree)
+
+Each file holds short trajectories of the REFERENCE (run through oracle/reference_loader.py):
+inputs (initial state, actions, the replay tape of the reference's own random draws) and every
+output the reference produced (state after step, sanitised actions, reward, done, info, observation,
+state and observation after reset).  The committed vectors are what pins the oracle on machines
+where the reference tree is absent (tests/test_oracle_golden.py) and what the CUDA path is checked
+against directly (tests/test_single_gpu.py).
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+from oracle import reference_loader as rl   # noqa: E402
+from oracle import replay                   # noqa: E402
+
+import torch                                # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+
+def single_trajectory(ref, N, S, mode, steps, seed, reset_every=1, manual=None, actions=None):
+    torch.manual_seed(seed)
+    rl.take_tape()
+    out = {'N': N, 'S': S, 'mode': mode, 'steps': steps}
+    if manual is None:
+        env = ref.SingleSnake(num_envs=N, size=S, observation_mode=mode)
+        out['init_spawn'] = replay.single_reset_tape(rl.take_tape(), np.ones(N), N, S)
+    else:
+        env = ref.SingleSnake(num_envs=N, size=S, observation_mode=mode, manual_setup=True)
+        env.envs = manual.clone()
+    out['init_envs'] = env.envs.numpy().astype(np.int16)
+    for t in range(steps):
+        a = torch.randint(0, 4, (N,)) if actions is None else actions[t].clone()
+        out[f'{t}/actions_in'] = a.numpy().copy()
+        obs, reward, done, info = env.step(a)
+        out[f'{t}/food_cell'] = replay.single_step_tape(rl.take_tape(), reward, N, S)
+        out[f'{t}/envs'] = env.envs.numpy().astype(np.int16)
+        assert np.array_equal(out[f'{t}/envs'].astype(np.float32), env.envs.numpy())
+        out[f'{t}/actions_out'] = a.numpy().copy()
+        out[f'{t}/reward'] = reward.numpy().reshape(-1)
+        out[f'{t}/done'] = done.numpy().reshape(-1).astype(np.uint8)
+        out[f'{t}/self_collision'] = info['self_collision'].numpy().astype(np.uint8)
+        out[f'{t}/edge_collision'] = info['edge_collision'].numpy().astype(np.uint8)
+        out[f'{t}/obs'] = obs.numpy()
+        do_reset = (t % reset_every) == reset_every - 1
+        out[f'{t}/did_reset'] = np.array(do_reset)
+        if do_reset:
+            obs2 = env.reset(done)
+            out[f'{t}/spawn'] = replay.single_reset_tape(rl.take_tape(), done.numpy(), N, S)
+            out[f'{t}/reset_envs'] = env.envs.numpy().astype(np.int16)
+            out[f'{t}/reset_obs'] = obs2.numpy()
+    return out
+
+
+def save(name, trajectories):
+    flat = {'count': np.array(len(trajectories))}
+    for i, tr in enumerate(trajectories):
+        for k, v in tr.items():
+            flat[f'{i}/{k}'] = np.asarray(v)
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name)
+    np.savez_compressed(path, **flat)
+    print(path, os.path.getsize(path) // 1024, 'KiB')
+
+
+def main():
+    ref = rl.load()
+    trs = []
+    for i, mode in enumerate(['partial_2', 'partial_3', 'default', 'raw', 'one_channel', 'positions']):
+        trs.append(single_trajectory(ref, 24, 9, mode, 24, seed=100 + i))
+        trs.append(single_trajectory(ref, 12, 13, mode, 16, seed=200 + i))
+    # dead envs stepped again without reset: heads leave the grid, bodies decay to nothing
+    for i, mode in enumerate(['default', 'one_channel', 'positions']):
+        trs.append(single_trajectory(ref, 16, 9, mode, 21, seed=300 + i, reset_every=7))
+    # the reference's own scenario fixtures (wurm/utils.py:68-110 get_test_env, size 12) under the
+    # action sequences of tests/test_single_snake_env.py:55,89,122,146,174
+    for orientation in ['up', 'right', 'down', 'left']:
+        for seq in ([0, 0, 3, 0, 0, 1], [0, 3, 3, 0, 0], [1] * 10, [0, 3, 3, 2, 1, 0, 0, 0], [2, 2, 2, 3]):
+            acts = torch.tensor(seq).unsqueeze(1).long()
+            trs.append(single_trajectory(ref, 1, 12, 'default', len(seq), seed=400, reset_every=10 ** 6,
+                                         manual=ref.utils.get_test_env(12, orientation), actions=acts))
+    save('single.npz', trs)
+
+
+if __name__ == '__main__':
+    main()

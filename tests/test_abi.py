@@ -1,0 +1,68 @@
+"""CPU: the C-ABI library loads, exports every symbol include/wurm_b200.h declares, and rejects bad
+arguments before touching the GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from wurm_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'wurm_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(wurm_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for name in header_symbols():
+        assert hasattr(L, name), f'{name} declared in include/wurm_b200.h but not exported'
+    assert L.wurm_abi_version() == _lib.ABI_VERSION
+
+
+def test_obs_elems():
+    L = _lib.lib()
+    for mode, n, expect in [(_lib.OBS_DEFAULT, 0, 3 * 81), (_lib.OBS_RAW, 0, 3 * 81), (_lib.OBS_ONE_CHANNEL, 0, 81),
+                            (_lib.OBS_POSITIONS, 0, 4), (_lib.OBS_PARTIAL, 2, 75), (_lib.OBS_NONE, 0, 0)]:
+        cfg = _lib.WurmSingleCfg(4, 9, mode, n)
+        assert L.wurm_single_obs_elems(ctypes.byref(cfg)) == expect
+
+
+@pytest.mark.parametrize('cfg,code', [
+    ((0, 9, 0, 0), _lib.E_INVALID),          # no envs
+    ((4, 8, 0, 0), _lib.E_INVALID),          # size <= 8 (reference single_snake.py:346)
+    ((4, 9, 7, 0), _lib.E_INVALID),          # unknown observation mode
+    ((4, 200, 0, 0), _lib.E_UNSUPPORTED),    # one env no longer fits a shared-memory tile
+])
+def test_bad_config_is_rejected_on_the_host(cfg, code):
+    L = _lib.lib()
+    c = _lib.WurmSingleCfg(*cfg)
+    rc = L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None)
+    assert rc == code
+    assert L.wurm_last_error()
+    with pytest.raises(_lib.WurmError):
+        _lib.check(rc)
+
+
+def test_null_pointers_are_rejected():
+    L = _lib.lib()
+    c = _lib.WurmSingleCfg(4, 9, 0, 0)
+    assert L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None) == _lib.E_INVALID
+    assert L.wurm_single_observe(ctypes.byref(c), None, None, None, None) == _lib.E_INVALID
+    assert L.wurm_single_step(ctypes.byref(c), None, None, 8, None, 0, 0, None, None, None, None, None, None,
+                              None) == _lib.E_INVALID
+
+
+def test_env_refuses_to_run_without_cuda_device():
+    """There is no CPU fallback: constructing an env on a non-CUDA device raises."""
+    from wurm_b200.envs import SingleSnake
+    with pytest.raises(RuntimeError):
+        SingleSnake(num_envs=2, size=9, device='cpu')

@@ -1,0 +1,259 @@
+"""GPU: SingleSnake through the C ABI (wurm_b200.envs.SingleSnake) against
+  (1) the reference's golden vectors, replaying the reference's own random draws,
+  (2) the CPU oracle on seeded random rollouts with Philox-derived draws (same seed on both sides),
+  (3) the reference's own scenario tests (tests/test_single_snake_env.py in the reference tree),
+  (4) size-independent invariants at BASELINE.json's full size (2^20 envs).
+Everything is compared bit for bit (fp32 as int32 patterns).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from golden_util import load, assert_same
+
+pytestmark = pytest.mark.gpu
+
+SINGLE = load('single.npz')
+DEV = 'cuda'
+
+
+def make_env(N, S, mode, **kw):
+    from wurm_b200.envs import SingleSnake
+    return SingleSnake(num_envs=N, size=S, observation_mode=mode, device=DEV, **kw)
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize('i', range(len(SINGLE)))
+def test_golden_replay(i):
+    """CUDA path == reference on the recorded trajectories (states, actions, rewards, dones, info, obs)."""
+    tr = SINGLE[i]
+    N, S, mode = tr.N, tr.S, tr.mode
+    env = make_env(N, S, mode, manual_setup=True)
+    if 'init_spawn' in tr:
+        env.envs = env._create_envs(N, spawn_replay=torch.from_numpy(tr['init_spawn']))
+        assert_same(np_(env.envs), tr['init_envs'].astype(np.float32), 'created envs')
+    else:
+        env.envs = torch.from_numpy(tr['init_envs'].astype(np.float32)).to(DEV)
+    for t in range(tr.steps):
+        a = torch.from_numpy(tr[f'{t}/actions_in'].copy()).to(DEV)
+        obs, reward, done, info = env.step(a, food_cell_replay=torch.from_numpy(tr[f'{t}/food_cell']))
+        tag = f'trajectory {i} ({mode}, S={S}) step {t}: '
+        assert_same(np_(env.envs), tr[f'{t}/envs'].astype(np.float32), tag + 'envs')
+        assert_same(np_(a), tr[f'{t}/actions_out'], tag + 'sanitised actions')
+        assert reward.shape == (N, 1) and done.shape == (N, 1) and done.dtype == torch.bool
+        assert_same(np_(reward).reshape(-1), tr[f'{t}/reward'], tag + 'reward')
+        assert_same(np_(done).reshape(-1).astype(np.uint8), tr[f'{t}/done'], tag + 'done')
+        assert_same(np_(info['self_collision']).astype(np.uint8), tr[f'{t}/self_collision'], tag + 'self_collision')
+        assert_same(np_(info['edge_collision']).astype(np.uint8), tr[f'{t}/edge_collision'], tag + 'edge_collision')
+        assert_same(np_(obs), tr[f'{t}/obs'], tag + 'observation')
+        if bool(tr[f'{t}/did_reset']):
+            obs2 = env.reset(done, spawn_replay=torch.from_numpy(tr[f'{t}/spawn']))
+            assert_same(np_(env.envs), tr[f'{t}/reset_envs'].astype(np.float32), tag + 'envs after reset')
+            assert_same(np_(obs2), tr[f'{t}/reset_obs'], tag + 'observation after reset')
+    env.check_status()
+
+
+ROLLOUTS = [
+    # N, S, mode, steps, reset_every, action dtype
+    (1000, 9, 'partial_2', 40, 1, torch.long),      # ragged last tile (1000 % 64 != 0)
+    (777, 9, 'partial_3', 30, 1, torch.int),
+    (513, 12, 'default', 30, 1, torch.short),
+    (300, 10, 'raw', 30, 1, torch.long),
+    (257, 17, 'one_channel', 30, 2, torch.long),
+    (129, 36, 'default', 40, 1, torch.long),        # BASELINE config 3 geometry
+    (66, 36, 'partial_4', 40, 1, torch.long),
+    (31, 64, 'positions', 25, 1, torch.long),
+    (5, 100, 'one_channel', 12, 1, torch.long),
+    (400, 9, 'default', 28, 7, torch.long),         # dead envs stepped again: heads leave the grid
+    (400, 11, 'positions', 28, 7, torch.long),
+    (1, 9, 'partial_2', 20, 1, torch.long),
+]
+
+
+@pytest.mark.parametrize('N,S,mode,steps,reset_every,adtype', ROLLOUTS)
+def test_rollout_matches_oracle(N, S, mode, steps, reset_every, adtype):
+    """Seeded random rollout, draws derived from Philox on both sides: every tensor identical."""
+    seed = 1234 + N + S
+    env = make_env(N, S, mode, seed=seed)
+    state = np.zeros((N, 3, S, S), np.float32)
+    orc.single_reset(state, np.ones(N, np.uint8), None, seed=seed, step=env._draws)
+    assert_same(np_(env.envs), state, 'created envs')
+    g = torch.Generator().manual_seed(seed)
+    for t in range(steps):
+        a_cpu = torch.randint(0, 4, (N,), generator=g)
+        if t % 5 == 4:
+            a_cpu = torch.randint(0, 9, (N,), generator=g)     # out-of-range actions go through fmod 4
+        a = a_cpu.to(device=DEV, dtype=adtype)
+        a_orc = a_cpu.numpy().astype(np.int64)
+        obs, reward, done, info = env.step(a)
+        r, d, sc, ec = orc.single_step(state, a_orc, None, seed=seed, step=env._draws)
+        o, bad = orc.single_observe(state, mode)
+        tag = f'step {t}: '
+        assert_same(np_(env.envs), state, tag + 'envs')
+        assert_same(np_(a).astype(np.int64), a_orc, tag + 'sanitised actions')
+        assert_same(np_(reward).reshape(-1), r, tag + 'reward')
+        assert_same(np_(done).reshape(-1).astype(np.uint8), d, tag + 'done')
+        assert_same(np_(info['self_collision']).astype(np.uint8), sc, tag + 'self_collision')
+        assert_same(np_(info['edge_collision']).astype(np.uint8), ec, tag + 'edge_collision')
+        assert_same(np_(obs), o, tag + 'observation')
+        if t % reset_every == reset_every - 1:
+            obs2 = env.reset(done)
+            orc.single_reset(state, d, None, seed=seed, step=env._draws)
+            assert_same(np_(env.envs), state, tag + 'envs after reset')
+            o2, _ = orc.single_observe(state, mode)
+            assert_same(np_(obs2), o2, tag + 'observation after reset')
+    if not mode.startswith('partial') and reset_every == 1:
+        env.check_status()
+
+
+def test_every_observe_mode_on_one_state():
+    N, S = 200, 14
+    env = make_env(N, S, 'partial_3', seed=5)
+    for t in range(6):
+        _, _, done, _ = env.step(torch.randint(0, 4, (N,), device=DEV))
+        env.reset(done, return_observations=False)
+    state = np_(env.envs)
+    for mode in ['default', 'raw', 'one_channel', 'positions', 'partial_3']:
+        o, bad = orc.single_observe(state, mode)
+        assert bad == 0
+        assert_same(np_(env._observe(mode)), o, mode)
+    rgb = env._get_rgb()
+    assert rgb.dtype == torch.short
+    assert_same(np_(rgb).astype(np.float32) / np.float32(255), orc.single_observe(state, 'default')[0], '_get_rgb')
+
+
+# ---- the reference's scenario tests, on the CUDA path (reference tests/test_single_snake_env.py) ----
+size = 12
+
+
+def get_test_env(orientation='up'):
+    """The reference's fixture (wurm/utils.py:68-110)."""
+    env = torch.zeros((1, 3, size, size))
+    cells = {'up': ([(3, 3), (3, 4), (4, 4), (5, 4)], (6, 6)), 'right': ([(3, 3), (3, 4), (4, 4), (4, 5)], (6, 9)),
+             'down': ([(8, 8), (7, 8), (6, 8), (5, 8)], (7, 2)), 'left': ([(8, 7), (7, 7), (6, 7), (6, 6)], (1, 2))}
+    body, food = cells[orientation]
+    for v, (y, x) in enumerate(body, 1):
+        env[0, 2, y, x] = v
+    env[0, 1, body[-1][0], body[-1][1]] = 1
+    env[0, 0, food[0], food[1]] = 1
+    return env
+
+
+def head_position(env):
+    idx = env.envs[0, 1].flatten().argmax().item()
+    return [idx // size, idx % size]
+
+
+def run_actions(actions, orientation='up'):
+    env = make_env(1, size, 'one_channel', manual_setup=True)
+    env.envs = get_test_env(orientation).to(DEV)
+    for a in actions:
+        yield env, env.step(torch.tensor([a], device=DEV))
+
+
+def test_basic_movement():
+    expected = [[6, 4], [7, 4], [7, 5], [8, 5], [9, 5], [9, 4]]
+    for i, (env, (obs, reward, done, info)) in enumerate(run_actions([0, 0, 3, 0, 0, 1])):
+        assert head_position(env) == expected[i]
+        assert not torch.any(done)
+
+
+def test_cannot_move_backwards():
+    expected = [[6, 4], [7, 4], [8, 4], [8, 5]]
+    for i, (env, (obs, reward, done, info)) in enumerate(run_actions([2, 2, 2, 3])):
+        assert head_position(env) == expected[i]
+        assert not torch.any(done)
+
+
+def test_eat_food():
+    rewards = []
+    for env, (obs, reward, done, info) in run_actions([0, 3, 3, 0, 0]):
+        assert not torch.any(done)
+        rewards.append(reward.item())
+    assert sum(rewards) == 1
+    assert env.envs[0, 2].max() == 5
+    assert env.envs[0, 0].sum() == 1
+    assert_consistent(env.envs)
+
+
+def test_hit_boundary():
+    assert any(torch.any(done).item() for env, (obs, reward, done, info) in run_actions([1] * 10))
+
+
+def test_hit_self():
+    for env, (obs, reward, done, info) in run_actions([0, 3, 3, 2, 1, 0, 0, 0]):
+        if torch.any(done):
+            assert info['self_collision'].item()
+            break
+    else:
+        assert False
+    assert env.envs[0, 0].sum() == 1
+
+
+def test_step_argument_errors():
+    env = make_env(4, 9, 'default')
+    with pytest.raises(TypeError):
+        env.step(torch.zeros(4, device=DEV))
+    with pytest.raises(RuntimeError):
+        env.step(torch.zeros(5, dtype=torch.long, device=DEV))
+    with pytest.raises(NotImplementedError):
+        make_env(4, 8, 'default')
+
+
+def assert_consistent(envs):
+    """The reference's invariants (wurm/utils.py:113-178 snake_consistency + env_consistency)."""
+    n = envs.shape[0]
+    food, head, body = envs[:, 0], envs[:, 1], envs[:, 2]
+    assert torch.all((food == 0) | (food == 1))
+    assert torch.all(head.reshape(n, -1).sum(-1) == 1)
+    sizes = body.reshape(n, -1).max(-1)[0]
+    assert torch.equal(sizes, (head * body).reshape(n, -1).sum(-1))
+    totals = body.reshape(n, -1).sum(-1)
+    assert torch.equal(totals, sizes * (sizes + 1) / 2)
+    assert torch.all(totals >= 6)
+    assert torch.all((head * food).reshape(n, -1).sum(-1) == 0)
+    assert torch.all(food.reshape(n, -1).sum(-1) == 1)
+
+
+def test_multiple_envs_invariants():
+    """reference test_multiple_envs / test_setup / test_reset (:17-47)."""
+    env = make_env(97, size, 'one_channel')
+    assert_consistent(env.envs)
+    assert torch.all(env.envs[:, 2].reshape(97, -1).sum(-1) == 6)
+    actions = torch.randint(4, size=(100, 97), device=DEV)
+    for a in actions:
+        obs, reward, done, info = env.step(a)
+        env.reset(done)
+        assert_consistent(env.envs)
+    env.check_status()
+
+
+def test_full_size_invariants_and_food_uniformity():
+    """BASELINE config 2 (2^20 envs, size 9, partial_2): invariants hold after every step+reset,
+    episode statistics are plausible, and the Philox food placement covers exactly the free cells."""
+    N, S = 1 << 20, 9
+    env = make_env(N, S, 'partial_2', seed=99)
+    assert_consistent(env.envs)
+    food0 = env.envs[:, 0].reshape(N, -1).argmax(-1)
+    counts = torch.bincount(food0, minlength=S * S).float().reshape(S, S)
+    assert counts[0].sum() == 0 and counts[-1].sum() == 0 and counts[:, 0].sum() == 0 and counts[:, -1].sum() == 0
+    assert counts[4, 4] == 0                           # the seed cell (4,4) always holds the snake
+    assert (counts > 0).sum().item() == 48             # 49 interior cells minus the seed cell
+    # cells never covered by the snake are chosen with probability 1/46 each
+    corner = counts[1, 1].item()
+    assert abs(corner - N / 46) < 6 * (N / 46) ** 0.5
+    ate = 0
+    for t in range(12):
+        a = torch.randint(0, 4, (N,), device=DEV)
+        obs, reward, done, info = env.step(a)
+        assert obs.shape == (N, 75)
+        ate += int(reward.sum().item())
+        assert torch.equal(done.squeeze(-1), info['self_collision'] | info['edge_collision'])
+        env.reset(done, return_observations=False)
+        assert_consistent(env.envs)
+    assert ate > 0
+    env.check_status()

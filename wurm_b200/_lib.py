@@ -1,0 +1,65 @@
+"""ctypes binding of the C ABI declared in include/wurm_b200.h.
+
+There is NO fallback: if the CUDA library has not been built this module raises, and so does every
+env constructor.  (The CPU implementation of this path is the reference itself.)
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
+
+ABI_VERSION = 1
+
+OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
+ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP = 1, 2, 4, 8
+OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1, 0, 1, 2, 3, 4
+
+# every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
+SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_reset',
+           'wurm_single_observe']
+
+
+class WurmSingleCfg(ctypes.Structure):
+    _fields_ = [('num_envs', ctypes.c_int32), ('size', ctypes.c_int32), ('obs_mode', ctypes.c_int32),
+                ('obs_n', ctypes.c_int32)]
+
+
+class WurmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f'wurm_b200 error {code}: {message}')
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} is missing: build it with `python -m wurm_b200.build` (needs nvcc). '
+                          'wurm_b200 has no CPU or PyTorch fallback.')
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    cfg = ctypes.POINTER(WurmSingleCfg)
+    L.wurm_abi_version.restype = i32
+    L.wurm_last_error.restype = ctypes.c_char_p
+    L.wurm_single_obs_elems.restype = ctypes.c_int64
+    L.wurm_single_obs_elems.argtypes = [cfg]
+    L.wurm_single_step.restype = i32
+    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_reset.restype = i32
+    L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp]
+    L.wurm_single_observe.restype = i32
+    L.wurm_single_observe.argtypes = [cfg, vp, vp, vp, vp]
+    if L.wurm_abi_version() != ABI_VERSION:
+        raise ImportError(f'{LIB_PATH} has ABI version {L.wurm_abi_version()}, expected {ABI_VERSION}: rebuild it')
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise WurmError(rc, lib().wurm_last_error().decode())

@@ -1,0 +1,544 @@
+// SingleSnake hot path for B200 (sm_100a): step / reset / observe as hand-written CUDA.
+//
+// Replaces wurm/envs/single_snake.py:104-387 and wurm/utils.py:36-65 of the reference (a ~214-op
+// ATen tensor program with three conv2d calls and >=5 host syncs per step) with ONE launch per call.
+//
+// Design:
+//   * one CTA per tile of T consecutive environments; the tile's (T,3,S,S) fp32 state is ONE
+//     contiguous span of global memory, moved to shared memory with a single TMA bulk copy
+//     (cp.async.bulk + mbarrier) and written back with a single bulk store -- every state byte
+//     crosses HBM exactly once in each direction, no per-element load/store instructions;
+//   * G consecutive lanes (a power of two, <=32) own one environment while it sits in shared
+//     memory; reductions over the grid (snake size, head cell, free-cell ranking for the food
+//     respawn) are warp shuffles / ballots restricted to the group's lane mask;
+//   * the reference's conv2d filters become index arithmetic on the head cell;
+//   * the observation is rendered from the shared tile straight into the caller's buffer with
+//     coalesced stores (for 'raw' it is a second bulk store of the same tile);
+//   * no tensor cores: nothing on this path is a dense contraction.
+#include <math.h>
+
+#include "../../include/wurm_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wurm {
+
+struct SingleParams {
+    float* envs;
+    void* actions;
+    const int32_t* food_replay;
+    float* obs;
+    float* reward;
+    uint8_t* done;
+    uint8_t* self_col;
+    uint8_t* edge_col;
+    int32_t* status;
+    uint64_t seed, step;
+    int N, S, C;          // envs, grid side, cells per channel
+    int T;                // envs per tile (= per CTA)
+    int action_bytes;     // 2 / 4 / 8
+    int obs_mode, obs_n, W;
+    uint32_t magic_S;     // ceil(2^32 / S): q / S == __umulhi(q, magic_S) for q < 2^16
+    int tile_bytes_padded;
+    int bulk_ok;          // base pointers 16-byte aligned and full-tile byte count a multiple of 16
+};
+
+__device__ __forceinline__ int div_S(int q, uint32_t magic) { return (int)__umulhi((uint32_t)q, magic); }
+
+// int16 colour (single_snake.py:99-123) of one cell, already divided by 255.0f with IEEE rounding
+// (the only values are 0, 127/255 and 1).
+__device__ __forceinline__ float rgb_channel(float food, float head, float body, bool border, int c) {
+    constexpr float kHalf = 127.0f / 255.0f;
+    float v = 1.0f;
+    if (body > kEps) v = (c == 1) ? kHalf : 0.0f;
+    if (head > kEps) v = (c == 1) ? 1.0f : 0.0f;
+    if (food > kEps) v = (c == 0) ? 1.0f : 0.0f;
+    return border ? 0.0f : v;
+}
+
+// wurm/utils.py:36-65 evaluated literally (zero-padded cross-correlation with the four filters);
+// only taken for states whose two largest body values are not a unique (size, size-1) pair.
+template <int G>
+__device__ __noinline__ int orientation_general(const float* body, int S, int C, uint32_t magic, float size, int l,
+                                                unsigned gm) {
+    const float shift = size - 2.0f;
+    auto neck = [&](float v) {
+        float n = v - shift;
+        n = n > 0.0f ? n : 0.0f;
+        if (n > 0.0f) n -= 1.5f;
+        return n * 2.0f;
+    };
+    float best = 0.0f;
+    int best_k = 0;
+    for (int k = 0; k < 4; ++k) {
+        float mk = -INFINITY;
+        for (int q = l; q < C; q += G) {
+            const int y = div_S(q, magic), x = q - y * S;
+            const int yy = y + off_y(k), xx = x + off_x(k);
+            const float nb = (yy >= 0 && yy < S && xx >= 0 && xx < S) ? neck(body[yy * S + xx]) : 0.0f;
+            mk = fmaxf(mk, nb - neck(body[q]));
+        }
+        mk = group_max<G>(mk, gm);
+        if (k == 0 || mk > best) { best = mk; best_k = k; }
+    }
+    return best_k;
+}
+
+// Uniform choice among the free interior cells of one env (single_snake.py:306-320), raster order,
+// ranked with ballots over the group's lanes.  Returns -1 if there is no free cell.
+template <int G>
+__device__ __noinline__ int pick_free_cell(const float* env, int S, int C, uint32_t magic, uint32_t rnd, int l,
+                                           unsigned gm) {
+    const unsigned shift = (G == 32) ? 0u : ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+    const unsigned low = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    auto free_bits = [&](int base) {
+        const int q = base + l;
+        bool f = false;
+        if (q < C) {
+            const int y = div_S(q, magic), x = q - y * S;
+            f = y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && (env[q] + env[C + q] + env[2 * C + q] < kEps);
+        }
+        return (__ballot_sync(gm, f) >> shift) & low;
+    };
+    int nfree = 0;
+    for (int base = 0; base < C; base += G) nfree += __popc(free_bits(base));
+    if (nfree == 0) return -1;
+    int r = (int)bounded(rnd, (uint32_t)nfree);
+    for (int base = 0; base < C; base += G) {
+        const unsigned bits = free_bits(base);
+        const int cnt = __popc(bits);
+        if (r < cnt) return base + (int)__fns(bits, 0, r + 1);
+        r -= cnt;
+    }
+    return -1;
+}
+
+// single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
+template <int G>
+__device__ __forceinline__ void step_env(const SingleParams& p, float* env, int e, int l, int* hp_out) {
+    const unsigned gm = group_mask<G>();
+    const int S = p.S, C = p.C;
+    float* food = env;
+    float* head = env + C;
+    float* body = env + 2 * C;
+
+    // snake size (:210) and head cell
+    float m = -INFINITY;
+    int hp = -1, hc = 0;
+    for (int q = l; q < C; q += G) {
+        m = fmaxf(m, body[q]);
+        if (head[q] != 0.0f) { hp = q; ++hc; }
+    }
+    const float size = group_max<G>(m, gm);
+    hp = group_max<G>(hp, gm);
+    hc = group_sum<G>(hc, gm);
+
+    // orientation (:212).  Canonical case: exactly one cell == size (head) and one == size-1
+    // (neck): the response of filter k peaks at 2 iff head = neck + OFF[k]; otherwise all four
+    // filters tie at 1 and argmax returns 0.
+    int c1 = 0, c2 = 0, p1 = -1, p2 = -1;
+    const float sm1 = size - 1.0f;
+    for (int q = l; q < C; q += G) {
+        const float v = body[q];
+        if (v == size) { ++c1; p1 = q; }
+        if (v == sm1) { ++c2; p2 = q; }
+    }
+    c1 = group_sum<G>(c1, gm);
+    c2 = group_sum<G>(c2, gm);
+    p1 = group_max<G>(p1, gm);
+    p2 = group_max<G>(p2, gm);
+    int k = 0;
+    if (c1 == 1 && c2 == 1) {
+        const int d = p1 - p2;
+        const int x2 = p2 - div_S(p2, p.magic_S) * S;
+        if (d == -S) k = 0;
+        else if (d == 1 && x2 != S - 1) k = 1;
+        else if (d == S) k = 2;
+        else if (d == -1 && x2 != 0) k = 3;
+    } else {
+        k = orientation_general<G>(body, S, C, p.magic_S, size, l, gm);
+    }
+
+    // action sanitisation, written back into the caller's tensor (:221-222)
+    long long a_in;
+    if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
+    else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
+    else a_in = ((const short*)p.actions)[e];
+    const long long a = (a_in + ((long long)k == a_in ? 2 : 0)) % 4;
+    if (l == 0 && a != a_in) {
+        if (p.action_bytes == 8) ((long long*)p.actions)[e] = a;
+        else if (p.action_bytes == 4) ((int*)p.actions)[e] = (int)a;
+        else ((short*)p.actions)[e] = (short)a;
+    }
+
+    // head move (:225-233): the conv2d with filter a translates the head channel by -OFF[a];
+    // a head that leaves the grid vanishes.
+    int np = -1, ny = -1, nx = -1;
+    if (hp >= 0) {
+        const int hy = div_S(hp, p.magic_S), hx = hp - hy * S;
+        ny = hy - (a >= 0 ? off_y((int)a) : 0);
+        nx = hx - (a >= 0 ? off_x((int)a) : 0);
+        if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
+    }
+
+    const float ov = (np >= 0) ? food[np] : 0.0f;                   // :242 head-food overlap
+    if (ov == 0.0f)                                                  // :246-249 decay unless it ate
+        for (int q = l; q < C; q += G) body[q] = fmaxf(body[q] - 1.0f, 0.0f);
+    __syncwarp(gm);
+    const bool sc = (np >= 0) && (body[np] > kEps);                  // :252 self collision
+    const bool interior = (np >= 0) && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
+    __syncwarp(gm);
+    if (l == 0 && hp >= 0) {
+        head[hp] = 0.0f;
+        if (np >= 0) {
+            head[np] = 1.0f;
+            body[np] += size + ov;                                   // :258-262 growth
+            food[np] += ov * -1.0f;                                  // :270-272 food removal
+        }
+    }
+    __syncwarp(gm);
+    if (ov != 0.0f) {                                                // :277-282 respawn
+        int cell;
+        if (p.food_replay) cell = p.food_replay[e];
+        else cell = pick_free_cell<G>(env, S, C, p.magic_S, draw(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood).x, l, gm);
+        if (l == 0 && cell >= 0) food[cell] += 1.0f;
+    }
+    if (l == 0) {
+        p.reward[e] = 0.0f - ov * -1.0f;                             // :271
+        p.self_col[e] = sc;
+        p.edge_col[e] = !interior;                                   // :290-293 no head in the interior
+        p.done[e] = sc || !interior;
+        *hp_out = np;
+        if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void find_head(const SingleParams& p, const float* env, int l, int* hp_out) {
+    const unsigned gm = group_mask<G>();
+    int hp = -1, hc = 0;
+    for (int q = l; q < p.C; q += G)
+        if (env[p.C + q] != 0.0f) { hp = q; ++hc; }
+    hp = group_max<G>(hp, gm);
+    hc = group_sum<G>(hc, gm);
+    if (l == 0) {
+        *hp_out = (hc == 1) ? hp : -1;
+        if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+    }
+}
+
+// single_snake.py:130-195 from the shared tile into the caller's observation buffer.
+template <int G>
+__device__ __forceinline__ void write_obs(const SingleParams& p, const float* tile, const int* hp_s, const uint32_t* tab,
+                                          int env0, int nvalid) {
+    const int S = p.S, C = p.C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (p.obs_mode == WURM_OBS_PARTIAL) {                            // :166-193
+        const int n = p.obs_n, E = 3 * p.W * p.W;
+        for (int t = warp; t < nvalid; t += nwarps) {
+            const float* env = tile + (size_t)t * 3 * C;
+            float* o = p.obs + (size_t)(env0 + t) * E;
+            const int hp = hp_s[t];
+            if (hp < 0) {
+                for (int r = lane; r < E; r += 32) o[r] = 0.0f;
+                if (lane == 0) atomicOr(p.status, WURM_ST_NO_HEAD_PARTIAL);
+                continue;
+            }
+            const int hy = div_S(hp, p.magic_S), hx = hp - hy * S;
+            for (int r = lane; r < E; r += 32) {
+                const uint32_t ent = tab[r];
+                const int c = ent & 3, y = hy - n + (int)((ent >> 2) & 0xff), x = hx - n + (int)(ent >> 10);
+                float v = 0.0f;
+                if (y >= 0 && y < S && x >= 0 && x < S) {
+                    const int q = y * S + x;
+                    v = rgb_channel(env[q], env[C + q], env[2 * C + q], y == 0 || x == 0 || y == S - 1 || x == S - 1, c);
+                }
+                o[r] = v;
+            }
+        }
+    } else if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
+        for (int t = warp; t < nvalid; t += nwarps) {
+            const float* env = tile + (size_t)t * 3 * C;
+            for (int q = lane; q < C; q += 32) {
+                const int y = div_S(q, p.magic_S), x = q - y * S;
+                const bool border = y == 0 || x == 0 || y == S - 1 || x == S - 1;
+                const float f = env[q], h = env[C + q], b = env[2 * C + q];
+                if (p.obs_mode == WURM_OBS_DEFAULT) {                // :131-138
+                    float* o = p.obs + (size_t)(env0 + t) * 3 * C;
+                    o[q] = rgb_channel(f, h, b, border, 0);
+                    o[C + q] = rgb_channel(f, h, b, border, 1);
+                    o[2 * C + q] = rgb_channel(f, h, b, border, 2);
+                } else {                                             // :142-151
+                    float v = (b > kEps ? 1.0f : 0.0f) * 0.5f;
+                    v += h * 0.5f;
+                    v += f * 1.5f;
+                    p.obs[(size_t)(env0 + t) * C + q] = border ? -1.0f : v;
+                }
+            }
+        }
+    } else if (p.obs_mode == WURM_OBS_POSITIONS) {                   // :152-165 first argmax of head / food
+        const unsigned gm = group_mask<G>();
+        const int t = threadIdx.x / G, l = threadIdx.x % G;
+        if (t < nvalid) {
+            const float* env = tile + (size_t)t * 3 * C;
+            int idx[2];
+            for (int ch = 0; ch < 2; ++ch) {
+                const float* v = env + (ch == 0 ? C : 0);
+                float bv = -INFINITY;
+                int bq = 0;
+                for (int q = l; q < C; q += G)
+                    if (v[q] > bv) { bv = v[q]; bq = q; }
+                const float gv = group_max<G>(bv, gm);
+                idx[ch] = -group_max<G>(bv == gv ? -bq : -(1 << 30), gm);   // smallest index attaining the max
+            }
+            if (l == 0) {
+                float* o = p.obs + (size_t)(env0 + t) * 4;
+                const int hy = div_S(idx[0], p.magic_S), fy = div_S(idx[1], p.magic_S);
+                o[0] = (float)hy; o[1] = (float)(idx[0] - hy * S);
+                o[2] = (float)fy; o[3] = (float)(idx[1] - fy * S);
+            }
+        }
+    }
+    // WURM_OBS_RAW is a second store of the tile, issued by the caller.
+}
+
+// One CTA = one tile of T envs.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
+template <int G, bool STEP>
+__global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* tile = reinterpret_cast<float*>(smem);
+    int* hp_s = reinterpret_cast<int*>(smem + p.tile_bytes_padded);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hp_s + ((p.T + 1) & ~1));
+    uint32_t* tab = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int env0 = blockIdx.x * p.T;
+    const int nvalid = min(p.T, p.N - env0);
+    const size_t goff = (size_t)env0 * 3 * p.C;
+    const int nfloats = nvalid * 3 * p.C;
+    const uint32_t bytes = (uint32_t)nfloats * 4u;
+    const bool bulk = p.bulk_ok && (bytes % 16u == 0u);
+
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_load(tile, p.envs + goff, bytes, bar);
+        }
+    } else {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) tile[i] = p.envs[goff + i];
+    }
+    if (p.obs_mode == WURM_OBS_PARTIAL) {   // (channel, row, col) of each element of one env's crop
+        const int W = p.W;
+        for (int r = threadIdx.x; r < 3 * W * W; r += blockDim.x) {
+            const int c = r / (W * W), ij = r - c * W * W, i = ij / W, j = ij - i * W;
+            tab[r] = (uint32_t)c | ((uint32_t)i << 2) | ((uint32_t)j << 10);
+        }
+    }
+    __syncthreads();                        // mbarrier init / fallback tile / tab visible
+    if (bulk) mbar_wait(bar, 0);
+
+    const int t = threadIdx.x / G, l = threadIdx.x % G;
+    if (STEP) {
+        if (t < nvalid) step_env<G>(p, tile + (size_t)t * 3 * p.C, env0 + t, l, hp_s + t);
+        if (bulk) fence_proxy_async();      // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                bulk_store(p.envs + goff, tile, bytes);
+                if (p.obs_mode == WURM_OBS_RAW) bulk_store(p.obs + goff, tile, bytes);
+                bulk_commit();
+            }
+        } else {
+            for (int i = threadIdx.x; i < nfloats; i += blockDim.x) {
+                p.envs[goff + i] = tile[i];
+                if (p.obs_mode == WURM_OBS_RAW) p.obs[goff + i] = tile[i];
+            }
+        }
+    } else {
+        if (p.obs_mode == WURM_OBS_PARTIAL) {
+            if (t < nvalid) find_head<G>(p, tile + (size_t)t * 3 * p.C, l, hp_s + t);
+            __syncthreads();
+        } else if (p.obs_mode == WURM_OBS_RAW) {
+            if (bulk) {
+                if (threadIdx.x == 0) { bulk_store(p.obs + goff, tile, bytes); bulk_commit(); }
+            } else {
+                for (int i = threadIdx.x; i < nfloats; i += blockDim.x) p.obs[goff + i] = tile[i];
+            }
+        }
+    }
+    if (p.obs_mode >= 0 && p.obs_mode != WURM_OBS_RAW) write_obs<G>(p, tile, hp_s, tab, env0, nvalid);
+    if (bulk && threadIdx.x == 0) bulk_wait_read_all();   // the tile must outlive the bulk store's reads
+}
+
+// single_snake.py:322-337 + 344-387: each warp inspects 32 done flags and re-creates the flagged
+// envs one after another with coalesced stores; untouched envs cost one byte of traffic.
+__global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p, const uint8_t* __restrict__ done_mask,
+                                                           const int32_t* __restrict__ spawn) {
+    const int lane = threadIdx.x & 31;
+    const int e_base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (e_base >= p.N) return;
+    const int e_mine = e_base + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, e_mine < p.N && done_mask[e_mine] != 0);
+    const int S = p.S, C = p.C;
+    while (todo) {
+        const int e = e_base + __ffs(todo) - 1;
+        todo &= todo - 1;
+        int y, x, d, cell;
+        if (spawn) {
+            y = spawn[4 * (size_t)e]; x = spawn[4 * (size_t)e + 1]; d = spawn[4 * (size_t)e + 2]; cell = spawn[4 * (size_t)e + 3];
+        } else {
+            const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamSingleReset);
+            y = 4 + (int)bounded(r.x, (uint32_t)(S - 8));            // :358 randint(4, S-4)
+            x = 4 + (int)bounded(r.y, (uint32_t)(S - 8));            // :359
+            d = (int)(r.z >> 30);                                    // :366 randint(4)
+            // :384 one free interior cell: the r-th interior cell in raster order, skipping the
+            // three snake cells (all interior because 4 <= y,x < S-4)
+            const int I = S - 2;
+            int s0 = (y - off_y(d) - 1) * I + (x - off_x(d) - 1), s1 = (y - 1) * I + (x - 1),
+                s2 = (y + off_y(d) - 1) * I + (x + off_x(d) - 1);
+            if (s0 > s2) { const int tmp = s0; s0 = s2; s2 = tmp; }  // s1 is always the middle one
+            int rr = (int)bounded(r.w, (uint32_t)(I * I - 3));
+            if (rr >= s0) ++rr;
+            if (rr >= s1) ++rr;
+            if (rr >= s2) ++rr;
+            const int fy = rr / I;
+            cell = (fy + 1) * S + (rr - fy * I + 1);
+        }
+        const int tail = (y - off_y(d)) * S + (x - off_x(d)), mid = y * S + x, hd = (y + off_y(d)) * S + (x + off_x(d));
+        float* env = p.envs + (size_t)e * 3 * C;
+        for (int i = lane; i < 3 * C; i += 32) {                     // :372-385 LENGTH_3_SNAKES stamp, head, food
+            float v = 0.0f;
+            if (i == cell) v = 1.0f;
+            if (i == C + hd) v = 1.0f;
+            if (i == 2 * C + tail) v = 1.0f;
+            if (i == 2 * C + mid) v = 2.0f;
+            if (i == 2 * C + hd) v = 3.0f;
+            env[i] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct SingleLaunch {
+    int G, T, threads, blocks, smem;
+};
+
+static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* L) {
+    if (!cfg) return fail(WURM_E_INVALID, "cfg is NULL");
+    const int N = cfg->num_envs, S = cfg->size;
+    if (N <= 0) return fail(WURM_E_INVALID, "num_envs must be positive");
+    if (S < 9) return fail(WURM_E_INVALID, "size must be >= 9 (reference single_snake.py:346)");
+    if (S > 128) return fail(WURM_E_UNSUPPORTED, "size > 128: one env no longer fits a shared-memory tile");
+    if (cfg->obs_mode < WURM_OBS_NONE || cfg->obs_mode > WURM_OBS_PARTIAL) return fail(WURM_E_INVALID, "bad obs_mode");
+    if (cfg->obs_mode == WURM_OBS_PARTIAL && (cfg->obs_n < 0 || cfg->obs_n > 127)) return fail(WURM_E_INVALID, "bad obs_n");
+    const int C = S * S;
+    int G = 1;
+    while (G < 32 && G * 32 < C) G <<= 1;
+    const int env_bytes = 3 * C * 4;
+    int T = 256 / G;
+    if (T * env_bytes > 64 * 1024) T = (64 * 1024) / env_bytes;
+    const int per_warp = 32 / G;                       // envs per warp
+    T = (T / per_warp) * per_warp;
+    if (T < per_warp) T = per_warp;
+    // prefer a tile whose byte count is a multiple of 16 so the bulk path applies
+    if (((size_t)T * env_bytes) % 16 != 0 && T >= 4) T &= ~3;
+    if (T < per_warp) T = per_warp;
+    const int W = 2 * cfg->obs_n + 1;
+    const int tile_bytes_padded = (T * env_bytes + 15) & ~15;
+    const int smem = tile_bytes_padded + ((T + 1) & ~1) * 4 + 8 + (cfg->obs_mode == WURM_OBS_PARTIAL ? 3 * W * W * 4 : 0);
+    if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "tile does not fit shared memory");
+    p->N = N; p->S = S; p->C = C; p->T = T;
+    p->obs_mode = cfg->obs_mode; p->obs_n = cfg->obs_n; p->W = W;
+    p->magic_S = (uint32_t)((0x100000000ull + (uint64_t)S - 1) / (uint64_t)S);
+    p->tile_bytes_padded = tile_bytes_padded;
+    L->G = G; L->T = T; L->threads = T * G; L->blocks = (N + T - 1) / T; L->smem = smem;
+    return WURM_OK;
+}
+
+template <int G, bool STEP>
+static int launch_tile(const SingleParams& p, const SingleLaunch& L, cudaStream_t stream) {
+    auto kern = single_tile_kernel<G, STEP>;
+    static int configured_smem = -1;                   // per instantiation
+    if (L.smem > configured_smem) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem);
+        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(single_tile_kernel)");
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured_smem = L.smem;
+    }
+    kern<<<L.blocks, L.threads, L.smem, stream>>>(p);
+    return check_launch("single_tile_kernel");
+}
+
+template <bool STEP>
+static int dispatch_tile(const SingleParams& p, const SingleLaunch& L, cudaStream_t stream) {
+    switch (L.G) {
+        case 1: return launch_tile<1, STEP>(p, L, stream);
+        case 2: return launch_tile<2, STEP>(p, L, stream);
+        case 4: return launch_tile<4, STEP>(p, L, stream);
+        case 8: return launch_tile<8, STEP>(p, L, stream);
+        case 16: return launch_tile<16, STEP>(p, L, stream);
+        default: return launch_tile<32, STEP>(p, L, stream);
+    }
+}
+
+static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
+
+}  // namespace wurm
+
+using namespace wurm;
+
+extern "C" int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg) {
+    if (!cfg) return -1;
+    const int64_t C = (int64_t)cfg->size * cfg->size, W = 2 * cfg->obs_n + 1;
+    switch (cfg->obs_mode) {
+        case WURM_OBS_DEFAULT:
+        case WURM_OBS_RAW: return 3 * C;
+        case WURM_OBS_ONE_CHANNEL: return C;
+        case WURM_OBS_POSITIONS: return 4;
+        case WURM_OBS_PARTIAL: return 3 * W * W;
+        default: return 0;
+    }
+}
+
+extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
+                                const int32_t* food_cell_replay, uint64_t seed, uint64_t step, float* obs, float* reward,
+                                uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status, void* stream) {
+    SingleParams p = {};
+    SingleLaunch L;
+    if (int rc = plan_single(cfg, &p, &L)) return rc;
+    if (!envs || !actions || !reward || !done || !self_col || !edge_col || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
+    if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
+    p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
+    p.seed = seed; p.step = step; p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
+    p.edge_col = edge_col; p.status = status;
+    p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
+    return dispatch_tile<true>(p, L, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream) {
+    SingleParams p = {};
+    SingleLaunch L;
+    if (int rc = plan_single(cfg, &p, &L)) return rc;
+    if (!envs || !obs || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    if (cfg->obs_mode == WURM_OBS_NONE) return WURM_OK;
+    p.envs = const_cast<float*>(envs); p.obs = obs; p.status = status;
+    p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
+    return dispatch_tile<false>(p, L, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* spawn_replay,
+                                 uint64_t seed, uint64_t step, void* stream) {
+    SingleParams p = {};
+    SingleLaunch L;
+    if (int rc = plan_single(cfg, &p, &L)) return rc;
+    if (!envs || !done_mask) return fail(WURM_E_INVALID, "NULL pointer");
+    p.envs = envs; p.seed = seed; p.step = step;
+    const int warps_per_block = 8;
+    const int blocks = (p.N + 32 * warps_per_block - 1) / (32 * warps_per_block);
+    single_reset_kernel<<<blocks, 32 * warps_per_block, 0, (cudaStream_t)stream>>>(p, done_mask, spawn_replay);
+    return check_launch("single_reset_kernel");
+}

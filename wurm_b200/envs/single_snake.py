@@ -1,0 +1,276 @@
+"""Batched classic-snake environment, B200-native.
+
+Drop-in for the reference's `wurm.envs.SingleSnake` (wurm/envs/single_snake.py:17-428): same
+constructor arguments, attributes (`envs`, `done`, `num_envs`, `size`, ...), `reset(done)`,
+`step(actions) -> (observations, reward, done, info)`, exceptions and side effects (the caller's
+`actions` tensor is sanitised in place, :222).  The state stays in the reference's own layout --
+`envs` is a plain `(num_envs, 3, size, size)` fp32 CUDA tensor callers may read and write -- and each
+call is ONE kernel launch through the C ABI of include/wurm_b200.h (wurm_b200/csrc/single_snake.cu).
+
+Randomness (food respawn, spawn position/direction) is an input of the kernels: by default it is
+derived on the device from Philox4x32-10 keyed by (`seed`, call counter, env); the keyword-only
+`food_cell_replay` / `spawn_replay` arguments inject recorded draws instead, which is how bit-exact
+parity with the reference is tested (the reference's own draws go through an unstable sort of a CPU
+randperm, wurm/utils.py:188,224, and cannot be regenerated).
+"""
+from collections import namedtuple
+from time import time
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..config import DEFAULT_DEVICE, BODY_CHANNEL, EPS, HEAD_CHANNEL, FOOD_CHANNEL  # noqa: F401
+
+Spec = namedtuple('Spec', ['reward_threshold'])
+
+_OBS_MODES = {'default': _lib.OBS_DEFAULT, 'raw': _lib.OBS_RAW, 'one_channel': _lib.OBS_ONE_CHANNEL,
+              'positions': _lib.OBS_POSITIONS}
+_ACTION_BYTES = {torch.short: 2, torch.int: 4, torch.long: 8}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class SingleSnake(object):
+    """Batched snake environment (state layout and dynamics: reference single_snake.py:18-47).
+
+    Channel 0 food (0/1), channel 1 head (0/1), channel 2 body (1 = tail ... L = head cell).
+    """
+
+    spec = Spec(float('inf'))
+    metadata = {
+        'render.modes': ['rgb_array'],
+        'video.frames_per_second': 12
+    }
+
+    def __init__(self,
+                 num_envs: int,
+                 size: int,
+                 max_timesteps: int = None,
+                 initial_snake_length: int = 3,
+                 on_death: str = 'restart',
+                 observation_mode: str = 'one_channel',
+                 device: str = DEFAULT_DEVICE,
+                 manual_setup: bool = False,
+                 verbose: int = 0,
+                 render_args: dict = None,
+                 seed: int = None):
+        self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
+        self.num_envs = num_envs
+        self.size = size
+        self.max_timesteps = max_timesteps
+        self.initial_snake_length = initial_snake_length
+        self.on_death = on_death
+        self.observation_mode = observation_mode
+        self.device = device
+        self.verbose = verbose
+        if torch.device(device).type != 'cuda':
+            raise RuntimeError(f"wurm_b200 envs run on CUDA devices only (got device={device!r}); "
+                               "the CPU implementation of this path is the reference itself")
+
+        if render_args is None:
+            self.render_args = {'num_rows': 1, 'num_cols': 1, 'size': 256}
+        else:
+            self.render_args = render_args
+
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, ()).item())    # follows torch.manual_seed
+        self.seed = seed
+        self._draws = 0          # Philox call counter: one tick per call that may draw
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+        self.envs = torch.zeros((num_envs, 3, size, size), device=self.device)
+        self.t = 0
+
+        if not manual_setup:
+            self.envs = self._create_envs(self.num_envs)
+
+        self.done = torch.zeros(num_envs, dtype=torch.bool, device=self.device)
+
+        self.viewer = None
+
+        self.body_colour = torch.tensor((0, 127, 0), dtype=torch.short, device=self.device)
+        self.head_colour = torch.tensor((0, 255, 0), dtype=torch.short, device=self.device)
+        self.food_colour = torch.tensor((255, 0, 0), dtype=torch.short, device=self.device)
+        self.edge_colour = torch.tensor((0, 0, 0), dtype=torch.short, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+    def _cfg(self, observation_mode, num_envs=None):
+        if observation_mode is None:
+            mode, n = _lib.OBS_NONE, 0
+        elif observation_mode.startswith('partial_'):
+            # the reference parses the window from self.observation_mode, not the argument (:167)
+            mode, n = _lib.OBS_PARTIAL, int(self.observation_mode.split('_')[-1])
+        elif observation_mode in _OBS_MODES:
+            mode, n = _OBS_MODES[observation_mode], 0
+        else:
+            raise Exception(f'Unrecognised observation mode {observation_mode!r}')   # :195
+        return _lib.WurmSingleCfg(self.num_envs if num_envs is None else num_envs, self.size, mode, n)
+
+    def _obs_shape(self, cfg):
+        n, s = cfg.num_envs, self.size
+        w = 2 * cfg.obs_n + 1
+        return {_lib.OBS_DEFAULT: (n, 3, s, s), _lib.OBS_RAW: (n, 3, s, s), _lib.OBS_ONE_CHANNEL: (n, 1, s, s),
+                _lib.OBS_POSITIONS: (n, 4), _lib.OBS_PARTIAL: (n, 3 * w * w)}[cfg.obs_mode]
+
+    def _state(self):
+        """`envs` may have been replaced or sliced by the caller (tests assign it): normalise."""
+        e = self.envs
+        if e.dtype != torch.float32 or not e.is_contiguous() or e.device.type != 'cuda':
+            e = e.to(device=self.device, dtype=torch.float32).contiguous()
+            self.envs = e
+        if tuple(e.shape) != (self.num_envs, 3, self.size, self.size):
+            raise RuntimeError(f'envs has shape {tuple(e.shape)}, expected {(self.num_envs, 3, self.size, self.size)}')
+        return e
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.envs.device).cuda_stream)
+
+    def check_status(self):
+        """Raises if a kernel met a state outside the supported set since the last check (one sync)."""
+        st = int(self._status.item())
+        if st:
+            self._status.zero_()
+            msgs = []
+            if st & _lib.ST_MULTI_HEAD:
+                msgs.append('an environment holds more than one head cell')
+            if st & _lib.ST_NO_HEAD_PARTIAL:
+                msgs.append("partial observation of an environment without a head (the reference raises a view-shape "
+                            "error here); zeros were written")
+            raise RuntimeError('; '.join(msgs) or f'status {st}')
+
+    # ------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------
+    def _observe(self, observation_mode: str = 'default'):
+        cfg = self._cfg(observation_mode)
+        envs = self._state()
+        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=envs.device)
+        with torch.cuda.device(envs.device):
+            _lib.check(self._lib.wurm_single_observe(ctypes.byref(cfg), _ptr(envs), _ptr(obs), _ptr(self._status),
+                                                     self._stream()))
+        return obs
+
+    def _get_rgb(self):
+        """int16 (N,3,S,S) image, as displayed by render() (reference :104-128)."""
+        return (self._observe('default') * 255).round().short()
+
+    def step(self, actions: torch.Tensor, *, food_cell_replay: torch.Tensor = None):
+        if actions.dtype not in (torch.short, torch.int, torch.long):
+            raise TypeError('actions Tensor must be an integer type i.e. '
+                            '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
+
+        if actions.shape[0] != self.num_envs:
+            raise RuntimeError('Must have the same number of actions as environments.')
+
+        t0 = time()
+        envs = self._state()
+        dev = envs.device
+        host_actions = None
+        if actions.device != dev or not actions.is_contiguous():
+            host_actions, actions = actions, actions.to(dev, non_blocking=True).contiguous()
+        cfg = self._cfg(self.observation_mode)
+        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=dev)
+        reward = torch.empty(self.num_envs, dtype=torch.float32, device=dev)
+        done = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
+        self_collision = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
+        edge_collision = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
+        if food_cell_replay is not None:
+            food_cell_replay = food_cell_replay.to(device=dev, dtype=torch.int32).contiguous()
+        self._draws += 1
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.wurm_single_step(
+                ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
+                self.seed, self._draws, _ptr(obs), _ptr(reward), _ptr(done), _ptr(self_collision),
+                _ptr(edge_collision), _ptr(self._status), self._stream()))
+        if host_actions is not None:
+            host_actions.copy_(actions, non_blocking=True)      # the sanitised actions (reference :222)
+        info = {'self_collision': self_collision, 'edge_collision': edge_collision}
+        self.done = done
+        if self.verbose > 0:
+            torch.cuda.synchronize(dev)
+            print(f'step: {time() - t0}s')
+        return obs, reward.unsqueeze(-1), done.unsqueeze(-1), info
+
+    def reset(self, done: torch.Tensor = None, *, spawn_replay: torch.Tensor = None,
+              return_observations: bool = True):
+        """Re-creates the environments flagged in `done` (reference :322-342).
+
+        `return_observations=False` (an extension, as MultiSnake.reset has in the reference) skips the
+        full observation the reference recomputes and its drivers discard (experiments/main.py:227).
+        """
+        if done is None:
+            done = self.done
+
+        done = done.view((done.shape[0]))
+        if done.shape[0] != self.num_envs:
+            raise RuntimeError('Must have one done flag per environment.')
+
+        t0 = time()
+        envs = self._state()
+        mask = (done != 0).to(device=envs.device).contiguous()
+        self._reset_mask(envs, mask, spawn_replay)
+
+        if self.verbose:
+            print(f'Resetting {done.sum().item()} envs: {time() - t0}s')
+
+        if return_observations:
+            return self._observe(self.observation_mode)
+
+    def _reset_mask(self, envs, mask, spawn_replay=None):
+        cfg = _lib.WurmSingleCfg(envs.shape[0], self.size, _lib.OBS_NONE, 0)
+        if spawn_replay is not None:
+            spawn_replay = spawn_replay.to(device=envs.device, dtype=torch.int32).contiguous()
+        self._draws += 1
+        with torch.cuda.device(envs.device):
+            _lib.check(self._lib.wurm_single_reset(ctypes.byref(cfg), _ptr(envs), _ptr(mask), _ptr(spawn_replay),
+                                                   self.seed, self._draws, self._stream()))
+
+    def _create_envs(self, num_envs: int, *, spawn_replay: torch.Tensor = None):
+        """Vectorised environment creation (reference :344-387)."""
+        if self.size <= 8:
+            raise NotImplementedError('Cannot make an env this small without making this code more clever')
+
+        if self.initial_snake_length != 3:
+            raise NotImplementedError('Only initial snake length = 3 has been implemented.')
+
+        envs = torch.empty((num_envs, 3, self.size, self.size), device=self.device)
+        self._reset_mask(envs, torch.ones(num_envs, dtype=torch.bool, device=self.device), spawn_replay)
+        return envs
+
+    def render(self, mode: str = 'human'):
+        """Human display (reference :389-428); host-side, outside the hot path."""
+        img = self._get_rgb().cpu().numpy()
+
+        if self.num_envs == 1:
+            num_cols = num_rows = 1
+            img = np.transpose(img[0], (1, 2, 0))
+        else:
+            num_rows = self.render_args['num_rows']
+            num_cols = self.render_args['num_cols']
+            output = np.zeros((self.size * num_rows, self.size * num_cols, 3))
+            for i in range(num_rows):
+                for j in range(num_cols):
+                    output[i * self.size:(i + 1) * self.size, j * self.size:(j + 1) * self.size, :] = \
+                        np.transpose(img[i * num_cols + j], (1, 2, 0))
+            img = output
+
+        from PIL import Image
+        img = np.array(Image.fromarray(img.astype(np.uint8)).resize(
+            (self.render_args['size'] * num_cols, self.render_args['size'] * num_rows)))
+
+        if mode == 'human':
+            if self.viewer is None:
+                from gym.envs.classic_control import rendering
+                self.viewer = rendering.SimpleImageViewer()
+            self.viewer.imshow(img)
+            return self.viewer.isopen
+        elif mode == 'rgb_array':
+            return img
+        else:
+            raise ValueError('Render mode not recognised.')
