@@ -1,0 +1,331 @@
+"""Benchmark of the wurm_b200 hot path: env-steps/s of the batched env step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C3|C1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" is one pass of the hot path over one batch of synthetic actions, in the reference's own
+benchmark shape (reference tests/test_single_snake_env.py:23-34, experiments/speeds.py:28-42):
+
+    obs, reward, done, info = env.step(actions[t]);  env.reset(done)
+
+At N GPUs every rank owns an independent slice of `num_envs` environments (weak scaling: the
+environments do not interact); the only collective is one all-reduce of the
+episode-statistics counters after the timed region.  Rank 0 prints ONE JSON line.
+
+  value      whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed, max over ranks
+  e2e        same loop through the public API with HOST buffers: every step copies that step's actions from
+             pinned host memory, and copies the sanitised actions, rewards and done flags back to pinned host
+             memory, all inside the timed region
+  roofline   for the dominant kernel (the step kernel): algorithmic bytes per launch (SURVEY.md section 8d:
+             read state + write state + write observation + per-env vectors) / its average launch duration,
+             measured live with CUDA events around every step launch of the timed region, against the
+             measured copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (oracle/wurm_oracle.c, a C/OpenMP port of the reference's algorithm) timed on
+             this box's host cores on a bounded sample of the same workload (rank 0, N=1 only)
+
+`--impl reference` times that same CPU port alone, with all host threads, and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (env, size, num_envs per GPU, observation mode)  -- BASELINE.json configs[1], [2], [0]
+    'C2': ('SingleSnake', 9, 1 << 20, 'partial_2'),
+    'C3': ('SingleSnake', 36, 1 << 16, 'default'),
+    'C1': ('SingleSnake', 9, 512, 'partial_2'),
+}
+ACTION_POOL = 16        # pre-generated action tensors cycled through by the timed loop
+
+
+def workload_name(key, n_envs=None):
+    env, S, N, mode = WORKLOADS[key]
+    N = n_envs or N
+    return f'{env} size={S} num_envs={N} {mode} obs, random actions, step+reset(done)'
+
+
+def algorithmic_bytes_per_env_step(S, obs_elems):
+    """read state + write state + write obs + per-env vectors
+    (actions r/w 16, reward 4, done 1, info 2)."""
+    return 2 * 3 * S * S * 4 + obs_elems * 4 + 23
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '50', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, f[2:]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def profiled_traffic(key):
+    """dram bytes per launch of the step kernel from the last `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get(key)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle) timing: cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+def time_cpu_port(key, n_envs, steps, warmup, threads):
+    """Times the oracle's step + observe + reset loop on `threads` host threads.  Returns (env-steps/s, s)."""
+    import numpy as np
+    from oracle import oracle as orc      # the checker; allowed here as the timed CPU baseline only
+    os.environ['OMP_NUM_THREADS'] = str(threads)
+    _, S, _, mode = WORKLOADS[key]
+    rng = np.random.default_rng(0)
+    state = np.zeros((n_envs, 3, S, S), np.float32)
+    orc.single_reset(state, np.ones(n_envs, np.uint8), None, seed=1234, step=0)
+    pool = [rng.integers(0, 4, n_envs).astype(np.int64) for _ in range(ACTION_POOL)]
+    t0 = None
+    for t in range(warmup + steps):
+        if t == warmup:
+            t0 = time.perf_counter()
+        r, d, sc, ec = orc.single_step(state, pool[t % ACTION_POOL], None, seed=1234, step=2 * t + 1)
+        obs, _ = orc.single_observe(state, mode)
+        orc.single_reset(state, d, None, seed=1234, step=2 * t + 2)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def cpu_sample_size(key):
+    _, S, N, _ = WORKLOADS[key]
+    return min(N, max(512, ((1 << 26) // (3 * S * S * 4)) // 1024 * 1024))    # ~64 MiB of state
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's algorithm on all host cores (rank 0 only)."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    key = args.workload
+    threads = os.cpu_count() or 1
+    n = cpu_sample_size(key)
+    steps = max(1, min(args.steps, 50))
+    warmup = max(1, min(args.warmup, 5))
+    value, dt = time_cpu_port(key, n, steps, warmup, threads)
+    _, S, N, mode = WORKLOADS[key]
+    sample = f'{n} envs x {steps} steps (+{warmup} warm-up) of the same workload, step+observe+reset, OpenMP'
+    line = {
+        'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(key), 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from wurm_b200.envs import SingleSnake
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run --nproc-per-node N for --gpus N > 1')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    key = args.workload
+    _, S, N, mode = WORKLOADS[key]
+    K, W = args.steps, max(3, args.warmup)
+    env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=1234 + rank)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (value) + per-launch step-kernel time (roofline) ----
+    for t in range(W):
+        obs, reward, done, info = env.step(pool[t % ACTION_POOL])
+        env.reset(done, return_observations=False)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.time()
+    start.record()
+    for t in range(K):
+        a, b = ev[t]
+        a.record()
+        obs, reward, done, info = env.step(pool[t % ACTION_POOL])
+        b.record()
+        env.reset(done, return_observations=False)
+    stop.record()
+    barrier()
+    t_wall1 = time.time()
+    sampler.stop()
+    ms_total = start.elapsed_time(stop)
+    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    obs_elems = obs[0].numel()
+    del ev
+
+    # ---- end to end through the public API with host buffers ----
+    host_pool = [p.cpu().pin_memory() for p in pool]
+    host_reward = torch.empty((N, 1), dtype=torch.float32).pin_memory()
+    host_done = torch.empty((N, 1), dtype=torch.bool).pin_memory()
+    Ke = max(10, K // 4)
+    for t in range(3):
+        obs, reward, done, info = env.step(host_pool[t % ACTION_POOL])
+        env.reset(done, return_observations=False)
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_start.record()
+    for t in range(Ke):
+        obs, reward, done, info = env.step(host_pool[t % ACTION_POOL])      # H2D actions, D2H sanitised actions
+        host_reward.copy_(reward, non_blocking=True)                        # D2H results
+        host_done.copy_(done, non_blocking=True)
+        env.reset(done, return_observations=False)
+    e_stop.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_stop)
+    act_bytes = N * pool[0].element_size()
+    h2d, d2h = act_bytes, act_bytes + N * 4 + N * 1
+
+    # ---- max over ranks, episode statistics (the only collective on this path) ----
+    times = torch.tensor([ms_total, e2e_ms, step_kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, step_kernel_ms = times.tolist()
+    stats = env.stats(reduce_group=True if world > 1 else None)
+    env.check_status()
+    clocks = sampler.summary(t_wall0, t_wall1)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, clocks)
+        sms = [c['sm_mhz'] for c in gathered if c['sm_mhz'] is not None]
+        clocks = {'sm_mhz': min(sms) if sms else None, 'sm_max_mhz': gathered[0]['sm_max_mhz'],
+                  'reasons': sorted(set(sum((c['reasons'] for c in gathered), []))),
+                  'samples': sum(c['samples'] for c in gathered)}
+
+    if rank == 0:
+        value = world * N * K / (ms_total * 1e-3)
+        e2e_value = world * N * Ke / (e2e_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        bytes_per_launch = algorithmic_bytes_per_env_step(S, obs_elems) * N
+        achieved = bytes_per_launch / (step_kernel_ms * 1e-3) / 1e9
+        line = {
+            'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(key), 'num_envs_per_gpu': N, 'size': S, 'observation_mode': mode,
+                       'actions': f'int64 randint(0,4), pool of {ACTION_POOL} pre-generated tensors per rank',
+                       'loop': 'obs,reward,done,info = env.step(a); env.reset(done, return_observations=False)',
+                       'l2': f'inputs larger than L2: state {N * 3 * S * S * 4 / 1e6:.0f} MB + obs '
+                             f'{N * obs_elems * 4 / 1e6:.0f} MB per step vs 126 MB L2',
+                       'parallelism': f'{world} independent env slices, NCCL all-reduce of episode stats only'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'steps': Ke, 'ms_per_step': e2e_ms / Ke},
+            'gpu_launches': 2 * K,
+            'roofline': {'bound': 'hbm', 'kernel': 'single_tile_kernel<G,STEP=true>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': profiled_traffic(key),
+                         'peak_source': peak_src, 'bytes_per_launch': bytes_per_launch,
+                         'kernel_ms': step_kernel_ms, 'frac_of_nominal_8TBs': achieved / 8000.0},
+            'episode_stats': stats,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n = cpu_sample_size(key)
+            threads = os.cpu_count() or 1
+            cpu_value, dt = time_cpu_port(key, n, 20, 3, threads)
+            line['cpu_baseline'] = {'value': cpu_value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'{n} envs x 20 steps of the same workload (step+observe+reset), '
+                                              f'oracle/wurm_oracle.c with OpenMP, {dt:.1f} s'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='wurm_b200', choices=['wurm_b200', 'reference'])
+    ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

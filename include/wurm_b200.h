@@ -50,6 +50,18 @@ extern "C" {
 #define WURM_OBS_PARTIAL 4     /* (N,3*(2n+1)^2) crop around the head */
 #define WURM_OBS_NONE -1       /* do not write an observation */
 
+/* Episode statistics accumulated by the step kernels (all-reduced over ranks by the caller; the
+ * fields of the reference drivers' log lines, experiments/main.py:264-311).  The buffer is
+ * WURM_STATS_SLOTS x WURM_STATS_FIELDS int64 counters; CTAs add to slot (block index % SLOTS) so no
+ * single L2 address is hot; the reader sums over slots. */
+#define WURM_STATS_SLOTS 32
+#define WURM_STATS_FIELDS 5
+#define WURM_STAT_ENV_STEPS 0
+#define WURM_STAT_EPISODES 1      /* done flags raised */
+#define WURM_STAT_REWARD 2        /* food eaten */
+#define WURM_STAT_SELF_COLLISIONS 3
+#define WURM_STAT_EDGE_COLLISIONS 4
+
 typedef struct WurmSingleCfg {
     int32_t num_envs; /* N */
     int32_t size;     /* S, >= 9 (single_snake.py:346) */
@@ -74,7 +86,8 @@ int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg);
  *            this step (-1: none); NULL -> uniform over free interior cells from Philox.        */
 int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                      const int32_t* food_cell_replay, uint64_t seed, uint64_t step, float* obs, float* reward,
-                     uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status, void* stream);
+                     uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status,
+                     int64_t* stats /* nullable */, void* stream);
 
 /* Replaces the state update of SingleSnake.reset / _create_envs (single_snake.py:322-337, 344-387):
  * envs whose done_mask byte is non-zero are re-created, all others untouched.

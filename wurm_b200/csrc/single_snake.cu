@@ -33,6 +33,7 @@ struct SingleParams {
     uint8_t* self_col;
     uint8_t* edge_col;
     int32_t* status;
+    unsigned long long* stats;   // nullable: WURM_STATS_SLOTS x WURM_STATS_FIELDS counters
     uint64_t seed, step;
     int N, S, C;          // envs, grid side, cells per channel
     int T;                // envs per tile (= per CTA)
@@ -115,7 +116,7 @@ __device__ __noinline__ int pick_free_cell(const float* env, int S, int C, uint3
 
 // single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
 template <int G>
-__device__ __forceinline__ void step_env(const SingleParams& p, float* env, int e, int l, int* hp_out) {
+__device__ __forceinline__ void step_env(const SingleParams& p, float* env, int e, int l, int* hp_out, int* cnt_s) {
     const unsigned gm = group_mask<G>();
     const int S = p.S, C = p.C;
     float* food = env;
@@ -210,6 +211,12 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
         p.done[e] = sc || !interior;
         *hp_out = np;
         if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+        if (p.stats) {                                               // episode statistics, per-CTA partials
+            if (sc || !interior) atomicAdd(cnt_s + 0, 1);
+            if (ov != 0.0f) atomicAdd(cnt_s + 1, (int)ov);
+            if (sc) atomicAdd(cnt_s + 2, 1);
+            if (!interior) atomicAdd(cnt_s + 3, 1);
+        }
     }
 }
 
@@ -309,7 +316,8 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     float* tile = reinterpret_cast<float*>(smem);
     int* hp_s = reinterpret_cast<int*>(smem + p.tile_bytes_padded);
     uint64_t* bar = reinterpret_cast<uint64_t*>(hp_s + ((p.T + 1) & ~1));
-    uint32_t* tab = reinterpret_cast<uint32_t*>(bar + 1);
+    int* cnt_s = reinterpret_cast<int*>(bar + 1);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(cnt_s + 4);
 
     const int env0 = blockIdx.x * p.T;
     const int nvalid = min(p.T, p.N - env0);
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     } else {
         for (int i = threadIdx.x; i < nfloats; i += blockDim.x) tile[i] = p.envs[goff + i];
     }
+    if (threadIdx.x < 4) cnt_s[threadIdx.x] = 0;
     if (p.obs_mode == WURM_OBS_PARTIAL) {   // (channel, row, col) of each element of one env's crop
         const int W = p.W;
         for (int r = threadIdx.x; r < 3 * W * W; r += blockDim.x) {
@@ -340,9 +349,14 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
 
     const int t = threadIdx.x / G, l = threadIdx.x % G;
     if (STEP) {
-        if (t < nvalid) step_env<G>(p, tile + (size_t)t * 3 * p.C, env0 + t, l, hp_s + t);
+        if (t < nvalid) step_env<G>(p, tile + (size_t)t * 3 * p.C, env0 + t, l, hp_s + t, cnt_s);
         if (bulk) fence_proxy_async();      // generic-proxy writes -> visible to the bulk store
         __syncthreads();
+        if (p.stats && threadIdx.x < WURM_STATS_FIELDS) {   // one striped slot per CTA: no hot address in L2
+            unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+            const int v = threadIdx.x == 0 ? nvalid : cnt_s[threadIdx.x - 1];
+            if (v) atomicAdd(slot + threadIdx.x, (unsigned long long)v);
+        }
         if (bulk) {
             if (threadIdx.x == 0) {
                 bulk_store(p.envs + goff, tile, bytes);
@@ -448,7 +462,7 @@ static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* 
     if (T < per_warp) T = per_warp;
     const int W = 2 * cfg->obs_n + 1;
     const int tile_bytes_padded = (T * env_bytes + 15) & ~15;
-    const int smem = tile_bytes_padded + ((T + 1) & ~1) * 4 + 8 + (cfg->obs_mode == WURM_OBS_PARTIAL ? 3 * W * W * 4 : 0);
+    const int smem = tile_bytes_padded + ((T + 1) & ~1) * 4 + 8 + 16 + (cfg->obs_mode == WURM_OBS_PARTIAL ? 3 * W * W * 4 : 0);
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "tile does not fit shared memory");
     p->N = N; p->S = S; p->C = C; p->T = T;
     p->obs_mode = cfg->obs_mode; p->obs_n = cfg->obs_n; p->W = W;
@@ -505,7 +519,8 @@ extern "C" int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg) {
 
 extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                                 const int32_t* food_cell_replay, uint64_t seed, uint64_t step, float* obs, float* reward,
-                                uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status, void* stream) {
+                                uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats,
+                                void* stream) {
     SingleParams p = {};
     SingleLaunch L;
     if (int rc = plan_single(cfg, &p, &L)) return rc;
@@ -514,7 +529,7 @@ extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* act
     if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
     p.seed = seed; p.step = step; p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
-    p.edge_col = edge_col; p.status = status;
+    p.edge_col = edge_col; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
     return dispatch_tile<true>(p, L, (cudaStream_t)stream);
 }

@@ -81,6 +81,8 @@ class SingleSnake(object):
         self.seed = seed
         self._draws = 0          # Philox call counter: one tick per call that may draw
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # episode statistics accumulated by the step kernel (see `stats`)
+        self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
 
         self.envs = torch.zeros((num_envs, 3, size, size), device=self.device)
         self.t = 0
@@ -130,6 +132,17 @@ class SingleSnake(object):
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.envs.device).cuda_stream)
+
+    def stats(self, reduce_group=None):
+        """Episode statistics accumulated on the device since construction: a dict of int counters
+        (env_steps, episodes, reward, self_collisions, edge_collisions).  With `reduce_group` (a
+        torch.distributed process group, or True for the default group) the counters are summed
+        over ranks with one small all-reduce -- the only collective this path has."""
+        totals = self._stats.sum(dim=0)
+        if reduce_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(totals, group=None if reduce_group is True else reduce_group)
+        return dict(zip(_lib.STAT_NAMES, totals.tolist()))
 
     def check_status(self):
         """Raises if a kernel met a state outside the supported set since the last check (one sync)."""
@@ -187,7 +200,7 @@ class SingleSnake(object):
             _lib.check(self._lib.wurm_single_step(
                 ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                 self.seed, self._draws, _ptr(obs), _ptr(reward), _ptr(done), _ptr(self_collision),
-                _ptr(edge_collision), _ptr(self._status), self._stream()))
+                _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
         if host_actions is not None:
             host_actions.copy_(actions, non_blocking=True)      # the sanitised actions (reference :222)
         info = {'self_collision': self_collision, 'edge_collision': edge_collision}
@@ -213,7 +226,10 @@ class SingleSnake(object):
 
         t0 = time()
         envs = self._state()
-        mask = (done != 0).to(device=envs.device).contiguous()
+        if done.dtype == torch.bool and done.device == envs.device and done.is_contiguous():
+            mask = done                     # the step's own flags: no conversion kernel on the hot loop
+        else:
+            mask = (done != 0).to(device=envs.device).contiguous()
         self._reset_mask(envs, mask, spawn_replay)
 
         if self.verbose:
