@@ -132,3 +132,17 @@ def take_tape():
     out = list(TAPE)
     del TAPE[:]
     return out
+
+
+def instrument_multi(env):
+    """Records, at the moment the reference's MultiSnake._add_food runs (multi_snake.py:368-410), which
+    envs it selects -- the row order of the draws made there (drop_duplicates :447 / rand :401)."""
+    original = env._add_food
+
+    def recording_add_food():
+        total = env.foods.view(env.num_envs, -1).sum(dim=-1)
+        selected = total < (1e-6 if env.food_mode == 'only_one' else env.max_food)
+        TAPE.append(('add_food_selected', 0, selected.clone()))
+        return original()
+    env._add_food = recording_add_food
+    return env

@@ -44,3 +44,85 @@ def single_reset_tape(tape, done, N, S):
     spawn[ids, 2] = tape[2][2].numpy()
     spawn[:, 3] = _rows_to_cells(tape[3][2], ids, N, S)
     return spawn
+
+
+# ------------------------------------------------------------------------------------------------
+# MultiSnake (call-site lines in wurm/envs/multi_snake.py)
+# ------------------------------------------------------------------------------------------------
+def multi_step_tape(tape, E, K, S):
+    """Tape of one MultiSnake.step -> dict for oracle.multi_step(draws=...) plus dense per-env arrays
+    for the CUDA library (`food_cell` (E,), `u_rate_dense` (E,S,S))."""
+    draws = {'boost_phase_ran': False, 'u_boost': None, 'u_cost': None, 'u_reg': None, 'food_cell': None, 'u_rate': None,
+             'u_rate_dense': None, 'selected': None}
+    death = [t[2] for t in tape if t[0] == 'rand_like' and t[1] == 424]
+    cost = [t[2] for t in tape if t[0] == 'rand' and t[1] == 579]
+    rate = [t[2] for t in tape if t[0] == 'rand' and t[1] == 401]
+    food = [t[2] for t in tape if t[0] == 'drop_duplicates' and t[1] == 447]
+    selected = [t[2] for t in tape if t[0] == 'add_food_selected']
+    assert len(selected) == 1 and len(cost) <= 1 and len(rate) <= 1 and len(food) <= 1 and len(death) <= 2
+    assert len(tape) == len(death) + len(cost) + len(rate) + len(food) + 1, [(t[0], t[1]) for t in tape]
+    if cost:
+        draws['boost_phase_ran'] = True
+        draws['u_cost'] = cost[0].numpy().reshape(E * K)
+        if len(death) == 2:
+            draws['u_boost'] = death[0].numpy().reshape(E, S, S)
+    if death:
+        draws['u_reg'] = death[-1].numpy().reshape(E, S, S)
+    assert len(death) <= (2 if cost else 1)
+    draws['selected'] = selected[0].numpy().astype(np.uint8)
+    sel = np.flatnonzero(selected[0].numpy())
+    if rate:
+        rows = rate[0].numpy().reshape(-1, S, S)
+        assert rows.shape[0] == len(sel)
+        draws['u_rate'] = rows
+        dense = np.ones((E, S, S), np.float32)
+        dense[sel] = rows
+        draws['u_rate_dense'] = dense
+    else:
+        cells = np.full(E, -1, np.int32)
+        if food:
+            for rank, _, y, x in food[0].numpy():
+                cells[sel[rank]] = y * S + x
+        draws['food_cell'] = cells
+    return draws
+
+
+def multi_create_tape(tape, env_ids, E, K, S):
+    """Consumes the records of one _create_envs call (:996-1019) from the front of `tape`.
+    Returns (create (E,K+1,2) int32, remaining tape)."""
+    create = np.full((E, K + 1, 2), -1, np.int32)
+    pos = 0
+    for k in range(K):
+        assert (tape[pos][0], tape[pos][1]) == ('drop_duplicates', 951), (tape[pos][0], tape[pos][1])
+        assert (tape[pos + 1][0], tape[pos + 1][1]) == ('randint', 960)
+        for rank, _, y, x in tape[pos][2].numpy():
+            create[env_ids[rank], k, 0] = y * S + x
+        create[env_ids, k, 1] = tape[pos + 1][2].numpy()
+        pos += 2
+    assert (tape[pos][0], tape[pos][1]) == ('drop_duplicates', 447)
+    for rank, _, y, x in tape[pos][2].numpy():
+        create[env_ids[rank], K, 0] = y * S + x
+    create[env_ids, K, 1] = 0
+    return create, tape[pos + 1:]
+
+
+def multi_reset_tape(tape, env_done, dones_before, colours_after, respawn_any, E, K, S):
+    """Tape of one MultiSnake.reset -> dict for oracle.multi_reset(draws=...) (multi_snake.py:771-831).
+    dones_before: the env's `dones` before the call; colours_after: `agent_colours` after it."""
+    env_done = np.asarray(env_done).reshape(-1).astype(bool)
+    draws = {'create': np.full((E, K + 1, 2), -1, np.int32), 'respawn': np.full((E, 2), -1, np.int32),
+             'colours': np.asarray(colours_after).astype(np.int16)}
+    if env_done.any():
+        draws['create'], tape = multi_create_tape(tape, np.flatnonzero(env_done), E, K, S)
+    if tape and tape[0][0] == 'rand' and tape[0][1] == 164:      # colours of the still-dead agents (:802)
+        tape = tape[1:]
+    dones = np.asarray(dones_before).reshape(E, K).astype(bool) & ~env_done[:, None]
+    if respawn_any and dones.any():
+        ids = np.flatnonzero(dones.any(axis=1))
+        assert (tape[0][0], tape[0][1]) == ('drop_duplicates', 870) and (tape[1][0], tape[1][1]) == ('randint', 881)
+        for rank, _, y, x in tape[0][2].numpy():
+            draws['respawn'][ids[rank], 0] = y * S + x
+        draws['respawn'][ids, 1] = tape[1][2].numpy()
+        tape = tape[2:]
+    assert not tape, [(t[0], t[1]) for t in tape]
+    return draws

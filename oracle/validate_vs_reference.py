@@ -82,6 +82,87 @@ def validate_single(ref, tally, N, S, mode, steps, seed, reset_every_step=True):
     return env_steps
 
 
+import collections
+EVENTS = collections.Counter()
+
+
+def ref_multi_state(env):
+    """The reference env's state as the dict of arrays the oracle's MultiState holds."""
+    return dict(foods=env.foods.numpy(), heads=env.heads.numpy(), bodies=env.bodies.numpy(),
+                dones=env.dones.numpy().astype(np.uint8), orientations=env.orientations.numpy(),
+                boost_this_step=env.boost_this_step.numpy().astype(np.uint8), agent_colours=env.agent_colours.numpy())
+
+
+def check_multi_state(tally, tag, env, st, colours=True):
+    ref = ref_multi_state(env)
+    for name in ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step') + (('agent_colours',) if colours else ()):
+        tally.check(f'{tag}/{name}', ref[name], getattr(st, name))
+
+
+def validate_multi(ref, tally, E, K, S, mode, steps, seed, **rules):
+    """step(actions); reset(done['__all__']) loop for one rule set (constructor kwargs in `rules`)."""
+    torch.manual_seed(seed)
+    rl.take_tape()
+    env = rl.instrument_multi(ref.MultiSnake(num_envs=E, num_snakes=K, size=S, observation_mode=mode, **rules))
+    cfg = orc.multi_cfg(E, K, S, **{k: v for k, v in rules.items() if k != 'agent_colours'},
+                        colour_mode=rules.get('agent_colours', 'random'))
+    st = orc.MultiState(E, K, S)
+    tape = rl.take_tape()
+    create, rest = replay.multi_create_tape(tape, np.arange(E), E, K, S)
+    assert len(rest) == 1 and rest[0][0] == 'rand'          # the colours (:145/148)
+    st.dones[:] = 1
+    st.agent_colours[:] = env.agent_colours.numpy()
+    failed = orc.multi_reset(cfg, st, np.ones(E, np.uint8), dict(create=create, respawn=np.full((E, 2), -1, np.int32),
+                                                                  colours=env.agent_colours.numpy()))
+    assert failed == 0
+    tag = f'multi/{mode}/K{K}S{S}/{sorted(rules.items())}'
+    check_multi_state(tally, tag + '/create', env, st)
+    env_steps = 0
+    respawn_any = rules.get('respawn_mode', 'all') == 'any'
+    for t in range(steps):
+        acts = torch.randint(0, 8, (E, K))
+        actions = {f'agent_{k}': acts[:, k].clone() for k in range(K)}
+        obs, rewards, dones, info = env.step(actions)
+        draws = replay.multi_step_tape(rl.take_tape(), E, K, S)
+        out = orc.multi_step(cfg, st, acts.numpy(), draws)
+        o, bad = orc.multi_observe(cfg, st, mode)
+        assert bad == 0
+        tg = f'{tag}/t{t}'
+        check_multi_state(tally, tg, env, st)
+        if draws['u_rate'] is not None:
+            tally.check(tg + '/rate_selected', out['rate_selected'], draws['selected'])
+        for k in range(K):
+            tally.check(f'{tg}/obs_{k}', obs[f'agent_{k}'].numpy(), o[k])
+            tally.check(f'{tg}/reward_{k}', rewards[f'agent_{k}'].numpy(), out['rewards'][:, k])
+            tally.check(f'{tg}/done_{k}', dones[f'agent_{k}'].numpy().astype(np.uint8), st.dones.reshape(E, K)[:, k])
+            tally.check(f'{tg}/snake_collision_{k}', info[f'snake_collision_{k}'].numpy().astype(np.uint8), out['snake_collision'][:, k])
+            tally.check(f'{tg}/edge_collision_{k}', info[f'edge_collision_{k}'].numpy().astype(np.uint8), out['edge_collision'][:, k])
+            tally.check(f'{tg}/food_{k}', info[f'food_{k}'].numpy(), out['food'][:, k])
+            tally.check(f'{tg}/boost_{k}', info[f'boost_{k}'].numpy().astype(np.uint8), st.boost_this_step.reshape(E, K)[:, k])
+            tally.check(f'{tg}/size_{k}', info[f'size_{k}'].numpy(), out['size'][:, k])
+        tally.check(tg + '/all_done', dones['__all__'].numpy().astype(np.uint8), out['all_done'])
+        tally.check(tg + '/env_images', env._get_env_images().numpy(), orc.multi_env_images(cfg, st))
+        env_steps += E
+        EVENTS['boost_phases'] += int(draws['boost_phase_ran'])
+        EVENTS['boosting_agents'] += int(st.boost_this_step.sum())
+        EVENTS['snake_collisions'] += int(out['snake_collision'].sum())
+        EVENTS['edge_collisions'] += int(out['edge_collision'].sum())
+        EVENTS['food_eaten'] += int(out['food'].sum())
+        EVENTS['env_recreations'] += int(out['all_done'].sum())
+        dones_before = env.dones.numpy().copy()
+        env_done = dones['__all__'].numpy().copy()
+        obs2 = env.reset(dones['__all__'])
+        rdraws = replay.multi_reset_tape(rl.take_tape(), env_done, dones_before, env.agent_colours.numpy(), respawn_any, E, K, S)
+        orc.multi_reset(cfg, st, env_done, rdraws)
+        EVENTS['respawns'] += int((rdraws['respawn'][:, 0] >= 0).sum())
+        EVENTS['failed_respawns'] += int(((rdraws['respawn'][:, 0] < 0) & (rdraws['respawn'][:, 1] >= 0)).sum())
+        check_multi_state(tally, tg + '/reset', env, st)
+        o2, bad = orc.multi_observe(cfg, st, mode)
+        for k in range(K):
+            tally.check(f'{tg}/reset_obs_{k}', obs2[f'agent_{k}'].numpy(), o2[k])
+    return env_steps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
@@ -97,6 +178,22 @@ def main():
     for mode in ['default', 'raw', 'one_channel', 'positions']:
         total += validate_single(ref, tally, 32 * scale, 9, mode, 42 * scale, seed=7, reset_every_step=False)
     print(f'single: {total} env-steps, {tally.checks} tensor comparisons, {len(tally.fails)} mismatches')
+    if tally.fails:
+        print('first failures:', tally.fails[:10])
+        sys.exit(1)
+    tally = Tally()
+    total = 0
+    rule_sets = [
+        dict(),                                                                          # constructor defaults
+        dict(food_mode='random_rate', food_rate=3e-3, respawn_mode='any', food_on_death_prob=0.33, boost_cost_prob=0.25),
+        dict(boost=False, food_on_death_prob=0.0, reward_on_death=-2),
+        dict(respawn_mode='any', food_on_death_prob=1.0, boost_cost_prob=1.0, agent_colours='fixed'),
+    ]
+    for rules in rule_sets:
+        for (E, K, S, mode) in [(24, 2, 12, 'full'), (16, 4, 25, 'partial_4'), (12, 4, 12, 'partial_5'), (6, 7, 20, 'full')]:
+            total += validate_multi(ref, tally, E * scale, K, S, mode, 40 * scale, seed=E + K + S, **rules)
+    print(f'multi: {total} env-steps, {tally.checks} tensor comparisons, {len(tally.fails)} mismatches')
+    print('multi events covered:', dict(EVENTS))
     if tally.fails:
         print('first failures:', tally.fails[:10])
         sys.exit(1)
