@@ -98,6 +98,97 @@ int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done
 /* Replaces SingleSnake._observe (single_snake.py:130-195) on the current state. */
 int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MultiSnake (wurm/envs/multi_snake.py)
+ * ---------------------------------------------------------------------------------------------- */
+#define WURM_MULTI_MAX_SNAKES 32
+#define WURM_MOBS_NONE -1
+#define WURM_MOBS_FULL 0    /* per agent (E,3,S,S): self green, others blue   (multi_snake.py:268-288) */
+#define WURM_MOBS_PARTIAL 1 /* per agent (E,3,W,W) crop of the env image      (multi_snake.py:289-332) */
+
+/* Constructor parameters of the reference that the kernels read (multi_snake.py:56-75, 121-129);
+ * the Python class keeps them as mutable attributes and rebuilds this struct at every call, because
+ * the reference's drivers anneal them between steps (experiments/multiagent.py:337-345). */
+typedef struct WurmMultiCfg {
+    int32_t num_envs;      /* E */
+    int32_t num_snakes;    /* K <= WURM_MULTI_MAX_SNAKES */
+    int32_t size;          /* S */
+    int32_t obs_mode;      /* WURM_MOBS_* */
+    int32_t obs_n;         /* n of partial_n */
+    int32_t boost;         /* self.boost */
+    int32_t food_on_death; /* food_on_death_prob > 0 */
+    float death_threshold; /* float32(1 - food_on_death_prob)          :424 */
+    float boost_cost_prob; /* float32(boost_cost_prob)                 :579 */
+    int32_t food_mode;     /* 0 'only_one', 1 'random_rate'            :369,380 */
+    float food_rate;       /* float32(food_rate)                       :403 */
+    float reward_on_death; /*                                          :684 */
+    int32_t respawn_any;   /* respawn_mode == 'any'                    :805 */
+    int32_t colour_random; /* colour_mode == 'random'                  :800 */
+} WurmMultiCfg;
+
+/* The state tensors of the reference (multi_snake.py:100-108,145), all device pointers. */
+typedef struct WurmMultiState {
+    float* foods;           /* (E,1,S,S)   */
+    float* heads;           /* (E*K,1,S,S) */
+    float* bodies;          /* (E*K,1,S,S) */
+    uint8_t* dones;         /* (E*K)       */
+    int64_t* orientations;  /* (E*K)       */
+    uint8_t* boost_this_step; /* (E*K)     */
+    int16_t* agent_colours; /* (E*K,3)     */
+} WurmMultiState;
+
+/* Replayed random draws of one step, dense per env (NULL struct pointer -> Philox).
+ * SURVEY.md Appendix B.2 gives the reference's schedule. */
+typedef struct WurmMultiStepDraws {
+    int32_t boost_phase_ran; /* the reference ran its boost phase (batch-global condition :503) */
+    const float* u_boost;    /* (E,S,S) rand_like :424 via :574, NULL if not drawn */
+    const float* u_cost;     /* (E*K)   rand :579,               NULL if not drawn */
+    const float* u_reg;      /* (E,S,S) rand_like :424 via :671, NULL if not drawn */
+    const int32_t* food_cell;/* (E)     only_one: respawned cell or -1             */
+    const float* u_rate;     /* (E,S,S) random_rate: rand :401 scattered to env rows */
+} WurmMultiStepDraws;
+
+/* Per-step outputs, (E,K) row-major unless noted: column k is the reference's dict entry of agent k. */
+typedef struct WurmMultiStepOut {
+    float* rewards;
+    uint8_t* snake_collision;
+    uint8_t* edge_collision;
+    float* food;            /* info food_k */
+    float* size;            /* info size_k */
+    uint8_t* dones;         /* copy of the updated done flags (the caller's to keep) */
+    uint8_t* boost;         /* info boost_k: copy of boost_this_step */
+    uint8_t* all_done;      /* (E) dones['__all__'] */
+    float* obs;             /* (K,E,3,S,S) or (K,E,3,W,W): obs[k] is agent k's tensor; NULL with WURM_MOBS_NONE */
+} WurmMultiStepOut;
+
+/* Replayed draws of one reset (NULL struct pointer -> Philox). */
+typedef struct WurmMultiResetDraws {
+    const int32_t* create;  /* (E,K+1,2): per snake (seed cell, direction), then (food cell, 0); re-created envs */
+    const int32_t* respawn; /* (E,2): (seed cell or -1, direction) for the env's first dead agent */
+    const int16_t* colours; /* (E*K,3): new colour of every agent that is still dead */
+} WurmMultiResetDraws;
+
+int64_t wurm_multi_obs_elems(const WurmMultiCfg* cfg); /* floats per (agent, env) */
+
+/* Replaces MultiSnake.step (multi_snake.py:462-731) incl. _move_heads, _get_food_overlap,
+ * _decay_bodies, _check_collisions, _check_edges, _food_from_death, _add_food, _get_env_images and
+ * _observe, in ONE launch.  actions: host array of K device pointers, each (E,) of action_bytes
+ * integers in [0,8) (agents in dict order). */
+int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions, int action_bytes,
+                    const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step, const WurmMultiStepOut* out,
+                    int32_t* status, int64_t* stats /* nullable */, void* stream);
+
+/* Replaces the state update of MultiSnake.reset (multi_snake.py:771-831) incl. _create_envs,
+ * _add_snake, _get_snake_addition and get_n_colours.  env_done (E): envs to re-create. */
+int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const uint8_t* env_done,
+                     const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, int32_t* status, void* stream);
+
+/* Replaces MultiSnake._observe (multi_snake.py:283-334) on the current state. */
+int wurm_multi_observe(const WurmMultiCfg* cfg, const WurmMultiState* state, float* obs, int32_t* status, void* stream);
+
+/* Replaces MultiSnake._get_env_images (multi_snake.py:194-227): img (E,3,S,S) int16. */
+int wurm_multi_env_images(const WurmMultiCfg* cfg, const WurmMultiState* state, int16_t* img, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,58 @@ def single_trajectory(ref, N, S, mode, steps, seed, reset_every=1, manual=None, 
     return out
 
 
+def multi_state(env):
+    return {'foods': env.foods.numpy().astype(np.int16), 'heads': env.heads.numpy().astype(np.int16),
+            'bodies': env.bodies.numpy().astype(np.int16), 'dones': env.dones.numpy().astype(np.uint8),
+            'orientations': env.orientations.numpy().astype(np.int64),
+            'boost_this_step': env.boost_this_step.numpy().astype(np.uint8),
+            'agent_colours': env.agent_colours.numpy().astype(np.int16)}
+
+
+def put(out, prefix, d):
+    for k, v in d.items():
+        if v is not None:
+            out[f'{prefix}/{k}'] = np.asarray(v)
+
+
+def multi_trajectory(ref, E, K, S, mode, steps, seed, **rules):
+    torch.manual_seed(seed)
+    rl.take_tape()
+    env = rl.instrument_multi(ref.MultiSnake(num_envs=E, num_snakes=K, size=S, observation_mode=mode, **rules))
+    out = {'E': E, 'K': K, 'S': S, 'mode': mode, 'steps': steps, 'rules': repr(sorted(rules.items()))}
+    for k, v in rules.items():
+        out[f'rule/{k}'] = v
+    create, rest = replay.multi_create_tape(rl.take_tape(), np.arange(E), E, K, S)
+    out['init/create'] = create
+    put(out, 'init', multi_state(env))
+    for t in range(steps):
+        acts = torch.randint(0, 8, (E, K))
+        out[f'{t}/actions'] = acts.numpy().copy()
+        obs, rewards, dones, info = env.step({f'agent_{k}': acts[:, k].clone() for k in range(K)})
+        draws = replay.multi_step_tape(rl.take_tape(), E, K, S)
+        put(out, f'{t}/draws', {k: v for k, v in draws.items() if k != 'u_rate_dense'})   # dense = scatter(u_rate, selected)
+        put(out, f'{t}/state', multi_state(env))
+        out[f'{t}/obs'] = np.stack([obs[f'agent_{k}'].numpy() for k in range(K)])
+        out[f'{t}/rewards'] = np.stack([rewards[f'agent_{k}'].numpy() for k in range(K)], axis=1)
+        out[f'{t}/dones'] = np.stack([dones[f'agent_{k}'].numpy() for k in range(K)], axis=1).astype(np.uint8)
+        out[f'{t}/all_done'] = dones['__all__'].numpy().astype(np.uint8)
+        for name in ('snake_collision', 'edge_collision', 'food', 'boost', 'size'):
+            a = np.stack([info[f'{name}_{k}'].numpy() for k in range(K)], axis=1)
+            out[f'{t}/{name}'] = a.astype(np.uint8) if a.dtype == bool else a
+        if t % 4 == 0:
+            out[f'{t}/env_images'] = env._get_env_images().numpy()
+        dones_before = env.dones.numpy().copy()
+        env_done = dones['__all__'].numpy().copy()
+        obs2 = env.reset(dones['__all__'])
+        rdraws = replay.multi_reset_tape(rl.take_tape(), env_done, dones_before, env.agent_colours.numpy(),
+                                         rules.get('respawn_mode', 'all') == 'any', E, K, S)
+        put(out, f'{t}/reset_draws', rdraws)
+        put(out, f'{t}/reset_state', multi_state(env))
+        if t % 4 == 0:
+            out[f'{t}/reset_obs'] = np.stack([obs2[f'agent_{k}'].numpy() for k in range(K)])
+    return out
+
+
 def save(name, trajectories):
     flat = {'count': np.array(len(trajectories))}
     for i, tr in enumerate(trajectories):
@@ -85,6 +137,18 @@ def main():
             trs.append(single_trajectory(ref, 1, 12, 'default', len(seq), seed=400, reset_every=10 ** 6,
                                          manual=ref.utils.get_test_env(12, orientation), actions=acts))
     save('single.npz', trs)
+
+    rule_sets = [
+        dict(),                                                                          # constructor defaults
+        dict(food_mode='random_rate', food_rate=3e-3, respawn_mode='any', food_on_death_prob=0.33, boost_cost_prob=0.25),
+        dict(boost=False, food_on_death_prob=0.0, reward_on_death=-2),
+        dict(respawn_mode='any', food_on_death_prob=1.0, boost_cost_prob=1.0, agent_colours='fixed'),
+    ]
+    trs = []
+    for i, rules in enumerate(rule_sets):
+        trs.append(multi_trajectory(ref, 6, 2, 12, 'full', 18, seed=500 + i, **rules))
+        trs.append(multi_trajectory(ref, 4, 4, 14, 'partial_3', 18, seed=600 + i, **rules))
+    save('multi.npz', trs)
 
 
 if __name__ == '__main__':

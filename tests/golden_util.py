@@ -47,3 +47,43 @@ class Trajectory(object):
 def load(name):
     z = np.load(os.path.join(GOLDEN, name))
     return [Trajectory(z, i) for i in range(int(z['count']))]
+
+
+# ---- MultiSnake trajectories (tests/golden/multi.npz) ----
+RULE_DEFAULTS = dict(food_on_death_prob=0.5, boost=True, boost_cost_prob=0.5, food_mode='only_one', food_rate=5e-4,
+                     respawn_mode='all', reward_on_death=-1, agent_colours='random')
+STATE_FIELDS = ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step', 'agent_colours')
+
+
+def multi_rules(tr):
+    """Constructor kwargs of the reference env the trajectory was recorded from."""
+    rules = dict(RULE_DEFAULTS)
+    for k in rules:
+        if f'rule/{k}' in tr:
+            v = tr[f'rule/{k}']
+            rules[k] = v.item() if v.dtype.kind in 'fib' else str(v)
+    return rules
+
+
+def multi_group(tr, prefix, keys):
+    return {k: (tr[f'{prefix}/{k}'] if f'{prefix}/{k}' in tr else None) for k in keys}
+
+
+def multi_step_draws(tr, t, dense_rate):
+    """The recorded draws of step t; `dense_rate`: scatter the random_rate rows to (E,S,S) for the CUDA library."""
+    d = multi_group(tr, f'{t}/draws', ('boost_phase_ran', 'u_boost', 'u_cost', 'u_reg', 'food_cell', 'u_rate', 'selected'))
+    d['boost_phase_ran'] = bool(d['boost_phase_ran'])
+    if dense_rate and d['u_rate'] is not None:
+        E, S = int(tr['E']), int(tr['S'])
+        dense = np.ones((E, S, S), np.float32)
+        dense[np.flatnonzero(d['selected'])] = d['u_rate']
+        d['u_rate'] = dense
+    return d
+
+
+def multi_state_arrays(tr, prefix):
+    """State arrays in the dtypes of the live tensors."""
+    st = multi_group(tr, prefix, STATE_FIELDS)
+    for k in ('foods', 'heads', 'bodies'):
+        st[k] = st[k].astype(np.float32)
+    return st

@@ -1,0 +1,370 @@
+"""GPU: MultiSnake through the C ABI (wurm_b200.envs.MultiSnake) against
+  (1) the reference's golden vectors, replaying the reference's own random draws,
+  (2) the CPU oracle on seeded random rollouts with Philox-derived draws (same seed on both sides),
+  (3) the reference's own scenario tests (tests/test_multi_snake_env.py in the reference tree),
+  (4) the reference's invariants (check_consistency) at BASELINE.json config-4 geometry.
+Everything is compared bit for bit (fp32 as int32 patterns).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from golden_util import (load, assert_same, multi_rules, multi_group, multi_step_draws, multi_state_arrays,
+                         STATE_FIELDS)
+
+pytestmark = pytest.mark.gpu
+
+MULTI = load('multi.npz')
+DEV = 'cuda'
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def make_env(E, K, S, mode, **kw):
+    from wurm_b200.envs import MultiSnake
+    return MultiSnake(num_envs=E, num_snakes=K, size=S, observation_mode=mode, device=DEV, **kw)
+
+
+def env_state(env):
+    return dict(foods=np_(env.foods), heads=np_(env.heads), bodies=np_(env.bodies), dones=np_(env.dones).astype(np.uint8),
+                orientations=np_(env.orientations), boost_this_step=np_(env.boost_this_step).astype(np.uint8),
+                agent_colours=np_(env.agent_colours))
+
+
+def check_state(env, expect, tag):
+    got = env_state(env)
+    for name in STATE_FIELDS:
+        e = expect[name] if isinstance(expect, dict) else getattr(expect, name)
+        assert_same(got[name], np.asarray(e).reshape(got[name].shape), f'{tag}: {name}')
+
+
+def stack_dict(d, K, prefix='agent_'):
+    return np.stack([np_(d[f'{prefix}{k}']) for k in range(K)], axis=1)
+
+
+def check_step_outputs(env, K, obs, rewards, dones, info, expect, tag):
+    """expect: dict with rewards/dones/all_done/snake_collision/edge_collision/food/boost/size (E,K) and obs (K,E,...)."""
+    assert_same(stack_dict(rewards, K), expect['rewards'], tag + ': rewards')
+    assert_same(stack_dict(dones, K).astype(np.uint8), expect['dones'], tag + ': dones')
+    assert_same(np_(dones['__all__']).astype(np.uint8), expect['all_done'], tag + ': __all__')
+    for name in ('snake_collision', 'edge_collision', 'boost'):
+        assert_same(stack_dict(info, K, name + '_').astype(np.uint8), expect[name], f'{tag}: {name}')
+    for name in ('food', 'size'):
+        assert_same(stack_dict(info, K, name + '_'), expect[name], f'{tag}: {name}')
+    assert_same(np.stack([np_(obs[f'agent_{k}']) for k in range(K)]), expect['obs'], tag + ': observations')
+
+
+@pytest.mark.parametrize('i', range(len(MULTI)))
+def test_golden_replay(i):
+    """CUDA path == reference on the recorded trajectories."""
+    tr = MULTI[i]
+    E, K, S, mode = int(tr['E']), int(tr['K']), int(tr['S']), str(tr['mode'])
+    env = make_env(E, K, S, mode, manual_setup=True, **multi_rules(tr))
+    init = multi_state_arrays(tr, 'init')
+    env.agent_colours = torch.from_numpy(init['agent_colours']).to(DEV)
+    env._create_all(draws=dict(create=tr['init/create'], respawn=np.full((E, 2), -1, np.int32), colours=init['agent_colours']))
+    check_state(env, init, f'trajectory {i} creation')
+    for t in range(int(tr['steps'])):
+        tag = f'trajectory {i} ({mode}, K={K}, S={S}, {tr["rules"]}) step {t}'
+        acts = torch.from_numpy(tr[f'{t}/actions']).to(DEV)
+        obs, rewards, dones, info = env.step({f'agent_{k}': acts[:, k].contiguous() for k in range(K)},
+                                             draws=multi_step_draws(tr, t, dense_rate=True))
+        check_state(env, multi_state_arrays(tr, f'{t}/state'), tag)
+        expect = {k: tr[f'{t}/{k}'] for k in ('rewards', 'dones', 'all_done', 'snake_collision', 'edge_collision', 'food',
+                                              'boost', 'size', 'obs')}
+        check_step_outputs(env, K, obs, rewards, dones, info, expect, tag)
+        if f'{t}/env_images' in tr:
+            assert_same(np_(env._get_env_images()), tr[f'{t}/env_images'], tag + ': env images')
+        obs2 = env.reset(dones['__all__'], draws=multi_group(tr, f'{t}/reset_draws', ('create', 'respawn', 'colours')))
+        check_state(env, multi_state_arrays(tr, f'{t}/reset_state'), tag + ' after reset')
+        if f'{t}/reset_obs' in tr:
+            assert_same(np.stack([np_(obs2[f'agent_{k}']) for k in range(K)]), tr[f'{t}/reset_obs'], tag + ': obs after reset')
+    env.check_status()
+
+
+DEFAULT_RULES = dict()
+ANNEAL_RULES = dict(food_mode='random_rate', food_rate=3e-3, respawn_mode='any', food_on_death_prob=0.33, boost_cost_prob=0.25)
+ROLLOUTS = [
+    # E, K, S, mode, steps, rules, action dtype
+    (200, 2, 12, 'full', 40, DEFAULT_RULES, torch.long),
+    (150, 4, 25, 'partial_4', 60, DEFAULT_RULES, torch.long),          # BASELINE config 4 geometry
+    (150, 4, 25, 'partial_5', 60, ANNEAL_RULES, torch.int),            # experiments/multiagent.py-style rules
+    (64, 4, 12, 'partial_3', 60, dict(respawn_mode='any', food_on_death_prob=1.0, boost_cost_prob=1.0), torch.short),
+    (64, 3, 13, 'full', 40, dict(boost=False, food_on_death_prob=0.0, reward_on_death=-2), torch.long),
+    (12, 16, 64, 'partial_4', 40, DEFAULT_RULES, torch.long),          # BASELINE config 5 geometry
+    (6, 16, 64, 'full', 12, ANNEAL_RULES, torch.long),
+    (40, 10, 36, 'partial_2', 40, dict(respawn_mode='any'), torch.long),   # experiments/speeds.py geometry
+    (3, 32, 40, 'partial_1', 20, DEFAULT_RULES, torch.long),           # the maximum number of snakes
+    (1, 1, 7, 'full', 20, DEFAULT_RULES, torch.long),                  # the smallest env
+]
+
+
+@pytest.mark.parametrize('E,K,S,mode,steps,rules,adtype', ROLLOUTS)
+def test_rollout_matches_oracle(E, K, S, mode, steps, rules, adtype):
+    """Seeded random rollout (actions in [0,8): moves and boosts), Philox draws on both sides."""
+    seed = 4321 + E + K + S
+    env = make_env(E, K, S, mode, seed=seed, **rules)
+    cfg = orc.multi_cfg(E, K, S, **rules)
+    st = orc.MultiState(E, K, S)
+    assert orc.multi_reset(cfg, st, np.ones(E, np.uint8), None, seed=seed, step=env._draws) == 0
+    st.agent_colours[:] = np_(env.agent_colours)       # construction-time colours come from torch.rand
+    check_state(env, st, 'creation')
+    g = torch.Generator().manual_seed(seed)
+    for t in range(steps):
+        acts = torch.randint(0, 8, (E, K), generator=g)
+        dev_acts = acts.to(device=DEV, dtype=adtype)
+        obs, rewards, dones, info = env.step({f'agent_{k}': dev_acts[:, k].contiguous() for k in range(K)})
+        out = orc.multi_step(cfg, st, acts.numpy(), None, seed=seed, step=env._draws)
+        tag = f'step {t}'
+        check_state(env, st, tag)
+        o, bad = orc.multi_observe(cfg, st, mode)
+        assert bad == 0
+        expect = dict(rewards=out['rewards'], dones=st.dones.reshape(E, K), all_done=out['all_done'],
+                      snake_collision=out['snake_collision'], edge_collision=out['edge_collision'], food=out['food'],
+                      boost=st.boost_this_step.reshape(E, K), size=out['size'], obs=o)
+        check_step_outputs(env, K, obs, rewards, dones, info, expect, tag)
+        assert_same(np_(env._get_env_images()), orc.multi_env_images(cfg, st), tag + ': env images')
+        obs2 = env.reset(dones['__all__'])
+        orc.multi_reset(cfg, st, out['all_done'], None, seed=seed, step=env._draws)
+        check_state(env, st, tag + ' after reset')
+        o2, _ = orc.multi_observe(cfg, st, mode)
+        assert_same(np.stack([np_(obs2[f'agent_{k}']) for k in range(K)]), o2, tag + ': obs after reset')
+        if t % 10 == 9:
+            env.check_consistency()
+    env.check_status()
+
+
+# ---- the reference's scenario tests on the CUDA path (reference tests/test_multi_snake_env.py) ----
+size = 12
+
+
+def get_test_env(num_envs=1, **kw):
+    """The reference's two-snake fixture (:21-47)."""
+    from wurm_b200.utils import determine_orientations
+    env = make_env(num_envs, 2, size, 'full', manual_setup=True, **kw)
+    for i in range(num_envs):
+        env.heads[2 * i, 0, 5, 5] = 1
+        env.bodies[2 * i, 0, 5, 5] = 4
+        env.bodies[2 * i, 0, 4, 5] = 3
+        env.bodies[2 * i, 0, 4, 4] = 2
+        env.bodies[2 * i, 0, 4, 3] = 1
+        env.heads[2 * i + 1, 0, 8, 7] = 1
+        env.bodies[2 * i + 1, 0, 8, 7] = 4
+        env.bodies[2 * i + 1, 0, 8, 8] = 3
+        env.bodies[2 * i + 1, 0, 8, 9] = 2
+        env.bodies[2 * i + 1, 0, 9, 9] = 1
+    _envs = torch.cat([env.foods.repeat_interleave(env.num_snakes, dim=0), env.heads, env.bodies], dim=1)
+    env.orientations = determine_orientations(_envs)
+    assert env.orientations.tolist() == [2, 3] * num_envs
+    return env
+
+
+def actions_at(all_actions, i):
+    return {agent: torch.tensor([a[i]], device=DEV) for agent, a in all_actions.items()}
+
+
+def head_of(env, agent):
+    idx = env.heads[agent, 0].flatten().argmax().item()
+    return [idx // size, idx % size]
+
+
+def test_basic_movement():
+    env = get_test_env()
+    env.foods[0, 0, 1, 1] = 1
+    all_actions = {'agent_0': [1, 2, 1, 1, 0, 3], 'agent_1': [0, 1, 3, 2, 1, 0]}
+    expected = [[[5, 4], [4, 4], [4, 3], [4, 2], [5, 2], [5, 3]], [[9, 7], [9, 6], [9, 5], [8, 5], [8, 4], [9, 4]]]
+    for i in range(6):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.check_consistency()
+        for k in range(2):
+            assert head_of(env, k) == expected[k][i]
+        assert not any(d.item() for d in dones.values())
+
+
+def test_edge_collision():
+    env = get_test_env()
+    env.food_on_death_prob = 1
+    env.foods[0, 0, 1, 1] = 1
+    all_actions = {'agent_0': [1, 1, 1, 1, 1], 'agent_1': [0, 2, 2, 6, 2]}
+    for i in range(5):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.check_consistency()
+        if i == 4:
+            assert rewards['agent_0'].item() == env.reward_on_death
+        if i == 2:
+            assert rewards['agent_1'].item() == env.reward_on_death
+        assert dones['agent_0'].item() == (i >= 4)
+        assert dones['agent_1'].item() == (i >= 2)
+
+
+def test_self_collision():
+    env = get_test_env()
+    env.food_on_death_prob = 1
+    env.foods[0, 0, 4, 3] = 1
+    all_actions = {'agent_0': [1, 2, 1, 1, 0, 3, 2, 0], 'agent_1': [0, 1, 3, 2, 1, 0, 0, 1]}
+    for i in range(8):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.check_consistency()
+        assert dones['agent_0'].item() == (i >= 6)
+
+
+def test_other_snake_collision():
+    env = get_test_env()
+    env.foods[0, 0, 1, 1] = 1
+    env.food_on_death_prob = 1
+    all_actions = {'agent_0': [1, 2, 3, 3, 3, 3, 3, 2], 'agent_1': [1, 2, 2, 2, 2, 2, 2, 2]}
+    for i in range(8):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.check_consistency()
+        assert dones['agent_1'].item() == (i >= 4)
+    assert env.foods[:, 0].sum().item() >= 2
+
+
+def test_eat_food():
+    env = get_test_env()
+    env.foods[:, 0, 9, 7] = 1
+    all_actions = {'agent_0': [1, 2, 1, 1, 0, 3], 'agent_1': [0, 1, 3, 2, 1, 0]}
+    for i in range(6):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.check_consistency()
+        assert not any(d.item() for d in dones.values())
+        if i == 0:
+            assert rewards['agent_1'].item() == 1
+    assert env.bodies.view(1, 2, -1).max(dim=2)[0].long().tolist() == [[4, 5]]
+    assert env.foods[0, 0, 9, 7].item() == 0
+    assert env.foods.sum().item() == 1
+
+
+def test_create_envs():
+    from wurm_b200.utils import determine_orientations
+    env = make_env(512, 2, size, 'full')
+    env.check_consistency()
+    _envs = torch.cat([env.foods.repeat_interleave(env.num_snakes, dim=0), env.heads, env.bodies], dim=1)
+    assert torch.equal(env.orientations, determine_orientations(_envs))
+
+
+def test_reset():
+    env = get_test_env()
+    env.foods[:, 0, 1, 1] = 1
+    all_actions = {'agent_0': [1, 2, 3, 3, 3, 3, 3, 3, 3], 'agent_1': [0, 1, 2, 2, 2, 2, 2, 2, 2]}
+    for i in range(9):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.reset(dones['__all__'])
+        env.check_consistency()
+    assert torch.all(env.bodies.view(1, 2, -1).max(dim=-1)[0] == env.initial_snake_length)
+
+
+def test_agent_observations():
+    env = get_test_env()
+    env.foods[:, 0, 1, 1] = 1
+    obs_0, obs_1 = env._observe_agent(0), env._observe_agent(1)
+    assert torch.allclose(obs_0[0, :, 4, 5] * 255, env.self_colour.float() / 2)
+    assert torch.allclose(obs_0[0, :, 8, 8] * 255, env.other_colour.float() / 2)
+    assert torch.allclose(obs_1[0, :, 4, 5] * 255, env.other_colour.float() / 2)
+    assert torch.allclose(obs_1[0, :, 8, 8] * 255, env.self_colour.float() / 2)
+
+
+def test_boost_through_food():
+    env = get_test_env()
+    env.boost = True
+    env.foods[:, 0, 6, 5] = 1
+    env.boost_cost_prob = 0
+    all_actions = {'agent_0': [4, 1, 2], 'agent_1': [0, 1, 3]}
+    for i in range(3):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.reset(dones['__all__'])
+        env.check_consistency()
+        if i == 0:
+            assert rewards['agent_0'].item() == 1
+
+
+def test_boost_cost_and_boost_leaves_food():
+    env = get_test_env()
+    env.boost = True
+    env.boost_cost_prob = 1
+    env.foods[:, 0, 1, 1] = 1
+    all_actions = {'agent_0': [4, 1, 2], 'agent_1': [0, 1, 3]}
+    for i in range(3):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.reset(dones['__all__'])
+        env.check_consistency()
+        assert env.bodies.view(1, 2, -1).max(dim=2)[0].long().tolist() == [[3, 4]]
+        if i == 0:
+            assert rewards['agent_0'].item() == -1
+    assert env.foods[0, 0, 4, 4].item() == 1
+
+
+def test_cant_boost_until_size_4():
+    from wurm_b200.utils import determine_orientations
+    env = make_env(1, 2, size, 'full', manual_setup=True, boost=True)
+    env.foods[:, 0, 1, 1] = 1
+    env.heads[0, 0, 5, 5] = 1
+    env.bodies[0, 0, 5, 5] = 3
+    env.bodies[0, 0, 4, 5] = 2
+    env.bodies[0, 0, 4, 4] = 1
+    env.heads[1, 0, 8, 7] = 1
+    env.bodies[1, 0, 8, 7] = 3
+    env.bodies[1, 0, 8, 8] = 2
+    env.bodies[1, 0, 8, 9] = 1
+    _envs = torch.cat([env.foods.repeat_interleave(env.num_snakes, dim=0), env.heads, env.bodies], dim=1)
+    env.orientations = determine_orientations(_envs)
+    expected = [[6, 5], [6, 4], [5, 4]]
+    all_actions = {'agent_0': [4, 1, 2], 'agent_1': [0, 1, 3]}
+    for i in range(3):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.reset(dones['__all__'])
+        env.check_consistency()
+        assert head_of(env, 0) == expected[i]
+
+
+def test_respawn_mode_any_without_room():
+    env = get_test_env()
+    env.respawn_mode = 'any'
+    for i in range(2, 9, 2):
+        for j in range(2, 9, 2):
+            env.foods[0, 0, i, j] = 1
+    all_actions = {'agent_0': [1, 1, 1, 1, 2, 2, 2, 3], 'agent_1': [0, 1, 0, 0, 0, 0, 0, 1]}
+    for i in range(8):
+        observations, rewards, dones, info = env.step(actions_at(all_actions, i))
+        env.reset(dones['__all__'])
+        env.check_consistency()
+
+
+def test_step_argument_errors():
+    env = make_env(4, 2, size, 'full')
+    good = torch.zeros(4, dtype=torch.long, device=DEV)
+    with pytest.raises(RuntimeError):
+        env.step({'agent_0': good})
+    with pytest.raises(TypeError):
+        env.step({'agent_0': good, 'agent_1': good.float()})
+    with pytest.raises(RuntimeError):
+        env.step({'agent_0': good, 'agent_1': torch.zeros(5, dtype=torch.long, device=DEV)})
+
+
+def test_overlapping_input_is_reported():
+    env = get_test_env()
+    env.bodies[1, 0, 4, 4] = 7          # two bodies on one cell: outside the supported states
+    env.step(actions_at({'agent_0': [1], 'agent_1': [0]}, 0))
+    with pytest.raises(RuntimeError):
+        env.check_status()
+
+
+def test_config4_invariants_with_boost_and_respawn():
+    """reference test_random_actions_with_boost (:94-124) at BASELINE config-4 geometry, scaled up."""
+    E, K = 4096, 4
+    env = make_env(E, K, 25, 'partial_4', respawn_mode='any', food_mode='random_rate', boost_cost_prob=0.25,
+                   food_on_death_prob=0.33, food_rate=2.5e-4, seed=11)
+    env.check_consistency()
+    for t in range(60):
+        actions = {f'agent_{k}': torch.randint(8, size=(E,), device=DEV) for k in range(K)}
+        observations, reward, done, info = env.step(actions)
+        assert observations['agent_0'].shape == (E, 3, 9, 9)
+        env.reset(done['__all__'], return_observations=False)
+        if t % 6 == 0:
+            env.check_consistency()
+    stats = env.stats()
+    assert stats['env_steps'] == 60 * E and stats['reward'] > 0 and stats['edge_collisions'] > 0
+    env.check_status()

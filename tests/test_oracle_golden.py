@@ -7,9 +7,11 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from golden_util import load, assert_same
+from golden_util import (load, assert_same, multi_rules, multi_group, multi_step_draws, multi_state_arrays,
+                         STATE_FIELDS)
 
 SINGLE = load('single.npz')
+MULTI = load('multi.npz')
 
 
 def test_philox_known_answers():
@@ -80,3 +82,106 @@ def test_reference_scenarios_known_answers():
             break
     assert dones[-1] == (1, 1)
     assert state[0, 0].sum() == 1
+
+
+def check_multi_state(st, expect, tag):
+    for name in STATE_FIELDS:
+        assert_same(getattr(st, name), expect[name], f'{tag}: {name}')
+
+
+@pytest.mark.parametrize('i', range(len(MULTI)))
+def test_multi_golden(i):
+    """MultiSnake: creation, step (all outputs, both observation modes, env images) and reset (re-creation,
+    re-colouring, respawn) of the oracle equal the reference's recorded trajectories."""
+    tr = MULTI[i]
+    E, K, S, mode = int(tr['E']), int(tr['K']), int(tr['S']), str(tr['mode'])
+    rules = multi_rules(tr)
+    colour_mode = rules.pop('agent_colours')
+    cfg = orc.multi_cfg(E, K, S, colour_mode=colour_mode, **rules)
+    st = orc.MultiState(E, K, S)
+    init = multi_state_arrays(tr, 'init')
+    st.agent_colours[:] = init['agent_colours']
+    assert orc.multi_reset(cfg, st, np.ones(E, np.uint8), dict(create=tr['init/create'], respawn=np.full((E, 2), -1, np.int32),
+                                                               colours=init['agent_colours'])) == 0
+    check_multi_state(st, init, f'trajectory {i} creation')
+    for t in range(int(tr['steps'])):
+        tag = f'trajectory {i} ({mode}, K={K}, S={S}, {tr["rules"]}) step {t}'
+        out = orc.multi_step(cfg, st, tr[f'{t}/actions'], multi_step_draws(tr, t, dense_rate=False))
+        check_multi_state(st, multi_state_arrays(tr, f'{t}/state'), tag)
+        assert_same(out['rewards'], tr[f'{t}/rewards'], tag + ': rewards')
+        assert_same(st.dones.reshape(E, K), tr[f'{t}/dones'], tag + ': dones')
+        assert_same(out['all_done'], tr[f'{t}/all_done'], tag + ': __all__')
+        assert_same(out['snake_collision'], tr[f'{t}/snake_collision'], tag + ': snake_collision')
+        assert_same(out['edge_collision'], tr[f'{t}/edge_collision'], tag + ': edge_collision')
+        assert_same(out['food'], tr[f'{t}/food'], tag + ': food')
+        assert_same(out['size'], tr[f'{t}/size'], tag + ': size')
+        assert_same(st.boost_this_step.reshape(E, K), tr[f'{t}/boost'], tag + ': boost')
+        obs, bad = orc.multi_observe(cfg, st, mode)
+        assert bad == 0
+        assert_same(obs, tr[f'{t}/obs'], tag + ': observations')
+        if f'{t}/env_images' in tr:
+            assert_same(orc.multi_env_images(cfg, st), tr[f'{t}/env_images'], tag + ': env images')
+        orc.multi_reset(cfg, st, tr[f'{t}/all_done'], multi_group(tr, f'{t}/reset_draws', ('create', 'respawn', 'colours')))
+        check_multi_state(st, multi_state_arrays(tr, f'{t}/reset_state'), tag + ' after reset')
+        if f'{t}/reset_obs' in tr:
+            assert_same(orc.multi_observe(cfg, st, mode)[0], tr[f'{t}/reset_obs'], tag + ': observations after reset')
+
+
+def multi_test_env(E=1):
+    """The reference's two-snake fixture (tests/test_multi_snake_env.py:21-47), size 12."""
+    st = orc.MultiState(E, 2, 12)
+    h, b = st.heads.reshape(E, 2, 12, 12), st.bodies.reshape(E, 2, 12, 12)
+    h[:, 0, 5, 5] = 1; b[:, 0, 5, 5] = 4; b[:, 0, 4, 5] = 3; b[:, 0, 4, 4] = 2; b[:, 0, 4, 3] = 1
+    h[:, 1, 8, 7] = 1; b[:, 1, 8, 7] = 4; b[:, 1, 8, 8] = 3; b[:, 1, 8, 9] = 2; b[:, 1, 9, 9] = 1
+    st.orientations[:] = np.tile([2, 3], E)          # determine_orientations of the fixture
+    return st
+
+
+def run_multi(st, cfg, agent_0, agent_1):
+    E = cfg.num_envs
+    for a0, a1 in zip(agent_0, agent_1):
+        out = orc.multi_step(cfg, st, np.tile([[a0, a1]], (E, 1)), None, seed=3, step=1)
+        yield out
+
+
+def test_reference_multi_scenarios_known_answers():
+    """Known answers asserted by the reference's own tests (tests/test_multi_snake_env.py)."""
+    # test_basic_movement :126-176
+    cfg = orc.multi_cfg(1, 2, 12)
+    st = multi_test_env(); st.foods[0, 0, 1, 1] = 1
+    tracks = ([(5, 4), (4, 4), (4, 3), (4, 2), (5, 2), (5, 3)], [(9, 7), (9, 6), (9, 5), (8, 5), (8, 4), (9, 4)])
+    for t, out in enumerate(run_multi(st, cfg, [1, 2, 1, 1, 0, 3], [0, 1, 3, 2, 1, 0])):
+        for k in range(2):
+            assert np.argmax(st.heads[k, 0]) == tracks[k][t][0] * 12 + tracks[k][t][1]
+        assert not st.dones.any()
+    # test_edge_collision :178-220 (food_on_death_prob = 1; action 6 = boost by a dead snake)
+    cfg = orc.multi_cfg(1, 2, 12, food_on_death_prob=1)
+    st = multi_test_env(); st.foods[0, 0, 1, 1] = 1
+    for t, out in enumerate(run_multi(st, cfg, [1, 1, 1, 1, 1], [0, 2, 2, 6, 2])):
+        assert st.dones[0] == (t >= 4) and st.dones[1] == (t >= 2)
+        if t == 4:
+            assert out['rewards'][0, 0] == -1
+        if t == 2:
+            assert out['rewards'][0, 1] == -1
+    # test_eat_food :285-336: reward at step 0 only, sizes [4,5], food moved
+    cfg = orc.multi_cfg(1, 2, 12)
+    st = multi_test_env(); st.foods[0, 0, 9, 7] = 1
+    for t, out in enumerate(run_multi(st, cfg, [1, 2, 1, 1, 0, 3], [0, 1, 3, 2, 1, 0])):
+        if t == 0:
+            assert out['rewards'][0, 1] == 1
+        assert not st.dones.any()
+    assert st.bodies.reshape(2, -1).max(axis=1).tolist() == [4, 5]
+    assert st.foods[0, 0, 9, 7] == 0 and st.foods.sum() == 1
+    # test_boost_cost :524-555: boost_cost_prob = 1 -> reward -1, sizes [3,4], tail became food at (4,3)
+    cfg = orc.multi_cfg(1, 2, 12, boost_cost_prob=1)
+    st = multi_test_env(); st.foods[0, 0, 1, 1] = 1
+    for t, out in enumerate(run_multi(st, cfg, [4, 1, 2], [0, 1, 3])):
+        if t == 0:
+            assert out['rewards'][0, 0] == -1
+        assert st.bodies.reshape(2, -1).max(axis=1).tolist() == [3, 4]
+    assert st.foods[0, 0, 4, 4] == 1                  # test_boost_leaves_food :458
+    # test_boost_through_food :398-426: boost_cost_prob = 0, food two cells ahead is eaten in the boost phase
+    cfg = orc.multi_cfg(1, 2, 12, boost_cost_prob=0)
+    st = multi_test_env(); st.foods[0, 0, 6, 5] = 1
+    out = next(run_multi(st, cfg, [4], [0]))
+    assert out['rewards'][0, 0] == 1

@@ -19,12 +19,42 @@ OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1
 
 # every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_reset',
-           'wurm_single_observe']
+           'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_reset', 'wurm_multi_observe',
+           'wurm_multi_env_images']
+MULTI_MAX_SNAKES = 32
+MOBS_NONE, MOBS_FULL, MOBS_PARTIAL = -1, 0, 1
 
 
 class WurmSingleCfg(ctypes.Structure):
     _fields_ = [('num_envs', ctypes.c_int32), ('size', ctypes.c_int32), ('obs_mode', ctypes.c_int32),
                 ('obs_n', ctypes.c_int32)]
+
+
+class WurmMultiCfg(ctypes.Structure):
+    _fields_ = [('num_envs', ctypes.c_int32), ('num_snakes', ctypes.c_int32), ('size', ctypes.c_int32),
+                ('obs_mode', ctypes.c_int32), ('obs_n', ctypes.c_int32), ('boost', ctypes.c_int32),
+                ('food_on_death', ctypes.c_int32), ('death_threshold', ctypes.c_float),
+                ('boost_cost_prob', ctypes.c_float), ('food_mode', ctypes.c_int32), ('food_rate', ctypes.c_float),
+                ('reward_on_death', ctypes.c_float), ('respawn_any', ctypes.c_int32), ('colour_random', ctypes.c_int32)]
+
+
+class WurmMultiState(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step',
+                                               'agent_colours')]
+
+
+class WurmMultiStepDraws(ctypes.Structure):
+    _fields_ = [('boost_phase_ran', ctypes.c_int32)] + [(n, ctypes.c_void_p) for n in ('u_boost', 'u_cost', 'u_reg',
+                                                                                        'food_cell', 'u_rate')]
+
+
+class WurmMultiStepOut(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('rewards', 'snake_collision', 'edge_collision', 'food', 'size', 'dones',
+                                               'boost', 'all_done', 'obs')]
+
+
+class WurmMultiResetDraws(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('create', 'respawn', 'colours')]
 
 
 class WurmError(RuntimeError):
@@ -56,6 +86,18 @@ def lib():
     L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp]
     L.wurm_single_observe.restype = i32
     L.wurm_single_observe.argtypes = [cfg, vp, vp, vp, vp]
+    mcfg, mst = ctypes.POINTER(WurmMultiCfg), ctypes.POINTER(WurmMultiState)
+    L.wurm_multi_obs_elems.restype = ctypes.c_int64
+    L.wurm_multi_obs_elems.argtypes = [mcfg]
+    L.wurm_multi_step.restype = i32
+    L.wurm_multi_step.argtypes = [mcfg, mst, ctypes.POINTER(vp), i32, ctypes.POINTER(WurmMultiStepDraws), u64, u64,
+                                  ctypes.POINTER(WurmMultiStepOut), vp, vp, vp]
+    L.wurm_multi_reset.restype = i32
+    L.wurm_multi_reset.argtypes = [mcfg, mst, vp, ctypes.POINTER(WurmMultiResetDraws), u64, u64, vp, vp]
+    L.wurm_multi_observe.restype = i32
+    L.wurm_multi_observe.argtypes = [mcfg, mst, vp, vp, vp]
+    L.wurm_multi_env_images.restype = i32
+    L.wurm_multi_env_images.argtypes = [mcfg, mst, vp, vp, vp]
     if L.wurm_abi_version() != ABI_VERSION:
         raise ImportError(f'{LIB_PATH} has ABI version {L.wurm_abi_version()}, expected {ABI_VERSION}: rebuild it')
     _lib = L

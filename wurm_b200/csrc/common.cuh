@@ -16,7 +16,15 @@ __device__ __forceinline__ int off_x(int k) { return (k == 1) ? 1 : (k == 3) ? -
 // Philox4x32-10 and the draw streams (must agree with oracle/wurm_oracle.c, which restates them
 // independently).  counter = (unit, stream, step_lo, step_hi), key = (seed_lo, seed_hi).
 // ---------------------------------------------------------------------------------------------
-enum DrawStream : uint32_t { kStreamSingleStepFood = 0, kStreamSingleReset = 1 };
+// The i-th 32-bit draw of stream s for env e at call counter `step` is word (i % 4) of
+// philox(counter = (e, s | (i / 4) << 4, step_lo, step_hi), key = (seed_lo, seed_hi)).
+enum DrawStream : uint32_t {
+    kStreamSingleStepFood = 0, kStreamSingleReset = 1,
+    kStreamMultiDeathBoost = 2, kStreamMultiBoostCost = 3, kStreamMultiDeathRegular = 4,
+    kStreamMultiFoodOne = 5, kStreamMultiFoodRate = 6, kStreamMultiCreateSnake = 7,
+    kStreamMultiCreateFood = 8, kStreamMultiRespawn = 9, kStreamMultiColour = 10
+};
+constexpr uint32_t kRejectionTries = 32;
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {
@@ -34,6 +42,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ uint4 draw(uint64_t seed, uint64_t step, uint32_t unit, uint32_t stream) {
     return philox4x32_10(unit, stream, (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
 }
+
+__device__ __forceinline__ uint32_t draw_i(uint64_t seed, uint64_t step, uint32_t unit, uint32_t stream, uint32_t i) {
+    const uint4 r = draw(seed, step, unit, stream | ((i >> 2) << 4));
+    const uint32_t w = i & 3u;
+    return w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
+}
+
+// uniform float in [0,1) with 24 random bits (the resolution of torch.rand)
+__device__ __forceinline__ float unit_float(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
 // uniform integer in [0, n) by multiply-shift
 __device__ __forceinline__ uint32_t bounded(uint32_t r, uint32_t n) { return __umulhi(r, n); }

@@ -1,0 +1,798 @@
+// MultiSnake hot path for B200 (sm_100a): step / reset / observe as hand-written CUDA.
+//
+// Replaces wurm/envs/multi_snake.py:163-1019 of the reference (a ~330-op ATen tensor program per
+// step with conv2d head moves, an (A,K,S,S) repeat_interleave for collisions, masked_select crops
+// and >=6 host syncs) with ONE launch per call.
+//
+// Design:
+//   * one CTA per environment.  The env's fp32 state -- (1+2K) grids of S*S floats, 22.5 KB at
+//     K=4,S=25 but 540 KB at K=16,S=64, more than an SM's shared memory -- is STREAMED once from
+//     HBM with coalesced 128-bit loads and folded on the fly into a compact shared-memory form:
+//     one 32-bit record per cell (owner snake, body value), one byte per cell for food, one head
+//     index per snake.  The state is almost entirely zeros, so the fold is a handful of shared
+//     atomics per env.
+//   * the whole step (boost phase, regular phase, food on death, boost cost, food respawn) runs on
+//     that compact form: the per-snake logic on one lane per snake of warp 0 (collisions are
+//     look-ups at the new head cell, head-to-head clashes a K-wide compare), the per-cell work
+//     (decay, food from dead bodies, deletion) as CTA-wide passes over the records;
+//   * the new state is expanded back to the reference's fp32 tensors with coalesced 128-bit
+//     stores, and the observations are rendered from the compact form straight into the policy's
+//     per-agent input buffers;
+//   * no tensor cores: nothing here is a dense contraction.
+//
+// Supported states: the reference's own invariant (MultiSnake.check_consistency, :733-769) --
+// bodies of different snakes never share a cell when a step starts, at most one head per snake,
+// dead snakes are all-zero.  A violating input raises WURM_ST_OVERLAP / WURM_ST_MULTI_HEAD.
+// The reference runs its boost phase when ANY agent of the batch boosts (:503); here each env
+// runs it when one of ITS agents boosts, which is identical on supported states (for an env
+// without boosting agents the phase changes nothing) -- except in replay mode, where the flag
+// recorded from the reference is followed literally.
+#include <math.h>
+
+#include "../../include/wurm_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wurm {
+
+constexpr int kMaxK = WURM_MULTI_MAX_SNAKES;
+
+struct MultiParams {
+    // state (reference layouts)
+    float* foods;
+    float* heads;
+    float* bodies;
+    uint8_t* dones;
+    long long* orientations;
+    uint8_t* boost_this_step;
+    short* colours;
+    // step inputs
+    const void* actions[kMaxK];
+    int action_bytes;
+    int replay, boost_phase_ran;
+    const float* u_boost;
+    const float* u_cost;
+    const float* u_reg;
+    const int* food_cell;
+    const float* u_rate;
+    uint64_t seed, step;
+    // rules
+    int E, K, S, C;
+    int boost, food_on_death, food_mode, respawn_any, colour_random;
+    float death_thr, boost_cost_prob, food_rate, reward_on_death;
+    // step outputs
+    float* rewards;
+    uint8_t* snake_col;
+    uint8_t* edge_col;
+    float* food_cons;
+    float* sizes;
+    uint8_t* dones_out;
+    uint8_t* boost_out;
+    uint8_t* all_done;
+    float* obs;
+    short* img;
+    int obs_mode, obs_n, W;
+    // reset inputs
+    const uint8_t* env_done;
+    const int* create;
+    const int* respawn;
+    const short* colours_replay;
+    int* status;
+    unsigned long long* stats;
+    uint32_t magic_S, magic_C;
+};
+
+__device__ __forceinline__ int fdiv(int q, uint32_t magic) { return (int)__umulhi((uint32_t)q, magic); }
+
+// cell record: bits 0-15 body value, bits 16-21 owner snake + 1; 0 = empty
+__device__ __forceinline__ uint32_t make_rec(int owner, int value) { return ((uint32_t)(owner + 1) << 16) | (uint32_t)value; }
+__device__ __forceinline__ int rec_owner(uint32_t r) { return (int)(r >> 16) - 1; }
+__device__ __forceinline__ int rec_value(uint32_t r) { return (int)(r & 0xffffu); }
+
+__device__ __forceinline__ float4 ld_stream(const float4* ptr) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+    return v;
+}
+
+// Calls f(i, v) for every non-zero base[i], i < n.  128-bit streaming loads, four in flight per thread.
+template <typename F>
+__device__ __forceinline__ void scan_nonzero(const float* base, int n, F&& f) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int lead = (4 - (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3)) & 3;
+    if (lead > n) lead = n;
+    if (tid < lead) {
+        const float v = base[tid];
+        if (v != 0.0f) f(tid, v);
+    }
+    const int nvec = (n - lead) >> 2;
+    const float4* vb = reinterpret_cast<const float4*>(base + lead);
+    for (int j0 = tid; j0 < nvec; j0 += 4 * nthr) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * nthr;
+            v[u] = (j < nvec) ? ld_stream(vb + j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u].x != 0.0f || v[u].y != 0.0f || v[u].z != 0.0f || v[u].w != 0.0f) {
+                const int i = lead + 4 * (j0 + u * nthr);
+                if (v[u].x != 0.0f) f(i, v[u].x);
+                if (v[u].y != 0.0f) f(i + 1, v[u].y);
+                if (v[u].z != 0.0f) f(i + 2, v[u].z);
+                if (v[u].w != 0.0f) f(i + 3, v[u].w);
+            }
+        }
+    }
+    const int tail0 = lead + 4 * nvec;
+    if (tid < n - tail0) {
+        const float v = base[tail0 + tid];
+        if (v != 0.0f) f(tail0 + tid, v);
+    }
+}
+
+// base[i] = gen(i) for i < n, 128-bit stores where the address allows.
+template <typename G>
+__device__ __forceinline__ void store_floats(float* base, int n, G&& gen) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int lead = (4 - (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3)) & 3;
+    if (lead > n) lead = n;
+    if (tid < lead) base[tid] = gen(tid);
+    const int nvec = (n - lead) >> 2;
+    float4* vb = reinterpret_cast<float4*>(base + lead);
+    for (int j = tid; j < nvec; j += nthr) {
+        const int i = lead + 4 * j;
+        vb[j] = make_float4(gen(i), gen(i + 1), gen(i + 2), gen(i + 3));
+    }
+    const int tail0 = lead + 4 * nvec;
+    if (tid < n - tail0) base[tail0 + tid] = gen(tail0 + tid);
+}
+
+struct MultiSmem {
+    uint32_t* cell;   // C records
+    uint8_t* food;    // C
+    int* hp;          // head cell per snake, -1 none
+    int* size;        // max body value per snake
+    int* hcnt;        // head cells seen per snake
+    int* done;
+    int* decay;
+    int* cost;
+    int* boost;
+    int* misc;        // [0] food count, [1] scratch
+    short* col;       // K*3
+    uint32_t* tab;    // partial-obs index table
+};
+
+__device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
+    MultiSmem s;
+    s.cell = reinterpret_cast<uint32_t*>(smem);
+    s.food = reinterpret_cast<uint8_t*>(s.cell + C);
+    s.hp = reinterpret_cast<int*>(s.food + ((C + 15) & ~15));
+    s.size = s.hp + 32; s.hcnt = s.size + 32; s.done = s.hcnt + 32; s.decay = s.done + 32; s.cost = s.decay + 32;
+    s.boost = s.cost + 32; s.misc = s.boost + 32;
+    s.col = reinterpret_cast<short*>(s.misc + 8);
+    s.tab = reinterpret_cast<uint32_t*>(s.col + 96);
+    return s;
+}
+
+static size_t multi_smem_bytes(int C, int W, int obs_mode) {
+    return (size_t)C * 4 + ((C + 15) & ~15) + 7 * 32 * 4 + 8 * 4 + 96 * 2 + (obs_mode == WURM_MOBS_PARTIAL ? 3 * W * W * 4 : 0) + 16;
+}
+
+// Streams env e's tensors from HBM into the compact shared-memory form.
+__device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e) {
+    const int C = p.C, K = p.K;
+    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float) { s.food[i] = 1; });
+    scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float) {
+        const int k = fdiv(i, p.magic_C);
+        atomicMax(&s.hp[k], i - k * C);
+        atomicAdd(&s.hcnt[k], 1);
+    });
+    bool overlap = false;
+    scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float v) {
+        const int k = fdiv(i, p.magic_C), val = (int)v;
+        if (atomicCAS(&s.cell[i - k * C], 0u, make_rec(k, val)) != 0u) overlap = true;
+        atomicMax(&s.size[k], val);
+    });
+    if (overlap) atomicOr(p.status, WURM_ST_OVERLAP);
+}
+
+// multi_snake.py:194-227 _get_env_images: int16 colour of cell q (canonical state: one owner per cell)
+__device__ __forceinline__ void env_pixel(const MultiParams& p, const MultiSmem& s, int q, int y, int x, int rgb[3]) {
+    const uint32_t rec = s.cell[q];
+    rgb[0] = rgb[1] = rgb[2] = 0;
+    if (rec) {
+        const int o = rec_owner(rec);
+        float inten = 1.0f * 1.0f / 3.0f + (s.hp[o] == q ? 1.0f : 0.0f) * 1.0f / 3.0f;      // :197
+        inten *= 1.0f + 0.5f * (s.boost[o] ? 1.0f : 0.0f);                                  // :198
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] = (int)(short)(inten * (float)s.col[3 * o + c]);  // :201-206
+    }
+    if (s.food[q]) rgb[0] += 255;                                                            // :208-209
+    if (rgb[0] == 0 && rgb[1] == 0 && rgb[2] == 0) rgb[0] = rgb[1] = rgb[2] = 255;           // :214-219
+    if (y == 0 || x == 0 || y == p.S - 1 || x == p.S - 1) rgb[0] = rgb[1] = rgb[2] = 0;      // :225
+}
+
+// multi_snake.py:283-334 from the compact form into the per-agent buffers obs[k][e].
+__device__ __forceinline__ void write_multi_obs(const MultiParams& p, const MultiSmem& s, int e) {
+    const int C = p.C, K = p.K, S = p.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (p.obs_mode == WURM_MOBS_PARTIAL) {                           // :289-332
+        const int n = p.obs_n, EL = 3 * p.W * p.W;
+        for (int k = warp; k < K; k += nwarps) {
+            float* o = p.obs + ((size_t)k * p.E + e) * EL;
+            const int hp = s.hp[k];
+            if (s.done[k] || hp < 0 || s.hcnt[k] > 1) {               // :320-323 zeros for dead agents
+                for (int r = lane; r < EL; r += 32) o[r] = 0.0f;
+                continue;
+            }
+            const int hy = fdiv(hp, p.magic_S), hx = hp - hy * S;
+            for (int r = lane; r < EL; r += 32) {
+                const uint32_t ent = s.tab[r];
+                const int c = ent & 3, y = hy - n + (int)((ent >> 2) & 0xff), x = hx - n + (int)(ent >> 10);
+                float v = 0.0f;                                       // zero padding :301-302
+                if (y >= 0 && y < S && x >= 0 && x < S) {
+                    int rgb[3];
+                    env_pixel(p, s, y * S + x, y, x, rgb);
+                    v = (float)(c == 0 ? rgb[0] : c == 1 ? rgb[1] : rgb[2]) / 255.0f;   // :296
+                }
+                o[r] = v;
+            }
+        }
+    } else if (p.obs_mode == WURM_MOBS_FULL) {                       // :268-281 _observe_agent
+        for (int k = warp; k < K; k += nwarps) {
+            float* o = p.obs + ((size_t)k * p.E + e) * 3 * C;
+            for (int q = lane; q < C; q += 32) {
+                const int y = fdiv(q, p.magic_S), x = q - y * S;
+                const uint32_t rec = s.cell[q];
+                int r = 255, g = 255, b = 255;
+                if (s.food[q]) { r = 255; g = 0; b = 0; }
+                if (rec) {
+                    const int ow = rec_owner(rec);
+                    const bool is_head = s.hp[ow] == q;
+                    if (ow == k) { r = 0; g = is_head ? 192 : 96; b = 0; }
+                    else { r = 0; g = 0; b = is_head ? 192 : 96; }
+                }
+                if (y == 0 || x == 0 || y == S - 1 || x == S - 1) r = g = b = 0;
+                o[q] = (float)r / 255.0f;
+                o[C + q] = (float)g / 255.0f;
+                o[2 * C + q] = (float)b / 255.0f;
+            }
+        }
+    }
+    if (p.img) {                                                     // _get_env_images as (E,3,S,S) int16
+        for (int q = threadIdx.x; q < C; q += blockDim.x) {
+            const int y = fdiv(q, p.magic_S), x = q - y * S;
+            int rgb[3];
+            env_pixel(p, s, q, y, x, rgb);
+            for (int c = 0; c < 3; ++c) p.img[((size_t)e * 3 + c) * C + q] = (short)rgb[c];
+        }
+    }
+}
+
+// One CTA = one environment.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
+template <bool STEP>
+__global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const MultiSmem s = carve(smem_raw, p.C);
+    const int C = p.C, K = p.K, S = p.S;
+    const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int q = tid; q < C; q += nthr) { s.cell[q] = 0u; s.food[q] = 0; }
+    if (tid < 32) {
+        s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.decay[tid] = 0; s.cost[tid] = 0;
+        s.done[tid] = (tid < K) ? (p.dones[(size_t)e * K + tid] != 0) : 1;
+        s.boost[tid] = (!STEP && tid < K) ? (p.boost_this_step[(size_t)e * K + tid] != 0) : 0;
+    }
+    if (tid < 8) s.misc[tid] = 0;
+    if (tid < 3 * K) s.col[tid] = p.colours[(size_t)e * K * 3 + tid];
+    if (p.obs_mode == WURM_MOBS_PARTIAL) {
+        const int W = p.W;
+        for (int r = tid; r < 3 * W * W; r += nthr) {
+            const int c = r / (W * W), ij = r - c * W * W, i = ij / W, j = ij - i * W;
+            s.tab[r] = (uint32_t)c | ((uint32_t)i << 2) | ((uint32_t)j << 10);
+        }
+    }
+    __syncthreads();
+    load_env(p, s, e);
+    __syncthreads();
+
+    if (STEP) {
+        // ---- per-snake registers, live on lane k of warp 0 ----
+        const int k = lane;
+        const bool valid = (warp == 0) && (k < K);
+        int a_hp = -1, a_size = 0, a_mv = 0;
+        bool a_done = true, a_done0 = true, a_boosted = false, a_scol = false, a_ecol = false;
+        float a_reward = 0.0f, a_foodc = 0.0f;
+        bool run_boost = false;
+        if (warp == 0) {
+            if (valid) {
+                const size_t n = (size_t)e * K + k;
+                long long a;
+                if (p.action_bytes == 8) a = ((const long long*)p.actions[k])[e];
+                else if (p.action_bytes == 4) a = ((const int*)p.actions[k])[e];
+                else a = ((const short*)p.actions[k])[e];
+                a_hp = s.hp[k]; a_size = s.size[k];
+                a_done = a_done0 = s.done[k] != 0;                    // :490
+                long long m = a % 4;                                  // :483
+                if (p.orientations[n] == m) m = (m + 2) % 4;          // :336-339
+                a_mv = (int)m;
+                p.orientations[n] = (m + 2) % 4;                      // :355-357 (dead agents too)
+                a_boosted = (a > 3) && (a_size >= 4);                 // :484,497-498
+                p.boost_this_step[n] = a_boosted;                     // :499
+                s.boost[k] = a_boosted;
+                if (s.hcnt[k] > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+            }
+            const bool any_boost = __ballot_sync(0xffffffffu, valid && a_boosted) != 0u;
+            run_boost = p.replay ? (p.boost_phase_ran != 0) : (p.boost && any_boost);     // :503
+            if (lane == 0) s.misc[2] = run_boost;
+        }
+        __syncthreads();
+        run_boost = s.misc[2] != 0;
+
+        for (int phase = run_boost ? 0 : 1; phase < 2; ++phase) {
+            const bool boost_phase = phase == 0;
+            const bool active = valid && (boost_phase ? a_boosted : true);
+            bool ov = false;
+            if (warp == 0) {
+                if (active && a_hp >= 0) {                            // :509 / :613 _move_heads
+                    const int y = fdiv(a_hp, p.magic_S), x = a_hp - y * S;
+                    const int ny = y - off_y(a_mv), nx = x - off_x(a_mv);
+                    a_hp = (ny >= 0 && ny < S && nx >= 0 && nx < S) ? ny * S + nx : -1;
+                }
+                if (valid) s.hp[k] = a_hp;
+                __syncwarp();
+                ov = valid && a_hp >= 0 && s.food[a_hp] != 0;         // :514 / :618 overlap of ALL heads
+                __syncwarp();
+                if (ov) s.food[a_hp] = 0;                             // :517 / :622
+                if (k < 32) s.decay[k] = active && !ov;               // :523-526 / :627-628
+                if (active && ov) { a_reward += 1.0f; a_foodc += 1.0f; }   // :527-529 / :629-631
+            }
+            __syncthreads();
+            for (int q = tid; q < C; q += nthr) {                     // _decay_bodies :362-363
+                const uint32_t rec = s.cell[q];
+                if (rec && s.decay[rec_owner(rec)]) s.cell[q] = (rec_value(rec) == 1) ? 0u : rec - 1u;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                bool col = false;
+                if (active && a_hp >= 0) {                            // :534-545 / :636-642
+                    col = s.cell[a_hp] != 0u;                         // any body, own included
+                    for (int j = 0; j < K; ++j) col |= (j != k) && (s.hp[j] == a_hp);   // another head
+                }
+                __syncwarp();
+                if (active) { a_done |= col; a_scol |= col; }         // :546-547 / :643-644
+                if (active && a_hp >= 0) {                            // :553 / :650 growth at the head cell
+                    const uint32_t add = (uint32_t)(a_size + (ov ? 1 : 0));
+                    const uint32_t old = atomicCAS(&s.cell[a_hp], 0u, make_rec(k, (int)add));
+                    if (old != 0u && rec_owner(old) == k) s.cell[a_hp] = old + add;   // self collision: values add up
+                    // a collider's head value on ANOTHER snake's cell is dropped: the collider is
+                    // deleted below and that cell counts as covered by the other body either way
+                    a_size += ov ? 1 : 0;                             // :555 / :652
+                    const int y = fdiv(a_hp, p.magic_S), x = a_hp - y * S;
+                    const bool edge = y == 0 || x == 0 || y == S - 1 || x == S - 1;   // :560 / :657
+                    a_done |= edge; a_ecol |= edge;
+                }
+                if (valid) s.done[k] = a_done;
+                if (boost_phase) {                                    // :579-592 boost cost
+                    bool cost = false;
+                    if (valid && a_boosted) {
+                        const float u = p.replay ? p.u_cost[(size_t)e * K + k]
+                                                 : unit_float(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiBoostCost, (uint32_t)k));
+                        cost = u < p.boost_cost_prob;
+                    }
+                    if (k < 32) s.cost[k] = cost;
+                    if (cost) { a_reward -= 1.0f; a_size -= 1; }      // :590-591
+                }
+            }
+            __syncthreads();
+            {   // food from dead bodies (:416-428), boost cost on the bodies (:583-589), deletion (:595 / :676)
+                const float* U = p.replay ? (boost_phase ? p.u_boost : p.u_reg) : nullptr;
+                const uint32_t stream = boost_phase ? kStreamMultiDeathBoost : kStreamMultiDeathRegular;
+                for (int q = tid; q < C; q += nthr) {
+                    uint32_t rec = s.cell[q];
+                    if (!rec) continue;
+                    const int o = rec_owner(rec);
+                    if (p.food_on_death && s.done[o]) {
+                        const int y = fdiv(q, p.magic_S), x = q - y * S;
+                        if (!(y == 1 || x == 0 || y == S - 1 || x == S - 1)) {   // sic: row 1 (:418)
+                            const float u = p.replay ? (U ? U[(size_t)e * C + q] : 0.0f)
+                                                     : unit_float(draw_i(p.seed, p.step, (uint32_t)e, stream, (uint32_t)q));
+                            if (u > p.death_thr) s.food[q] = 1;
+                        }
+                    }
+                    if (boost_phase && s.cost[o]) {
+                        if (rec_value(rec) == 1) { s.food[q] = 1; rec = 0u; }   // the tail becomes food
+                        else rec -= 1u;
+                    }
+                    if (s.done[o]) rec = 0u;
+                    s.cell[q] = rec;
+                }
+            }
+            if (warp == 0 && valid && a_done) { a_hp = -1; s.hp[k] = -1; }
+            __syncthreads();
+        }
+
+        // ---- _add_food (:368-410) ----
+        {
+            int cnt = 0;
+            for (int q = tid; q < C; q += nthr) cnt += s.food[q];
+            cnt = group_sum<32>(cnt, 0xffffffffu);
+            if (lane == 0 && cnt) atomicAdd(&s.misc[0], cnt);
+            __syncthreads();
+            const int nfood = s.misc[0];
+            auto cell_free = [&](int q) { return s.cell[q] == 0u && s.food[q] == 0; };
+            if (p.food_mode == 0) {                                   // only_one
+                if (nfood == 0 && tid == 0) {
+                    int cell = -1;
+                    if (p.replay) cell = p.food_cell[e];
+                    else {
+                        const int I = S - 2;
+                        for (uint32_t t = 0; t < kRejectionTries && cell < 0; ++t) {
+                            const int cand = (int)bounded(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiFoodOne, t), (uint32_t)(I * I));
+                            const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
+                            if (cell_free(q)) cell = q;
+                        }
+                        if (cell < 0) {                               // nearly full board: rank the free cells
+                            int nfree = 0;
+                            for (int y = 1; y < S - 1; ++y)
+                                for (int x = 1; x < S - 1; ++x) nfree += cell_free(y * S + x);
+                            if (nfree > 0) {
+                                int r = (int)bounded(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiFoodOne, kRejectionTries), (uint32_t)nfree);
+                                for (int y = 1; y < S - 1 && cell < 0; ++y)
+                                    for (int x = 1; x < S - 1; ++x)
+                                        if (cell_free(y * S + x) && r-- == 0) { cell = y * S + x; break; }
+                            }
+                        }
+                    }
+                    if (cell >= 0) s.food[cell] = 1;
+                }
+            } else if (nfood < 8 * K) {                               // random_rate, max_food :127
+                for (int q = tid; q < C; q += nthr) {
+                    const int y = fdiv(q, p.magic_S), x = q - y * S;
+                    if (y < 1 || y > S - 2 || x < 1 || x > S - 2 || !cell_free(q)) continue;
+                    const float u = p.replay ? p.u_rate[(size_t)e * C + q]
+                                             : unit_float(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiFoodRate, (uint32_t)q));
+                    if (u < p.food_rate) s.food[q] = 1;
+                }
+            }
+        }
+
+        // ---- per-agent outputs ----
+        if (warp == 0) {
+            if (valid) {
+                const size_t n = (size_t)e * K + k;
+                if (a_done && !a_done0) a_reward += p.reward_on_death;   // :683-685
+                p.rewards[n] = a_reward;
+                p.snake_col[n] = a_scol;
+                p.edge_col[n] = a_ecol;
+                p.food_cons[n] = a_foodc;
+                p.sizes[n] = (float)a_size;
+                p.dones[n] = a_done;
+                p.dones_out[n] = a_done;
+                p.boost_out[n] = a_boosted;
+            }
+            const unsigned alive = __ballot_sync(0xffffffffu, valid && !a_done);
+            const unsigned scols = __ballot_sync(0xffffffffu, valid && a_scol);
+            const unsigned ecols = __ballot_sync(0xffffffffu, valid && a_ecol);
+            const int eaten = group_sum<32>(valid ? (int)a_foodc : 0, 0xffffffffu);
+            if (lane == 0) {
+                p.all_done[e] = alive == 0u;                          // :703
+                if (p.stats) {
+                    unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+                    atomicAdd(slot + WURM_STAT_ENV_STEPS, 1ull);
+                    if (alive == 0u) atomicAdd(slot + WURM_STAT_EPISODES, 1ull);
+                    if (eaten) atomicAdd(slot + WURM_STAT_REWARD, (unsigned long long)eaten);
+                    if (scols) atomicAdd(slot + WURM_STAT_SELF_COLLISIONS, (unsigned long long)__popc(scols));
+                    if (ecols) atomicAdd(slot + WURM_STAT_EDGE_COLLISIONS, (unsigned long long)__popc(ecols));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- expand the compact form back into the reference's tensors ----
+        store_floats(p.foods + (size_t)e * C, C, [&](int i) { return s.food[i] ? 1.0f : 0.0f; });
+        store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv(i, p.magic_C);
+            return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
+        });
+        store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv(i, p.magic_C);
+            const uint32_t rec = s.cell[i - kk * C];
+            return (rec && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
+        });
+    }
+    write_multi_obs(p, s, e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset (multi_snake.py:771-831): one CTA per env; envs with nothing to do exit after K+1 bytes.
+// ---------------------------------------------------------------------------------------------
+// Block-wide: number of cells q < C with pred(q); if r >= 0 also the r-th such cell in raster order
+// (through *out).  `counts` is blockDim.x + 1 ints of shared scratch.
+template <typename P>
+__device__ __forceinline__ int block_rank(int C, int* counts, int r, int* out, P&& pred) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int chunk = (C + nthr - 1) / nthr, q0 = tid * chunk, q1 = min(C, q0 + chunk);
+    int mine = 0;
+    for (int q = q0; q < q1; ++q) mine += pred(q) ? 1 : 0;
+    counts[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int t = 0; t < nthr; ++t) { const int c = counts[t]; counts[t] = acc; acc += c; }
+        counts[nthr] = acc;
+    }
+    __syncthreads();
+    const int total = counts[nthr];
+    if (r >= 0 && r < total && r >= counts[tid] && r < counts[tid] + mine) {
+        int left = r - counts[tid];
+        for (int q = q0; q < q1; ++q)
+            if (pred(q) && left-- == 0) { *out = q; break; }
+    }
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = p.C, K = p.K, S = p.S;
+    uint8_t* occ = smem_raw;                                          // C occupancy bytes
+    int* counts = reinterpret_cast<int*>(smem_raw + ((C + 15) & ~15)); // blockDim.x + 1
+    int* pick = counts + blockDim.x + 1;                              // [0] chosen cell
+    int* snake_cell = pick + 4;                                       // K
+    int* snake_dir = snake_cell + 32;                                 // K
+    const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+
+    const bool recreate = p.env_done[e] != 0;
+    int first_dead = -1, ndead = 0;
+    for (int k = K - 1; k >= 0; --k)
+        if (p.dones[(size_t)e * K + k]) { first_dead = k; ++ndead; }
+    if (!recreate && ndead == 0) return;                              // nothing to do for this env
+
+    auto inner = [&](int q) {
+        const int y = fdiv(q, p.magic_S), x = q - y * S;
+        return y >= 2 && y <= S - 3 && x >= 2 && x <= S - 3;
+    };
+    auto spawnable = [&](int q) {                                      // :846-858 / :927-941
+        if (!inner(q)) return false;
+        const int y = fdiv(q, p.magic_S), x = q - y * S;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+                if (occ[(y + dy) * S + x + dx]) return false;
+        return true;
+    };
+    auto stamp = [&](int cell, int d) {                                // LENGTH_3_SNAKES
+        const int y = fdiv(cell, p.magic_S), x = cell - y * S;
+        occ[(y - off_y(d)) * S + (x - off_x(d))] = 1; occ[cell] = 1; occ[(y + off_y(d)) * S + (x + off_x(d))] = 1;
+    };
+    auto snake_value = [&](int cell, int d, int q, bool head) -> float {
+        const int y = fdiv(cell, p.magic_S), x = cell - y * S;
+        const int hd = (y + off_y(d)) * S + (x + off_x(d)), tl = (y - off_y(d)) * S + (x - off_x(d));
+        if (head) return q == hd ? 1.0f : 0.0f;
+        return q == hd ? 3.0f : q == cell ? 2.0f : q == tl ? 1.0f : 0.0f;
+    };
+
+    if (recreate) {                                                   // :787-798 + _create_envs :996-1019
+        for (int q = tid; q < C; q += nthr) occ[q] = 0;
+        __syncthreads();
+        for (int k = 0; k < K; ++k) {                                 // _add_snake, one snake after the other
+            if (tid == 0) pick[0] = -1;
+            __syncthreads();
+            int d;
+            if (p.create) {
+                if (tid == 0) pick[0] = p.create[((size_t)e * (K + 1) + k) * 2];
+                d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
+                __syncthreads();
+            } else {
+                const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
+                const int n = block_rank(C, counts, -1, pick, spawnable);
+                if (n > 0) block_rank(C, counts, (int)bounded(r.x, (uint32_t)n), pick, spawnable);
+                d = (int)(r.y >> 30);
+            }
+            const int cell = pick[0];
+            __syncthreads();
+            if (tid == 0) {
+                snake_cell[k] = cell; snake_dir[k] = d;
+                if (cell >= 0) stamp(cell, d);
+                else atomicOr(p.status, WURM_ST_NO_SPAWN);            // the reference raises (:947)
+            }
+            __syncthreads();
+        }
+        if (tid == 0) pick[0] = -1;
+        __syncthreads();
+        auto free_interior = [&](int q) {
+            const int y = fdiv(q, p.magic_S), x = q - y * S;
+            return y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && !occ[q];
+        };
+        if (p.create) {
+            if (tid == 0) pick[0] = p.create[((size_t)e * (K + 1) + K) * 2];
+            __syncthreads();
+        } else {                                                      // :1016 one food on a free interior cell
+            const int n = block_rank(C, counts, -1, pick, free_interior);
+            if (n > 0) block_rank(C, counts, (int)bounded(draw(p.seed, p.step, (uint32_t)e, kStreamMultiCreateFood).x, (uint32_t)n), pick, free_interior);
+        }
+        const int fcell = pick[0];
+        store_floats(p.foods + (size_t)e * C, C, [&](int i) { return i == fcell ? 1.0f : 0.0f; });
+        store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv(i, p.magic_C);
+            return snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, true) : 0.0f;
+        });
+        store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv(i, p.magic_C);
+            return snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, false) : 0.0f;
+        });
+        if (tid < K) {
+            if (snake_cell[tid] >= 0) p.orientations[(size_t)e * K + tid] = snake_dir[tid];   // :793
+            p.dones[(size_t)e * K + tid] = 0;                                                 // :798
+        }
+        return;                                                       // every agent alive: no colours, no respawn
+    }
+
+    if (p.colour_random && tid < K && p.dones[(size_t)e * K + tid]) { // :800-803 new colours for the dead
+        short* col = p.colours + 3 * ((size_t)e * K + tid);
+        if (p.colours_replay) {
+            for (int c = 0; c < 3; ++c) col[c] = p.colours_replay[3 * ((size_t)e * K + tid) + c];
+        } else {                                                      // get_n_colours :163-169
+            const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamMultiColour | ((uint32_t)tid << 4));
+            const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
+            const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+            col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f); col[2] = (short)(c2 / norm * 192.0f);
+        }
+    }
+    if (!p.respawn_any) return;
+
+    // :805-829 respawn the first dead snake of the env where there is room
+    for (int q = tid; q < C; q += nthr) occ[q] = 0;
+    if (tid == 0) pick[0] = -1;
+    __syncthreads();
+    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float) { occ[i] = 1; });
+    scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float) { occ[i - fdiv(i, p.magic_C) * C] = 1; });
+    scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float) { occ[i - fdiv(i, p.magic_C) * C] = 1; });
+    __syncthreads();
+    int d;
+    if (p.respawn) {
+        if (tid == 0) pick[0] = p.respawn[2 * (size_t)e];
+        d = p.respawn[2 * (size_t)e + 1];
+        __syncthreads();
+    } else {
+        const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamMultiRespawn);
+        const int n = block_rank(C, counts, -1, pick, spawnable);
+        if (n > 0) block_rank(C, counts, (int)bounded(r.x, (uint32_t)n), pick, spawnable);
+        d = (int)(r.y >> 30);
+    }
+    const int cell = pick[0];
+    const size_t n = (size_t)e * K + first_dead;
+    store_floats(p.heads + n * C, C, [&](int i) { return cell >= 0 ? snake_value(cell, d, i, true) : 0.0f; });    // :826-827
+    store_floats(p.bodies + n * C, C, [&](int i) { return cell >= 0 ? snake_value(cell, d, i, false) : 0.0f; });
+    if (tid == 0) {
+        p.orientations[n] = d;                                        // :828 even when the spawn failed
+        p.dones[n] = cell < 0;                                        // :829
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiParams* p) {
+    if (!cfg || !st) return fail(WURM_E_INVALID, "cfg or state is NULL");
+    if (cfg->num_envs <= 0) return fail(WURM_E_INVALID, "num_envs must be positive");
+    if (cfg->num_snakes <= 0 || cfg->num_snakes > kMaxK) return fail(WURM_E_UNSUPPORTED, "num_snakes must be in [1, 32]");
+    if (cfg->size < 7) return fail(WURM_E_INVALID, "size must be >= 7 (a length-3 snake two cells from the wall)");
+    if (cfg->size > 181) return fail(WURM_E_UNSUPPORTED, "size > 181: body values no longer fit the 16-bit cell record");
+    if (cfg->obs_mode < WURM_MOBS_NONE || cfg->obs_mode > WURM_MOBS_PARTIAL) return fail(WURM_E_INVALID, "bad obs_mode");
+    if (cfg->obs_mode == WURM_MOBS_PARTIAL && (cfg->obs_n < 0 || cfg->obs_n > 127)) return fail(WURM_E_INVALID, "bad obs_n");
+    if (cfg->food_mode != 0 && cfg->food_mode != 1) return fail(WURM_E_INVALID, "bad food_mode");
+    if (!st->foods || !st->heads || !st->bodies || !st->dones || !st->orientations || !st->boost_this_step || !st->agent_colours)
+        return fail(WURM_E_INVALID, "NULL state pointer");
+    p->foods = st->foods; p->heads = st->heads; p->bodies = st->bodies; p->dones = st->dones;
+    p->orientations = reinterpret_cast<long long*>(st->orientations); p->boost_this_step = st->boost_this_step;
+    p->colours = st->agent_colours;
+    p->E = cfg->num_envs; p->K = cfg->num_snakes; p->S = cfg->size; p->C = cfg->size * cfg->size;
+    p->boost = cfg->boost; p->food_on_death = cfg->food_on_death; p->food_mode = cfg->food_mode;
+    p->respawn_any = cfg->respawn_any; p->colour_random = cfg->colour_random;
+    p->death_thr = cfg->death_threshold; p->boost_cost_prob = cfg->boost_cost_prob; p->food_rate = cfg->food_rate;
+    p->reward_on_death = cfg->reward_on_death;
+    p->obs_mode = cfg->obs_mode; p->obs_n = cfg->obs_n; p->W = 2 * cfg->obs_n + 1;
+    p->magic_S = (uint32_t)((0x100000000ull + (uint64_t)p->S - 1) / (uint64_t)p->S);
+    p->magic_C = (uint32_t)((0x100000000ull + (uint64_t)p->C - 1) / (uint64_t)p->C);
+    return WURM_OK;
+}
+
+template <bool STEP>
+static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
+    auto kern = multi_env_kernel<STEP>;
+    const size_t smem = multi_smem_bytes(p.C, p.W, p.obs_mode);
+    if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
+    static size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(multi_env_kernel)");
+        configured = smem;
+    }
+    const int threads = p.C <= 1024 ? 128 : 256;
+    kern<<<p.E, threads, smem, stream>>>(p);
+    return check_launch("multi_env_kernel");
+}
+
+}  // namespace wurm
+
+using namespace wurm;
+
+extern "C" int64_t wurm_multi_obs_elems(const WurmMultiCfg* cfg) {
+    if (!cfg) return -1;
+    const int64_t C = (int64_t)cfg->size * cfg->size, W = 2 * cfg->obs_n + 1;
+    return cfg->obs_mode == WURM_MOBS_FULL ? 3 * C : cfg->obs_mode == WURM_MOBS_PARTIAL ? 3 * W * W : 0;
+}
+
+extern "C" int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions,
+                               int action_bytes, const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step,
+                               const WurmMultiStepOut* out, int32_t* status, int64_t* stats, void* stream) {
+    MultiParams p = {};
+    if (int rc = plan_multi(cfg, state, &p)) return rc;
+    if (!actions || !out || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
+    for (int k = 0; k < p.K; ++k) {
+        if (!actions[k]) return fail(WURM_E_INVALID, "NULL action pointer");
+        p.actions[k] = actions[k];
+    }
+    if (!out->rewards || !out->snake_collision || !out->edge_collision || !out->food || !out->size || !out->all_done ||
+        !out->dones || !out->boost)
+        return fail(WURM_E_INVALID, "NULL output pointer");
+    if (cfg->obs_mode != WURM_MOBS_NONE && !out->obs) return fail(WURM_E_INVALID, "obs is NULL");
+    p.action_bytes = action_bytes;
+    if (draws) {
+        p.replay = 1; p.boost_phase_ran = draws->boost_phase_ran;
+        p.u_boost = draws->u_boost; p.u_cost = draws->u_cost; p.u_reg = draws->u_reg;
+        p.food_cell = draws->food_cell; p.u_rate = draws->u_rate;
+        if (p.boost_phase_ran && !p.u_cost) return fail(WURM_E_INVALID, "replay: boost phase ran but u_cost is NULL");
+        if (p.food_on_death && !p.u_reg) return fail(WURM_E_INVALID, "replay: u_reg is NULL");
+        if (p.food_on_death && p.boost_phase_ran && !p.u_boost) return fail(WURM_E_INVALID, "replay: u_boost is NULL");
+        if (p.food_mode == 0 && !p.food_cell) return fail(WURM_E_INVALID, "replay: food_cell is NULL");
+        if (p.food_mode == 1 && !p.u_rate) return fail(WURM_E_INVALID, "replay: u_rate is NULL");
+    }
+    p.seed = seed; p.step = step;
+    p.rewards = out->rewards; p.snake_col = out->snake_collision; p.edge_col = out->edge_collision;
+    p.food_cons = out->food; p.sizes = out->size; p.all_done = out->all_done; p.obs = out->obs;
+    p.dones_out = out->dones; p.boost_out = out->boost;
+    p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
+    return launch_multi_env<true>(p, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_multi_observe(const WurmMultiCfg* cfg, const WurmMultiState* state, float* obs, int32_t* status,
+                                  void* stream) {
+    MultiParams p = {};
+    if (int rc = plan_multi(cfg, state, &p)) return rc;
+    if (!obs || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    if (cfg->obs_mode == WURM_MOBS_NONE) return WURM_OK;
+    p.obs = obs; p.status = status;
+    return launch_multi_env<false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_multi_env_images(const WurmMultiCfg* cfg, const WurmMultiState* state, int16_t* img, int32_t* status,
+                                     void* stream) {
+    MultiParams p = {};
+    if (int rc = plan_multi(cfg, state, &p)) return rc;
+    if (!img || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    p.obs_mode = WURM_MOBS_NONE; p.img = img; p.status = status;
+    return launch_multi_env<false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const uint8_t* env_done,
+                                const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, int32_t* status,
+                                void* stream) {
+    MultiParams p = {};
+    if (int rc = plan_multi(cfg, state, &p)) return rc;
+    if (!env_done || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    p.env_done = env_done; p.seed = seed; p.step = step; p.status = status;
+    if (draws) {
+        p.replay = 1; p.create = draws->create; p.respawn = draws->respawn; p.colours_replay = draws->colours;
+        if (!p.create || (p.respawn_any && !p.respawn) || (p.colour_random && !p.colours_replay))
+            return fail(WURM_E_INVALID, "replay: NULL draw array");
+    }
+    const int threads = p.C <= 1024 ? 128 : 256;
+    const size_t smem = ((p.C + 15) & ~15) + (size_t)(threads + 1 + 4 + 64) * 4 + 16;
+    multi_reset_kernel<<<p.E, threads, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("multi_reset_kernel");
+}

@@ -201,7 +201,20 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
     if (ov != 0.0f) {                                                // :277-282 respawn
         int cell;
         if (p.food_replay) cell = p.food_replay[e];
-        else cell = pick_free_cell<G>(env, S, C, p.magic_S, draw(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood).x, l, gm);
+        else {
+            // uniform over the free interior cells by rejection (every lane of the group draws the
+            // same candidates); after kRejectionTries misses the free cells are ranked explicitly
+            const int I = S - 2;
+            cell = -1;
+            for (uint32_t t = 0; t < kRejectionTries && cell < 0; ++t) {
+                const int cand = (int)bounded(draw_i(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood, t), (uint32_t)(I * I));
+                const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
+                if (env[q] + env[C + q] + env[2 * C + q] < kEps) cell = q;
+            }
+            if (cell < 0)
+                cell = pick_free_cell<G>(env, S, C, p.magic_S,
+                                         draw_i(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
+        }
         if (l == 0 && cell >= 0) food[cell] += 1.0f;
     }
     if (l == 0) {

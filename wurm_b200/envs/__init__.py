@@ -1,1 +1,2 @@
 from .single_snake import SingleSnake  # noqa: F401
+from .multi_snake import MultiSnake  # noqa: F401

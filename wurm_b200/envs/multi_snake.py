@@ -1,0 +1,440 @@
+"""Batched slither-style multi-snake environment, B200-native.
+
+Drop-in for the reference's `wurm.envs.MultiSnake` (wurm/envs/multi_snake.py:18-1019): same
+constructor arguments and defaults, the same state attributes in the same layouts (`foods`, `heads`,
+`bodies`, `dones`, `orientations`, `boost_this_step`, `agent_colours`, all readable and writable),
+the same mutable rule attributes (`food_rate`, `food_on_death_prob`, `boost`, `boost_cost_prob`,
+`food_mode`, `respawn_mode`, `reward_on_death` -- re-read at every call because the reference's
+drivers anneal them, experiments/multiagent.py:337-345), and the same `step(dict) -> (obs dict,
+rewards dict, dones dict incl. '__all__', info dict)`, `reset(done, return_observations)`,
+`check_consistency()`, `_observe()`.  Every call is ONE kernel launch through the C ABI of
+include/wurm_b200.h (wurm_b200/csrc/multi_snake.cu).
+
+Randomness is an input of the kernels: by default derived on the device from Philox4x32-10 keyed by
+(`seed`, call counter, env); the keyword-only `draws` arguments inject recorded draws instead, which is
+how bit-exact parity with the reference is tested.
+"""
+from collections import namedtuple, OrderedDict
+from time import time
+from typing import Dict, Optional
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..config import DEFAULT_DEVICE, EPS  # noqa: F401
+
+Spec = namedtuple('Spec', ['reward_threshold'])
+
+_ACTION_BYTES = {torch.short: 2, torch.int: 4, torch.long: 8}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class MultiSnake(object):
+    """Batched multi-snake environment (state layout and dynamics: reference multi_snake.py:18-48)."""
+
+    spec = Spec(float('inf'))
+    metadata = {
+        'render.modes': ['rgb_array'],
+        'video.frames_per_second': 12
+    }
+
+    def __init__(self,
+                 num_envs: int,
+                 num_snakes: int,
+                 size: int,
+                 initial_snake_length: int = 3,
+                 on_death: str = 'restart',
+                 observation_mode: str = 'full',
+                 device: str = DEFAULT_DEVICE,
+                 dtype: torch.dtype = torch.float,
+                 manual_setup: bool = False,
+                 food_on_death_prob: float = 0.5,
+                 boost: bool = True,
+                 boost_cost_prob: float = 0.5,
+                 food_mode: str = 'only_one',
+                 food_rate: float = 5e-4,
+                 respawn_mode: str = 'all',
+                 reward_on_death: int = -1,
+                 verbose: int = 0,
+                 render_args: dict = None,
+                 agent_colours: str = 'random',
+                 seed: int = None):
+        self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
+        self.num_envs = num_envs
+        self.num_snakes = num_snakes
+        self.size = size
+        self.initial_snake_length = initial_snake_length
+        self.on_death = on_death
+        self.device = device
+        self.verbose = verbose
+        self.dtype = dtype
+        self.observation_mode = observation_mode
+        if torch.device(device).type != 'cuda':
+            raise RuntimeError(f"wurm_b200 envs run on CUDA devices only (got device={device!r}); "
+                               "the CPU implementation of this path is the reference itself")
+        if dtype != torch.float:
+            raise NotImplementedError('wurm_b200.MultiSnake keeps the state in float32 only')
+        if num_snakes > _lib.MULTI_MAX_SNAKES:
+            raise NotImplementedError(f'at most {_lib.MULTI_MAX_SNAKES} snakes per environment')
+        if observation_mode.startswith('partial_'):
+            self.observation_width = int(observation_mode.split('_')[1])
+            self.observation_size = 2 * int(observation_mode.split('_')[1]) + 1
+
+        if render_args is None:
+            self.render_args = {'num_rows': 1, 'num_cols': 1, 'size': 256}
+        else:
+            self.render_args = render_args
+
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, ()).item())    # follows torch.manual_seed
+        self.seed = seed
+        self._draws = 0
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
+
+        E, K, S = num_envs, num_snakes, size
+        self.foods = torch.zeros((E, 1, S, S), dtype=self.dtype, device=self.device)
+        self.heads = torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device)
+        self.bodies = torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device)
+        self.dones = torch.zeros(E * K, dtype=torch.bool, device=self.device)
+        self.boost_this_step = torch.zeros(E * K, dtype=torch.bool, device=self.device)
+        self.rewards = torch.zeros(E * K, dtype=torch.float, device=self.device)
+        self.env_lifetimes = torch.zeros(E, dtype=torch.long, device=self.device)
+        self.snake_lifetimes = torch.zeros((E, K), dtype=torch.long, device=self.device)
+        self.orientations = torch.zeros(E * K, dtype=torch.long, device=self.device)
+        self.viewer = None
+
+        # Environment dynamics parameters (mutable; read at every call)
+        self.respawn_mode = respawn_mode
+        self.food_on_death_prob = food_on_death_prob
+        self.boost = boost
+        self.boost_cost_prob = boost_cost_prob
+        self.food_mode = food_mode
+        self.food_rate = food_rate
+        self.max_food = self.num_snakes * 8
+        self.max_env_lifetime = 5000
+        self.reward_on_death = reward_on_death
+
+        # Rendering parameters
+        self.self_colour = torch.tensor((0, 192, 0), dtype=torch.short, device=self.device)
+        self.self_boost_colour = torch.tensor((0, 255, 0), dtype=torch.short, device=self.device)
+        self.other_colour = torch.tensor((0, 0, 192), dtype=torch.short, device=self.device)
+        self.other_boost_colour = torch.tensor((0, 0, 255), dtype=torch.short, device=self.device)
+        self.food_colour = torch.tensor((255, 0, 0), dtype=torch.short, device=self.device)
+        self.edge_colour = torch.tensor((0, 0, 0), dtype=torch.short, device=self.device)
+
+        if agent_colours == 'random':
+            self.colour_mode = 'random'
+            self.agent_colours = self.get_n_colours(E * K)
+        elif agent_colours == 'fixed':
+            self.colour_mode = 'fixed'
+            self.agent_colours = self.get_n_colours(K).repeat(E, 1)
+        else:
+            raise ValueError('agent_colours must in {random, fixed}')
+        self.num_colours = self.agent_colours.shape[0]
+
+        self.info = {}
+
+        self.edge_locations_mask = torch.zeros((1, 1, S, S), dtype=self.dtype, device=self.device)
+        self.edge_locations_mask[:, :, :1, :] = 1
+        self.edge_locations_mask[:, :, :, :1] = 1
+        self.edge_locations_mask[:, :, -1:, :] = 1
+        self.edge_locations_mask[:, :, :, -1:] = 1
+
+        if not manual_setup:
+            self._create_all()
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+    def get_n_colours(self, n: int) -> torch.Tensor:
+        """Random agent colours (reference :163-169); construction-time helper, not on the hot path."""
+        colours = torch.rand((n, 3), device=self.device)
+        colours[:, 0] /= 1.5
+        colours /= colours.norm(2, dim=1, keepdim=True)
+        colours *= 192
+        return colours.short()
+
+    def _log(self, msg: str):
+        if self.verbose > 0:
+            print(msg)
+
+    def _cfg(self, mode=None):
+        if mode is None:
+            obs_mode, n = _lib.MOBS_NONE, 0
+        elif mode == 'full':
+            obs_mode, n = _lib.MOBS_FULL, 0
+        elif mode.startswith('partial_'):
+            obs_mode, n = _lib.MOBS_PARTIAL, int(mode.split('_')[1])
+        else:
+            raise ValueError('Unrecognised observation mode.')
+        if self.food_mode not in ('only_one', 'random_rate'):
+            raise ValueError('food_mechanics not recognised')
+        f32 = np.float32
+        return _lib.WurmMultiCfg(
+            self.num_envs, self.num_snakes, self.size, obs_mode, n, int(bool(self.boost)),
+            int(self.food_on_death_prob > 0), float(f32(1 - self.food_on_death_prob)), float(f32(self.boost_cost_prob)),
+            0 if self.food_mode == 'only_one' else 1, float(f32(self.food_rate)), float(self.reward_on_death),
+            int(self.respawn_mode == 'any'), int(self.colour_mode == 'random'))
+
+    def _norm(self, name, dtype, shape):
+        t = getattr(self, name)
+        if t.dtype != dtype or not t.is_contiguous() or t.device.type != 'cuda':
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+            setattr(self, name, t)
+        if tuple(t.shape) != shape:
+            raise RuntimeError(f'{name} has shape {tuple(t.shape)}, expected {shape}')
+        return t
+
+    def _state(self):
+        """The state attributes may have been replaced by the caller (tests assign them): normalise."""
+        E, K, S = self.num_envs, self.num_snakes, self.size
+        return _lib.WurmMultiState(
+            _ptr(self._norm('foods', torch.float32, (E, 1, S, S))), _ptr(self._norm('heads', torch.float32, (E * K, 1, S, S))),
+            _ptr(self._norm('bodies', torch.float32, (E * K, 1, S, S))), _ptr(self._norm('dones', torch.bool, (E * K,))),
+            _ptr(self._norm('orientations', torch.long, (E * K,))), _ptr(self._norm('boost_this_step', torch.bool, (E * K,))),
+            _ptr(self._norm('agent_colours', torch.short, (E * K, 3))))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.foods.device).cuda_stream)
+
+    def _obs_shape(self, cfg):
+        E, K, S = self.num_envs, self.num_snakes, self.size
+        w = 2 * cfg.obs_n + 1
+        return (K, E, 3, S, S) if cfg.obs_mode == _lib.MOBS_FULL else (K, E, 3, w, w)
+
+    def stats(self, reduce_group=None):
+        """Episode statistics accumulated on the device since construction (env_steps, episodes = envs in
+        which every snake died, reward = food eaten, self_collisions = snake collisions, edge_collisions);
+        with `reduce_group` summed over ranks by one small all-reduce."""
+        totals = self._stats.sum(dim=0)
+        if reduce_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(totals, group=None if reduce_group is True else reduce_group)
+        return dict(zip(_lib.STAT_NAMES, totals.tolist()))
+
+    def check_status(self):
+        """Raises if a kernel met a condition it reports through the status word since the last check."""
+        st = int(self._status.item())
+        if st:
+            self._status.zero_()
+            if st & _lib.ST_NO_SPAWN:
+                raise RuntimeError('There is no available locations to create snake!')     # reference :865,947
+            msgs = []
+            if st & _lib.ST_OVERLAP:
+                msgs.append('an environment contains overlapping snakes at the start of a step')
+            if st & _lib.ST_MULTI_HEAD:
+                msgs.append('a snake has more than one head cell')
+            raise RuntimeError('; '.join(msgs) or f'status {st}')
+
+    # ------------------------------------------------------------------------------------------
+    # observations
+    # ------------------------------------------------------------------------------------------
+    def _observe_tensor(self, mode):
+        cfg = self._cfg(mode)
+        st = self._state()
+        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=self.foods.device)
+        with torch.cuda.device(self.foods.device):
+            _lib.check(self._lib.wurm_multi_observe(ctypes.byref(cfg), ctypes.byref(st), _ptr(obs), _ptr(self._status),
+                                                    self._stream()))
+        return obs
+
+    def _observe(self, mode: str = None) -> Dict[str, torch.Tensor]:
+        if mode is None:
+            mode = self.observation_mode
+        obs = self._observe_tensor(mode)
+        return OrderedDict([(f'agent_{i}', obs[i]) for i in range(self.num_snakes)])
+
+    def _observe_agent(self, agent: int) -> torch.Tensor:
+        return self._observe_tensor('full')[agent]
+
+    def _get_env_images(self):
+        """int16 (E,3,S,S) image of every env (reference :194-227)."""
+        cfg = self._cfg(None)
+        st = self._state()
+        img = torch.empty((self.num_envs, 3, self.size, self.size), dtype=torch.short, device=self.foods.device)
+        with torch.cuda.device(self.foods.device):
+            _lib.check(self._lib.wurm_multi_env_images(ctypes.byref(cfg), ctypes.byref(st), _ptr(img), _ptr(self._status),
+                                                       self._stream()))
+        return img
+
+    # ------------------------------------------------------------------------------------------
+    # step
+    # ------------------------------------------------------------------------------------------
+    def step(self, actions: Dict[str, torch.Tensor], *, draws: dict = None):
+        if len(actions) != self.num_snakes:
+            raise RuntimeError('Must have a Tensor of actions for each snake')
+
+        for agent, act in actions.items():
+            if act.dtype not in (torch.short, torch.int, torch.long):
+                raise TypeError('actions Tensor must be an integer type i.e. '
+                                '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
+
+            if act.shape[0] != self.num_envs:
+                raise RuntimeError('Must have the same number of actions as environments.')
+
+        t0 = time()
+        E, K = self.num_envs, self.num_snakes
+        st = self._state()
+        dev = self.foods.device
+        acts = list(actions.values())                     # dict order, key names are never parsed (reference :482)
+        dtype = acts[0].dtype
+        if any(a.dtype != dtype for a in acts):
+            dtype = torch.long
+        acts = [a if (a.device == dev and a.dtype == dtype and a.is_contiguous())
+                else a.to(device=dev, dtype=dtype, non_blocking=True).contiguous() for a in acts]
+        act_ptrs = (ctypes.c_void_p * K)(*[a.data_ptr() for a in acts])
+
+        cfg = self._cfg(self.observation_mode)
+        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=dev)
+        rewards = torch.empty((E, K), dtype=torch.float32, device=dev)
+        food = torch.empty((E, K), dtype=torch.float32, device=dev)
+        size = torch.empty((E, K), dtype=torch.float32, device=dev)
+        flags = torch.empty((4, E, K), dtype=torch.bool, device=dev)     # snake_collision, edge_collision, dones, boost
+        all_done = torch.empty(E, dtype=torch.bool, device=dev)
+        out = _lib.WurmMultiStepOut(_ptr(rewards), _ptr(flags[0]), _ptr(flags[1]), _ptr(food), _ptr(size), _ptr(flags[2]),
+                                    _ptr(flags[3]), _ptr(all_done), _ptr(obs))
+        dr, keep = None, []
+        if draws is not None:
+            def dev_t(key, dt):
+                t = draws.get(key)
+                if t is None:
+                    return None
+                t = torch.as_tensor(t).to(device=dev, dtype=dt).contiguous()
+                keep.append(t)
+                return t.data_ptr()
+            dr = _lib.WurmMultiStepDraws(int(bool(draws['boost_phase_ran'])), dev_t('u_boost', torch.float32),
+                                         dev_t('u_cost', torch.float32), dev_t('u_reg', torch.float32),
+                                         dev_t('food_cell', torch.int32), dev_t('u_rate', torch.float32))
+        self._draws += 1
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.wurm_multi_step(
+                ctypes.byref(cfg), ctypes.byref(st), act_ptrs, _ACTION_BYTES[dtype],
+                ctypes.byref(dr) if dr is not None else None, self.seed, self._draws, ctypes.byref(out),
+                _ptr(self._status), _ptr(self._stats), self._stream()))
+
+        self.rewards = rewards.view(E * K)
+        observations = OrderedDict([(f'agent_{i}', obs[i]) for i in range(K)])
+        dones = {f'agent_{i}': flags[2][:, i] for i in range(K)}
+        dones['__all__'] = all_done
+        rewards_dict = {f'agent_{i}': rewards[:, i] for i in range(K)}
+        self.info = {}
+        for i in range(K):
+            self.info[f'boost_{i}'] = flags[3][:, i]
+            self.info[f'snake_collision_{i}'] = flags[0][:, i]
+            self.info[f'edge_collision_{i}'] = flags[1][:, i]
+        for i in range(K):
+            self.info[f'food_{i}'] = food[:, i]
+        for i in range(K):
+            self.info[f'size_{i}'] = size[:, i]
+        if self.verbose > 0:
+            torch.cuda.synchronize(dev)
+            self._log(f'step: {1000 * (time() - t0)}ms')
+        return observations, rewards_dict, dones, self.info
+
+    # ------------------------------------------------------------------------------------------
+    # reset
+    # ------------------------------------------------------------------------------------------
+    def _reset_mask(self, env_done, draws=None):
+        cfg = self._cfg(None)
+        st = self._state()
+        dev = self.foods.device
+        dr, keep = None, []
+        if draws is not None:
+            def dev_t(key, dt):
+                t = torch.as_tensor(draws[key]).to(device=dev, dtype=dt).contiguous()
+                keep.append(t)
+                return t.data_ptr()
+            dr = _lib.WurmMultiResetDraws(dev_t('create', torch.int32), dev_t('respawn', torch.int32),
+                                          dev_t('colours', torch.short))
+        self._draws += 1
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.wurm_multi_reset(ctypes.byref(cfg), ctypes.byref(st), _ptr(env_done),
+                                                  ctypes.byref(dr) if dr is not None else None, self.seed, self._draws,
+                                                  _ptr(self._status), self._stream()))
+
+    def _create_all(self, draws=None):
+        """__init__'s _create_envs(num_envs) (reference :113, :996-1019)."""
+        self._reset_mask(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), draws)
+        self.check_status()      # RuntimeError('There is no available locations to create snake!') like :947
+
+    def reset(self, done: torch.Tensor = None, return_observations: bool = True, *,
+              draws: dict = None) -> Optional[Dict[str, torch.Tensor]]:
+        """Re-creates the envs flagged in `done`, re-colours dead snakes, respawns one dead snake per
+        env in respawn_mode 'any' (reference :771-836)."""
+        t0 = time()
+        if done is None:
+            done = self.dones.view(self.num_envs, self.num_snakes).all(dim=1)
+
+        done = done.view((done.shape[0]))
+        if done.shape[0] != self.num_envs:
+            raise RuntimeError('Must have one done flag per environment.')
+        dev = self.foods.device
+        if not (done.dtype == torch.bool and done.device == dev and done.is_contiguous()):
+            done = (done != 0).to(device=dev).contiguous()
+        self._reset_mask(done, draws)
+        # env_lifetimes is never incremented by the reference (:106,128,705,797), so there is nothing to clear
+        if self.verbose > 0:
+            torch.cuda.synchronize(dev)
+            self._log(f'reset: {1000 * (time() - t0)}ms')
+
+        if return_observations:
+            return self._observe()
+
+    # ------------------------------------------------------------------------------------------
+    # invariants and display (off the hot path)
+    # ------------------------------------------------------------------------------------------
+    def check_consistency(self):
+        """The reference's invariants (reference :733-769 + wurm/utils.py:113-164 snake_consistency)."""
+        from ..utils import snake_consistency
+        E, K, S = self.num_envs, self.num_snakes, self.size
+        _envs = torch.cat([self.foods.repeat_interleave(K, dim=0), self.heads, self.bodies], dim=1)
+        snake_consistency(_envs[~self.dones].round())
+
+        overlapping = self.bodies.view(E, K, S, S).gt(EPS).sum(dim=1).view(E, -1).max(dim=-1)[0].gt(1)
+        if torch.any(overlapping):
+            raise RuntimeError('An environment contains overlapping snakes')
+
+        if not torch.all(self.heads.view(E, K, S, S).sum(dim=1) <= K):
+            raise RuntimeError('An environment contains more snakes than it should.')
+
+        if not _envs[self.dones][:, 1:].sum() == 0:
+            raise RuntimeError('Dead snake contains non-zero elements.')
+        self.check_status()
+
+    def render(self, mode: str = 'human', env: int = None):
+        """Human display (reference :229-266); host-side, outside the hot path."""
+        img = self._get_env_images().cpu().numpy()
+
+        if self.num_envs == 1 or env is not None:
+            num_cols = num_rows = 1
+            img = np.transpose(img[env or 0], (1, 2, 0))
+        else:
+            num_rows = self.render_args['num_rows']
+            num_cols = self.render_args['num_cols']
+            output = np.zeros((self.size * num_rows, self.size * num_cols, 3))
+            for i in range(num_rows):
+                for j in range(num_cols):
+                    output[i * self.size:(i + 1) * self.size, j * self.size:(j + 1) * self.size, :] = \
+                        np.transpose(img[i * num_cols + j], (1, 2, 0))
+            img = output
+
+        from PIL import Image
+        img = np.array(Image.fromarray(img.astype(np.uint8)).resize(
+            (self.render_args['size'] * num_cols, self.render_args['size'] * num_rows)))
+
+        if mode == 'human':
+            if self.viewer is None:
+                from gym.envs.classic_control import rendering
+                self.viewer = rendering.SimpleImageViewer()
+            self.viewer.imshow(img)
+            return self.viewer.isopen
+        elif mode == 'rgb_array':
+            return img
+        else:
+            raise ValueError('Render mode not recognised.')
