@@ -40,24 +40,120 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (env, size, num_envs per GPU, observation mode)  -- BASELINE.json configs[1], [2], [0]
-    'C2': ('SingleSnake', 9, 1 << 20, 'partial_2'),
-    'C3': ('SingleSnake', 36, 1 << 16, 'default'),
-    'C1': ('SingleSnake', 9, 512, 'partial_2'),
+    # name: (env, size, num_envs per GPU, observation mode, num_snakes)  -- BASELINE.json configs[1], [2], [0], [3], [4]
+    'C2': ('SingleSnake', 9, 1 << 20, 'partial_2', 1),
+    'C3': ('SingleSnake', 36, 1 << 16, 'default', 1),
+    'C1': ('SingleSnake', 9, 512, 'partial_2', 1),
+    'C4': ('MultiSnake', 25, 1 << 16, 'partial_4', 4),
+    'C5': ('MultiSnake', 64, 1 << 15, 'partial_4', 16),
 }
 ACTION_POOL = 16        # pre-generated action tensors cycled through by the timed loop
 
 
 def workload_name(key, n_envs=None):
-    env, S, N, mode = WORKLOADS[key]
+    env, S, N, mode, K = WORKLOADS[key]
     N = n_envs or N
+    if env == 'MultiSnake':
+        return (f'{env} {K} snakes size={S} num_envs={N} {mode} obs, constructor-default rules, random actions in [0,8), '
+                f"step+reset(done['__all__'])")
     return f'{env} size={S} num_envs={N} {mode} obs, random actions, step+reset(done)'
 
 
-def algorithmic_bytes_per_env_step(S, obs_elems):
+def algorithmic_bytes_per_env_step(key, obs_elems_per_env):
     """read state + write state + write obs + per-env vectors
-    (actions r/w 16, reward 4, done 1, info 2)."""
-    return 2 * 3 * S * S * 4 + obs_elems * 4 + 23
+    (single: actions r/w 16, reward 4, done 1, info 2; multi: ~42.5 B per agent)."""
+    env, S, _, _, K = WORKLOADS[key]
+    if env == 'MultiSnake':
+        return 2 * (1 + 2 * K) * S * S * 4 + obs_elems_per_env * 4 + (170 * K) // 4
+    return 2 * 3 * S * S * 4 + obs_elems_per_env * 4 + 23
+
+
+class SingleAdapter(object):
+    """Uniform loop interface over the two env classes (GPU arm)."""
+    kernel = 'single_tile_kernel<G,STEP=true>'
+
+    def __init__(self, key, dev, seed, rank):
+        import torch
+        from wurm_b200.envs import SingleSnake
+        _, S, N, mode, _ = WORKLOADS[key]
+        self.N, self.torch = N, torch
+        self.env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=seed)
+        g = torch.Generator(device=dev).manual_seed(4321 + rank)
+        self.pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]
+        self.host_pool = None
+        self.action_desc = f'int64 randint(0,4), pool of {ACTION_POOL} pre-generated tensors per rank'
+        self.loop_desc = 'obs,reward,done,info = env.step(a); env.reset(done, return_observations=False)'
+
+    def step(self, t):
+        obs, reward, done, info = self.env.step(self.pool[t % ACTION_POOL])
+        return obs, reward, done
+
+    def reset(self, done):
+        self.env.reset(done, return_observations=False)
+
+    def obs_elems(self, obs):
+        return obs[0].numel()
+
+    def host_setup(self):
+        torch = self.torch
+        self.host_pool = [p.cpu().pin_memory() for p in self.pool]
+        self.host_reward = torch.empty((self.N, 1), dtype=torch.float32).pin_memory()
+        self.host_done = torch.empty((self.N, 1), dtype=torch.bool).pin_memory()
+        act = self.N * self.pool[0].element_size()
+        return act, act + self.N * 4 + self.N          # h2d: actions; d2h: sanitised actions + reward + done
+
+    def host_step(self, t):
+        obs, reward, done, info = self.env.step(self.host_pool[t % ACTION_POOL])   # H2D actions, D2H sanitised actions
+        self.host_reward.copy_(reward, non_blocking=True)
+        self.host_done.copy_(done, non_blocking=True)
+        return done
+
+
+class MultiAdapter(object):
+    kernel = 'multi_env_kernel<STEP=true>'
+
+    def __init__(self, key, dev, seed, rank):
+        import torch
+        from wurm_b200.envs import MultiSnake
+        _, S, N, mode, K = WORKLOADS[key]
+        self.N, self.K, self.torch = N, K, torch
+        self.env = MultiSnake(num_envs=N, num_snakes=K, size=S, observation_mode=mode, device=dev, seed=seed)
+        g = torch.Generator(device=dev).manual_seed(4321 + rank)
+        self.pool = [{f'agent_{k}': torch.randint(0, 8, (N,), device=dev, generator=g) for k in range(K)}
+                     for _ in range(ACTION_POOL)]
+        self.action_desc = f'int64 randint(0,8) per agent, pool of {ACTION_POOL} pre-generated dicts per rank'
+        self.loop_desc = ("obs,rewards,dones,info = env.step(actions); "
+                          "env.reset(dones['__all__'], return_observations=False)")
+
+    def step(self, t):
+        obs, rewards, dones, info = self.env.step(self.pool[t % ACTION_POOL])
+        return obs, rewards, dones['__all__']
+
+    def reset(self, done):
+        self.env.reset(done, return_observations=False)
+
+    def obs_elems(self, obs):
+        return sum(o[0].numel() for o in obs.values())
+
+    def host_setup(self):
+        torch = self.torch
+        self.host_pool = [{a: t.cpu().pin_memory() for a, t in d.items()} for d in self.pool]
+        self.host_rewards = torch.empty((self.N, self.K), dtype=torch.float32).pin_memory()
+        self.host_dones = torch.empty((self.N, self.K), dtype=torch.bool).pin_memory()
+        self.host_all = torch.empty(self.N, dtype=torch.bool).pin_memory()
+        act = self.N * self.K * 8
+        return act, self.N * self.K * 5 + self.N       # h2d: actions; d2h: rewards + dones + __all__
+
+    def host_step(self, t):
+        obs, rewards, dones, info = self.env.step(self.host_pool[t % ACTION_POOL])   # H2D of K action tensors
+        self.host_rewards.copy_(self.env.rewards.view(self.N, self.K), non_blocking=True)
+        self.host_dones.copy_(self.env.dones.view(self.N, self.K), non_blocking=True)
+        self.host_all.copy_(dones['__all__'], non_blocking=True)
+        return dones['__all__']
+
+
+def make_adapter(key, dev, seed, rank):
+    return (MultiAdapter if WORKLOADS[key][0] == 'MultiSnake' else SingleAdapter)(key, dev, seed, rank)
 
 
 class ClockSampler(object):
@@ -133,8 +229,22 @@ def time_cpu_port(key, n_envs, steps, warmup, threads):
     import numpy as np
     from oracle import oracle as orc      # the checker; allowed here as the timed CPU baseline only
     os.environ['OMP_NUM_THREADS'] = str(threads)
-    _, S, _, mode = WORKLOADS[key]
+    env_name, S, _, mode, K = WORKLOADS[key]
     rng = np.random.default_rng(0)
+    if env_name == 'MultiSnake':
+        cfg = orc.multi_cfg(n_envs, K, S)
+        st = orc.MultiState(n_envs, K, S)
+        orc.multi_reset(cfg, st, np.ones(n_envs, np.uint8), None, seed=1234, step=0)
+        pool = [rng.integers(0, 8, (n_envs, K)).astype(np.int64) for _ in range(ACTION_POOL)]
+        t0 = None
+        for t in range(warmup + steps):
+            if t == warmup:
+                t0 = time.perf_counter()
+            out = orc.multi_step(cfg, st, pool[t % ACTION_POOL], None, seed=1234, step=2 * t + 1)
+            obs, _ = orc.multi_observe(cfg, st, mode)
+            orc.multi_reset(cfg, st, out['all_done'], None, seed=1234, step=2 * t + 2)
+        dt = time.perf_counter() - t0
+        return n_envs * steps / dt, dt
     state = np.zeros((n_envs, 3, S, S), np.float32)
     orc.single_reset(state, np.ones(n_envs, np.uint8), None, seed=1234, step=0)
     pool = [rng.integers(0, 4, n_envs).astype(np.int64) for _ in range(ACTION_POOL)]
@@ -150,8 +260,11 @@ def time_cpu_port(key, n_envs, steps, warmup, threads):
 
 
 def cpu_sample_size(key):
-    _, S, N, _ = WORKLOADS[key]
-    return min(N, max(512, ((1 << 26) // (3 * S * S * 4)) // 1024 * 1024))    # ~64 MiB of state
+    _, S, N, _, K = WORKLOADS[key]
+    per_env = (3 if K == 1 else 1 + 2 * K) * S * S * 4
+    if per_env > (1 << 16):
+        return min(N, max(64, (1 << 26) // per_env // 64 * 64))
+    return min(N, max(512, ((1 << 26) // per_env) // 1024 * 1024))    # ~64 MiB of state
 
 
 def run_reference(args):
@@ -164,7 +277,6 @@ def run_reference(args):
     steps = max(1, min(args.steps, 50))
     warmup = max(1, min(args.warmup, 5))
     value, dt = time_cpu_port(key, n, steps, warmup, threads)
-    _, S, N, mode = WORKLOADS[key]
     sample = f'{n} envs x {steps} steps (+{warmup} warm-up) of the same workload, step+observe+reset, OpenMP'
     line = {
         'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
@@ -199,11 +311,10 @@ def run_gpu(args):
         dist.init_process_group('nccl', device_id=dev)
 
     key = args.workload
-    _, S, N, mode = WORKLOADS[key]
+    _, S, N, mode, _ = WORKLOADS[key]
     K, W = args.steps, max(3, args.warmup)
-    env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=1234 + rank)
-    g = torch.Generator(device=dev).manual_seed(4321 + rank)
-    pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]
+    ad = make_adapter(key, dev, 1234 + rank, rank)
+    env = ad.env
 
     def barrier():
         if world > 1:
@@ -212,8 +323,8 @@ def run_gpu(args):
 
     # ---- device-resident throughput (value) + per-launch step-kernel time (roofline) ----
     for t in range(W):
-        obs, reward, done, info = env.step(pool[t % ACTION_POOL])
-        env.reset(done, return_observations=False)
+        obs, reward, done = ad.step(t)
+        ad.reset(done)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
@@ -224,39 +335,31 @@ def run_gpu(args):
     for t in range(K):
         a, b = ev[t]
         a.record()
-        obs, reward, done, info = env.step(pool[t % ACTION_POOL])
+        obs, reward, done = ad.step(t)
         b.record()
-        env.reset(done, return_observations=False)
+        ad.reset(done)
     stop.record()
     barrier()
     t_wall1 = time.time()
     sampler.stop()
     ms_total = start.elapsed_time(stop)
     step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
-    obs_elems = obs[0].numel()
+    obs_elems = ad.obs_elems(obs)
     del ev
 
     # ---- end to end through the public API with host buffers ----
-    host_pool = [p.cpu().pin_memory() for p in pool]
-    host_reward = torch.empty((N, 1), dtype=torch.float32).pin_memory()
-    host_done = torch.empty((N, 1), dtype=torch.bool).pin_memory()
+    h2d, d2h = ad.host_setup()
     Ke = max(10, K // 4)
     for t in range(3):
-        obs, reward, done, info = env.step(host_pool[t % ACTION_POOL])
-        env.reset(done, return_observations=False)
+        ad.reset(ad.host_step(t))
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record()
     for t in range(Ke):
-        obs, reward, done, info = env.step(host_pool[t % ACTION_POOL])      # H2D actions, D2H sanitised actions
-        host_reward.copy_(reward, non_blocking=True)                        # D2H results
-        host_done.copy_(done, non_blocking=True)
-        env.reset(done, return_observations=False)
+        ad.reset(ad.host_step(t))
     e_stop.record()
     barrier()
     e2e_ms = e_start.elapsed_time(e_stop)
-    act_bytes = N * pool[0].element_size()
-    h2d, d2h = act_bytes, act_bytes + N * 4 + N * 1
 
     # ---- max over ranks, episode statistics (the only collective on this path) ----
     times = torch.tensor([ms_total, e2e_ms, step_kernel_ms], dtype=torch.float64, device=dev)
@@ -278,23 +381,22 @@ def run_gpu(args):
         value = world * N * K / (ms_total * 1e-3)
         e2e_value = world * N * Ke / (e2e_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        bytes_per_launch = algorithmic_bytes_per_env_step(S, obs_elems) * N
+        bytes_per_launch = algorithmic_bytes_per_env_step(key, obs_elems) * N
         achieved = bytes_per_launch / (step_kernel_ms * 1e-3) / 1e9
         line = {
             'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': workload_name(key), 'num_envs_per_gpu': N, 'size': S, 'observation_mode': mode,
-                       'actions': f'int64 randint(0,4), pool of {ACTION_POOL} pre-generated tensors per rank',
-                       'loop': 'obs,reward,done,info = env.step(a); env.reset(done, return_observations=False)',
-                       'l2': f'inputs larger than L2: state {N * 3 * S * S * 4 / 1e6:.0f} MB + obs '
+                       'actions': ad.action_desc, 'loop': ad.loop_desc,
+                       'l2': f'inputs larger than L2: state {(bytes_per_launch - N * obs_elems * 4) / 2e6:.0f} MB + obs '
                              f'{N * obs_elems * 4 / 1e6:.0f} MB per step vs 126 MB L2',
                        'parallelism': f'{world} independent env slices, NCCL all-reduce of episode stats only'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': Ke, 'ms_per_step': e2e_ms / Ke},
             'gpu_launches': 2 * K,
-            'roofline': {'bound': 'hbm', 'kernel': 'single_tile_kernel<G,STEP=true>', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': ad.kernel, 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': profiled_traffic(key),
                          'peak_source': peak_src, 'bytes_per_launch': bytes_per_launch,
                          'kernel_ms': step_kernel_ms, 'frac_of_nominal_8TBs': achieved / 8000.0},
