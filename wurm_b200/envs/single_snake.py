@@ -140,8 +140,8 @@ class SingleSnake(object):
         over ranks with one small all-reduce -- the only collective this path has."""
         totals = self._stats.sum(dim=0)
         if reduce_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(totals, group=None if reduce_group is True else reduce_group)
+            from ..distributed import all_reduce_stats
+            all_reduce_stats(totals, None if reduce_group is True else reduce_group)
         return dict(zip(_lib.STAT_NAMES, totals.tolist()))
 
     def check_status(self):
