@@ -79,7 +79,7 @@ struct MultiParams {
     const short* colours_replay;
     int* status;
     unsigned long long* stats;
-    uint32_t magic_S, magic_C;
+    uint32_t magic_S, magic_C, magic_W;
 };
 
 __device__ __forceinline__ int fdiv(int q, uint32_t magic) { return (int)__umulhi((uint32_t)q, magic); }
@@ -149,9 +149,20 @@ __device__ __forceinline__ void store_floats(float* base, int n, G&& gen) {
     if (tid < n - tail0) base[tail0 + tid] = gen(tail0 + tid);
 }
 
+// (float)v / 255.0f, correctly rounded, for integer v in [-1024, 70000] (verified exhaustively on the
+// host and by the parity tests): quotient estimate + one fused residual correction instead of the
+// ~12-instruction IEEE division sequence.
+__device__ __forceinline__ float div255(int v) {
+    constexpr float kRcp = 1.0f / 255.0f;
+    const float a = (float)v, q = a * kRcp;
+    return fmaf(fmaf(-q, 255.0f, a), kRcp, q);
+}
+
 struct MultiSmem {
     uint32_t* cell;   // C records
+    uint32_t* cell0;  // C records as loaded (for the sparse write-back)
     uint8_t* food;    // C
+    uint8_t* food0;   // C as loaded
     int* hp;          // head cell per snake, -1 none
     int* size;        // max body value per snake
     int* hcnt;        // head cells seen per snake
@@ -159,43 +170,48 @@ struct MultiSmem {
     int* decay;
     int* cost;
     int* boost;
-    int* misc;        // [0] food count, [1] scratch
+    int* misc;        // [0] food count, [2] run_boost, [3] force full write-back
     short* col;       // K*3
-    uint32_t* tab;    // partial-obs index table
 };
 
 __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
     MultiSmem s;
     s.cell = reinterpret_cast<uint32_t*>(smem);
-    s.food = reinterpret_cast<uint8_t*>(s.cell + C);
-    s.hp = reinterpret_cast<int*>(s.food + ((C + 15) & ~15));
+    s.cell0 = s.cell + C;
+    s.food = reinterpret_cast<uint8_t*>(s.cell0 + C);
+    s.food0 = s.food + ((C + 15) & ~15);
+    s.hp = reinterpret_cast<int*>(s.food0 + ((C + 15) & ~15));
     s.size = s.hp + 32; s.hcnt = s.size + 32; s.done = s.hcnt + 32; s.decay = s.done + 32; s.cost = s.decay + 32;
     s.boost = s.cost + 32; s.misc = s.boost + 32;
     s.col = reinterpret_cast<short*>(s.misc + 8);
-    s.tab = reinterpret_cast<uint32_t*>(s.col + 96);
     return s;
 }
 
 static size_t multi_smem_bytes(int C, int W, int obs_mode) {
-    return (size_t)C * 4 + ((C + 15) & ~15) + 7 * 32 * 4 + 8 * 4 + 96 * 2 + (obs_mode == WURM_MOBS_PARTIAL ? 3 * W * W * 4 : 0) + 16;
+    return (size_t)C * 8 + 2 * ((C + 15) & ~15) + 7 * 32 * 4 + 8 * 4 + 96 * 2 + 16;
 }
 
 // Streams env e's tensors from HBM into the compact shared-memory form.
 __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e) {
     const int C = p.C, K = p.K;
-    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float) { s.food[i] = 1; });
-    scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float) {
+    // `odd`: a value the compact form cannot carry exactly (food/head != 1, non-integral body): the env
+    // is then written back in full (which normalises it) instead of cell by cell.
+    bool overlap = false, odd = false;
+    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float v) { s.food[i] = 1; odd |= v != 1.0f; });
+    scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float v) {
         const int k = fdiv(i, p.magic_C);
         atomicMax(&s.hp[k], i - k * C);
         atomicAdd(&s.hcnt[k], 1);
+        odd |= v != 1.0f;
     });
-    bool overlap = false;
     scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float v) {
         const int k = fdiv(i, p.magic_C), val = (int)v;
         if (atomicCAS(&s.cell[i - k * C], 0u, make_rec(k, val)) != 0u) overlap = true;
         atomicMax(&s.size[k], val);
+        odd |= (float)val != v || val < 1 || val > 65535;
     });
     if (overlap) atomicOr(p.status, WURM_ST_OVERLAP);
+    if (overlap || odd) s.misc[3] = 1;
 }
 
 // multi_snake.py:194-227 _get_env_images: int16 colour of cell q (canonical state: one owner per cell)
@@ -219,25 +235,25 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
     const int C = p.C, K = p.K, S = p.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (p.obs_mode == WURM_MOBS_PARTIAL) {                           // :289-332
-        const int n = p.obs_n, EL = 3 * p.W * p.W;
+        const int n = p.obs_n, W = p.W, WW = W * W;
         for (int k = warp; k < K; k += nwarps) {
-            float* o = p.obs + ((size_t)k * p.E + e) * EL;
+            float* o = p.obs + ((size_t)k * p.E + e) * 3 * WW;
             const int hp = s.hp[k];
             if (s.done[k] || hp < 0 || s.hcnt[k] > 1) {               // :320-323 zeros for dead agents
-                for (int r = lane; r < EL; r += 32) o[r] = 0.0f;
+                for (int r = lane; r < 3 * WW; r += 32) o[r] = 0.0f;
                 continue;
             }
             const int hy = fdiv(hp, p.magic_S), hx = hp - hy * S;
-            for (int r = lane; r < EL; r += 32) {
-                const uint32_t ent = s.tab[r];
-                const int c = ent & 3, y = hy - n + (int)((ent >> 2) & 0xff), x = hx - n + (int)(ent >> 10);
-                float v = 0.0f;                                       // zero padding :301-302
+            for (int ij = lane; ij < WW; ij += 32) {                  // one window cell per lane, three channel rows
+                const int i = fdiv(ij, p.magic_W), j = ij - i * W;
+                const int y = hy - n + i, x = hx - n + j;
+                float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;                // zero padding :301-302
                 if (y >= 0 && y < S && x >= 0 && x < S) {
                     int rgb[3];
                     env_pixel(p, s, y * S + x, y, x, rgb);
-                    v = (float)(c == 0 ? rgb[0] : c == 1 ? rgb[1] : rgb[2]) / 255.0f;   // :296
+                    v0 = div255(rgb[0]); v1 = div255(rgb[1]); v2 = div255(rgb[2]);        // :296
                 }
-                o[r] = v;
+                o[ij] = v0; o[WW + ij] = v1; o[2 * WW + ij] = v2;
             }
         }
     } else if (p.obs_mode == WURM_MOBS_FULL) {                       // :268-281 _observe_agent
@@ -255,9 +271,9 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
                     else { r = 0; g = 0; b = is_head ? 192 : 96; }
                 }
                 if (y == 0 || x == 0 || y == S - 1 || x == S - 1) r = g = b = 0;
-                o[q] = (float)r / 255.0f;
-                o[C + q] = (float)g / 255.0f;
-                o[2 * C + q] = (float)b / 255.0f;
+                o[q] = div255(r);
+                o[C + q] = div255(g);
+                o[2 * C + q] = div255(b);
             }
         }
     }
@@ -287,22 +303,17 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
     }
     if (tid < 8) s.misc[tid] = 0;
     if (tid < 3 * K) s.col[tid] = p.colours[(size_t)e * K * 3 + tid];
-    if (p.obs_mode == WURM_MOBS_PARTIAL) {
-        const int W = p.W;
-        for (int r = tid; r < 3 * W * W; r += nthr) {
-            const int c = r / (W * W), ij = r - c * W * W, i = ij / W, j = ij - i * W;
-            s.tab[r] = (uint32_t)c | ((uint32_t)i << 2) | ((uint32_t)j << 10);
-        }
-    }
     __syncthreads();
     load_env(p, s, e);
     __syncthreads();
+    if (STEP)
+        for (int q = tid; q < C; q += nthr) { s.cell0[q] = s.cell[q]; s.food0[q] = s.food[q]; }
 
     if (STEP) {
         // ---- per-snake registers, live on lane k of warp 0 ----
         const int k = lane;
         const bool valid = (warp == 0) && (k < K);
-        int a_hp = -1, a_size = 0, a_mv = 0;
+        int a_hp = -1, a_hp0 = -1, a_size = 0, a_mv = 0;
         bool a_done = true, a_done0 = true, a_boosted = false, a_scol = false, a_ecol = false;
         float a_reward = 0.0f, a_foodc = 0.0f;
         bool run_boost = false;
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
                 if (p.action_bytes == 8) a = ((const long long*)p.actions[k])[e];
                 else if (p.action_bytes == 4) a = ((const int*)p.actions[k])[e];
                 else a = ((const short*)p.actions[k])[e];
-                a_hp = s.hp[k]; a_size = s.size[k];
+                a_hp = a_hp0 = s.hp[k]; a_size = s.size[k];
                 a_done = a_done0 = s.done[k] != 0;                    // :490
                 long long m = a % 4;                                  // :483
                 if (p.orientations[n] == m) m = (m + 2) % 4;          // :336-339
@@ -491,17 +502,40 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
         }
         __syncthreads();
 
-        // ---- expand the compact form back into the reference's tensors ----
-        store_floats(p.foods + (size_t)e * C, C, [&](int i) { return s.food[i] ? 1.0f : 0.0f; });
-        store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
-            const int kk = fdiv(i, p.magic_C);
-            return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
-        });
-        store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
-            const int kk = fdiv(i, p.magic_C);
-            const uint32_t rec = s.cell[i - kk * C];
-            return (rec && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
-        });
+        // ---- write the new state back ----
+        if (s.misc[3]) {
+            // non-canonical input: expand the whole compact form into the reference's tensors
+            store_floats(p.foods + (size_t)e * C, C, [&](int i) { return s.food[i] ? 1.0f : 0.0f; });
+            store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
+                const int kk = fdiv(i, p.magic_C);
+                return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
+            });
+            store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
+                const int kk = fdiv(i, p.magic_C);
+                const uint32_t rec = s.cell[i - kk * C];
+                return (rec && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
+            });
+        } else {
+            // The compact form knows exactly which cells changed: only those are stored (the sectors
+            // were read by this CTA microseconds ago, so the partial writes merge in L2).  A step
+            // touches O(snake length) cells of an S*S grid: write traffic drops from the full state
+            // to a few sectors per snake.
+            float* bodies = p.bodies + (size_t)e * K * C;
+            for (int q = tid; q < C; q += nthr) {
+                const uint32_t was = s.cell0[q], now = s.cell[q];
+                if (was != now) {
+                    const int ko = was ? rec_owner(was) : -1, kn = now ? rec_owner(now) : -1;
+                    if (ko >= 0 && ko != kn) bodies[(size_t)ko * C + q] = 0.0f;
+                    if (kn >= 0) bodies[(size_t)kn * C + q] = (float)rec_value(now);
+                }
+                if (s.food0[q] != s.food[q]) p.foods[(size_t)e * C + q] = s.food[q] ? 1.0f : 0.0f;
+            }
+            if (valid && a_hp0 != a_hp) {
+                float* head = p.heads + ((size_t)e * K + k) * C;
+                if (a_hp0 >= 0) head[a_hp0] = 0.0f;
+                if (a_hp >= 0) head[a_hp] = 1.0f;
+            }
+        }
     }
     write_multi_obs(p, s, e);
 }
@@ -697,6 +731,7 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     p->obs_mode = cfg->obs_mode; p->obs_n = cfg->obs_n; p->W = 2 * cfg->obs_n + 1;
     p->magic_S = (uint32_t)((0x100000000ull + (uint64_t)p->S - 1) / (uint64_t)p->S);
     p->magic_C = (uint32_t)((0x100000000ull + (uint64_t)p->C - 1) / (uint64_t)p->C);
+    p->magic_W = (uint32_t)((0x100000000ull + (uint64_t)p->W - 1) / (uint64_t)p->W);
     return WURM_OK;
 }
 

@@ -16,6 +16,7 @@
 //     coalesced stores (for 'raw' it is a second bulk store of the same tile);
 //   * no tensor cores: nothing on this path is a dense contraction.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/wurm_b200.h"
 #include "common.cuh"
@@ -40,7 +41,9 @@ struct SingleParams {
     int action_bytes;     // 2 / 4 / 8
     int obs_mode, obs_n, W;
     uint32_t magic_S;     // ceil(2^32 / S): q / S == __umulhi(q, magic_S) for q < 2^16
+    uint32_t magic_W;     // same for the partial-observation window width
     int tile_bytes_padded;
+    int stage_bytes;      // shared staging area of the tile's partial observations (0 = none)
     int bulk_ok;          // base pointers 16-byte aligned and full-tile byte count a multiple of 16
 };
 
@@ -116,7 +119,7 @@ __device__ __noinline__ int pick_free_cell(const float* env, int S, int C, uint3
 
 // single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
 template <int G>
-__device__ __forceinline__ void step_env(const SingleParams& p, float* env, int e, int l, int* hp_out, int* cnt_s) {
+__device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e, int l, int* cnt_s) {
     const unsigned gm = group_mask<G>();
     const int S = p.S, C = p.C;
     float* food = env;
@@ -126,6 +129,7 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
     // snake size (:210) and head cell
     float m = -INFINITY;
     int hp = -1, hc = 0;
+#pragma unroll 4
     for (int q = l; q < C; q += G) {
         m = fmaxf(m, body[q]);
         if (head[q] != 0.0f) { hp = q; ++hc; }
@@ -139,6 +143,7 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
     // filters tie at 1 and argmax returns 0.
     int c1 = 0, c2 = 0, p1 = -1, p2 = -1;
     const float sm1 = size - 1.0f;
+#pragma unroll 4
     for (int q = l; q < C; q += G) {
         const float v = body[q];
         if (v == size) { ++c1; p1 = q; }
@@ -183,8 +188,10 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
     }
 
     const float ov = (np >= 0) ? food[np] : 0.0f;                   // :242 head-food overlap
-    if (ov == 0.0f)                                                  // :246-249 decay unless it ate
+    if (ov == 0.0f) {                                                // :246-249 decay unless it ate
+#pragma unroll 4
         for (int q = l; q < C; q += G) body[q] = fmaxf(body[q] - 1.0f, 0.0f);
+    }
     __syncwarp(gm);
     const bool sc = (np >= 0) && (body[np] > kEps);                  // :252 self collision
     const bool interior = (np >= 0) && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
@@ -222,7 +229,6 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
         p.self_col[e] = sc;
         p.edge_col[e] = !interior;                                   // :290-293 no head in the interior
         p.done[e] = sc || !interior;
-        *hp_out = np;
         if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
         if (p.stats) {                                               // episode statistics, per-CTA partials
             if (sc || !interior) atomicAdd(cnt_s + 0, 1);
@@ -231,52 +237,56 @@ __device__ __forceinline__ void step_env(const SingleParams& p, float* env, int 
             if (!interior) atomicAdd(cnt_s + 3, 1);
         }
     }
+    __syncwarp(gm);                                                  // lane 0's cell updates -> the group's render
+    return np;
 }
 
 template <int G>
-__device__ __forceinline__ void find_head(const SingleParams& p, const float* env, int l, int* hp_out) {
+__device__ __forceinline__ int find_head(const SingleParams& p, const float* env, int l) {
     const unsigned gm = group_mask<G>();
     int hp = -1, hc = 0;
     for (int q = l; q < p.C; q += G)
         if (env[p.C + q] != 0.0f) { hp = q; ++hc; }
     hp = group_max<G>(hp, gm);
     hc = group_sum<G>(hc, gm);
-    if (l == 0) {
-        *hp_out = (hc == 1) ? hp : -1;
-        if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+    if (l == 0 && hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+    return (hc == 1) ? hp : -1;
+}
+
+// single_snake.py:166-193 partial_n: the (3,W,W) crop of rgb/255 around the head, zero outside the grid,
+// rendered by the env's own lane group into the tile's shared staging area (one window cell per lane
+// and iteration, three channel rows), from where the whole tile's observations leave in one bulk store.
+template <int G>
+__device__ __forceinline__ void render_partial(const SingleParams& p, const float* env, int hp, float* out, int l) {
+    const int S = p.S, C = p.C, W = p.W, WW = W * W, n = p.obs_n;
+    if (hp < 0) {                                                    // the reference raises here (:191)
+        for (int r = l; r < 3 * WW; r += G) out[r] = 0.0f;
+        if (l == 0) atomicOr(p.status, WURM_ST_NO_HEAD_PARTIAL);
+        return;
+    }
+    constexpr float kHalf = 127.0f / 255.0f;
+    const int hy = div_S(hp, p.magic_S), hx = hp - hy * S;
+    for (int ij = l; ij < WW; ij += G) {
+        const int i = (int)__umulhi((uint32_t)ij, p.magic_W), j = ij - i * W;
+        const int y = hy - n + i, x = hx - n + j;
+        float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+        if (y >= 0 && y < S && x >= 0 && x < S && !(y == 0 || x == 0 || y == S - 1 || x == S - 1)) {
+            const int q = y * S + x;
+            v0 = v1 = v2 = 1.0f;                                     // empty cell: white
+            if (env[2 * C + q] > kEps) { v0 = 0.0f; v1 = kHalf; v2 = 0.0f; }
+            if (env[C + q] > kEps) { v0 = 0.0f; v1 = 1.0f; v2 = 0.0f; }
+            if (env[q] > kEps) { v0 = 1.0f; v1 = 0.0f; v2 = 0.0f; }
+        }
+        out[ij] = v0; out[WW + ij] = v1; out[2 * WW + ij] = v2;
     }
 }
 
 // single_snake.py:130-195 from the shared tile into the caller's observation buffer.
 template <int G>
-__device__ __forceinline__ void write_obs(const SingleParams& p, const float* tile, const int* hp_s, const uint32_t* tab,
-                                          int env0, int nvalid) {
+__device__ __forceinline__ void write_obs(const SingleParams& p, const float* tile, int env0, int nvalid) {
     const int S = p.S, C = p.C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (p.obs_mode == WURM_OBS_PARTIAL) {                            // :166-193
-        const int n = p.obs_n, E = 3 * p.W * p.W;
-        for (int t = warp; t < nvalid; t += nwarps) {
-            const float* env = tile + (size_t)t * 3 * C;
-            float* o = p.obs + (size_t)(env0 + t) * E;
-            const int hp = hp_s[t];
-            if (hp < 0) {
-                for (int r = lane; r < E; r += 32) o[r] = 0.0f;
-                if (lane == 0) atomicOr(p.status, WURM_ST_NO_HEAD_PARTIAL);
-                continue;
-            }
-            const int hy = div_S(hp, p.magic_S), hx = hp - hy * S;
-            for (int r = lane; r < E; r += 32) {
-                const uint32_t ent = tab[r];
-                const int c = ent & 3, y = hy - n + (int)((ent >> 2) & 0xff), x = hx - n + (int)(ent >> 10);
-                float v = 0.0f;
-                if (y >= 0 && y < S && x >= 0 && x < S) {
-                    const int q = y * S + x;
-                    v = rgb_channel(env[q], env[C + q], env[2 * C + q], y == 0 || x == 0 || y == S - 1 || x == S - 1, c);
-                }
-                o[r] = v;
-            }
-        }
-    } else if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
+    if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
         for (int t = warp; t < nvalid; t += nwarps) {
             const float* env = tile + (size_t)t * 3 * C;
             for (int q = lane; q < C; q += 32) {
@@ -319,7 +329,8 @@ __device__ __forceinline__ void write_obs(const SingleParams& p, const float* ti
             }
         }
     }
-    // WURM_OBS_RAW is a second store of the tile, issued by the caller.
+    // WURM_OBS_RAW is a second store of the tile and WURM_OBS_PARTIAL a store of the staging area, both
+    // issued by the caller.
 }
 
 // One CTA = one tile of T envs.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
@@ -327,10 +338,9 @@ template <int G, bool STEP>
 __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* tile = reinterpret_cast<float*>(smem);
-    int* hp_s = reinterpret_cast<int*>(smem + p.tile_bytes_padded);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(hp_s + ((p.T + 1) & ~1));
+    float* stage = reinterpret_cast<float*>(smem + p.tile_bytes_padded);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.tile_bytes_padded + p.stage_bytes);
     int* cnt_s = reinterpret_cast<int*>(bar + 1);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(cnt_s + 4);
 
     const int env0 = blockIdx.x * p.T;
     const int nvalid = min(p.T, p.N - env0);
@@ -338,6 +348,8 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     const int nfloats = nvalid * 3 * p.C;
     const uint32_t bytes = (uint32_t)nfloats * 4u;
     const bool bulk = p.bulk_ok && (bytes % 16u == 0u);
+    const bool partial = p.obs_mode == WURM_OBS_PARTIAL;
+    const int E = 3 * p.W * p.W;                    // floats per env of a partial observation
 
     if (bulk) {
         if (threadIdx.x == 0) {
@@ -350,52 +362,53 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
         for (int i = threadIdx.x; i < nfloats; i += blockDim.x) tile[i] = p.envs[goff + i];
     }
     if (threadIdx.x < 4) cnt_s[threadIdx.x] = 0;
-    if (p.obs_mode == WURM_OBS_PARTIAL) {   // (channel, row, col) of each element of one env's crop
-        const int W = p.W;
-        for (int r = threadIdx.x; r < 3 * W * W; r += blockDim.x) {
-            const int c = r / (W * W), ij = r - c * W * W, i = ij / W, j = ij - i * W;
-            tab[r] = (uint32_t)c | ((uint32_t)i << 2) | ((uint32_t)j << 10);
-        }
-    }
-    __syncthreads();                        // mbarrier init / fallback tile / tab visible
+    __syncthreads();                        // mbarrier init / fallback tile visible
     if (bulk) mbar_wait(bar, 0);
 
     const int t = threadIdx.x / G, l = threadIdx.x % G;
-    if (STEP) {
-        if (t < nvalid) step_env<G>(p, tile + (size_t)t * 3 * p.C, env0 + t, l, hp_s + t, cnt_s);
-        if (bulk) fence_proxy_async();      // generic-proxy writes -> visible to the bulk store
-        __syncthreads();
-        if (p.stats && threadIdx.x < WURM_STATS_FIELDS) {   // one striped slot per CTA: no hot address in L2
-            unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
-            const int v = threadIdx.x == 0 ? nvalid : cnt_s[threadIdx.x - 1];
-            if (v) atomicAdd(slot + threadIdx.x, (unsigned long long)v);
+    if (t < nvalid) {
+        float* env = tile + (size_t)t * 3 * p.C;
+        int hp = -1;
+        if (STEP) hp = step_env<G>(p, env, env0 + t, l, cnt_s);
+        else if (partial) hp = find_head<G>(p, env, l);
+        if (partial) render_partial<G>(p, env, hp, stage + (size_t)t * E, l);
+    }
+    fence_proxy_async();                    // generic-proxy writes -> visible to the bulk stores
+    __syncthreads();
+    if (STEP && p.stats && threadIdx.x < WURM_STATS_FIELDS) {   // one striped slot per CTA: no hot address in L2
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        const int v = threadIdx.x == 0 ? nvalid : cnt_s[threadIdx.x - 1];
+        if (v) atomicAdd(slot + threadIdx.x, (unsigned long long)v);
+    }
+    const bool raw = p.obs_mode == WURM_OBS_RAW;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            if (STEP) bulk_store(p.envs + goff, tile, bytes);
+            if (raw) bulk_store(p.obs + goff, tile, bytes);
         }
-        if (bulk) {
-            if (threadIdx.x == 0) {
-                bulk_store(p.envs + goff, tile, bytes);
-                if (p.obs_mode == WURM_OBS_RAW) bulk_store(p.obs + goff, tile, bytes);
-                bulk_commit();
-            }
-        } else {
-            for (int i = threadIdx.x; i < nfloats; i += blockDim.x) {
-                p.envs[goff + i] = tile[i];
-                if (p.obs_mode == WURM_OBS_RAW) p.obs[goff + i] = tile[i];
-            }
-        }
-    } else {
-        if (p.obs_mode == WURM_OBS_PARTIAL) {
-            if (t < nvalid) find_head<G>(p, tile + (size_t)t * 3 * p.C, l, hp_s + t);
-            __syncthreads();
-        } else if (p.obs_mode == WURM_OBS_RAW) {
-            if (bulk) {
-                if (threadIdx.x == 0) { bulk_store(p.obs + goff, tile, bytes); bulk_commit(); }
-            } else {
-                for (int i = threadIdx.x; i < nfloats; i += blockDim.x) p.obs[goff + i] = tile[i];
-            }
+    } else if (STEP || raw) {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) {
+            if (STEP) p.envs[goff + i] = tile[i];
+            if (raw) p.obs[goff + i] = tile[i];
         }
     }
-    if (p.obs_mode >= 0 && p.obs_mode != WURM_OBS_RAW) write_obs<G>(p, tile, hp_s, tab, env0, nvalid);
-    if (bulk && threadIdx.x == 0) bulk_wait_read_all();   // the tile must outlive the bulk store's reads
+    bool obs_bulk = false;
+    if (partial) {                          // the tile's partial observations are one contiguous span too
+        float* dst = p.obs + (size_t)env0 * E;
+        const uint32_t obytes = (uint32_t)(nvalid * E) * 4u;
+        obs_bulk = p.bulk_ok && (obytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+        if (obs_bulk) {
+            if (threadIdx.x == 0) bulk_store(dst, stage, obytes);
+        } else {
+            for (int i = threadIdx.x; i < nvalid * E; i += blockDim.x) dst[i] = stage[i];
+        }
+    } else if (p.obs_mode >= 0 && !raw) {
+        write_obs<G>(p, tile, env0, nvalid);
+    }
+    if ((bulk || obs_bulk) && threadIdx.x == 0) {
+        bulk_commit();
+        bulk_wait_read_all();               // shared memory must outlive the bulk stores' reads
+    }
 }
 
 // single_snake.py:322-337 + 344-387: each warp inspects 32 done flags and re-creates the flagged
@@ -462,25 +475,41 @@ static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* 
     if (cfg->obs_mode < WURM_OBS_NONE || cfg->obs_mode > WURM_OBS_PARTIAL) return fail(WURM_E_INVALID, "bad obs_mode");
     if (cfg->obs_mode == WURM_OBS_PARTIAL && (cfg->obs_n < 0 || cfg->obs_n > 127)) return fail(WURM_E_INVALID, "bad obs_n");
     const int C = S * S;
-    int G = 1;
-    while (G < 32 && G * 32 < C) G <<= 1;
+    const int W = 2 * cfg->obs_n + 1;
     const int env_bytes = 3 * C * 4;
-    int T = 256 / G;
-    if (T * env_bytes > 64 * 1024) T = (64 * 1024) / env_bytes;
-    const int per_warp = 32 / G;                       // envs per warp
+    const int stage_env_bytes = cfg->obs_mode == WURM_OBS_PARTIAL ? 3 * W * W * 4 : 0;
+    int G = 1;
+    while (G < 32 && G * 32 < C) G <<= 1;               // ~32 cells per lane
+    if (const char* v = getenv("WURM_SINGLE_G")) {       // tuning overrides (power of two <= 32)
+        const int g = atoi(v);
+        if (g >= 1 && g <= 32 && (g & (g - 1)) == 0) G = g;
+    }
+    const int per_warp = 32 / G;                        // envs per warp
+    // partial observations are staged next to the tile: small CTAs (measured best on B200: 64 threads,
+    // ~20 KB, ~10 resident per SM overlapping each other's load / compute / store; see
+    // profiles/r01_sweep_single_c2.txt); otherwise up to 256 threads and 64 KB tiles
+    int max_threads = stage_env_bytes ? 64 : 256, budget = (stage_env_bytes ? 44 : 64) * 1024;
+    if (const char* v = getenv("WURM_SINGLE_THREADS")) max_threads = atoi(v);
+    if (const char* v = getenv("WURM_SINGLE_SMEM_KB")) budget = atoi(v) * 1024;
+    if (max_threads < 32) max_threads = 32;
+    if (max_threads > 256) max_threads = 256;
+    int T = max_threads / G;
+    if (T * (env_bytes + stage_env_bytes) > budget) T = budget / (env_bytes + stage_env_bytes);
     T = (T / per_warp) * per_warp;
     if (T < per_warp) T = per_warp;
     // prefer a tile whose byte count is a multiple of 16 so the bulk path applies
     if (((size_t)T * env_bytes) % 16 != 0 && T >= 4) T &= ~3;
     if (T < per_warp) T = per_warp;
-    const int W = 2 * cfg->obs_n + 1;
     const int tile_bytes_padded = (T * env_bytes + 15) & ~15;
-    const int smem = tile_bytes_padded + ((T + 1) & ~1) * 4 + 8 + 16 + (cfg->obs_mode == WURM_OBS_PARTIAL ? 3 * W * W * 4 : 0);
+    const int stage_bytes = (T * stage_env_bytes + 15) & ~15;
+    const int smem = tile_bytes_padded + stage_bytes + 8 + 16;
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "tile does not fit shared memory");
     p->N = N; p->S = S; p->C = C; p->T = T;
     p->obs_mode = cfg->obs_mode; p->obs_n = cfg->obs_n; p->W = W;
     p->magic_S = (uint32_t)((0x100000000ull + (uint64_t)S - 1) / (uint64_t)S);
+    p->magic_W = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
     p->tile_bytes_padded = tile_bytes_padded;
+    p->stage_bytes = stage_bytes;
     L->G = G; L->T = T; L->threads = T * G; L->blocks = (N + T - 1) / T; L->smem = smem;
     return WURM_OK;
 }
