@@ -14,9 +14,9 @@ environments do not interact); the only collective is one 
 episode-statistics counters after the timed region.  Rank 0 prints ONE JSON line.
 
   value      whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed, max over ranks
-  e2e        same loop through the public API with HOST buffers: every step copies that step's actions from
-             pinned host memory, and copies the sanitised actions, rewards and done flags back to pinned host
-             memory, all inside the timed region
+  e2e        same loop through the public host-buffer API (wurm_b200.HostStepper): every step copies that step's
+             actions from pinned host memory, and copies the sanitised actions, rewards and done flags back to
+             pinned host memory, all inside the timed region (copies of neighbouring steps overlap the kernels)
   roofline   for the dominant kernel (the step kernel): algorithmic bytes per launch (SURVEY.md section 8d:
              read state + write state + write observation + per-env vectors) / its average launch duration,
              measured live with CUDA events around every step launch of the timed region, against the
@@ -80,7 +80,6 @@ class SingleAdapter(object):
         self.env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=seed)
         g = torch.Generator(device=dev).manual_seed(4321 + rank)
         self.pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]
-        self.host_pool = None
         self.action_desc = f'int64 randint(0,4), pool of {ACTION_POOL} pre-generated tensors per rank'
         self.loop_desc = 'obs,reward,done,info = env.step(a); env.reset(done, return_observations=False)'
 
@@ -94,19 +93,8 @@ class SingleAdapter(object):
     def obs_elems(self, obs):
         return obs[0].numel()
 
-    def host_setup(self):
-        torch = self.torch
-        self.host_pool = [p.cpu().pin_memory() for p in self.pool]
-        self.host_reward = torch.empty((self.N, 1), dtype=torch.float32).pin_memory()
-        self.host_done = torch.empty((self.N, 1), dtype=torch.bool).pin_memory()
-        act = self.N * self.pool[0].element_size()
-        return act, act + self.N * 4 + self.N          # h2d: actions; d2h: sanitised actions + reward + done
-
-    def host_step(self, t):
-        obs, reward, done, info = self.env.step(self.host_pool[t % ACTION_POOL])   # H2D actions, D2H sanitised actions
-        self.host_reward.copy_(reward, non_blocking=True)
-        self.host_done.copy_(done, non_blocking=True)
-        return done
+    def host_pool(self):
+        return [p.cpu().pin_memory() for p in self.pool]
 
 
 class MultiAdapter(object):
@@ -135,21 +123,8 @@ class MultiAdapter(object):
     def obs_elems(self, obs):
         return sum(o[0].numel() for o in obs.values())
 
-    def host_setup(self):
-        torch = self.torch
-        self.host_pool = [{a: t.cpu().pin_memory() for a, t in d.items()} for d in self.pool]
-        self.host_rewards = torch.empty((self.N, self.K), dtype=torch.float32).pin_memory()
-        self.host_dones = torch.empty((self.N, self.K), dtype=torch.bool).pin_memory()
-        self.host_all = torch.empty(self.N, dtype=torch.bool).pin_memory()
-        act = self.N * self.K * 8
-        return act, self.N * self.K * 5 + self.N       # h2d: actions; d2h: rewards + dones + __all__
-
-    def host_step(self, t):
-        obs, rewards, dones, info = self.env.step(self.host_pool[t % ACTION_POOL])   # H2D of K action tensors
-        self.host_rewards.copy_(self.env.rewards.view(self.N, self.K), non_blocking=True)
-        self.host_dones.copy_(self.env.dones.view(self.N, self.K), non_blocking=True)
-        self.host_all.copy_(dones['__all__'], non_blocking=True)
-        return dones['__all__']
+    def host_pool(self):
+        return [{a: t.cpu().pin_memory() for a, t in d.items()} for d in self.pool]
 
 
 def make_adapter(key, dev, seed, rank):
@@ -347,19 +322,32 @@ def run_gpu(args):
     obs_elems = ad.obs_elems(obs)
     del ev
 
-    # ---- end to end through the public API with host buffers ----
-    h2d, d2h = ad.host_setup()
-    Ke = max(10, K // 4)
-    for t in range(3):
-        ad.reset(ad.host_step(t))
+    # ---- end to end through the public API with host buffers (wurm_b200.HostStepper) ----
+    # every step: H2D copy of that step's actions from pinned host memory, step + reset kernels, D2H copy of
+    # the step's results (rewards, done flags, sanitised actions) into pinned host memory; the copies of
+    # neighbouring steps overlap the kernels (double-buffered, one copy stream per direction)
+    from wurm_b200 import HostStepper
+    stepper = HostStepper(env, depth=2)
+    host_pool = ad.host_pool()
+    Ke = max(10, K // 2)
+    tickets = []
+    for t in range(4):
+        tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
+    while tickets:
+        tickets.pop(0).wait()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record()
     for t in range(Ke):
-        ad.reset(ad.host_step(t))
-    e_stop.record()
+        tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
+        if len(tickets) > stepper.depth:
+            tickets.pop(0).wait()
+    while tickets:
+        last = tickets.pop(0).wait()
+    e_stop.record(stepper.d2h)
     barrier()
     e2e_ms = e_start.elapsed_time(e_stop)
+    h2d, d2h = stepper.h2d_bytes_per_step, stepper.d2h_bytes_per_step
 
     # ---- max over ranks, episode statistics (the only collective on this path) ----
     times = torch.tensor([ms_total, e2e_ms, step_kernel_ms], dtype=torch.float64, device=dev)

@@ -368,3 +368,24 @@ def test_config4_invariants_with_boost_and_respawn():
     stats = env.stats()
     assert stats['env_steps'] == 60 * E and stats['reward'] > 0 and stats['edge_collisions'] > 0
     env.check_status()
+
+
+def test_host_stepper_matches_direct_stepping():
+    from wurm_b200 import HostStepper
+    E, K, S, steps = 500, 4, 25, 10
+    acts = torch.randint(0, 8, (steps, K, E), generator=torch.Generator().manual_seed(5))
+    direct = make_env(E, K, S, 'partial_4', seed=21)
+    piped = make_env(E, K, S, 'partial_4', seed=21)
+    piped.agent_colours = direct.agent_colours.clone()
+    stepper = HostStepper(piped, depth=2)
+    expect = []
+    for t in range(steps):
+        obs, rewards, dones, info = direct.step({f'agent_{k}': acts[t, k].to(DEV) for k in range(K)})
+        expect.append((stack_dict(rewards, K), stack_dict(dones, K), np_(dones['__all__'])))
+        direct.reset(dones['__all__'], return_observations=False)
+    for t in range(steps):
+        ticket = stepper.submit({f'agent_{k}': acts[t, k].clone().pin_memory() for k in range(K)}).wait()
+        assert_same(ticket.reward.numpy(), expect[t][0], f'step {t}: rewards')
+        assert_same(ticket.done.numpy(), expect[t][1], f'step {t}: dones')
+        assert_same(ticket.all_done.numpy(), expect[t][2], f'step {t}: __all__')
+    check_state(piped, env_state(direct), 'final state')

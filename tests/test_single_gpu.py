@@ -257,3 +257,28 @@ def test_full_size_invariants_and_food_uniformity():
         assert_consistent(env.envs)
     assert ate > 0
     env.check_status()
+
+
+def test_host_stepper_matches_direct_stepping():
+    """wurm_b200.HostStepper (pinned host buffers, pipelined copies) == stepping with device tensors."""
+    from wurm_b200 import HostStepper
+    N, S, steps = 3000, 9, 12
+    a = torch.randint(0, 4, (steps, N), generator=torch.Generator().manual_seed(3))
+    direct = make_env(N, S, 'partial_2', seed=77)
+    piped = make_env(N, S, 'partial_2', seed=77)
+    stepper = HostStepper(piped, depth=2)
+    expect = []
+    for t in range(steps):
+        acts = a[t].to(DEV)
+        obs, reward, done, info = direct.step(acts)
+        direct.reset(done, return_observations=False)
+        expect.append((np_(obs), np_(reward), np_(done), np_(acts)))
+    tickets = [stepper.submit(a[t].clone().pin_memory()) for t in range(steps)]      # far ahead of the waits
+    for t, ticket in enumerate(tickets):
+        ticket.wait()
+        if t >= steps - 3:              # the slots of the last `depth + 1` tickets have not been recycled
+            assert_same(ticket.reward.numpy(), expect[t][1], f'step {t}: reward')
+            assert_same(ticket.done.numpy(), expect[t][2], f'step {t}: done')
+            assert_same(ticket.actions.numpy(), expect[t][3], f'step {t}: sanitised actions')
+    assert_same(np_(piped.envs), np_(direct.envs), 'final state')
+    assert stepper.h2d_bytes_per_step == N * 8 and stepper.d2h_bytes_per_step == N * 13

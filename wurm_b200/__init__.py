@@ -1,3 +1,4 @@
 """wurm_b200: B200-native batched snake environments behind the API of oscarknagg/wurm's
 `wurm.envs.SingleSnake` / `wurm.envs.MultiSnake` (hand-written sm_100a CUDA behind a C ABI)."""
 from .envs import SingleSnake, MultiSnake  # noqa: F401
+from .host_io import HostStepper  # noqa: F401,E402

@@ -125,6 +125,13 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
     float* food = env;
     float* head = env + C;
     float* body = env + 2 * C;
+    // A step changes O(snake length) cells of the env.  Only those are written back to HBM, cell by
+    // cell, at the point where the shared copy is updated (the sectors were loaded through L2 by this
+    // CTA's bulk copy microseconds ago, so the partial writes merge there); the tile is never stored
+    // wholesale.
+    float* gfood = p.envs + (size_t)e * 3 * C;
+    float* ghead = gfood + C;
+    float* gbody = gfood + 2 * C;
 
     // snake size (:210) and head cell
     float m = -INFINITY;
@@ -190,18 +197,22 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
     const float ov = (np >= 0) ? food[np] : 0.0f;                   // :242 head-food overlap
     if (ov == 0.0f) {                                                // :246-249 decay unless it ate
 #pragma unroll 4
-        for (int q = l; q < C; q += G) body[q] = fmaxf(body[q] - 1.0f, 0.0f);
+        for (int q = l; q < C; q += G) {
+            const float v = body[q], nv = fmaxf(v - 1.0f, 0.0f);
+            if (nv != v) { body[q] = nv; gbody[q] = nv; }
+        }
     }
     __syncwarp(gm);
     const bool sc = (np >= 0) && (body[np] > kEps);                  // :252 self collision
     const bool interior = (np >= 0) && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
     __syncwarp(gm);
     if (l == 0 && hp >= 0) {
-        head[hp] = 0.0f;
+        head[hp] = 0.0f; ghead[hp] = 0.0f;
         if (np >= 0) {
-            head[np] = 1.0f;
-            body[np] += size + ov;                                   // :258-262 growth
-            food[np] += ov * -1.0f;                                  // :270-272 food removal
+            head[np] = 1.0f; ghead[np] = 1.0f;
+            const float grown = body[np] + (size + ov);              // :258-262 growth
+            body[np] = grown; gbody[np] = grown;
+            if (ov != 0.0f) { const float left = food[np] + ov * -1.0f; food[np] = left; gfood[np] = left; }   // :270-272
         }
     }
     __syncwarp(gm);
@@ -222,7 +233,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
                 cell = pick_free_cell<G>(env, S, C, p.magic_S,
                                          draw_i(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
         }
-        if (l == 0 && cell >= 0) food[cell] += 1.0f;
+        if (l == 0 && cell >= 0) { const float f = food[cell] + 1.0f; food[cell] = f; gfood[cell] = f; }
     }
     if (l == 0) {
         p.reward[e] = 0.0f - ov * -1.0f;                             // :271
@@ -381,15 +392,11 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
         if (v) atomicAdd(slot + threadIdx.x, (unsigned long long)v);
     }
     const bool raw = p.obs_mode == WURM_OBS_RAW;
-    if (bulk) {
-        if (threadIdx.x == 0) {
-            if (STEP) bulk_store(p.envs + goff, tile, bytes);
-            if (raw) bulk_store(p.obs + goff, tile, bytes);
-        }
-    } else if (STEP || raw) {
-        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) {
-            if (STEP) p.envs[goff + i] = tile[i];
-            if (raw) p.obs[goff + i] = tile[i];
+    if (raw) {                              // the 'raw' observation is a copy of the (updated) tile
+        if (bulk) {
+            if (threadIdx.x == 0) bulk_store(p.obs + goff, tile, bytes);
+        } else {
+            for (int i = threadIdx.x; i < nfloats; i += blockDim.x) p.obs[goff + i] = tile[i];
         }
     }
     bool obs_bulk = false;
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     } else if (p.obs_mode >= 0 && !raw) {
         write_obs<G>(p, tile, env0, nvalid);
     }
-    if ((bulk || obs_bulk) && threadIdx.x == 0) {
+    if (((bulk && raw) || obs_bulk) && threadIdx.x == 0) {
         bulk_commit();
         bulk_wait_read_all();               // shared memory must outlive the bulk stores' reads
     }

@@ -319,6 +319,7 @@ class MultiSnake(object):
                 _ptr(self._status), _ptr(self._stats), self._stream()))
 
         self.rewards = rewards.view(E * K)
+        self._step_dones = flags[2]          # (E,K) copy of the done flags owned by this step's outputs
         observations = OrderedDict([(f'agent_{i}', obs[i]) for i in range(K)])
         dones = {f'agent_{i}': flags[2][:, i] for i in range(K)}
         dones['__all__'] = all_done
