@@ -1,0 +1,136 @@
+"""Single-agent rollout driver: the caller of the hot path.
+
+Own copy of the *rollout* half of the reference's `experiments/main.py` (its call sequence, :195-227 and
+:252-320, and the CLI flags that concern the env, :30-54), with the three defects of the shipped driver
+repaired (trap 2: `A2C(model, ...)` signature, `RandomAgent` on flat
+observations, log-prob/value broadcasting).  The env comes from `wurm_b200.envs`; the policy stand-ins
+(uniform random, 2x64 feed-forward) are plain torch -- policies and the A2C learner are outside this
+repository's scope.
+
+    python -m experiments.main --env snake --num-envs 512 --size 9 --agent random --observation partial_2 \
+        --total-steps 1e6
+
+Call sequence kept from the reference:  state = env.reset();  loop:  probs, value = model(state);
+action ~ Categorical(probs);  state, reward, done, info = env.step(action);
+env_consistency(env.envs[~done]);  env.reset(done)  -- whose observation is discarded (main.py:227), so
+`return_observations=False` is passed here.
+"""
+import argparse
+from itertools import count
+from time import time
+
+import torch
+from torch import nn
+from torch.distributions import Categorical
+
+from wurm_b200.envs import SingleSnake
+
+LOG_INTERVAL = 100
+
+
+def boolean(x):
+    return x.lower()[0] == 't'
+
+
+class RandomAgent(nn.Module):
+    def __init__(self, num_actions, device):
+        super().__init__()
+        self.num_actions, self.device = num_actions, device
+
+    def forward(self, x):
+        n = x.shape[0]
+        return torch.full((n, self.num_actions), 1.0 / self.num_actions, device=self.device), torch.zeros(n, device=self.device)
+
+
+class FeedforwardAgent(nn.Module):
+    """2 x 64 MLP on flat observations with action and value heads (the shape of the reference's agent)."""
+
+    def __init__(self, num_actions, num_layers, hidden_units, num_inputs):
+        super().__init__()
+        layers, width = [], num_inputs
+        for _ in range(num_layers):
+            layers += [nn.Linear(width, hidden_units), nn.ReLU()]
+            width = hidden_units
+        self.body = nn.Sequential(*layers)
+        self.action_head = nn.Linear(hidden_units, num_actions)
+        self.value_head = nn.Linear(hidden_units, 1)
+
+    def forward(self, x):
+        x = self.body(x.reshape(x.shape[0], -1))
+        return torch.softmax(self.action_head(x), dim=-1), self.value_head(x)
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--env', type=str, default='snake')
+    parser.add_argument('--num-envs', type=int, default=512)
+    parser.add_argument('--size', type=int, default=9)
+    parser.add_argument('--agent', type=str, default='random')
+    parser.add_argument('--train', default=False, type=boolean)
+    parser.add_argument('--observation', default='default', type=str)
+    parser.add_argument('--render', default=False, type=boolean)
+    parser.add_argument('--render-window-size', default=256, type=int)
+    parser.add_argument('--render-cols', default=1, type=int)
+    parser.add_argument('--render-rows', default=1, type=int)
+    parser.add_argument('--total-steps', default=float('inf'), type=float)
+    parser.add_argument('--total-episodes', default=float('inf'), type=float)
+    parser.add_argument('--check-consistency', default=True, type=boolean,
+                        help='run env_consistency on the live envs every step, as the reference driver does')
+    parser.add_argument('--device', default='cuda', type=str)
+    parser.add_argument('--seed', default=None, type=int)
+    args = parser.parse_args(argv)
+
+    if args.env != 'snake':
+        raise ValueError('Unrecognised environment (this driver covers --env snake)')
+    if args.train:
+        raise NotImplementedError('the A2C learner is outside the scope of wurm_b200 (DESIGN.md section 7); use --train false')
+
+    render_args = {'size': args.render_window_size, 'num_rows': args.render_rows, 'num_cols': args.render_cols}
+    env = SingleSnake(num_envs=args.num_envs, size=args.size, device=args.device, observation_mode=args.observation,
+                      render_args=render_args, seed=args.seed)
+
+    state = env.reset()
+    if args.agent == 'random':
+        model = RandomAgent(num_actions=4, device=args.device)
+    elif args.agent == 'feedforward':
+        model = FeedforwardAgent(num_actions=4, num_layers=2, hidden_units=64, num_inputs=state[0].numel()).to(args.device)
+    else:
+        raise ValueError('Unrecognised agent (this driver covers random and feedforward)')
+
+    num_steps = num_episodes = 0
+    t0 = time()
+    summary = {}
+    for i_step in count(1):
+        if args.render:
+            env.render()
+
+        with torch.no_grad():
+            probs, state_value = model(state)
+        action = Categorical(probs).sample().clone().long()
+
+        state, reward, done, info = env.step(action)
+
+        if args.check_consistency:
+            env.check_consistency(skip=done)      # == env_consistency(env.envs[~done.squeeze(-1)]) (main.py:215), fused
+
+        env.reset(done, return_observations=False)
+
+        num_steps += args.num_envs
+        if i_step % LOG_INTERVAL == 0 or num_steps >= args.total_steps:
+            stats = env.stats()                       # device counters kept by the step kernel: one tiny D2H read
+            num_episodes = stats['episodes']
+            dt = time() - t0
+            summary = dict(steps=num_steps, episodes=num_episodes, reward_rate=stats['reward'] / max(stats['env_steps'], 1),
+                           edge_collisions=stats['edge_collisions'], self_collisions=stats['self_collisions'],
+                           avg_size=env.envs[:, 2].reshape(args.num_envs, -1).max(dim=-1)[0].mean().item(),
+                           steps_per_second=num_steps / dt)
+            print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
+
+        if num_steps >= args.total_steps or num_episodes >= args.total_episodes:
+            break
+    env.check_status()
+    return summary
+
+
+if __name__ == '__main__':
+    main()

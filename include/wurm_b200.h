@@ -17,6 +17,9 @@
  *   - Randomness is an input: each draw is either replayed from a caller-supplied tape (the
  *     `*_replay` pointers, how bit-exact parity with the reference is established) or, when the
  *     tape pointer is NULL, derived from Philox4x32-10 keyed by (seed, step, env, stream).
+ *     `step` is the caller's call counter; `step_dev` (nullable device pointer) is added to it on
+ *     the device, so that a launch captured in a CUDA graph draws fresh numbers at every replay
+ *     (the graph bumps the device counter between replays).
  */
 #ifndef WURM_B200_H
 #define WURM_B200_H
@@ -27,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WURM_ABI_VERSION 1
+#define WURM_ABI_VERSION 2
 
 /* return codes */
 #define WURM_OK 0
@@ -85,7 +88,8 @@ int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg);
  *   food_cell_replay (N,) int32 or NULL: cell index y*S+x of the respawned food for envs that eat
  *            this step (-1: none); NULL -> uniform over free interior cells from Philox.        */
 int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
-                     const int32_t* food_cell_replay, uint64_t seed, uint64_t step, float* obs, float* reward,
+                     const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                     float* obs, float* reward,
                      uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status,
                      int64_t* stats /* nullable */, void* stream);
 
@@ -93,10 +97,31 @@ int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int a
  * envs whose done_mask byte is non-zero are re-created, all others untouched.
  *   spawn_replay (N,4) int32 or NULL: rows (y, x, dir, food_cell), read for done envs only.     */
 int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* spawn_replay,
-                      uint64_t seed, uint64_t step, void* stream);
+                      uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream);
 
 /* Replaces SingleSnake._observe (single_snake.py:130-195) on the current state. */
 int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream);
+
+/* Invariant checks (wurm/utils.py:113-178 snake_consistency + env_consistency, and
+ * MultiSnake.check_consistency multi_snake.py:733-769) fused into ONE reduction kernel per call.  The
+ * reference's drivers run these every step (experiments/main.py:215, experiments/multiagent.py:378)
+ * as ~10 full-state reductions with a host sync each.  report: device int32[WURM_CHECK_REPORT]:
+ *   [0] OR over the checked envs of the WURM_CHK_* bits (in the order the reference tests them)
+ *   [1] number of violating envs (agents for MultiSnake)      [2] smallest violating env index  */
+#define WURM_CHECK_REPORT 4
+#define WURM_CHK_FOOD_VALUE 1      /* 'An environment has an invalid food pixel'                          utils.py:119-125 */
+#define WURM_CHK_HEAD_COUNT 2      /* '...multiple num_heads for a single snake.'                         :127-131 */
+#define WURM_CHK_NO_SNAKE 4        /* "environments don't contain a snake."                               :134-136 */
+#define WURM_CHK_HEAD_NOT_AT_END 8 /* "...it's head not at the end of the body."                          :139-143 */
+#define WURM_CHK_BODY_VALUES 16    /* '...a body with inconsistent values i.e. not range(n)'              :147-153 */
+#define WURM_CHK_TOO_SHORT 32      /* 'A snake has size of less than 3.'                                  :156-157 */
+#define WURM_CHK_HEAD_ON_FOOD 64   /* 'A food and head pixel is overlapping...'                           :160-164 */
+#define WURM_CHK_FOOD_COUNT 128    /* "...doesn't contain exactly one food instance" (SingleSnake only)   :176-178 */
+#define WURM_CHK_OVERLAP 256       /* 'An environment contains overlapping snakes'                 multi_snake.py:746-758 */
+#define WURM_CHK_DEAD_NOT_ZERO 512 /* 'Dead snake contains non-zero elements.'                     multi_snake.py:766-769 */
+
+/* skip (N) nullable: envs whose byte is non-zero are not checked (the driver checks envs[~done]). */
+int wurm_single_check(const WurmSingleCfg* cfg, const float* envs, const uint8_t* skip, int32_t* report, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MultiSnake (wurm/envs/multi_snake.py)
@@ -175,19 +200,24 @@ int64_t wurm_multi_obs_elems(const WurmMultiCfg* cfg); /* floats per (agent, env
  * _observe, in ONE launch.  actions: host array of K device pointers, each (E,) of action_bytes
  * integers in [0,8) (agents in dict order). */
 int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions, int action_bytes,
-                    const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step, const WurmMultiStepOut* out,
-                    int32_t* status, int64_t* stats /* nullable */, void* stream);
+                    const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                    const WurmMultiStepOut* out, int32_t* status, int64_t* stats /* nullable */, void* stream);
 
 /* Replaces the state update of MultiSnake.reset (multi_snake.py:771-831) incl. _create_envs,
  * _add_snake, _get_snake_addition and get_n_colours.  env_done (E): envs to re-create. */
 int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const uint8_t* env_done,
-                     const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, int32_t* status, void* stream);
+                     const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                     int32_t* status, void* stream);
 
 /* Replaces MultiSnake._observe (multi_snake.py:283-334) on the current state. */
 int wurm_multi_observe(const WurmMultiCfg* cfg, const WurmMultiState* state, float* obs, int32_t* status, void* stream);
 
 /* Replaces MultiSnake._get_env_images (multi_snake.py:194-227): img (E,3,S,S) int16. */
 int wurm_multi_env_images(const WurmMultiCfg* cfg, const WurmMultiState* state, int16_t* img, int32_t* status, void* stream);
+
+/* MultiSnake.check_consistency (multi_snake.py:733-769): living snakes against snake_consistency,
+ * no two bodies on one cell, dead snakes all-zero.  report as for wurm_single_check (counts agents). */
+int wurm_multi_check(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* report, void* stream);
 
 #ifdef __cplusplus
 }

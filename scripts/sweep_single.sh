@@ -1,6 +1,6 @@
 #!/bin/bash
 # Launch-configuration sweep of the SingleSnake step kernel on C2 (scratch; results go to gpurun_out/).
-for cfg in "4 128 44" "4 256 84" "4 64 22" "2 128 44" "2 64 44" "1 32 44" "1 64 84" "8 128 44" "4 128 88" "2 128 88"; do
+for cfg in "4 64 44" "4 32 44" "8 64 44" "8 128 44" "8 32 44" "16 64 44" "2 64 44" "4 128 44"; do
   set -- $cfg
   echo -n "G=$1 THREADS=$2 SMEM_KB=$3: "
   WURM_SINGLE_G=$1 WURM_SINGLE_THREADS=$2 WURM_SINGLE_SMEM_KB=$3 python bench.py --workload C2 --steps 200 --warmup 10 --no-cpu-baseline 2>&1 | python -c "

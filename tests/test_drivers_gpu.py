@@ -1,0 +1,24 @@
+"""GPU: the caller side of the boundary -- the rollout driver (the reference's experiments/main.py call
+sequence) and the MultiSnake speed sweep (experiments/speeds.py) run on the CUDA path."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('agent,observation', [('random', 'partial_2'), ('feedforward', 'partial_2'),
+                                               ('feedforward', 'default')])
+def test_rollout_driver(agent, observation):
+    """BASELINE config 1 (README example): snake, 512 envs, size 9, consistency checked every step."""
+    from experiments.main import main
+    summary = main(['--env', 'snake', '--num-envs', '512', '--size', '9', '--agent', agent, '--observation', observation,
+                    '--total-steps', str(512 * 150), '--seed', '3'])
+    assert summary['steps'] == 512 * 150
+    assert summary['episodes'] > 0 and summary['edge_collisions'] > 0
+    assert 3.0 <= summary['avg_size'] < 6.0
+
+
+def test_multisnake_speed_sweep():
+    from experiments.speeds import sweep
+    fps = sweep(num_agents=4, size=20, min_log2=4, max_log2=8, num_steps=5, check=True, verbose=False)
+    assert [n for n, _ in fps] == [16, 32, 64, 128, 256]
+    assert all(rate > 0 for _, rate in fps)

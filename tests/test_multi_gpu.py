@@ -389,3 +389,30 @@ def test_host_stepper_matches_direct_stepping():
         assert_same(ticket.done.numpy(), expect[t][1], f'step {t}: dones')
         assert_same(ticket.all_done.numpy(), expect[t][2], f'step {t}: __all__')
     check_state(piped, env_state(direct), 'final state')
+
+
+def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
+    from wurm_b200 import GraphedStepper
+    E, K, S, steps = 128, 4, 25, 25
+    rules = dict(respawn_mode='any', food_mode='random_rate', food_rate=2e-3)
+    plain = make_env(E, K, S, 'partial_4', seed=31, **rules)
+    graphed = make_env(E, K, S, 'partial_4', seed=31, **rules)
+    graphed.agent_colours = plain.agent_colours.clone()
+    acts = torch.randint(0, 8, (steps + 1, K, E), generator=torch.Generator().manual_seed(2)).to(DEV)
+    static = {f'agent_{k}': acts[0, k].clone() for k in range(K)}
+    stepper = GraphedStepper(graphed, static, warmup=2)
+    for _ in range(2):
+        _, _, dones, _ = plain.step({f'agent_{k}': acts[0, k] for k in range(K)})
+        plain.reset(dones['__all__'], return_observations=False)
+    check_state(graphed, env_state(plain), 'state after warm-up')
+    for t in range(1, steps + 1):
+        for k in range(K):
+            static[f'agent_{k}'].copy_(acts[t, k])
+        obs, rewards, dones, info = stepper.step()
+        obs2, rewards2, dones2, info2 = plain.step({f'agent_{k}': acts[t, k] for k in range(K)})
+        for k in range(K):
+            assert_same(np_(obs[f'agent_{k}']), np_(obs2[f'agent_{k}']), f'step {t}: obs {k}')
+        assert_same(stack_dict(rewards, K), stack_dict(rewards2, K), f'step {t}: rewards')
+        assert_same(stack_dict(dones, K), stack_dict(dones2, K), f'step {t}: dones')
+        plain.reset(dones2['__all__'], return_observations=False)
+        check_state(graphed, env_state(plain), f'step {t}: state after reset')

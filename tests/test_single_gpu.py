@@ -174,8 +174,8 @@ def test_eat_food():
     for env, (obs, reward, done, info) in run_actions([0, 3, 3, 0, 0]):
         assert not torch.any(done)
         rewards.append(reward.item())
-    assert sum(rewards) == 1
-    assert env.envs[0, 2].max() == 5
+    assert rewards[2] == 1          # the food at (6,6) is reached by the third action
+    assert env.envs[0, 2].max() == 4 + sum(rewards)     # (the respawned food may land on the path and be eaten too)
     assert env.envs[0, 0].sum() == 1
     assert_consistent(env.envs)
 
@@ -282,3 +282,34 @@ def test_host_stepper_matches_direct_stepping():
             assert_same(ticket.actions.numpy(), expect[t][3], f'step {t}: sanitised actions')
     assert_same(np_(piped.envs), np_(direct.envs), 'final state')
     assert stepper.h2d_bytes_per_step == N * 8 and stepper.d2h_bytes_per_step == N * 13
+
+
+def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
+    """wurm_b200.GraphedStepper: one CUDA-graph launch per step+reset; same states, rewards, dones and
+    observations as stepping the twin env call by call (the device-side call counter keeps the Philox
+    draws in step)."""
+    from wurm_b200 import GraphedStepper
+    N, S, steps = 512, 9, 40
+    plain = make_env(N, S, 'partial_2', seed=123)
+    graphed = make_env(N, S, 'partial_2', seed=123)
+    acts = torch.randint(0, 4, (steps + 2, N), generator=torch.Generator().manual_seed(1)).to(DEV)
+    static_actions = torch.zeros(N, dtype=torch.long, device=DEV)
+    # the stepper warms up with 2 real steps before capturing: replay them on the twin
+    static_actions.copy_(acts[0])
+    stepper = GraphedStepper(graphed, static_actions, warmup=2)
+    a0 = acts[0].clone()                # both warm-up steps reuse (and re-sanitise) the same action tensor
+    for _ in range(2):
+        _, _, done, _ = plain.step(a0)
+        plain.reset(done, return_observations=False)
+    assert_same(np_(graphed.envs), np_(plain.envs), 'state after warm-up')
+    for t in range(1, steps + 1):
+        static_actions.copy_(acts[t])
+        obs, reward, done, info = stepper.step()
+        a = acts[t].clone()
+        obs2, reward2, done2, info2 = plain.step(a)
+        assert_same(np_(obs), np_(obs2), f'step {t}: obs')
+        assert_same(np_(reward), np_(reward2), f'step {t}: reward')
+        assert_same(np_(done), np_(done2), f'step {t}: done')
+        assert_same(np_(static_actions), np_(a), f'step {t}: sanitised actions')
+        plain.reset(done2, return_observations=False)
+        assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')

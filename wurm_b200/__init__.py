@@ -2,3 +2,4 @@
 `wurm.envs.SingleSnake` / `wurm.envs.MultiSnake` (hand-written sm_100a CUDA behind a C ABI)."""
 from .envs import SingleSnake, MultiSnake  # noqa: F401
 from .host_io import HostStepper  # noqa: F401,E402
+from .graph import GraphedStepper  # noqa: F401,E402

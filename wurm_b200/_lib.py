@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
 ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP = 1, 2, 4, 8
@@ -20,7 +20,21 @@ OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1
 # every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_reset',
            'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_reset', 'wurm_multi_observe',
-           'wurm_multi_env_images']
+           'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check']
+CHECK_REPORT = 4
+# WURM_CHK_* bits in the order the reference tests them, with the reference's messages
+CHECK_MESSAGES = [
+    (1, 'An environment has an invalid food pixel'),
+    (2, 'An environment has multiple num_heads for a single snake.'),
+    (4, "environments don't contain a snake."),
+    (8, "An environment has a snake with it's head not at the end of the body."),
+    (16, 'An environment has a body with inconsistent values i.e. not range(n)'),
+    (32, 'A snake has size of less than 3.'),
+    (64, 'A food and head pixel is overlapping'),
+    (128, "An environment doesn't contain exactly one food instance"),
+    (256, 'An environment contains overlapping snakes'),
+    (512, 'Dead snake contains non-zero elements.'),
+]
 MULTI_MAX_SNAKES = 32
 MOBS_NONE, MOBS_FULL, MOBS_PARTIAL = -1, 0, 1
 
@@ -81,23 +95,27 @@ def lib():
     L.wurm_single_obs_elems.restype = ctypes.c_int64
     L.wurm_single_obs_elems.argtypes = [cfg]
     L.wurm_single_step.restype = i32
-    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.wurm_single_reset.restype = i32
-    L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp]
+    L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp, vp]
     L.wurm_single_observe.restype = i32
     L.wurm_single_observe.argtypes = [cfg, vp, vp, vp, vp]
     mcfg, mst = ctypes.POINTER(WurmMultiCfg), ctypes.POINTER(WurmMultiState)
     L.wurm_multi_obs_elems.restype = ctypes.c_int64
     L.wurm_multi_obs_elems.argtypes = [mcfg]
     L.wurm_multi_step.restype = i32
-    L.wurm_multi_step.argtypes = [mcfg, mst, ctypes.POINTER(vp), i32, ctypes.POINTER(WurmMultiStepDraws), u64, u64,
+    L.wurm_multi_step.argtypes = [mcfg, mst, ctypes.POINTER(vp), i32, ctypes.POINTER(WurmMultiStepDraws), u64, u64, vp,
                                   ctypes.POINTER(WurmMultiStepOut), vp, vp, vp]
     L.wurm_multi_reset.restype = i32
-    L.wurm_multi_reset.argtypes = [mcfg, mst, vp, ctypes.POINTER(WurmMultiResetDraws), u64, u64, vp, vp]
+    L.wurm_multi_reset.argtypes = [mcfg, mst, vp, ctypes.POINTER(WurmMultiResetDraws), u64, u64, vp, vp, vp]
     L.wurm_multi_observe.restype = i32
     L.wurm_multi_observe.argtypes = [mcfg, mst, vp, vp, vp]
     L.wurm_multi_env_images.restype = i32
     L.wurm_multi_env_images.argtypes = [mcfg, mst, vp, vp, vp]
+    L.wurm_single_check.restype = i32
+    L.wurm_single_check.argtypes = [cfg, vp, vp, vp, vp]
+    L.wurm_multi_check.restype = i32
+    L.wurm_multi_check.argtypes = [mcfg, mst, vp, vp]
     if L.wurm_abi_version() != ABI_VERSION:
         raise ImportError(f'{LIB_PATH} has ABI version {L.wurm_abi_version()}, expected {ABI_VERSION}: rebuild it')
     _lib = L
@@ -107,3 +125,14 @@ def lib():
 def check(rc):
     if rc != OK:
         raise WurmError(rc, lib().wurm_last_error().decode())
+
+
+def raise_on_report(report, only=None):
+    """report: the 3 ints a check kernel produced.  Raises the reference's RuntimeError for the first failing
+    check (in the reference's order); `only` restricts to a subset of bits."""
+    bits, count, first = int(report[0]), int(report[1]), int(report[2])
+    if only is not None:
+        bits &= only
+    for bit, message in CHECK_MESSAGES:
+        if bits & bit:
+            raise RuntimeError(f'{message} ({count} violating, first at index {first})')

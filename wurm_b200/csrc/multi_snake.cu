@@ -56,6 +56,7 @@ struct MultiParams {
     const int* food_cell;
     const float* u_rate;
     uint64_t seed, step;
+    const unsigned long long* step_dev;   // nullable: added to `step` on the device (CUDA-graph replays)
     // rules
     int E, K, S, C;
     int boost, food_on_death, food_mode, respawn_any, colour_random;
@@ -82,12 +83,21 @@ struct MultiParams {
     uint32_t magic_S, magic_C, magic_W;
 };
 
+__device__ __forceinline__ uint64_t call_counter(const MultiParams& p) { return p.step + (p.step_dev ? *p.step_dev : 0ull); }
+
 __device__ __forceinline__ int fdiv(int q, uint32_t magic) { return (int)__umulhi((uint32_t)q, magic); }
 
-// cell record: bits 0-15 body value, bits 16-21 owner snake + 1; 0 = empty
+// One 32-bit record per cell holds everything the step needs to know about it:
+//   bits  0-15  body value            bits 16-21  owner snake + 1      (together: the "live" body, 0 = none)
+//   bits 22-27  owner + 1 when loaded bit 28      body modified since the load
+//   bit  29     food                  bit 30      food when loaded
+// so that the write-back can tell exactly which cells of which tensors changed.
+constexpr uint32_t kLive = 0x003FFFFFu, kDirty = 1u << 28, kFood = 1u << 29, kFood0 = 1u << 30;
 __device__ __forceinline__ uint32_t make_rec(int owner, int value) { return ((uint32_t)(owner + 1) << 16) | (uint32_t)value; }
-__device__ __forceinline__ int rec_owner(uint32_t r) { return (int)(r >> 16) - 1; }
+__device__ __forceinline__ int rec_owner(uint32_t r) { return (int)((r >> 16) & 63u) - 1; }
+__device__ __forceinline__ int rec_owner0(uint32_t r) { return (int)((r >> 22) & 63u) - 1; }
 __device__ __forceinline__ int rec_value(uint32_t r) { return (int)(r & 0xffffu); }
+__device__ __forceinline__ bool rec_body(uint32_t r) { return (r & kLive) != 0u; }
 
 __device__ __forceinline__ float4 ld_stream(const float4* ptr) {
     float4 v;
@@ -160,9 +170,6 @@ __device__ __forceinline__ float div255(int v) {
 
 struct MultiSmem {
     uint32_t* cell;   // C records
-    uint32_t* cell0;  // C records as loaded (for the sparse write-back)
-    uint8_t* food;    // C
-    uint8_t* food0;   // C as loaded
     int* hp;          // head cell per snake, -1 none
     int* size;        // max body value per snake
     int* hcnt;        // head cells seen per snake
@@ -170,44 +177,58 @@ struct MultiSmem {
     int* decay;
     int* cost;
     int* boost;
-    int* misc;        // [0] food count, [2] run_boost, [3] force full write-back
+    int* sum;         // sum of body values per snake (invariant check)
+    int* misc;        // [0] food cells, [2] run_boost, [3] force full write-back
     short* col;       // K*3
 };
 
 __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
     MultiSmem s;
     s.cell = reinterpret_cast<uint32_t*>(smem);
-    s.cell0 = s.cell + C;
-    s.food = reinterpret_cast<uint8_t*>(s.cell0 + C);
-    s.food0 = s.food + ((C + 15) & ~15);
-    s.hp = reinterpret_cast<int*>(s.food0 + ((C + 15) & ~15));
+    s.hp = reinterpret_cast<int*>(s.cell + C);
     s.size = s.hp + 32; s.hcnt = s.size + 32; s.done = s.hcnt + 32; s.decay = s.done + 32; s.cost = s.decay + 32;
-    s.boost = s.cost + 32; s.misc = s.boost + 32;
+    s.boost = s.cost + 32; s.sum = s.boost + 32; s.misc = s.sum + 32;
     s.col = reinterpret_cast<short*>(s.misc + 8);
     return s;
 }
 
 static size_t multi_smem_bytes(int C, int W, int obs_mode) {
-    return (size_t)C * 8 + 2 * ((C + 15) & ~15) + 7 * 32 * 4 + 8 * 4 + 96 * 2 + 16;
+    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + 16;
+}
+
+// Food transitions keep the env's food-cell count (misc[0]) current, so _add_food needs no counting pass.
+__device__ __forceinline__ void set_food(const MultiSmem& s, int q) {
+    if (!(atomicOr(&s.cell[q], kFood) & kFood)) atomicAdd(&s.misc[0], 1);
+}
+__device__ __forceinline__ void clear_food(const MultiSmem& s, int q) {
+    if (atomicAnd(&s.cell[q], ~kFood) & kFood) atomicSub(&s.misc[0], 1);
 }
 
 // Streams env e's tensors from HBM into the compact shared-memory form.
+template <bool CHECK = false>
 __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e) {
     const int C = p.C, K = p.K;
     // `odd`: a value the compact form cannot carry exactly (food/head != 1, non-integral body): the env
     // is then written back in full (which normalises it) instead of cell by cell.
     bool overlap = false, odd = false;
-    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float v) { s.food[i] = 1; odd |= v != 1.0f; });
+    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float v) {
+        atomicOr(&s.cell[i], kFood | kFood0);
+        atomicAdd(&s.misc[0], 1);
+        odd |= v != 1.0f;
+        if (CHECK && v != 1.0f) s.misc[5] = 1;                       // a food pixel that is neither 0 nor 1
+    });
     scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float v) {
         const int k = fdiv(i, p.magic_C);
         atomicMax(&s.hp[k], i - k * C);
-        atomicAdd(&s.hcnt[k], 1);
+        atomicAdd(&s.hcnt[k], v == 1.0f ? 1 : 2);                    // a head value other than 1 counts as "not one head"
         odd |= v != 1.0f;
     });
     scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float v) {
         const int k = fdiv(i, p.magic_C), val = (int)v;
-        if (atomicCAS(&s.cell[i - k * C], 0u, make_rec(k, val)) != 0u) overlap = true;
+        const uint32_t owner = (uint32_t)(k + 1);
+        if (atomicOr(&s.cell[i - k * C], (owner << 22) | (owner << 16) | ((uint32_t)val & 0xffffu)) & kLive) overlap = true;
         atomicMax(&s.size[k], val);
+        if (CHECK) atomicAdd(&s.sum[k], val);
         odd |= (float)val != v || val < 1 || val > 65535;
     });
     if (overlap) atomicOr(p.status, WURM_ST_OVERLAP);
@@ -218,14 +239,14 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
 __device__ __forceinline__ void env_pixel(const MultiParams& p, const MultiSmem& s, int q, int y, int x, int rgb[3]) {
     const uint32_t rec = s.cell[q];
     rgb[0] = rgb[1] = rgb[2] = 0;
-    if (rec) {
+    if (rec_body(rec)) {
         const int o = rec_owner(rec);
         float inten = 1.0f * 1.0f / 3.0f + (s.hp[o] == q ? 1.0f : 0.0f) * 1.0f / 3.0f;      // :197
         inten *= 1.0f + 0.5f * (s.boost[o] ? 1.0f : 0.0f);                                  // :198
 #pragma unroll
         for (int c = 0; c < 3; ++c) rgb[c] = (int)(short)(inten * (float)s.col[3 * o + c]);  // :201-206
     }
-    if (s.food[q]) rgb[0] += 255;                                                            // :208-209
+    if (rec & kFood) rgb[0] += 255;                                                          // :208-209
     if (rgb[0] == 0 && rgb[1] == 0 && rgb[2] == 0) rgb[0] = rgb[1] = rgb[2] = 255;           // :214-219
     if (y == 0 || x == 0 || y == p.S - 1 || x == p.S - 1) rgb[0] = rgb[1] = rgb[2] = 0;      // :225
 }
@@ -263,8 +284,8 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
                 const int y = fdiv(q, p.magic_S), x = q - y * S;
                 const uint32_t rec = s.cell[q];
                 int r = 255, g = 255, b = 255;
-                if (s.food[q]) { r = 255; g = 0; b = 0; }
-                if (rec) {
+                if (rec & kFood) { r = 255; g = 0; b = 0; }
+                if (rec_body(rec)) {
                     const int ow = rec_owner(rec);
                     const bool is_head = s.hp[ow] == q;
                     if (ow == k) { r = 0; g = is_head ? 192 : 96; b = 0; }
@@ -288,16 +309,18 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
 }
 
 // One CTA = one environment.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
-template <bool STEP>
-__global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
+// THREADS = 128 for small grids (S*S <= 1024; register budget capped so that 12 CTAs stay resident per SM:
+// these envs are latency-bound, more envs in flight is what hides the load and barrier latencies), 256 otherwise.
+template <bool STEP, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 12 : 4) multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MultiSmem s = carve(smem_raw, p.C);
     const int C = p.C, K = p.K, S = p.S;
     const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int q = tid; q < C; q += nthr) { s.cell[q] = 0u; s.food[q] = 0; }
+    for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
     if (tid < 32) {
-        s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.decay[tid] = 0; s.cost[tid] = 0;
+        s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.decay[tid] = 0; s.cost[tid] = 0; s.sum[tid] = 0;
         s.done[tid] = (tid < K) ? (p.dones[(size_t)e * K + tid] != 0) : 1;
         s.boost[tid] = (!STEP && tid < K) ? (p.boost_this_step[(size_t)e * K + tid] != 0) : 0;
     }
@@ -306,8 +329,6 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
     __syncthreads();
     load_env(p, s, e);
     __syncthreads();
-    if (STEP)
-        for (int q = tid; q < C; q += nthr) { s.cell0[q] = s.cell[q]; s.food0[q] = s.food[q]; }
 
     if (STEP) {
         // ---- per-snake registers, live on lane k of warp 0 ----
@@ -354,30 +375,32 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
                 }
                 if (valid) s.hp[k] = a_hp;
                 __syncwarp();
-                ov = valid && a_hp >= 0 && s.food[a_hp] != 0;         // :514 / :618 overlap of ALL heads
+                ov = valid && a_hp >= 0 && (s.cell[a_hp] & kFood);    // :514 / :618 overlap of ALL heads
                 __syncwarp();
-                if (ov) s.food[a_hp] = 0;                             // :517 / :622
+                if (ov) clear_food(s, a_hp);                          // :517 / :622
                 if (k < 32) s.decay[k] = active && !ov;               // :523-526 / :627-628
                 if (active && ov) { a_reward += 1.0f; a_foodc += 1.0f; }   // :527-529 / :629-631
             }
             __syncthreads();
             for (int q = tid; q < C; q += nthr) {                     // _decay_bodies :362-363
                 const uint32_t rec = s.cell[q];
-                if (rec && s.decay[rec_owner(rec)]) s.cell[q] = (rec_value(rec) == 1) ? 0u : rec - 1u;
+                if (rec_body(rec) && s.decay[rec_owner(rec)])
+                    s.cell[q] = ((rec_value(rec) == 1) ? (rec & ~kLive) : rec - 1u) | kDirty;
             }
             __syncthreads();
             if (warp == 0) {
                 bool col = false;
                 if (active && a_hp >= 0) {                            // :534-545 / :636-642
-                    col = s.cell[a_hp] != 0u;                         // any body, own included
+                    col = rec_body(s.cell[a_hp]);                     // any body, own included
                     for (int j = 0; j < K; ++j) col |= (j != k) && (s.hp[j] == a_hp);   // another head
                 }
                 __syncwarp();
                 if (active) { a_done |= col; a_scol |= col; }         // :546-547 / :643-644
                 if (active && a_hp >= 0) {                            // :553 / :650 growth at the head cell
                     const uint32_t add = (uint32_t)(a_size + (ov ? 1 : 0));
-                    const uint32_t old = atomicCAS(&s.cell[a_hp], 0u, make_rec(k, (int)add));
-                    if (old != 0u && rec_owner(old) == k) s.cell[a_hp] = old + add;   // self collision: values add up
+                    const uint32_t cur = s.cell[a_hp];
+                    if (!rec_body(cur)) atomicCAS(&s.cell[a_hp], cur, cur | make_rec(k, (int)add) | kDirty);   // head-on: first claim wins
+                    else if (rec_owner(cur) == k) s.cell[a_hp] = (cur + add) | kDirty;   // self collision: values add up
                     // a collider's head value on ANOTHER snake's cell is dropped: the collider is
                     // deleted below and that cell counts as covered by the other body either way
                     a_size += ov ? 1 : 0;                             // :555 / :652
@@ -390,7 +413,7 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
                     bool cost = false;
                     if (valid && a_boosted) {
                         const float u = p.replay ? p.u_cost[(size_t)e * K + k]
-                                                 : unit_float(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiBoostCost, (uint32_t)k));
+                                                 : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiBoostCost, (uint32_t)k));
                         cost = u < p.boost_cost_prob;
                     }
                     if (k < 32) s.cost[k] = cost;
@@ -403,22 +426,24 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
                 const uint32_t stream = boost_phase ? kStreamMultiDeathBoost : kStreamMultiDeathRegular;
                 for (int q = tid; q < C; q += nthr) {
                     uint32_t rec = s.cell[q];
-                    if (!rec) continue;
+                    if (!rec_body(rec)) continue;
                     const int o = rec_owner(rec);
+                    bool food = false;
                     if (p.food_on_death && s.done[o]) {
                         const int y = fdiv(q, p.magic_S), x = q - y * S;
                         if (!(y == 1 || x == 0 || y == S - 1 || x == S - 1)) {   // sic: row 1 (:418)
                             const float u = p.replay ? (U ? U[(size_t)e * C + q] : 0.0f)
-                                                     : unit_float(draw_i(p.seed, p.step, (uint32_t)e, stream, (uint32_t)q));
-                            if (u > p.death_thr) s.food[q] = 1;
+                                                     : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, stream, (uint32_t)q));
+                            food = u > p.death_thr;
                         }
                     }
                     if (boost_phase && s.cost[o]) {
-                        if (rec_value(rec) == 1) { s.food[q] = 1; rec = 0u; }   // the tail becomes food
-                        else rec -= 1u;
+                        if (rec_value(rec) == 1) { food = true; rec = (rec & ~kLive) | kDirty; }   // the tail becomes food
+                        else rec = (rec - 1u) | kDirty;
                     }
-                    if (s.done[o]) rec = 0u;
+                    if (s.done[o]) rec = (rec & ~kLive) | kDirty;
                     s.cell[q] = rec;
+                    if (food) set_food(s, q);
                 }
             }
             if (warp == 0 && valid && a_done) { a_hp = -1; s.hp[k] = -1; }
@@ -427,13 +452,8 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
 
         // ---- _add_food (:368-410) ----
         {
-            int cnt = 0;
-            for (int q = tid; q < C; q += nthr) cnt += s.food[q];
-            cnt = group_sum<32>(cnt, 0xffffffffu);
-            if (lane == 0 && cnt) atomicAdd(&s.misc[0], cnt);
-            __syncthreads();
             const int nfood = s.misc[0];
-            auto cell_free = [&](int q) { return s.cell[q] == 0u && s.food[q] == 0; };
+            auto cell_free = [&](int q) { return (s.cell[q] & (kLive | kFood)) == 0u; };
             if (p.food_mode == 0) {                                   // only_one
                 if (nfood == 0 && tid == 0) {
                     int cell = -1;
@@ -441,7 +461,7 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
                     else {
                         const int I = S - 2;
                         for (uint32_t t = 0; t < kRejectionTries && cell < 0; ++t) {
-                            const int cand = (int)bounded(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiFoodOne, t), (uint32_t)(I * I));
+                            const int cand = (int)bounded(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodOne, t), (uint32_t)(I * I));
                             const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
                             if (cell_free(q)) cell = q;
                         }
@@ -450,22 +470,22 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
                             for (int y = 1; y < S - 1; ++y)
                                 for (int x = 1; x < S - 1; ++x) nfree += cell_free(y * S + x);
                             if (nfree > 0) {
-                                int r = (int)bounded(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiFoodOne, kRejectionTries), (uint32_t)nfree);
+                                int r = (int)bounded(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodOne, kRejectionTries), (uint32_t)nfree);
                                 for (int y = 1; y < S - 1 && cell < 0; ++y)
                                     for (int x = 1; x < S - 1; ++x)
                                         if (cell_free(y * S + x) && r-- == 0) { cell = y * S + x; break; }
                             }
                         }
                     }
-                    if (cell >= 0) s.food[cell] = 1;
+                    if (cell >= 0) set_food(s, cell);
                 }
             } else if (nfood < 8 * K) {                               // random_rate, max_food :127
                 for (int q = tid; q < C; q += nthr) {
                     const int y = fdiv(q, p.magic_S), x = q - y * S;
                     if (y < 1 || y > S - 2 || x < 1 || x > S - 2 || !cell_free(q)) continue;
                     const float u = p.replay ? p.u_rate[(size_t)e * C + q]
-                                             : unit_float(draw_i(p.seed, p.step, (uint32_t)e, kStreamMultiFoodRate, (uint32_t)q));
-                    if (u < p.food_rate) s.food[q] = 1;
+                                             : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodRate, (uint32_t)q));
+                    if (u < p.food_rate) s.cell[q] |= kFood;            // (the count is not needed any more)
                 }
             }
         }
@@ -505,7 +525,7 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
         // ---- write the new state back ----
         if (s.misc[3]) {
             // non-canonical input: expand the whole compact form into the reference's tensors
-            store_floats(p.foods + (size_t)e * C, C, [&](int i) { return s.food[i] ? 1.0f : 0.0f; });
+            store_floats(p.foods + (size_t)e * C, C, [&](int i) { return (s.cell[i] & kFood) ? 1.0f : 0.0f; });
             store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
                 const int kk = fdiv(i, p.magic_C);
                 return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
@@ -513,7 +533,7 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
             store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
                 const int kk = fdiv(i, p.magic_C);
                 const uint32_t rec = s.cell[i - kk * C];
-                return (rec && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
+                return (rec_body(rec) && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
             });
         } else {
             // The compact form knows exactly which cells changed: only those are stored (the sectors
@@ -522,13 +542,13 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
             // to a few sectors per snake.
             float* bodies = p.bodies + (size_t)e * K * C;
             for (int q = tid; q < C; q += nthr) {
-                const uint32_t was = s.cell0[q], now = s.cell[q];
-                if (was != now) {
-                    const int ko = was ? rec_owner(was) : -1, kn = now ? rec_owner(now) : -1;
+                const uint32_t rec = s.cell[q];
+                if (rec & kDirty) {
+                    const int ko = rec_owner0(rec), kn = rec_body(rec) ? rec_owner(rec) : -1;
                     if (ko >= 0 && ko != kn) bodies[(size_t)ko * C + q] = 0.0f;
-                    if (kn >= 0) bodies[(size_t)kn * C + q] = (float)rec_value(now);
+                    if (kn >= 0) bodies[(size_t)kn * C + q] = (float)rec_value(rec);
                 }
-                if (s.food0[q] != s.food[q]) p.foods[(size_t)e * C + q] = s.food[q] ? 1.0f : 0.0f;
+                if (((rec >> 29) ^ (rec >> 30)) & 1u) p.foods[(size_t)e * C + q] = (rec & kFood) ? 1.0f : 0.0f;
             }
             if (valid && a_hp0 != a_hp) {
                 float* head = p.heads + ((size_t)e * K + k) * C;
@@ -538,6 +558,44 @@ __global__ void __launch_bounds__(256) multi_env_kernel(const MultiParams p) {
         }
     }
     write_multi_obs(p, s, e);
+}
+
+// MultiSnake.check_consistency (multi_snake.py:733-769) on the compact form: one CTA per env streams the
+// state once; the per-snake verdicts come from the head index, body maximum / sum and the cell records.
+__global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, int* report) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const MultiSmem s = carve(smem_raw, p.C);
+    const int C = p.C, K = p.K, e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
+    if (tid < 32) {
+        s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.sum[tid] = 0;
+        s.done[tid] = (tid < K) ? (p.dones[(size_t)e * K + tid] != 0) : 1;
+    }
+    if (tid < 8) s.misc[tid] = 0;
+    __syncthreads();
+    MultiParams q = p;
+    q.status = &s.misc[4];                      // overlap / multi-head of THIS env, not the env object's status word
+    load_env<true>(q, s, e);
+    __syncthreads();
+    if (tid < K) {
+        const int k = tid;
+        int bits = 0;
+        const int hp = s.hp[k], size = s.size[k], total = s.sum[k];
+        if (s.done[k]) {                        // :766-769 dead snakes hold nothing
+            if (hp >= 0 || total > 0) bits |= WURM_CHK_DEAD_NOT_ZERO;
+        } else {                                // :741-742 snake_consistency of the living
+            if (s.misc[5]) bits |= WURM_CHK_FOOD_VALUE;
+            if (s.hcnt[k] != 1) bits |= WURM_CHK_HEAD_COUNT;
+            if (total <= 0) bits |= WURM_CHK_NO_SNAKE;
+            const uint32_t rec = hp >= 0 ? s.cell[hp] : 0u;
+            if (!(hp >= 0 && rec_body(rec) && rec_owner(rec) == k && rec_value(rec) == size)) bits |= WURM_CHK_HEAD_NOT_AT_END;
+            if ((sqrtf(8.0f * (float)total + 1.0f) - 1.0f) / 2.0f != (float)size) bits |= WURM_CHK_BODY_VALUES;
+            if (total < 6) bits |= WURM_CHK_TOO_SHORT;
+            if (hp >= 0 && (rec & kFood)) bits |= WURM_CHK_HEAD_ON_FOOD;
+        }
+        if (k == 0 && (s.misc[4] & WURM_ST_OVERLAP)) bits |= WURM_CHK_OVERLAP;               // :746-758
+        if (bits) { atomicOr(report, bits); atomicAdd(report + 1, 1); atomicMin(report + 2, e); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -620,7 +678,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
                 d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
                 __syncthreads();
             } else {
-                const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
+                const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
                 const int n = block_rank(C, counts, -1, pick, spawnable);
                 if (n > 0) block_rank(C, counts, (int)bounded(r.x, (uint32_t)n), pick, spawnable);
                 d = (int)(r.y >> 30);
@@ -645,7 +703,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
             __syncthreads();
         } else {                                                      // :1016 one food on a free interior cell
             const int n = block_rank(C, counts, -1, pick, free_interior);
-            if (n > 0) block_rank(C, counts, (int)bounded(draw(p.seed, p.step, (uint32_t)e, kStreamMultiCreateFood).x, (uint32_t)n), pick, free_interior);
+            if (n > 0) block_rank(C, counts, (int)bounded(draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateFood).x, (uint32_t)n), pick, free_interior);
         }
         const int fcell = pick[0];
         store_floats(p.foods + (size_t)e * C, C, [&](int i) { return i == fcell ? 1.0f : 0.0f; });
@@ -669,7 +727,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
         if (p.colours_replay) {
             for (int c = 0; c < 3; ++c) col[c] = p.colours_replay[3 * ((size_t)e * K + tid) + c];
         } else {                                                      // get_n_colours :163-169
-            const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamMultiColour | ((uint32_t)tid << 4));
+            const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiColour | ((uint32_t)tid << 4));
             const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
             const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
             col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f); col[2] = (short)(c2 / norm * 192.0f);
@@ -691,7 +749,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
         d = p.respawn[2 * (size_t)e + 1];
         __syncthreads();
     } else {
-        const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamMultiRespawn);
+        const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiRespawn);
         const int n = block_rank(C, counts, -1, pick, spawnable);
         if (n > 0) block_rank(C, counts, (int)bounded(r.x, (uint32_t)n), pick, spawnable);
         d = (int)(r.y >> 30);
@@ -735,9 +793,9 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     return WURM_OK;
 }
 
-template <bool STEP>
-static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
-    auto kern = multi_env_kernel<STEP>;
+template <bool STEP, int THREADS>
+static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
+    auto kern = multi_env_kernel<STEP, THREADS>;
     const size_t smem = multi_smem_bytes(p.C, p.W, p.obs_mode);
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
     static size_t configured = 0;
@@ -746,9 +804,13 @@ static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
         if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(multi_env_kernel)");
         configured = smem;
     }
-    const int threads = p.C <= 1024 ? 128 : 256;
-    kern<<<p.E, threads, smem, stream>>>(p);
+    kern<<<p.E, THREADS, smem, stream>>>(p);
     return check_launch("multi_env_kernel");
+}
+
+template <bool STEP>
+static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
+    return p.C <= 1024 ? launch_multi_env_t<STEP, 128>(p, stream) : launch_multi_env_t<STEP, 256>(p, stream);
 }
 
 }  // namespace wurm
@@ -763,7 +825,8 @@ extern "C" int64_t wurm_multi_obs_elems(const WurmMultiCfg* cfg) {
 
 extern "C" int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions,
                                int action_bytes, const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step,
-                               const WurmMultiStepOut* out, int32_t* status, int64_t* stats, void* stream) {
+                               const uint64_t* step_dev, const WurmMultiStepOut* out, int32_t* status, int64_t* stats,
+                               void* stream) {
     MultiParams p = {};
     if (int rc = plan_multi(cfg, state, &p)) return rc;
     if (!actions || !out || !status) return fail(WURM_E_INVALID, "NULL pointer");
@@ -787,7 +850,7 @@ extern "C" int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* st
         if (p.food_mode == 0 && !p.food_cell) return fail(WURM_E_INVALID, "replay: food_cell is NULL");
         if (p.food_mode == 1 && !p.u_rate) return fail(WURM_E_INVALID, "replay: u_rate is NULL");
     }
-    p.seed = seed; p.step = step;
+    p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     p.rewards = out->rewards; p.snake_col = out->snake_collision; p.edge_col = out->edge_collision;
     p.food_cons = out->food; p.sizes = out->size; p.all_done = out->all_done; p.obs = out->obs;
     p.dones_out = out->dones; p.boost_out = out->boost;
@@ -815,12 +878,13 @@ extern "C" int wurm_multi_env_images(const WurmMultiCfg* cfg, const WurmMultiSta
 }
 
 extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const uint8_t* env_done,
-                                const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, int32_t* status,
-                                void* stream) {
+                                const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                int32_t* status, void* stream) {
     MultiParams p = {};
     if (int rc = plan_multi(cfg, state, &p)) return rc;
     if (!env_done || !status) return fail(WURM_E_INVALID, "NULL pointer");
     p.env_done = env_done; p.seed = seed; p.step = step; p.status = status;
+    p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     if (draws) {
         p.replay = 1; p.create = draws->create; p.respawn = draws->respawn; p.colours_replay = draws->colours;
         if (!p.create || (p.respawn_any && !p.respawn) || (p.colour_random && !p.colours_replay))
@@ -830,4 +894,19 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
     const size_t smem = ((p.C + 15) & ~15) + (size_t)(threads + 1 + 4 + 64) * 4 + 16;
     multi_reset_kernel<<<p.E, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
+}
+
+extern "C" int wurm_multi_check(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* report, void* stream) {
+    MultiParams p = {};
+    if (int rc = plan_multi(cfg, state, &p)) return rc;
+    if (!report) return fail(WURM_E_INVALID, "NULL pointer");
+    const size_t smem = multi_smem_bytes(p.C, p.W, p.obs_mode);
+    static size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(multi_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(multi_check_kernel)");
+        configured = smem;
+    }
+    multi_check_kernel<<<p.E, p.C <= 1024 ? 128 : 256, smem, (cudaStream_t)stream>>>(p, report);
+    return check_launch("multi_check_kernel");
 }

@@ -6,14 +6,17 @@
 // Design:
 //   * one CTA per tile of T consecutive environments; the tile's (T,3,S,S) fp32 state is ONE
 //     contiguous span of global memory, moved to shared memory with a single TMA bulk copy
-//     (cp.async.bulk + mbarrier) and written back with a single bulk store -- every state byte
-//     crosses HBM exactly once in each direction, no per-element load/store instructions;
+//     (cp.async.bulk + mbarrier, SASS UBLKCP) -- no per-element load instructions for state;
 //   * G consecutive lanes (a power of two, <=32) own one environment while it sits in shared
 //     memory; reductions over the grid (snake size, head cell, free-cell ranking for the food
 //     respawn) are warp shuffles / ballots restricted to the group's lane mask;
 //   * the reference's conv2d filters become index arithmetic on the head cell;
-//   * the observation is rendered from the shared tile straight into the caller's buffer with
-//     coalesced stores (for 'raw' it is a second bulk store of the same tile);
+//   * a step changes O(snake length) cells of an env: only those are written back, cell by cell,
+//     where the shared copy is updated (the sectors were just loaded through L2, so the partial
+//     writes merge there) -- HBM write traffic drops from the full state to a few sectors per env;
+//   * partial_n observations are rendered by the env's own lane group into a shared staging area
+//     and leave as ONE bulk store per tile (the tile's observations are contiguous too); `raw` is
+//     a bulk store of the tile itself; the full-grid modes are coalesced row stores;
 //   * no tensor cores: nothing on this path is a dense contraction.
 #include <math.h>
 #include <stdlib.h>
@@ -36,6 +39,7 @@ struct SingleParams {
     int32_t* status;
     unsigned long long* stats;   // nullable: WURM_STATS_SLOTS x WURM_STATS_FIELDS counters
     uint64_t seed, step;
+    const unsigned long long* step_dev;   // nullable: added to `step` on the device (CUDA-graph replays)
     int N, S, C;          // envs, grid side, cells per channel
     int T;                // envs per tile (= per CTA)
     int action_bytes;     // 2 / 4 / 8
@@ -46,6 +50,8 @@ struct SingleParams {
     int stage_bytes;      // shared staging area of the tile's partial observations (0 = none)
     int bulk_ok;          // base pointers 16-byte aligned and full-tile byte count a multiple of 16
 };
+
+__device__ __forceinline__ uint64_t call_counter(const SingleParams& p) { return p.step + (p.step_dev ? *p.step_dev : 0ull); }
 
 __device__ __forceinline__ int div_S(int q, uint32_t magic) { return (int)__umulhi((uint32_t)q, magic); }
 
@@ -225,13 +231,13 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
             const int I = S - 2;
             cell = -1;
             for (uint32_t t = 0; t < kRejectionTries && cell < 0; ++t) {
-                const int cand = (int)bounded(draw_i(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood, t), (uint32_t)(I * I));
+                const int cand = (int)bounded(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamSingleStepFood, t), (uint32_t)(I * I));
                 const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
                 if (env[q] + env[C + q] + env[2 * C + q] < kEps) cell = q;
             }
             if (cell < 0)
                 cell = pick_free_cell<G>(env, S, C, p.magic_S,
-                                         draw_i(p.seed, p.step, (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
+                                         draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
         }
         if (l == 0 && cell >= 0) { const float f = food[cell] + 1.0f; food[cell] = f; gfood[cell] = f; }
     }
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p,
         if (spawn) {
             y = spawn[4 * (size_t)e]; x = spawn[4 * (size_t)e + 1]; d = spawn[4 * (size_t)e + 2]; cell = spawn[4 * (size_t)e + 3];
         } else {
-            const uint4 r = draw(p.seed, p.step, (uint32_t)e, kStreamSingleReset);
+            const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamSingleReset);
             y = 4 + (int)bounded(r.x, (uint32_t)(S - 8));            // :358 randint(4, S-4)
             x = 4 + (int)bounded(r.y, (uint32_t)(S - 8));            // :359
             d = (int)(r.z >> 30);                                    // :366 randint(4)
@@ -466,6 +472,44 @@ __global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p,
     }
 }
 
+// wurm/utils.py:113-178 (snake_consistency + env_consistency) as one pass: one warp per env streams its
+// 3*S*S floats straight from HBM (coalesced), seven running sums are reduced with shuffles, and the
+// verdict of all envs is folded into a 3-word report with atomics.
+__global__ void __launch_bounds__(256) single_check_kernel(const float* __restrict__ envs, const uint8_t* __restrict__ skip,
+                                                           int N, int C, int* report) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= N || (skip && skip[e])) return;
+    const float* env = envs + (size_t)e * 3 * C;
+    float sum_food = 0.0f, sum_head = 0.0f, sum_body = 0.0f, max_body = -INFINITY, head_body = 0.0f, head_food = 0.0f;
+    int bad_food = 0;
+    for (int q = lane; q < C; q += 32) {
+        const float f = env[q], h = env[C + q], b = env[2 * C + q];
+        bad_food += !(f == 0.0f || f == 1.0f);
+        sum_food += f; sum_head += h; sum_body += b;
+        max_body = fmaxf(max_body, b);
+        head_body += h * b; head_food += h * f;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_food += __shfl_xor_sync(0xffffffffu, sum_food, o); sum_head += __shfl_xor_sync(0xffffffffu, sum_head, o);
+        sum_body += __shfl_xor_sync(0xffffffffu, sum_body, o); head_body += __shfl_xor_sync(0xffffffffu, head_body, o);
+        head_food += __shfl_xor_sync(0xffffffffu, head_food, o); bad_food += __shfl_xor_sync(0xffffffffu, bad_food, o);
+        max_body = fmaxf(max_body, __shfl_xor_sync(0xffffffffu, max_body, o));
+    }
+    if (lane == 0) {
+        int bits = 0;
+        if (bad_food) bits |= WURM_CHK_FOOD_VALUE;
+        if (sum_head != 1.0f) bits |= WURM_CHK_HEAD_COUNT;
+        if (!(sum_body > 0.0f)) bits |= WURM_CHK_NO_SNAKE;
+        if (head_body != max_body) bits |= WURM_CHK_HEAD_NOT_AT_END;
+        if ((sqrtf(8.0f * sum_body + 1.0f) - 1.0f) / 2.0f != max_body) bits |= WURM_CHK_BODY_VALUES;
+        if (sum_body < 6.0f) bits |= WURM_CHK_TOO_SHORT;
+        if (head_food != 0.0f) bits |= WURM_CHK_HEAD_ON_FOOD;
+        if (sum_food != 1.0f) bits |= WURM_CHK_FOOD_COUNT;
+        if (bits) { atomicOr(report, bits); atomicAdd(report + 1, 1); atomicMin(report + 2, e); }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -492,10 +536,10 @@ static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* 
         if (g >= 1 && g <= 32 && (g & (g - 1)) == 0) G = g;
     }
     const int per_warp = 32 / G;                        // envs per warp
-    // partial observations are staged next to the tile: small CTAs (measured best on B200: 64 threads,
-    // ~20 KB, ~10 resident per SM overlapping each other's load / compute / store; see
-    // profiles/r01_sweep_single_c2.txt); otherwise up to 256 threads and 64 KB tiles
-    int max_threads = stage_env_bytes ? 64 : 256, budget = (stage_env_bytes ? 44 : 64) * 1024;
+    // partial observations are staged next to the tile: one-warp CTAs (measured best on B200: 32 threads,
+    // ~10 KB, ~20 resident per SM overlapping each other's load / compute / store, no CTA barrier stalls; see
+    // profiles/r01_sweep_single_c2*.txt); otherwise up to 256 threads and 64 KB tiles
+    int max_threads = stage_env_bytes ? 32 : 256, budget = (stage_env_bytes ? 44 : 64) * 1024;
     if (const char* v = getenv("WURM_SINGLE_THREADS")) max_threads = atoi(v);
     if (const char* v = getenv("WURM_SINGLE_SMEM_KB")) budget = atoi(v) * 1024;
     if (max_threads < 32) max_threads = 32;
@@ -567,7 +611,8 @@ extern "C" int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg) {
 }
 
 extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
-                                const int32_t* food_cell_replay, uint64_t seed, uint64_t step, float* obs, float* reward,
+                                const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                float* obs, float* reward,
                                 uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats,
                                 void* stream) {
     SingleParams p = {};
@@ -577,7 +622,8 @@ extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* act
     if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
     if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
-    p.seed = seed; p.step = step; p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
+    p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
+    p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
     p.edge_col = edge_col; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
     return dispatch_tile<true>(p, L, (cudaStream_t)stream);
@@ -595,14 +641,23 @@ extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, 
 }
 
 extern "C" int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* spawn_replay,
-                                 uint64_t seed, uint64_t step, void* stream) {
+                                 uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream) {
     SingleParams p = {};
     SingleLaunch L;
     if (int rc = plan_single(cfg, &p, &L)) return rc;
     if (!envs || !done_mask) return fail(WURM_E_INVALID, "NULL pointer");
-    p.envs = envs; p.seed = seed; p.step = step;
+    p.envs = envs; p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     const int warps_per_block = 8;
     const int blocks = (p.N + 32 * warps_per_block - 1) / (32 * warps_per_block);
     single_reset_kernel<<<blocks, 32 * warps_per_block, 0, (cudaStream_t)stream>>>(p, done_mask, spawn_replay);
     return check_launch("single_reset_kernel");
+}
+
+extern "C" int wurm_single_check(const WurmSingleCfg* cfg, const float* envs, const uint8_t* skip, int32_t* report,
+                                 void* stream) {
+    if (!cfg || !envs || !report) return fail(WURM_E_INVALID, "NULL pointer");
+    if (cfg->num_envs <= 0 || cfg->size < 1) return fail(WURM_E_INVALID, "bad num_envs / size");
+    const int warps = 8, blocks = (cfg->num_envs + warps - 1) / warps;
+    single_check_kernel<<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(envs, skip, cfg->num_envs, cfg->size * cfg->size, report);
+    return check_launch("single_check_kernel");
 }

@@ -94,6 +94,8 @@ class MultiSnake(object):
             seed = int(torch.randint(0, 2 ** 62, ()).item())    # follows torch.manual_seed
         self.seed = seed
         self._draws = 0
+        # device-side addend of the call counter: stays 0 in normal use, bumped between CUDA-graph replays
+        self._draws_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
 
@@ -315,7 +317,8 @@ class MultiSnake(object):
         with torch.cuda.device(dev):
             _lib.check(self._lib.wurm_multi_step(
                 ctypes.byref(cfg), ctypes.byref(st), act_ptrs, _ACTION_BYTES[dtype],
-                ctypes.byref(dr) if dr is not None else None, self.seed, self._draws, ctypes.byref(out),
+                ctypes.byref(dr) if dr is not None else None, self.seed, self._draws, _ptr(self._draws_dev),
+                ctypes.byref(out),
                 _ptr(self._status), _ptr(self._stats), self._stream()))
 
         self.rewards = rewards.view(E * K)
@@ -357,7 +360,7 @@ class MultiSnake(object):
         with torch.cuda.device(dev):
             _lib.check(self._lib.wurm_multi_reset(ctypes.byref(cfg), ctypes.byref(st), _ptr(env_done),
                                                   ctypes.byref(dr) if dr is not None else None, self.seed, self._draws,
-                                                  _ptr(self._status), self._stream()))
+                                                  _ptr(self._draws_dev), _ptr(self._status), self._stream()))
 
     def _create_all(self, draws=None):
         """__init__'s _create_envs(num_envs) (reference :113, :996-1019)."""
@@ -391,21 +394,15 @@ class MultiSnake(object):
     # invariants and display (off the hot path)
     # ------------------------------------------------------------------------------------------
     def check_consistency(self):
-        """The reference's invariants (reference :733-769 + wurm/utils.py:113-164 snake_consistency)."""
-        from ..utils import snake_consistency
-        E, K, S = self.num_envs, self.num_snakes, self.size
-        _envs = torch.cat([self.foods.repeat_interleave(K, dim=0), self.heads, self.bodies], dim=1)
-        snake_consistency(_envs[~self.dones].round())
-
-        overlapping = self.bodies.view(E, K, S, S).gt(EPS).sum(dim=1).view(E, -1).max(dim=-1)[0].gt(1)
-        if torch.any(overlapping):
-            raise RuntimeError('An environment contains overlapping snakes')
-
-        if not torch.all(self.heads.view(E, K, S, S).sum(dim=1) <= K):
-            raise RuntimeError('An environment contains more snakes than it should.')
-
-        if not _envs[self.dones][:, 1:].sum() == 0:
-            raise RuntimeError('Dead snake contains non-zero elements.')
+        """The reference's invariants (reference :733-769 + wurm/utils.py:113-164 snake_consistency on the
+        living snakes), as one fused kernel and one host sync."""
+        cfg = self._cfg(None)
+        st = self._state()
+        dev = self.foods.device
+        report = torch.tensor([0, 0, 2 ** 31 - 1, 0], dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.wurm_multi_check(ctypes.byref(cfg), ctypes.byref(st), _ptr(report), self._stream()))
+        _lib.raise_on_report(report.tolist())
         self.check_status()
 
     def render(self, mode: str = 'human', env: int = None):

@@ -80,6 +80,8 @@ class SingleSnake(object):
             seed = int(torch.randint(0, 2 ** 62, ()).item())    # follows torch.manual_seed
         self.seed = seed
         self._draws = 0          # Philox call counter: one tick per call that may draw
+        # device-side addend of the call counter: stays 0 in normal use, bumped between CUDA-graph replays
+        self._draws_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         # episode statistics accumulated by the step kernel (see `stats`)
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
@@ -144,6 +146,14 @@ class SingleSnake(object):
             all_reduce_stats(totals, None if reduce_group is True else reduce_group)
         return dict(zip(_lib.STAT_NAMES, totals.tolist()))
 
+    def check_consistency(self, skip: torch.Tensor = None):
+        """env_consistency (reference wurm/utils.py:167-178) of every env whose `skip` flag is not set, in one
+        fused kernel -- what the reference driver does with `env_consistency(env.envs[~done])` (main.py:215),
+        without the boolean-mask gather.  Raises the reference's RuntimeError messages."""
+        from ..utils import _fused_check
+        _lib.raise_on_report(_fused_check(self._state(), skip))
+        self.check_status()
+
     def check_status(self):
         """Raises if a kernel met a state outside the supported set since the last check (one sync)."""
         st = int(self._status.item())
@@ -199,7 +209,7 @@ class SingleSnake(object):
         with torch.cuda.device(dev):
             _lib.check(self._lib.wurm_single_step(
                 ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
-                self.seed, self._draws, _ptr(obs), _ptr(reward), _ptr(done), _ptr(self_collision),
+                self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done), _ptr(self_collision),
                 _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
         if host_actions is not None:
             host_actions.copy_(actions, non_blocking=True)      # the sanitised actions (reference :222)
@@ -245,7 +255,7 @@ class SingleSnake(object):
         self._draws += 1
         with torch.cuda.device(envs.device):
             _lib.check(self._lib.wurm_single_reset(ctypes.byref(cfg), _ptr(envs), _ptr(mask), _ptr(spawn_replay),
-                                                   self.seed, self._draws, self._stream()))
+                                                   self.seed, self._draws, _ptr(self._draws_dev), self._stream()))
 
     def _create_envs(self, num_envs: int, *, spawn_replay: torch.Tensor = None):
         """Vectorised environment creation (reference :344-387)."""

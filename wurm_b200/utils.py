@@ -36,10 +36,37 @@ def determine_orientations(envs: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _fused_check(envs: torch.Tensor, skip=None):
+    """One launch of wurm_single_check on a contiguous fp32 CUDA batch; returns the 3-int report (one sync)."""
+    import ctypes
+    from . import _lib
+    n, _, S, _ = envs.shape
+    report = torch.tensor([0, 0, 2 ** 31 - 1, 0], dtype=torch.int32, device=envs.device)
+    cfg = _lib.WurmSingleCfg(n, S, _lib.OBS_NONE, 0)
+    if skip is not None:
+        skip = skip.reshape(-1)
+        if skip.dtype != torch.bool or skip.device != envs.device or not skip.is_contiguous():
+            skip = (skip != 0).to(envs.device).contiguous()
+    with torch.cuda.device(envs.device):
+        _lib.check(_lib.lib().wurm_single_check(ctypes.byref(cfg), envs.data_ptr(), None if skip is None else skip.data_ptr(),
+                                                report.data_ptr(),
+                                                ctypes.c_void_p(torch.cuda.current_stream(envs.device).cuda_stream)))
+    return report.tolist()
+
+
+def _is_fusable(envs):
+    return envs.is_cuda and envs.dtype == torch.float32 and envs.dim() == 4 and envs.shape[1] == 3 and envs.is_contiguous()
+
+
 def snake_consistency(envs: torch.Tensor):
-    """Invariants of a 3-channel single-snake view (reference wurm/utils.py:113-164)."""
+    """Invariants of a 3-channel single-snake view (reference wurm/utils.py:113-164).  Contiguous fp32 CUDA
+    batches go through the fused checker kernel (one launch, one sync); anything else through torch ops."""
     n = envs.shape[0]
     if n == 0:
+        return
+    if _is_fusable(envs):
+        from . import _lib
+        _lib.raise_on_report(_fused_check(envs), only=127)
         return
     f, h, b = food(envs), head(envs), body(envs)
     if not torch.all((f == 0) | (f == 1)):
@@ -63,9 +90,13 @@ def snake_consistency(envs: torch.Tensor):
 
 def env_consistency(envs: torch.Tensor):
     """snake_consistency plus exactly one food per env (reference wurm/utils.py:167-178)."""
-    snake_consistency(envs)
     n = envs.shape[0]
     if n == 0:
         return
+    if _is_fusable(envs):
+        from . import _lib
+        _lib.raise_on_report(_fused_check(envs))
+        return
+    snake_consistency(envs)
     if not torch.all(food(envs).reshape(n, -1).sum(dim=-1) == 1):
         raise RuntimeError('An environment doesn\'t contain exactly one food instance')
