@@ -93,6 +93,17 @@ int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int a
                      uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status,
                      int64_t* stats /* nullable */, void* stream);
 
+/* Fused fast path: wurm_single_step followed by wurm_single_reset(done) in ONE launch -- the pair the
+ * reference's driver issues every iteration (experiments/main.py:212-227).  Outputs are those of the
+ * step (the observation of an env that just ended is its terminal one, which is what main.py feeds
+ * its policy next, :227); the state left in `envs` is the one after the reset.  Draws: the step's with
+ * call counter `step`, the reset's with `step` + 1, i.e. bit-identical to the two calls in sequence.
+ *   spawn_replay (N,4) int32 or NULL: as for wurm_single_reset. */
+int wurm_single_step_reset(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
+                           const int32_t* food_cell_replay, const int32_t* spawn_replay, uint64_t seed, uint64_t step,
+                           const uint64_t* step_dev, float* obs, float* reward, uint8_t* done, uint8_t* self_col,
+                           uint8_t* edge_col, int32_t* status, int64_t* stats /* nullable */, void* stream);
+
 /* Replaces the state update of SingleSnake.reset / _create_envs (single_snake.py:322-337, 344-387):
  * envs whose done_mask byte is non-zero are re-created, all others untouched.
  *   spawn_replay (N,4) int32 or NULL: rows (y, x, dir, food_cell), read for done envs only.     */

@@ -313,3 +313,43 @@ def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
         assert_same(np_(static_actions), np_(a), f'step {t}: sanitised actions')
         plain.reset(done2, return_observations=False)
         assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')
+
+
+@pytest.mark.parametrize('N,S,mode', [(1000, 9, 'partial_2'), (300, 12, 'default'), (130, 36, 'one_channel')])
+def test_fused_step_reset_equals_step_then_reset(N, S, mode):
+    """step(a, auto_reset=True) == step(a); reset(done): same outputs, same state afterwards, same draws."""
+    two_calls = make_env(N, S, mode, seed=55)
+    fused = make_env(N, S, mode, seed=55)
+    g = torch.Generator().manual_seed(8)
+    for t in range(30):
+        a = torch.randint(0, 4, (N,), generator=g).to(DEV)
+        a2 = a.clone()
+        obs, reward, done, info = two_calls.step(a)
+        two_calls.reset(done, return_observations=False)
+        obs_f, reward_f, done_f, info_f = fused.step(a2, auto_reset=True)
+        tag = f'step {t}: '
+        assert_same(np_(obs_f), np_(obs), tag + 'observation (terminal for finished envs)')
+        assert_same(np_(reward_f), np_(reward), tag + 'reward')
+        assert_same(np_(done_f), np_(done), tag + 'done')
+        assert_same(np_(a2), np_(a), tag + 'sanitised actions')
+        assert_same(np_(info_f['edge_collision']), np_(info['edge_collision']), tag + 'edge_collision')
+        assert_same(np_(fused.envs), np_(two_calls.envs), tag + 'state after reset')
+    assert fused._draws == two_calls._draws
+
+
+@pytest.mark.parametrize('i', [i for i in range(len(SINGLE)) if 'init_spawn' in SINGLE[i] and bool(SINGLE[i]['0/did_reset'])])
+def test_fused_step_reset_golden_replay(i):
+    """The fused launch against the reference's recorded step+reset trajectories (both tapes replayed)."""
+    tr = SINGLE[i]
+    N, S, mode = tr.N, tr.S, tr.mode
+    env = make_env(N, S, mode, manual_setup=True)
+    env.envs = env._create_envs(N, spawn_replay=torch.from_numpy(tr['init_spawn']))
+    for t in range(tr.steps):
+        a = torch.from_numpy(tr[f'{t}/actions_in'].copy()).to(DEV)
+        obs, reward, done, info = env.step(a, auto_reset=True, food_cell_replay=torch.from_numpy(tr[f'{t}/food_cell']),
+                                           spawn_replay=torch.from_numpy(tr[f'{t}/spawn']))
+        tag = f'trajectory {i} ({mode}, S={S}) step {t}: '
+        assert_same(np_(obs), tr[f'{t}/obs'], tag + 'observation')
+        assert_same(np_(reward).reshape(-1), tr[f'{t}/reward'], tag + 'reward')
+        assert_same(np_(done).reshape(-1).astype(np.uint8), tr[f'{t}/done'], tag + 'done')
+        assert_same(np_(env.envs), tr[f'{t}/reset_envs'].astype(np.float32), tag + 'envs after the fused reset')

@@ -18,7 +18,8 @@ STAT_NAMES = ['env_steps', 'episodes', 'reward', 'self_collisions', 'edge_collis
 OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1, 0, 1, 2, 3, 4
 
 # every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
-SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_reset',
+SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_step_reset',
+           'wurm_single_reset',
            'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_reset', 'wurm_multi_observe',
            'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check']
 CHECK_REPORT = 4
@@ -96,6 +97,8 @@ def lib():
     L.wurm_single_obs_elems.argtypes = [cfg]
     L.wurm_single_step.restype = i32
     L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_step_reset.restype = i32
+    L.wurm_single_step_reset.argtypes = [cfg, vp, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.wurm_single_reset.restype = i32
     L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp, vp]
     L.wurm_single_observe.restype = i32

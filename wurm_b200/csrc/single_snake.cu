@@ -40,6 +40,8 @@ struct SingleParams {
     unsigned long long* stats;   // nullable: WURM_STATS_SLOTS x WURM_STATS_FIELDS counters
     uint64_t seed, step;
     const unsigned long long* step_dev;   // nullable: added to `step` on the device (CUDA-graph replays)
+    int auto_reset;       // fused step+reset: envs that end this step are re-created by the same launch
+    const int32_t* spawn; // (N,4) replayed (y, x, dir, food_cell) of the fused / stand-alone reset, or NULL
     int N, S, C;          // envs, grid side, cells per channel
     int T;                // envs per tile (= per CTA)
     int action_bytes;     // 2 / 4 / 8
@@ -121,6 +123,46 @@ __device__ __noinline__ int pick_free_cell(const float* env, int S, int C, uint3
         r -= cnt;
     }
     return -1;
+}
+
+// single_snake.py:344-387 _create_envs for env e: seed cell (y, x), direction d and food cell of the new
+// env, replayed from `spawn` or drawn from Philox with call counter `ctr`.
+__device__ __forceinline__ void new_env_layout(const SingleParams& p, const int32_t* spawn, uint64_t ctr, int e, int& tail,
+                                               int& mid, int& hd, int& cell) {
+    const int S = p.S;
+    int y, x, d;
+    if (spawn) {
+        y = spawn[4 * (size_t)e]; x = spawn[4 * (size_t)e + 1]; d = spawn[4 * (size_t)e + 2]; cell = spawn[4 * (size_t)e + 3];
+    } else {
+        const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamSingleReset);
+        y = 4 + (int)bounded(r.x, (uint32_t)(S - 8));                // :358 randint(4, S-4)
+        x = 4 + (int)bounded(r.y, (uint32_t)(S - 8));                // :359
+        d = (int)(r.z >> 30);                                        // :366 randint(4)
+        // :384 one free interior cell: the r-th interior cell in raster order, skipping the three snake
+        // cells (all interior because 4 <= y,x < S-4)
+        const int I = S - 2;
+        int s0 = (y - off_y(d) - 1) * I + (x - off_x(d) - 1), s1 = (y - 1) * I + (x - 1),
+            s2 = (y + off_y(d) - 1) * I + (x + off_x(d) - 1);
+        if (s0 > s2) { const int tmp = s0; s0 = s2; s2 = tmp; }      // s1 is always the middle one
+        int rr = (int)bounded(r.w, (uint32_t)(I * I - 3));
+        if (rr >= s0) ++rr;
+        if (rr >= s1) ++rr;
+        if (rr >= s2) ++rr;
+        const int fy = rr / I;
+        cell = (fy + 1) * S + (rr - fy * I + 1);
+    }
+    tail = (y - off_y(d)) * S + (x - off_x(d)); mid = y * S + x; hd = (y + off_y(d)) * S + (x + off_x(d));
+}
+
+// value of element i of the (3,S,S) state of a freshly created env (:372-385 LENGTH_3_SNAKES stamp, head, food)
+__device__ __forceinline__ float new_env_value(int i, int C, int tail, int mid, int hd, int cell) {
+    float v = 0.0f;
+    if (i == cell) v = 1.0f;
+    if (i == C + hd) v = 1.0f;
+    if (i == 2 * C + tail) v = 1.0f;
+    if (i == 2 * C + mid) v = 2.0f;
+    if (i == 2 * C + hd) v = 3.0f;
+    return v;
 }
 
 // single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
@@ -255,6 +297,18 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
         }
     }
     __syncwarp(gm);                                                  // lane 0's cell updates -> the group's render
+    if (p.auto_reset && (sc || !interior)) {
+        // Fused reset (:322-337): the env ended, re-create it in HBM right away.  The shared copy keeps the
+        // terminal state (the observation returned by step is the terminal one, and it is what the
+        // reference's driver feeds its policy next, main.py:227); HBM holds exactly that state at this
+        // point, so only the cells whose value differs in the new env are written.
+        int tail, mid, hd, cell;
+        new_env_layout(p, p.spawn, call_counter(p) + 1, e, tail, mid, hd, cell);
+        for (int i = l; i < 3 * C; i += G) {
+            const float nv = new_env_value(i, C, tail, mid, hd, cell);
+            if (env[i] != nv) gfood[i] = nv;
+        }
+    }
     return np;
 }
 
@@ -433,42 +487,14 @@ __global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p,
     if (e_base >= p.N) return;
     const int e_mine = e_base + lane;
     unsigned todo = __ballot_sync(0xffffffffu, e_mine < p.N && done_mask[e_mine] != 0);
-    const int S = p.S, C = p.C;
+    const int C = p.C;
     while (todo) {
         const int e = e_base + __ffs(todo) - 1;
         todo &= todo - 1;
-        int y, x, d, cell;
-        if (spawn) {
-            y = spawn[4 * (size_t)e]; x = spawn[4 * (size_t)e + 1]; d = spawn[4 * (size_t)e + 2]; cell = spawn[4 * (size_t)e + 3];
-        } else {
-            const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamSingleReset);
-            y = 4 + (int)bounded(r.x, (uint32_t)(S - 8));            // :358 randint(4, S-4)
-            x = 4 + (int)bounded(r.y, (uint32_t)(S - 8));            // :359
-            d = (int)(r.z >> 30);                                    // :366 randint(4)
-            // :384 one free interior cell: the r-th interior cell in raster order, skipping the
-            // three snake cells (all interior because 4 <= y,x < S-4)
-            const int I = S - 2;
-            int s0 = (y - off_y(d) - 1) * I + (x - off_x(d) - 1), s1 = (y - 1) * I + (x - 1),
-                s2 = (y + off_y(d) - 1) * I + (x + off_x(d) - 1);
-            if (s0 > s2) { const int tmp = s0; s0 = s2; s2 = tmp; }  // s1 is always the middle one
-            int rr = (int)bounded(r.w, (uint32_t)(I * I - 3));
-            if (rr >= s0) ++rr;
-            if (rr >= s1) ++rr;
-            if (rr >= s2) ++rr;
-            const int fy = rr / I;
-            cell = (fy + 1) * S + (rr - fy * I + 1);
-        }
-        const int tail = (y - off_y(d)) * S + (x - off_x(d)), mid = y * S + x, hd = (y + off_y(d)) * S + (x + off_x(d));
+        int tail, mid, hd, cell;
+        new_env_layout(p, spawn, call_counter(p), e, tail, mid, hd, cell);
         float* env = p.envs + (size_t)e * 3 * C;
-        for (int i = lane; i < 3 * C; i += 32) {                     // :372-385 LENGTH_3_SNAKES stamp, head, food
-            float v = 0.0f;
-            if (i == cell) v = 1.0f;
-            if (i == C + hd) v = 1.0f;
-            if (i == 2 * C + tail) v = 1.0f;
-            if (i == 2 * C + mid) v = 2.0f;
-            if (i == 2 * C + hd) v = 3.0f;
-            env[i] = v;
-        }
+        for (int i = lane; i < 3 * C; i += 32) env[i] = new_env_value(i, C, tail, mid, hd, cell);
     }
 }
 
@@ -610,11 +636,10 @@ extern "C" int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg) {
     }
 }
 
-extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
-                                const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
-                                float* obs, float* reward,
-                                uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats,
-                                void* stream) {
+static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
+                            const int32_t* food_cell_replay, int auto_reset, const int32_t* spawn_replay, uint64_t seed,
+                            uint64_t step, const uint64_t* step_dev, float* obs, float* reward, uint8_t* done,
+                            uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, void* stream) {
     SingleParams p = {};
     SingleLaunch L;
     if (int rc = plan_single(cfg, &p, &L)) return rc;
@@ -622,11 +647,28 @@ extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* act
     if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
     if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
+    p.auto_reset = auto_reset; p.spawn = spawn_replay;
     p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
     p.edge_col = edge_col; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
     return dispatch_tile<true>(p, L, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
+                                const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                                float* obs, float* reward, uint8_t* done, uint8_t* self_col, uint8_t* edge_col,
+                                int32_t* status, int64_t* stats, void* stream) {
+    return single_step_impl(cfg, envs, actions, action_bytes, food_cell_replay, 0, nullptr, seed, step, step_dev, obs, reward,
+                            done, self_col, edge_col, status, stats, stream);
+}
+
+extern "C" int wurm_single_step_reset(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
+                                      const int32_t* food_cell_replay, const int32_t* spawn_replay, uint64_t seed,
+                                      uint64_t step, const uint64_t* step_dev, float* obs, float* reward, uint8_t* done,
+                                      uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, void* stream) {
+    return single_step_impl(cfg, envs, actions, action_bytes, food_cell_replay, 1, spawn_replay, seed, step, step_dev, obs,
+                            reward, done, self_col, edge_col, status, stats, stream);
 }
 
 extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream) {

@@ -183,7 +183,12 @@ class SingleSnake(object):
         """int16 (N,3,S,S) image, as displayed by render() (reference :104-128)."""
         return (self._observe('default') * 255).round().short()
 
-    def step(self, actions: torch.Tensor, *, food_cell_replay: torch.Tensor = None):
+    def step(self, actions: torch.Tensor, *, food_cell_replay: torch.Tensor = None, auto_reset: bool = False,
+             spawn_replay: torch.Tensor = None):
+        """reference :197-304.  `auto_reset=True` (an extension) fuses the `reset(done)` the reference's driver
+        issues right after every step (experiments/main.py:227) into the same launch: the returned observation,
+        reward, done and info are the step's (terminal observation for envs that just ended, as in the
+        reference's loop), `envs` holds the re-created environments; bit-identical to the two calls."""
         if actions.dtype not in (torch.short, torch.int, torch.long):
             raise TypeError('actions Tensor must be an integer type i.e. '
                             '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
@@ -205,12 +210,21 @@ class SingleSnake(object):
         edge_collision = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
         if food_cell_replay is not None:
             food_cell_replay = food_cell_replay.to(device=dev, dtype=torch.int32).contiguous()
+        if spawn_replay is not None:
+            spawn_replay = spawn_replay.to(device=dev, dtype=torch.int32).contiguous()
         self._draws += 1
         with torch.cuda.device(dev):
-            _lib.check(self._lib.wurm_single_step(
-                ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
-                self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done), _ptr(self_collision),
-                _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
+            if auto_reset:
+                _lib.check(self._lib.wurm_single_step_reset(
+                    ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
+                    _ptr(spawn_replay), self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
+                    _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
+                self._draws += 1            # the fused reset consumed the next counter value
+            else:
+                _lib.check(self._lib.wurm_single_step(
+                    ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
+                    self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
+                    _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
         if host_actions is not None:
             host_actions.copy_(actions, non_blocking=True)      # the sanitised actions (reference :222)
         info = {'self_collision': self_collision, 'edge_collision': edge_collision}

@@ -6,7 +6,8 @@ allocations, the Python between them).  `GraphedStepper` captures
 
     obs, reward, done, info = env.step(actions);  env.reset(done, return_observations=False)
 
-once into a CUDA graph and replays it: one `cudaGraphLaunch` per env step.  The kernels read their
+once into a CUDA graph and replays it: one `cudaGraphLaunch` per env step (for SingleSnake the pair is
+additionally fused into a single kernel, `wurm_single_step_reset`).  The kernels read their
 Philox call counter as `step + *step_dev` (include/wurm_b200.h); the graph bumps the device word
 after every replay, so replays draw fresh random numbers and a graphed rollout is bit-identical to the
 same rollout stepped call by call.
@@ -47,9 +48,9 @@ class GraphedStepper(object):
             out = (obs, rewards, dones, info)
             done = dones['__all__']
         else:
-            obs, reward, done, info = env.step(self.actions)
+            obs, reward, done, info = env.step(self.actions, auto_reset=self.auto_reset)   # fused step+reset launch
             out = (obs, reward, done, info)
-        if self.auto_reset:
+        if self.auto_reset and self.multi:
             env.reset(done, return_observations=False)
         if capturing:
             env._draws_dev.add_(2 if self.auto_reset else 1)      # one tick per step, one per reset

@@ -19,6 +19,9 @@ un-pipelined form of the same thing.
 import torch
 
 
+FUSED_RESET_MAX_ENVS = 1 << 16      # measured on B200: profiles/r01_small_batch.txt, r01_bench_C2_v5.json
+
+
 class Ticket(object):
     """Result of one submitted step; host tensors are valid after wait()."""
 
@@ -94,17 +97,21 @@ class HostStepper(object):
             uploaded = torch.cuda.Event()
             uploaded.record(self.h2d)
         compute.wait_event(uploaded)
+        fused = False
         if self.multi:
             obs, rewards, dones, info = self.env.step(dev_actions)
             reward_t = self.env.rewards.view(self.env.num_envs, self.env.num_snakes)
             done_t = self.env._step_dones
             env_done = dones['__all__']
         else:
-            obs, reward_t, done_t, info = self.env.step(dev_actions)
+            # below ~64K envs the step is launch-bound and the fused step+reset launch wins; above it the
+            # (instruction-bound) step kernel is better left alone and the cheap reset kernel follows it
+            fused = self.auto_reset and self.env.num_envs <= FUSED_RESET_MAX_ENVS
+            obs, reward_t, done_t, info = self.env.step(dev_actions, auto_reset=fused)
             env_done = done_t
         stepped = torch.cuda.Event()
         stepped.record(compute)
-        if self.auto_reset:
+        if self.auto_reset and (self.multi or not fused):
             self.env.reset(env_done, return_observations=False)
         self.d2h.wait_event(stepped)
         with torch.cuda.stream(self.d2h):
