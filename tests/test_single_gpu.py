@@ -353,3 +353,21 @@ def test_fused_step_reset_golden_replay(i):
         assert_same(np_(reward).reshape(-1), tr[f'{t}/reward'], tag + 'reward')
         assert_same(np_(done).reshape(-1).astype(np.uint8), tr[f'{t}/done'], tag + 'done')
         assert_same(np_(env.envs), tr[f'{t}/reset_envs'].astype(np.float32), tag + 'envs after the fused reset')
+
+
+def test_obs_out_renders_into_a_trajectory_buffer():
+    """step(..., obs_out=buffer[t]): the kernel writes the observation straight into the caller's buffer."""
+    N, S, T = 500, 9, 6
+    a = make_env(N, S, 'partial_2', seed=4)
+    b = make_env(N, S, 'partial_2', seed=4)
+    ring = torch.zeros((T, N, 75), device=DEV)
+    acts = torch.randint(0, 4, (T, N), generator=torch.Generator().manual_seed(4)).to(DEV)
+    for t in range(T):
+        obs, _, done, _ = a.step(acts[t].clone())
+        a.reset(done, return_observations=False)
+        obs_b, _, done_b, _ = b.step(acts[t].clone(), obs_out=ring[t])
+        b.reset(done_b, return_observations=False)
+        assert obs_b.data_ptr() == ring[t].data_ptr()
+        assert_same(np_(ring[t]), np_(obs), f'step {t}')
+    with pytest.raises(RuntimeError):
+        b.step(acts[0].clone(), obs_out=torch.zeros((N, 74), device=DEV))

@@ -599,49 +599,59 @@ __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// reset (multi_snake.py:771-831): one CTA per env; envs with nothing to do exit after K+1 bytes.
+// reset (multi_snake.py:771-831)
 // ---------------------------------------------------------------------------------------------
-// Block-wide: number of cells q < C with pred(q); if r >= 0 also the r-th such cell in raster order
-// (through *out).  `counts` is blockDim.x + 1 ints of shared scratch.
+// Block-wide uniform choice among the cells q < C with pred(q), in raster order: every thread counts its
+// contiguous chunk, a shuffle scan ranks the chunks, `rnd` picks a rank and the owning thread finds the
+// cell (written to *out).  Returns the number of candidate cells.  `counts`: >= 33 ints of shared scratch.
 template <typename P>
-__device__ __forceinline__ int block_rank(int C, int* counts, int r, int* out, P&& pred) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+__device__ __forceinline__ int block_pick(int C, int* counts, uint32_t rnd, int* out, P&& pred) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int chunk = (C + nthr - 1) / nthr, q0 = tid * chunk, q1 = min(C, q0 + chunk);
     int mine = 0;
     for (int q = q0; q < q1; ++q) mine += pred(q) ? 1 : 0;
-    counts[tid] = mine;
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int t = 0; t < nthr; ++t) { const int c = counts[t]; counts[t] = acc; acc += c; }
-        counts[nthr] = acc;
+    int incl = mine;                                                  // inclusive scan within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    if (lane == 31) counts[warp] = incl;
     __syncthreads();
-    const int total = counts[nthr];
-    if (r >= 0 && r < total && r >= counts[tid] && r < counts[tid] + mine) {
-        int left = r - counts[tid];
-        for (int q = q0; q < q1; ++q)
-            if (pred(q) && left-- == 0) { *out = q; break; }
+    int before = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = counts[w];
+        if (w < warp) before += c;
+        total += c;
+    }
+    const int first = before + incl - mine;                           // rank of this thread's first candidate
+    if (total > 0) {
+        const int r = (int)bounded(rnd, (uint32_t)total);
+        if (r >= first && r < first + mine) {
+            int left = r - first;
+            for (int q = q0; q < q1; ++q)
+                if (pred(q) && left-- == 0) { *out = q; break; }
+        }
     }
     __syncthreads();
     return total;
 }
 
-__global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// The reset of ONE env by the whole CTA (every thread calls it with the same e).
+__device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned char* smem_raw, int e) {
     const int C = p.C, K = p.K, S = p.S;
     uint8_t* occ = smem_raw;                                          // C occupancy bytes
     int* counts = reinterpret_cast<int*>(smem_raw + ((C + 15) & ~15)); // blockDim.x + 1
     int* pick = counts + blockDim.x + 1;                              // [0] chosen cell
     int* snake_cell = pick + 4;                                       // K
     int* snake_dir = snake_cell + 32;                                 // K
-    const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
 
     const bool recreate = p.env_done[e] != 0;
     int first_dead = -1, ndead = 0;
     for (int k = K - 1; k >= 0; --k)
         if (p.dones[(size_t)e * K + k]) { first_dead = k; ++ndead; }
-    if (!recreate && ndead == 0) return;                              // nothing to do for this env
+    if (!recreate && (ndead == 0 || !p.respawn_any)) return;          // nothing to do for this env
 
     auto inner = [&](int q) {
         const int y = fdiv(q, p.magic_S), x = q - y * S;
@@ -679,8 +689,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
                 __syncthreads();
             } else {
                 const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
-                const int n = block_rank(C, counts, -1, pick, spawnable);
-                if (n > 0) block_rank(C, counts, (int)bounded(r.x, (uint32_t)n), pick, spawnable);
+                block_pick(C, counts, r.x, pick, spawnable);
                 d = (int)(r.y >> 30);
             }
             const int cell = pick[0];
@@ -702,19 +711,35 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
             if (tid == 0) pick[0] = p.create[((size_t)e * (K + 1) + K) * 2];
             __syncthreads();
         } else {                                                      // :1016 one food on a free interior cell
-            const int n = block_rank(C, counts, -1, pick, free_interior);
-            if (n > 0) block_rank(C, counts, (int)bounded(draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateFood).x, (uint32_t)n), pick, free_interior);
+            block_pick(C, counts, draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateFood).x, pick, free_interior);
         }
         const int fcell = pick[0];
-        store_floats(p.foods + (size_t)e * C, C, [&](int i) { return i == fcell ? 1.0f : 0.0f; });
-        store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
+        // Write the new env.  An env is re-created when all its snakes are dead, i.e. (on a consistent state)
+        // its head and body grids are already all-zero: instead of storing (1+2K)*S*S values, the old tensors
+        // are scanned (cheap 128-bit loads) and only non-zero leftovers that differ from the new env are
+        // overwritten, then the 4K+1 cells of the new snakes and the new food are stored.
+        float* gfood = p.foods + (size_t)e * C;
+        float* ghead = p.heads + (size_t)e * K * C;
+        float* gbody = p.bodies + (size_t)e * K * C;
+        scan_nonzero(gfood, C, [&](int i, float v) { if (i != fcell) gfood[i] = 0.0f; (void)v; });
+        scan_nonzero(ghead, K * C, [&](int i, float v) {
             const int kk = fdiv(i, p.magic_C);
-            return snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, true) : 0.0f;
+            const float nv = snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, true) : 0.0f;
+            if (nv != v) ghead[i] = nv;
         });
-        store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
+        scan_nonzero(gbody, K * C, [&](int i, float v) {
             const int kk = fdiv(i, p.magic_C);
-            return snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, false) : 0.0f;
+            const float nv = snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, false) : 0.0f;
+            if (nv != v) gbody[i] = nv;
         });
+        if (tid == 0 && fcell >= 0) gfood[fcell] = 1.0f;
+        if (tid < K && snake_cell[tid] >= 0) {
+            const int cell = snake_cell[tid], d = snake_dir[tid];
+            const int y = fdiv(cell, p.magic_S), x = cell - y * S;
+            const int hd = (y + off_y(d)) * S + (x + off_x(d)), tl = (y - off_y(d)) * S + (x - off_x(d));
+            ghead[(size_t)tid * C + hd] = 1.0f;
+            gbody[(size_t)tid * C + hd] = 3.0f; gbody[(size_t)tid * C + cell] = 2.0f; gbody[(size_t)tid * C + tl] = 1.0f;
+        }
         if (tid < K) {
             if (snake_cell[tid] >= 0) p.orientations[(size_t)e * K + tid] = snake_dir[tid];   // :793
             p.dones[(size_t)e * K + tid] = 0;                                                 // :798
@@ -722,17 +747,6 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
         return;                                                       // every agent alive: no colours, no respawn
     }
 
-    if (p.colour_random && tid < K && p.dones[(size_t)e * K + tid]) { // :800-803 new colours for the dead
-        short* col = p.colours + 3 * ((size_t)e * K + tid);
-        if (p.colours_replay) {
-            for (int c = 0; c < 3; ++c) col[c] = p.colours_replay[3 * ((size_t)e * K + tid) + c];
-        } else {                                                      // get_n_colours :163-169
-            const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiColour | ((uint32_t)tid << 4));
-            const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
-            const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
-            col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f); col[2] = (short)(c2 / norm * 192.0f);
-        }
-    }
     if (!p.respawn_any) return;
 
     // :805-829 respawn the first dead snake of the env where there is room
@@ -750,8 +764,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
         __syncthreads();
     } else {
         const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiRespawn);
-        const int n = block_rank(C, counts, -1, pick, spawnable);
-        if (n > 0) block_rank(C, counts, (int)bounded(r.x, (uint32_t)n), pick, spawnable);
+        block_pick(C, counts, r.x, pick, spawnable);
         d = (int)(r.y >> 30);
     }
     const int cell = pick[0];
@@ -761,6 +774,51 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
     if (tid == 0) {
         p.orientations[n] = d;                                        // :828 even when the spawn failed
         p.dones[n] = cell < 0;                                        // :829
+    }
+}
+
+// One CTA looks at 32 consecutive envs: lane i of warp 0 reads env i's flags (coalesced), a ballot gives
+// the envs with work to do, and the CTA handles those one after another.  In the common case (nothing
+// died) an env costs K+1 bytes of traffic and a share of one warp instruction, not a CTA launch.
+__global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned todo_s;
+    const int e0 = blockIdx.x * 32, K = p.K;
+    if (threadIdx.x < 32) {
+        const int e = e0 + (int)threadIdx.x;
+        bool work = false;
+        if (e < p.E) {
+            const bool recreate = p.env_done[e] != 0;
+            bool any_dead = false;
+            if (!recreate)                                            // a re-created env has every snake alive again
+                for (int k = 0; k < K; ++k) {
+                    if (!p.dones[(size_t)e * K + k]) continue;
+                    any_dead = true;
+                    if (p.colour_random) {                            // :800-803 a new colour for every dead snake
+                        short* col = p.colours + 3 * ((size_t)e * K + k);
+                        if (p.colours_replay) {
+                            for (int c = 0; c < 3; ++c) col[c] = p.colours_replay[3 * ((size_t)e * K + k) + c];
+                        } else {                                      // get_n_colours :163-169
+                            const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiColour | ((uint32_t)k << 4));
+                            const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
+                            const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+                            col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f);
+                            col[2] = (short)(c2 / norm * 192.0f);
+                        }
+                    }
+                }
+            work = recreate || (any_dead && p.respawn_any);          // CTA-wide work: re-creation or a respawn
+        }
+        const unsigned todo = __ballot_sync(0xffffffffu, work);
+        if (threadIdx.x == 0) todo_s = todo;
+    }
+    __syncthreads();
+    unsigned todo = todo_s;
+    while (todo) {
+        const int e = e0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        __syncthreads();                                              // the previous env is done with shared memory
+        reset_one_env(p, smem_raw, e);
     }
 }
 
@@ -892,7 +950,7 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
     }
     const int threads = p.C <= 1024 ? 128 : 256;
     const size_t smem = ((p.C + 15) & ~15) + (size_t)(threads + 1 + 4 + 64) * 4 + 16;
-    multi_reset_kernel<<<p.E, threads, smem, (cudaStream_t)stream>>>(p);
+    multi_reset_kernel<<<(p.E + 31) / 32, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
 }
 

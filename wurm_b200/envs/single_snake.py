@@ -184,11 +184,13 @@ class SingleSnake(object):
         return (self._observe('default') * 255).round().short()
 
     def step(self, actions: torch.Tensor, *, food_cell_replay: torch.Tensor = None, auto_reset: bool = False,
-             spawn_replay: torch.Tensor = None):
+             spawn_replay: torch.Tensor = None, obs_out: torch.Tensor = None):
         """reference :197-304.  `auto_reset=True` (an extension) fuses the `reset(done)` the reference's driver
         issues right after every step (experiments/main.py:227) into the same launch: the returned observation,
         reward, done and info are the step's (terminal observation for envs that just ended, as in the
-        reference's loop), `envs` holds the re-created environments; bit-identical to the two calls."""
+        reference's loop), `envs` holds the re-created environments; bit-identical to the two calls.
+        `obs_out` (an extension): a contiguous fp32 CUDA tensor of the observation's shape -- e.g. one time slice of
+        a trajectory buffer or the policy's input buffer -- that the kernel renders into directly."""
         if actions.dtype not in (torch.short, torch.int, torch.long):
             raise TypeError('actions Tensor must be an integer type i.e. '
                             '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
@@ -203,7 +205,13 @@ class SingleSnake(object):
         if actions.device != dev or not actions.is_contiguous():
             host_actions, actions = actions, actions.to(dev, non_blocking=True).contiguous()
         cfg = self._cfg(self.observation_mode)
-        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=dev)
+        if obs_out is None:
+            obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=dev)
+        else:
+            obs = obs_out
+            if (tuple(obs.shape) != self._obs_shape(cfg) or obs.dtype != torch.float32 or obs.device != dev
+                    or not obs.is_contiguous()):
+                raise RuntimeError(f'obs_out must be a contiguous float32 tensor of shape {self._obs_shape(cfg)} on {dev}')
         reward = torch.empty(self.num_envs, dtype=torch.float32, device=dev)
         done = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
         self_collision = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
