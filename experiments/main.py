@@ -23,7 +23,7 @@ import torch
 from torch import nn
 from torch.distributions import Categorical
 
-from wurm_b200.envs import SingleSnake
+from wurm_b200.envs import SingleSnake, SimpleGridworld
 
 LOG_INTERVAL = 100
 
@@ -80,14 +80,18 @@ def main(argv=None):
     parser.add_argument('--seed', default=None, type=int)
     args = parser.parse_args(argv)
 
-    if args.env != 'snake':
-        raise ValueError('Unrecognised environment (this driver covers --env snake)')
+    if args.env not in ('snake', 'gridworld'):
+        raise ValueError('Unrecognised environment')
     if args.train:
         raise NotImplementedError('the A2C learner is outside the scope of wurm_b200 (DESIGN.md section 7); use --train false')
 
     render_args = {'size': args.render_window_size, 'num_rows': args.render_rows, 'num_cols': args.render_cols}
-    env = SingleSnake(num_envs=args.num_envs, size=args.size, device=args.device, observation_mode=args.observation,
-                      render_args=render_args, seed=args.seed)
+    if args.env == 'gridworld':                          # reference main.py:166-168
+        env = SimpleGridworld(num_envs=args.num_envs, size=args.size, start_location=(args.size // 2, args.size // 2),
+                              observation_mode=args.observation, device=args.device, seed=args.seed)
+    else:
+        env = SingleSnake(num_envs=args.num_envs, size=args.size, device=args.device, observation_mode=args.observation,
+                          render_args=render_args, seed=args.seed)
 
     state = env.reset()
     if args.agent == 'random':
@@ -110,7 +114,7 @@ def main(argv=None):
 
         state, reward, done, info = env.step(action)
 
-        if args.check_consistency:
+        if args.check_consistency and args.env == 'snake':
             env.check_consistency(skip=done)      # == env_consistency(env.envs[~done.squeeze(-1)]) (main.py:215), fused
 
         env.reset(done, return_observations=False)
@@ -122,7 +126,7 @@ def main(argv=None):
             dt = time() - t0
             summary = dict(steps=num_steps, episodes=num_episodes, reward_rate=stats['reward'] / max(stats['env_steps'], 1),
                            edge_collisions=stats['edge_collisions'], self_collisions=stats['self_collisions'],
-                           avg_size=env.envs[:, 2].reshape(args.num_envs, -1).max(dim=-1)[0].mean().item(),
+                           avg_size=env.envs[:, -1].reshape(args.num_envs, -1).max(dim=-1)[0].mean().item(),
                            steps_per_second=num_steps / dt)
             print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
 

@@ -226,6 +226,31 @@ int wurm_multi_observe(const WurmMultiCfg* cfg, const WurmMultiState* state, flo
 /* Replaces MultiSnake._get_env_images (multi_snake.py:194-227): img (E,3,S,S) int16. */
 int wurm_multi_env_images(const WurmMultiCfg* cfg, const WurmMultiState* state, int16_t* img, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SimpleGridworld (wurm/envs/simple_gridworld.py): the reference's two-channel debug env, selectable
+ * from its driver (experiments/main.py:166-168).  envs (N,2,S,S) f32: food, agent.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct WurmGridCfg {
+    int32_t num_envs; /* N */
+    int32_t size;     /* S > 4 (simple_gridworld.py:239) */
+    int32_t obs_mode; /* WURM_OBS_DEFAULT (N,3,S,S) | WURM_OBS_RAW (N,2,S,S) | WURM_OBS_POSITIONS (N,4) | WURM_OBS_NONE */
+    int32_t start_y;  /* start_location of the agent (reset only) */
+    int32_t start_x;
+} WurmGridCfg;
+
+/* Replaces SimpleGridworld.step (simple_gridworld.py:135-201) incl. _get_food_addition (:208-220) and
+ * _observe (:88-133) in one launch.  Actions are not sanitised (there is no orientation). */
+int wurm_grid_step(const WurmGridCfg* cfg, float* envs, const void* actions, int action_bytes,
+                   const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev, float* obs,
+                   float* reward, uint8_t* done, int32_t* status, int64_t* stats /* nullable */, void* stream);
+
+/* Replaces the state update of SimpleGridworld.reset / _create_envs (simple_gridworld.py:222-262). */
+int wurm_grid_reset(const WurmGridCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* food_cell_replay,
+                    uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream);
+
+/* Replaces SimpleGridworld._observe (simple_gridworld.py:108-133). */
+int wurm_grid_observe(const WurmGridCfg* cfg, const float* envs, float* obs, void* stream);
+
 /* MultiSnake.check_consistency (multi_snake.py:733-769): living snakes against snake_consistency,
  * no two bodies on one cell, dead snakes all-zero.  report as for wurm_single_check (counts agents). */
 int wurm_multi_check(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* report, void* stream);

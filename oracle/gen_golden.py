@@ -109,6 +109,33 @@ def multi_trajectory(ref, E, K, S, mode, steps, seed, **rules):
     return out
 
 
+def grid_trajectory(ref, N, S, mode, steps, seed, manual=None, actions=None):
+    torch.manual_seed(seed)
+    rl.take_tape()
+    start = (S // 2, S // 2)
+    out = {'N': N, 'S': S, 'mode': mode, 'steps': steps, 'start': np.array(start)}
+    if manual is None:
+        env = ref.SimpleGridworld(num_envs=N, size=S, observation_mode=mode, start_location=start)
+        out['init_food'] = replay.grid_food_tape(rl.take_tape(), np.ones(N), N, S)
+    else:
+        env = ref.SimpleGridworld(num_envs=N, size=S, observation_mode=mode, start_location=start, manual_setup=True)
+        env.envs = manual.clone()
+    out['init_envs'] = env.envs.numpy().astype(np.int16)
+    for t in range(steps):
+        a = torch.randint(0, 4, (N,)) if actions is None else actions[t].clone()
+        out[f'{t}/actions'] = a.numpy().copy()
+        obs, reward, done, info = env.step(a)
+        out[f'{t}/food_cell'] = replay.grid_food_tape(rl.take_tape(), reward.numpy() != 0, N, S)
+        out[f'{t}/envs'] = env.envs.numpy().astype(np.int16)
+        out[f'{t}/reward'] = reward.numpy().reshape(-1)
+        out[f'{t}/done'] = done.numpy().reshape(-1).astype(np.uint8)
+        out[f'{t}/obs'] = obs.numpy()
+        env.reset(done)
+        out[f'{t}/reset_food'] = replay.grid_food_tape(rl.take_tape(), done.numpy(), N, S)
+        out[f'{t}/reset_envs'] = env.envs.numpy().astype(np.int16)
+    return out
+
+
 def save(name, trajectories):
     flat = {'count': np.array(len(trajectories))}
     for i, tr in enumerate(trajectories):
@@ -137,6 +164,17 @@ def main():
             trs.append(single_trajectory(ref, 1, 12, 'default', len(seq), seed=400, reset_every=10 ** 6,
                                          manual=ref.utils.get_test_env(12, orientation), actions=acts))
     save('single.npz', trs)
+
+    trs = [grid_trajectory(ref, 32, 7, 'default', 30, seed=700), grid_trajectory(ref, 16, 11, 'raw', 30, seed=701),
+           grid_trajectory(ref, 1, 7, 'positions', 30, seed=702)]
+    # the reference's own scenarios (tests/test_simple_gridworld.py:13-69), size 7
+    for head, seq in [((3, 3), [0, 1, 2, 3, 2, 1]), ((2, 2), [0, 2, 2, 1]), ((3, 3), [0, 0, 0, 0])]:
+        manual = torch.zeros((1, 2, 7, 7))
+        manual[0, 0, 1, 1] = 1
+        manual[0, 1, head[0], head[1]] = 1
+        trs.append(grid_trajectory(ref, 1, 7, 'default', len(seq), seed=703, manual=manual,
+                                   actions=torch.tensor(seq).unsqueeze(1).long()))
+    save('gridworld.npz', trs)
 
     rule_sets = [
         dict(),                                                                          # constructor defaults

@@ -223,3 +223,39 @@ def multi_reset(cfg, st, env_done, draws=None, seed=0, step=0):
     return lib().wurm_oracle_multi_reset(ctypes.byref(cfg), _p(st.foods), _p(st.heads), _p(st.bodies), _p(st.dones),
                                          _p(st.orientations), _p(st.agent_colours), _p(env_done), ctypes.byref(d),
                                          ctypes.c_uint64(seed), ctypes.c_uint64(step))
+
+
+# ------------------------------------------------------------------------------------------------
+# SimpleGridworld
+# ------------------------------------------------------------------------------------------------
+def grid_step(envs, actions, food_cell=None, seed=0, step=0):
+    """In place on `envs` (N,2,S,S) f32.  Returns reward, done (= edge_collision)."""
+    assert envs.dtype == np.float32 and envs.flags.c_contiguous
+    N, _, S, _ = envs.shape
+    actions = _c(actions, np.int64)
+    reward = np.zeros(N, np.float32); done = np.zeros(N, np.uint8)
+    if food_cell is not None:
+        food_cell = _c(food_cell, np.int32)
+    lib().wurm_oracle_grid_step(N, S, _p(envs), _p(actions), _p(food_cell), ctypes.c_uint64(seed), ctypes.c_uint64(step),
+                                _p(reward), _p(done))
+    return reward, done
+
+
+def grid_reset(envs, done, start_location, food_cell=None, seed=0, step=0):
+    assert envs.dtype == np.float32 and envs.flags.c_contiguous
+    N, _, S, _ = envs.shape
+    done = _c(done, np.uint8)
+    if food_cell is not None:
+        food_cell = _c(food_cell, np.int32)
+    lib().wurm_oracle_grid_reset(N, S, _p(envs), _p(done), int(start_location[0]), int(start_location[1]), _p(food_cell),
+                                 ctypes.c_uint64(seed), ctypes.c_uint64(step))
+
+
+def grid_observe(envs, mode):
+    assert envs.dtype == np.float32 and envs.flags.c_contiguous
+    N, _, S, _ = envs.shape
+    m = OBS_MODES[mode]
+    shape = {0: (N, 3, S, S), 1: (N, 2, S, S), 3: (N, 4)}[m]
+    obs = np.zeros(shape, np.float32)
+    lib().wurm_oracle_grid_observe(N, S, _p(envs), m, _p(obs))
+    return obs

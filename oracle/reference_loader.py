@@ -111,8 +111,9 @@ def load():
     import wurm.utils as ref_utils
     import wurm.envs.single_snake as ref_single
     import wurm.envs.multi_snake as ref_multi
+    import wurm.envs.simple_gridworld as ref_grid
 
-    for mod in (ref_single, ref_multi):
+    for mod in (ref_single, ref_multi, ref_grid):
         orig = mod.drop_duplicates
 
         def recording_drop_duplicates(tensor, column, random=True, _orig=orig):
@@ -123,7 +124,8 @@ def load():
         mod.torch = _TorchProxy(mod.__name__)
 
     _loaded.update(dict(config=ref_config, utils=ref_utils, single=ref_single, multi=ref_multi,
-                        SingleSnake=ref_single.SingleSnake, MultiSnake=ref_multi.MultiSnake))
+                        SingleSnake=ref_single.SingleSnake, MultiSnake=ref_multi.MultiSnake,
+                        SimpleGridworld=ref_grid.SimpleGridworld))
     return types.SimpleNamespace(**_loaded)
 
 

@@ -126,3 +126,18 @@ def multi_reset_tape(tape, env_done, dones_before, colours_after, respawn_any, E
         tape = tape[2:]
     assert not tape, [(t[0], t[1]) for t in tape]
     return draws
+
+
+# ------------------------------------------------------------------------------------------------
+# SimpleGridworld (wurm/envs/simple_gridworld.py:218)
+# ------------------------------------------------------------------------------------------------
+def grid_food_tape(tape, env_mask, N, S):
+    """Tape of one SimpleGridworld.step (envs that ate) or reset/_create_envs (done envs) -> food_cell (N,) int32."""
+    ids = np.flatnonzero(np.asarray(env_mask).reshape(-1))
+    recs = [t for t in tape if t[0] == 'drop_duplicates']
+    assert len(recs) == len(tape) and len(recs) <= 1
+    if not recs:
+        assert len(ids) == 0
+        return np.full(N, -1, np.int32)
+    assert recs[0][1] == 218
+    return _rows_to_cells(recs[0][2], ids, N, S)

@@ -163,6 +163,33 @@ def validate_multi(ref, tally, E, K, S, mode, steps, seed, **rules):
     return env_steps
 
 
+def validate_grid(ref, tally, N, S, mode, steps, seed):
+    """SimpleGridworld: step(a); reset(done) loop, every output compared."""
+    torch.manual_seed(seed)
+    rl.take_tape()
+    start = (S // 2, S // 2)
+    env = ref.SimpleGridworld(num_envs=N, size=S, observation_mode=mode, start_location=start)
+    state = np.zeros((N, 2, S, S), np.float32)
+    orc.grid_reset(state, np.ones(N, np.uint8), start, replay.grid_food_tape(rl.take_tape(), np.ones(N), N, S))
+    tally.check(f'grid/{mode}/create', env.envs.numpy(), state)
+    for t in range(steps):
+        a = torch.randint(0, 4, (N,))
+        obs, reward, done, info = env.step(a)
+        r, d = orc.grid_step(state, a.numpy(), replay.grid_food_tape(rl.take_tape(), reward.numpy() != 0, N, S))
+        tag = f'grid/{mode}/S{S}/t{t}'
+        tally.check(tag + '/envs', env.envs.numpy(), state)
+        tally.check(tag + '/reward', reward.numpy().reshape(-1), r)
+        tally.check(tag + '/done', done.numpy().reshape(-1).astype(np.uint8), d)
+        tally.check(tag + '/edge_collision', info['edge_collision'].numpy().astype(np.uint8), d)
+        if mode != 'positions' or N == 1:
+            tally.check(tag + '/obs', obs.numpy(), orc.grid_observe(state, mode))
+        env.reset(done)
+        orc.grid_reset(state, done.numpy().reshape(-1).astype(np.uint8), start,
+                       replay.grid_food_tape(rl.take_tape(), done.numpy(), N, S))
+        tally.check(tag + '/reset_envs', env.envs.numpy(), state)
+    return N * steps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
@@ -178,6 +205,16 @@ def main():
     for mode in ['default', 'raw', 'one_channel', 'positions']:
         total += validate_single(ref, tally, 32 * scale, 9, mode, 42 * scale, seed=7, reset_every_step=False)
     print(f'single: {total} env-steps, {tally.checks} tensor comparisons, {len(tally.fails)} mismatches')
+    if tally.fails:
+        print('first failures:', tally.fails[:10])
+        sys.exit(1)
+    tally = Tally()
+    total = 0
+    for mode in ['default', 'raw']:
+        for S, N in [(7, 64), (12, 32)]:
+            total += validate_grid(ref, tally, N * scale, S, mode, 60 * scale, seed=S)
+    total += validate_grid(ref, tally, 1, 7, 'positions', 60 * scale, seed=1)
+    print(f'gridworld: {total} env-steps, {tally.checks} tensor comparisons, {len(tally.fails)} mismatches')
     if tally.fails:
         print('first failures:', tally.fails[:10])
         sys.exit(1)

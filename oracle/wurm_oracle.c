@@ -901,3 +901,110 @@ int wurm_oracle_multi_reset(const WurmOracleMultiCfg* cfg, float* foods, float* 
     }
     return failed;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* SimpleGridworld (wurm/envs/simple_gridworld.py): 2 channels, food and agent ("head").          */
+/* ------------------------------------------------------------------------------------------ */
+enum { STREAM_GRID_STEP_FOOD = 11, STREAM_GRID_RESET = 12 };
+
+static int grid_pick_free(int S, const float* env, uint64_t seed, uint64_t step, uint32_t e, uint32_t stream) {
+    int C = S * S, I = S - 2;                                                /* :208-216 free = food + agent < EPS, interior */
+    for (uint32_t t = 0; t < REJECTION_TRIES; ++t) {
+        int cand = (int)bounded(draw_i(seed, step, e, stream, t), (uint32_t)(I * I));
+        int q = (1 + cand / I) * S + 1 + cand % I;
+        if (env[q] + env[C + q] < EPS) return q;
+    }
+    int nfree = 0;
+    for (int y = 1; y < S - 1; ++y)
+        for (int x = 1; x < S - 1; ++x) nfree += env[y * S + x] + env[C + y * S + x] < EPS;
+    if (nfree == 0) return -1;
+    int r = (int)bounded(draw_i(seed, step, e, stream, REJECTION_TRIES), (uint32_t)nfree);
+    for (int y = 1; y < S - 1; ++y)
+        for (int x = 1; x < S - 1; ++x)
+            if (env[y * S + x] + env[C + y * S + x] < EPS && r-- == 0) return y * S + x;
+    return -1;
+}
+
+/* simple_gridworld.py:135-201.  food_cell_replay as for the snake envs; actions are NOT sanitised. */
+void wurm_oracle_grid_step(int N, int S, float* envs, const int64_t* actions, const int32_t* food_cell_replay,
+                           uint64_t seed, uint64_t step, float* reward, uint8_t* done) {
+    int C = S * S;
+#pragma omp parallel
+    {
+        float* moved = (float*)malloc(sizeof(float) * C);
+#pragma omp for schedule(static)
+        for (int e = 0; e < N; ++e) {
+            float* food = envs + (size_t)e * 2 * C;
+            float* head = food + C;
+            int a = (int)actions[e];
+            for (int y = 0; y < S; ++y)                                      /* :149-158 head += conv2d(head)[a]; round */
+                for (int x = 0; x < S; ++x) {
+                    int yy = y + OFF_Y[a], xx = x + OFF_X[a], p = y * S + x;
+                    float nb = (yy >= 0 && yy < S && xx >= 0 && xx < S) ? head[yy * S + xx] : 0.0f;
+                    moved[p] = nearbyintf(head[p] + (nb - head[p]));
+                }
+            memcpy(head, moved, sizeof(float) * C);
+            float removed = 0.0f;                                            /* :169-171 */
+            for (int p = 0; p < C; ++p) {
+                float rem = head[p] * food[p] * -1.0f;
+                removed += rem;
+                food[p] += rem;
+            }
+            reward[e] = 0.0f - removed;
+            if (removed * -1.0f != 0.0f) {                                   /* :176-181 */
+                int cell = food_cell_replay ? food_cell_replay[e] : grid_pick_free(S, food, seed, step, (uint32_t)e, STREAM_GRID_STEP_FOOD);
+                if (cell >= 0) food[cell] += 1.0f;
+            }
+            float interior = 0.0f;                                           /* :189-192 */
+            for (int y = 1; y < S - 1; ++y)
+                for (int x = 1; x < S - 1; ++x) interior += head[y * S + x];
+            done[e] = interior < EPS;
+            for (int p = 0; p < 2 * C; ++p) food[p] = nearbyintf(food[p]);   /* :197 */
+        }
+        free(moved);
+    }
+}
+
+/* simple_gridworld.py:222-262: done envs get the agent at (start_y, start_x) and one food. */
+void wurm_oracle_grid_reset(int N, int S, float* envs, const uint8_t* done, int start_y, int start_x,
+                            const int32_t* food_cell_replay, uint64_t seed, uint64_t step) {
+    int C = S * S;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < N; ++e) {
+        if (!done[e]) continue;
+        float* env = envs + (size_t)e * 2 * C;
+        memset(env, 0, sizeof(float) * 2 * C);
+        env[C + start_y * S + start_x] = 1.0f;                               /* :255 */
+        int cell = food_cell_replay ? food_cell_replay[e] : grid_pick_free(S, env, seed, step, (uint32_t)e, STREAM_GRID_RESET);
+        if (cell >= 0) env[cell] += 1.0f;                                    /* :258-259 */
+    }
+}
+
+/* simple_gridworld.py:88-133.  mode 0 'default' (N,3,S,S): BLACK background (:90 zeros * 255), agent
+ * (0,255,0), food (255,0,0), edges 0, /255; mode 1 'raw' (N,2,S,S); mode 3 'positions' (N,4) (the
+ * reference builds (1,4) and only works for N == 1). */
+void wurm_oracle_grid_observe(int N, int S, const float* envs, int mode, float* obs) {
+    int C = S * S;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < N; ++e) {
+        const float* env = envs + (size_t)e * 2 * C;
+        if (mode == OBS_DEFAULT) {
+            float* o = obs + (size_t)e * 3 * C;
+            for (int y = 0; y < S; ++y)
+                for (int x = 0; x < S; ++x) {
+                    int p = y * S + x;
+                    int16_t rgb[3] = {0, 0, 0};
+                    if (env[C + p] > EPS) { rgb[0] = 0; rgb[1] = 255; rgb[2] = 0; }
+                    if (env[p] > EPS) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+                    if (y == 0 || x == 0 || y == S - 1 || x == S - 1) rgb[0] = rgb[1] = rgb[2] = 0;
+                    for (int c = 0; c < 3; ++c) o[c * C + p] = (float)rgb[c] / 255.0f;
+                }
+        } else if (mode == OBS_RAW) {
+            memcpy(obs + (size_t)e * 2 * C, env, sizeof(float) * 2 * C);
+        } else {
+            float* o = obs + (size_t)e * 4;
+            int h = argmax_first(env + C, C), f = argmax_first(env, C);
+            o[0] = (float)(h / S); o[1] = (float)(h % S); o[2] = (float)(f / S); o[3] = (float)(f % S);
+        }
+    }
+}

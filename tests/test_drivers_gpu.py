@@ -22,3 +22,10 @@ def test_multisnake_speed_sweep():
     fps = sweep(num_agents=4, size=20, min_log2=4, max_log2=8, num_steps=5, check=True, verbose=False)
     assert [n for n, _ in fps] == [16, 32, 64, 128, 256]
     assert all(rate > 0 for _, rate in fps)
+
+
+def test_rollout_driver_gridworld():
+    from experiments.main import main
+    summary = main(['--env', 'gridworld', '--num-envs', '256', '--size', '7', '--agent', 'feedforward', '--observation',
+                    'default', '--total-steps', str(256 * 100), '--seed', '3'])
+    assert summary['steps'] == 256 * 100 and summary['episodes'] > 0

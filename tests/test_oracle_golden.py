@@ -12,6 +12,7 @@ from golden_util import (load, assert_same, multi_rules, multi_group, multi_step
 
 SINGLE = load('single.npz')
 MULTI = load('multi.npz')
+GRID = load('gridworld.npz')
 
 
 def test_philox_known_answers():
@@ -185,3 +186,25 @@ def test_reference_multi_scenarios_known_answers():
     st = multi_test_env(); st.foods[0, 0, 6, 5] = 1
     out = next(run_multi(st, cfg, [4], [0]))
     assert out['rewards'][0, 0] == 1
+
+
+@pytest.mark.parametrize('i', range(len(GRID)))
+def test_gridworld_golden(i):
+    """SimpleGridworld oracle == the reference's recorded trajectories (incl. its test scenarios)."""
+    tr = GRID[i]
+    N, S, mode, start = tr.N, tr.S, tr.mode, tuple(tr['start'])
+    if 'init_food' in tr:
+        state = np.zeros((N, 2, S, S), np.float32)
+        orc.grid_reset(state, np.ones(N, np.uint8), start, tr['init_food'])
+        assert_same(state, tr['init_envs'].astype(np.float32), 'created envs')
+    else:
+        state = tr['init_envs'].astype(np.float32)
+    for t in range(tr.steps):
+        r, d = orc.grid_step(state, tr[f'{t}/actions'], tr[f'{t}/food_cell'])
+        tag = f'gridworld trajectory {i} ({mode}, S={S}) step {t}: '
+        assert_same(state, tr[f'{t}/envs'].astype(np.float32), tag + 'envs')
+        assert_same(r, tr[f'{t}/reward'], tag + 'reward')
+        assert_same(d, tr[f'{t}/done'], tag + 'done')
+        assert_same(orc.grid_observe(state, mode), tr[f'{t}/obs'], tag + 'observation')
+        orc.grid_reset(state, d, start, tr[f'{t}/reset_food'])
+        assert_same(state, tr[f'{t}/reset_envs'].astype(np.float32), tag + 'envs after reset')

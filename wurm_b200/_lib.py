@@ -21,7 +21,8 @@ OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1
 SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_step_reset',
            'wurm_single_reset',
            'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_reset', 'wurm_multi_observe',
-           'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check']
+           'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check', 'wurm_grid_step', 'wurm_grid_reset',
+           'wurm_grid_observe']
 CHECK_REPORT = 4
 # WURM_CHK_* bits in the order the reference tests them, with the reference's messages
 CHECK_MESSAGES = [
@@ -43,6 +44,11 @@ MOBS_NONE, MOBS_FULL, MOBS_PARTIAL = -1, 0, 1
 class WurmSingleCfg(ctypes.Structure):
     _fields_ = [('num_envs', ctypes.c_int32), ('size', ctypes.c_int32), ('obs_mode', ctypes.c_int32),
                 ('obs_n', ctypes.c_int32)]
+
+
+class WurmGridCfg(ctypes.Structure):
+    _fields_ = [('num_envs', ctypes.c_int32), ('size', ctypes.c_int32), ('obs_mode', ctypes.c_int32),
+                ('start_y', ctypes.c_int32), ('start_x', ctypes.c_int32)]
 
 
 class WurmMultiCfg(ctypes.Structure):
@@ -115,6 +121,13 @@ def lib():
     L.wurm_multi_observe.argtypes = [mcfg, mst, vp, vp, vp]
     L.wurm_multi_env_images.restype = i32
     L.wurm_multi_env_images.argtypes = [mcfg, mst, vp, vp, vp]
+    gcfg = ctypes.POINTER(WurmGridCfg)
+    L.wurm_grid_step.restype = i32
+    L.wurm_grid_step.argtypes = [gcfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_grid_reset.restype = i32
+    L.wurm_grid_reset.argtypes = [gcfg, vp, vp, vp, u64, u64, vp, vp]
+    L.wurm_grid_observe.restype = i32
+    L.wurm_grid_observe.argtypes = [gcfg, vp, vp, vp]
     L.wurm_single_check.restype = i32
     L.wurm_single_check.argtypes = [cfg, vp, vp, vp, vp]
     L.wurm_multi_check.restype = i32

@@ -1,0 +1,220 @@
+// SimpleGridworld (wurm/envs/simple_gridworld.py) for B200 (sm_100a): the reference's two-channel debug
+// env -- an agent pixel and one food pixel, the same move / eat / respawn / edge machinery as SingleSnake
+// without a body.  An env is 2*S*S floats (392 B at the reference's size 7), far too small to stage:
+// one warp per env works straight on global memory with coalesced strided loads, finds the agent with a
+// ballot, and stores only the two or three cells a step changes.
+#include <math.h>
+
+#include "../../include/wurm_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wurm {
+
+enum : uint32_t { kStreamGridStepFood = 11, kStreamGridReset = 12 };
+
+struct GridParams {
+    float* envs;
+    const void* actions;
+    const int32_t* food_replay;
+    float* obs;
+    float* reward;
+    uint8_t* done;
+    int32_t* status;
+    unsigned long long* stats;
+    const unsigned long long* step_dev;
+    uint64_t seed, step;
+    int N, S, C, action_bytes, obs_mode, start_cell;
+    uint32_t magic_S;
+};
+
+__device__ __forceinline__ uint64_t call_counter(const GridParams& p) { return p.step + (p.step_dev ? *p.step_dev : 0ull); }
+
+// uniform free interior cell (food + agent < EPS, simple_gridworld.py:208-216): rejection sampling by the
+// whole warp in lock step, explicit ranking after kRejectionTries misses.  `env` is read through L2.
+__device__ __forceinline__ int grid_pick_free(const GridParams& p, const float* env, uint64_t ctr, int e, uint32_t stream) {
+    const int S = p.S, C = p.C, I = S - 2;
+    auto is_free = [&](int q) { return __ldcg(env + q) + __ldcg(env + C + q) < kEps; };
+    for (uint32_t t = 0; t < kRejectionTries; ++t) {
+        const int cand = (int)bounded(draw_i(p.seed, ctr, (uint32_t)e, stream, t), (uint32_t)(I * I));
+        const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
+        if (is_free(q)) return q;
+    }
+    int nfree = 0;
+    for (int y = 1; y < S - 1; ++y)
+        for (int x = 1; x < S - 1; ++x) nfree += is_free(y * S + x);
+    if (nfree == 0) return -1;
+    int r = (int)bounded(draw_i(p.seed, ctr, (uint32_t)e, stream, kRejectionTries), (uint32_t)nfree);
+    for (int y = 1; y < S - 1; ++y)
+        for (int x = 1; x < S - 1; ++x)
+            if (is_free(y * S + x) && r-- == 0) return y * S + x;
+    return -1;
+}
+
+// simple_gridworld.py:88-133 for env e by one warp (reads through L2: the step's own stores are visible)
+__device__ __forceinline__ void grid_observe_env(const GridParams& p, int e, int lane) {
+    const int S = p.S, C = p.C;
+    const float* env = p.envs + (size_t)e * 2 * C;
+    if (p.obs_mode == WURM_OBS_DEFAULT) {                            // black background (:90), agent green, food red
+        float* o = p.obs + (size_t)e * 3 * C;
+        for (int q = lane; q < C; q += 32) {
+            const int y = (int)__umulhi((uint32_t)q, p.magic_S), x = q - y * S;
+            float r = 0.0f, g = 0.0f;
+            if (__ldcg(env + C + q) > kEps) { r = 0.0f; g = 1.0f; }
+            if (__ldcg(env + q) > kEps) { r = 1.0f; g = 0.0f; }
+            if (y == 0 || x == 0 || y == S - 1 || x == S - 1) r = g = 0.0f;
+            o[q] = r; o[C + q] = g; o[2 * C + q] = 0.0f;
+        }
+    } else if (p.obs_mode == WURM_OBS_RAW) {
+        for (int i = lane; i < 2 * C; i += 32) p.obs[(size_t)e * 2 * C + i] = __ldcg(env + i);
+    } else if (p.obs_mode == WURM_OBS_POSITIONS) {                   // first argmax of agent / food (:119-130)
+        int idx[2];
+        for (int ch = 0; ch < 2; ++ch) {
+            const float* v = env + (ch == 0 ? C : 0);
+            float bv = -INFINITY;
+            int bq = 0;
+            for (int q = lane; q < C; q += 32) {
+                const float x = __ldcg(v + q);
+                if (x > bv) { bv = x; bq = q; }
+            }
+            const float gv = group_max<32>(bv, 0xffffffffu);
+            idx[ch] = -group_max<32>(bv == gv ? -bq : -(1 << 30), 0xffffffffu);
+        }
+        if (lane == 0) {
+            float* o = p.obs + (size_t)e * 4;
+            o[0] = (float)(idx[0] / S); o[1] = (float)(idx[0] % S); o[2] = (float)(idx[1] / S); o[3] = (float)(idx[1] % S);
+        }
+    }
+}
+
+// simple_gridworld.py:135-201, one warp per env
+template <bool STEP>
+__global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= p.N) return;
+    if (STEP) {
+        const int S = p.S, C = p.C;
+        float* food = p.envs + (size_t)e * 2 * C;
+        float* head = food + C;
+        int hp = -1, hc = 0;
+        for (int q = lane; q < C; q += 32)
+            if (head[q] != 0.0f) { hp = q; ++hc; }
+        hp = group_max<32>(hp, 0xffffffffu);
+        hc = group_sum<32>(hc, 0xffffffffu);
+        long long a;
+        if (p.action_bytes == 8) a = ((const long long*)p.actions)[e];
+        else if (p.action_bytes == 4) a = ((const int*)p.actions)[e];
+        else a = ((const short*)p.actions)[e];
+        int np = -1, ny = -1, nx = -1;                                // :149-158 the conv2d translates the agent by -OFF[a]
+        if (hp >= 0) {
+            const int hy = (int)__umulhi((uint32_t)hp, p.magic_S), hx = hp - hy * S;
+            ny = hy - off_y((int)a); nx = hx - off_x((int)a);
+            if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
+        }
+        const float ov = np >= 0 ? food[np] : 0.0f;                   // :169 agent-food overlap
+        __syncwarp();
+        if (lane == 0 && hp >= 0) {
+            head[hp] = 0.0f;
+            if (np >= 0) {
+                head[np] = 1.0f;
+                if (ov != 0.0f) food[np] = ov + ov * -1.0f;           // :171
+            }
+        }
+        __syncwarp();
+        if (ov != 0.0f) {                                             // :176-181 respawn
+            const int cell = p.food_replay ? p.food_replay[e]
+                                           : grid_pick_free(p, food, call_counter(p), e, kStreamGridStepFood);
+            if (lane == 0 && cell >= 0) food[cell] = __ldcg(food + cell) + 1.0f;
+        }
+        const bool interior = np >= 0 && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
+        if (lane == 0) {
+            p.reward[e] = 0.0f - ov * -1.0f;
+            p.done[e] = !interior;                                    // :189-194 edge collision is the only way to end
+            if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+            if (p.stats) {
+                unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+                atomicAdd(slot + WURM_STAT_ENV_STEPS, 1ull);
+                if (!interior) { atomicAdd(slot + WURM_STAT_EPISODES, 1ull); atomicAdd(slot + WURM_STAT_EDGE_COLLISIONS, 1ull); }
+                if (ov != 0.0f) atomicAdd(slot + WURM_STAT_REWARD, 1ull);
+            }
+        }
+        __syncwarp();
+    }
+    if (p.obs_mode >= 0) grid_observe_env(p, e, lane);
+}
+
+// simple_gridworld.py:222-262: done envs get the agent at the start location and one food
+__global__ void __launch_bounds__(256) grid_reset_kernel(const GridParams p, const uint8_t* __restrict__ done_mask) {
+    const int lane = threadIdx.x & 31;
+    const int e_base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (e_base >= p.N) return;
+    const int e_mine = e_base + lane, C = p.C;
+    unsigned todo = __ballot_sync(0xffffffffu, e_mine < p.N && done_mask[e_mine] != 0);
+    while (todo) {
+        const int e = e_base + __ffs(todo) - 1;
+        todo &= todo - 1;
+        float* env = p.envs + (size_t)e * 2 * C;
+        for (int i = lane; i < 2 * C; i += 32) env[i] = (i == C + p.start_cell) ? 1.0f : 0.0f;
+        __syncwarp();
+        const int cell = p.food_replay ? p.food_replay[e] : grid_pick_free(p, env, call_counter(p), e, kStreamGridReset);
+        if (lane == 0 && cell >= 0) env[cell] = 1.0f;
+        __syncwarp();
+    }
+}
+
+static int plan_grid(const WurmGridCfg* cfg, GridParams* p) {
+    if (!cfg) return fail(WURM_E_INVALID, "cfg is NULL");
+    if (cfg->num_envs <= 0) return fail(WURM_E_INVALID, "num_envs must be positive");
+    if (cfg->size <= 4) return fail(WURM_E_INVALID, "size must be > 4 (reference simple_gridworld.py:239)");
+    if (cfg->size > 256) return fail(WURM_E_UNSUPPORTED, "size > 256");
+    if (cfg->obs_mode != WURM_OBS_NONE && cfg->obs_mode != WURM_OBS_DEFAULT && cfg->obs_mode != WURM_OBS_RAW &&
+        cfg->obs_mode != WURM_OBS_POSITIONS)
+        return fail(WURM_E_INVALID, "bad obs_mode (default, raw or positions)");
+    p->N = cfg->num_envs; p->S = cfg->size; p->C = cfg->size * cfg->size; p->obs_mode = cfg->obs_mode;
+    p->start_cell = cfg->start_y * cfg->size + cfg->start_x;
+    p->magic_S = (uint32_t)((0x100000000ull + (uint64_t)p->S - 1) / (uint64_t)p->S);
+    return WURM_OK;
+}
+
+}  // namespace wurm
+
+using namespace wurm;
+
+extern "C" int wurm_grid_step(const WurmGridCfg* cfg, float* envs, const void* actions, int action_bytes,
+                              const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
+                              float* obs, float* reward, uint8_t* done, int32_t* status, int64_t* stats, void* stream) {
+    GridParams p = {};
+    if (int rc = plan_grid(cfg, &p)) return rc;
+    if (!envs || !actions || !reward || !done || !status) return fail(WURM_E_INVALID, "NULL pointer");
+    if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
+    if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
+    p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
+    p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
+    p.obs = obs; p.reward = reward; p.done = done; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
+    grid_env_kernel<true><<<(p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("grid_env_kernel");
+}
+
+extern "C" int wurm_grid_observe(const WurmGridCfg* cfg, const float* envs, float* obs, void* stream) {
+    GridParams p = {};
+    if (int rc = plan_grid(cfg, &p)) return rc;
+    if (!envs || !obs) return fail(WURM_E_INVALID, "NULL pointer");
+    if (cfg->obs_mode == WURM_OBS_NONE) return WURM_OK;
+    p.envs = const_cast<float*>(envs); p.obs = obs;
+    grid_env_kernel<false><<<(p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("grid_env_kernel");
+}
+
+extern "C" int wurm_grid_reset(const WurmGridCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* food_cell_replay,
+                               uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream) {
+    GridParams p = {};
+    if (int rc = plan_grid(cfg, &p)) return rc;
+    if (!envs || !done_mask) return fail(WURM_E_INVALID, "NULL pointer");
+    if (cfg->start_y < 0 || cfg->start_y >= cfg->size || cfg->start_x < 0 || cfg->start_x >= cfg->size)
+        return fail(WURM_E_INVALID, "start location outside the grid");
+    p.envs = envs; p.food_replay = food_cell_replay; p.seed = seed; p.step = step;
+    p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
+    grid_reset_kernel<<<(p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, done_mask);
+    return check_launch("grid_reset_kernel");
+}
