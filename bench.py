@@ -46,6 +46,8 @@ WORKLOADS = {
     'C1': ('SingleSnake', 9, 512, 'partial_2', 1),
     'C4': ('MultiSnake', 25, 1 << 16, 'partial_4', 4),
     'C5': ('MultiSnake', 64, 1 << 15, 'partial_4', 16),
+    'C5F': ('MultiSnake', 64, 1 << 14, 'full', 16),            # SURVEY section 8d variant: class-default 'full' observations
+    'G1': ('SimpleGridworld', 7, 1 << 20, 'default', 1),      # next-row env, reference test size
 }
 ACTION_POOL = 16        # pre-generated action tensors cycled through by the timed loop
 
@@ -65,6 +67,8 @@ def algorithmic_bytes_per_env_step(key, obs_elems_per_env):
     env, S, _, _, K = WORKLOADS[key]
     if env == 'MultiSnake':
         return 2 * (1 + 2 * K) * S * S * 4 + obs_elems_per_env * 4 + (170 * K) // 4
+    if env == 'SimpleGridworld':
+        return 2 * 2 * S * S * 4 + obs_elems_per_env * 4 + 13
     return 2 * 3 * S * S * 4 + obs_elems_per_env * 4 + 23
 
 
@@ -100,6 +104,24 @@ class SingleAdapter(object):
         return [p.cpu().pin_memory() for p in self.pool]
 
 
+class GridAdapter(SingleAdapter):
+    kernel = 'grid_env_kernel<STEP=true>'
+
+    def __init__(self, key, dev, seed, rank):
+        import torch
+        from wurm_b200.envs import SimpleGridworld
+        _, S, N, mode, _ = WORKLOADS[key]
+        self.N, self.torch = N, torch
+        self.env = SimpleGridworld(num_envs=N, size=S, observation_mode=mode, device=dev, start_location=(S // 2, S // 2),
+                                   seed=seed)
+        g = torch.Generator(device=dev).manual_seed(4321 + rank)
+        self.pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]
+        self.action_desc = f'int64 randint(0,4), pool of {ACTION_POOL} pre-generated tensors per rank'
+        self.loop_desc = 'obs,reward,done,info = env.step(a); env.reset(done, return_observations=False)'
+
+    fused_step = None
+
+
 class MultiAdapter(object):
     kernel = 'multi_env_kernel<STEP=true>'
 
@@ -131,7 +153,8 @@ class MultiAdapter(object):
 
 
 def make_adapter(key, dev, seed, rank):
-    return (MultiAdapter if WORKLOADS[key][0] == 'MultiSnake' else SingleAdapter)(key, dev, seed, rank)
+    cls = {'MultiSnake': MultiAdapter, 'SimpleGridworld': GridAdapter}.get(WORKLOADS[key][0], SingleAdapter)
+    return cls(key, dev, seed, rank)
 
 
 class ClockSampler(object):
@@ -223,6 +246,20 @@ def time_cpu_port(key, n_envs, steps, warmup, threads):
             orc.multi_reset(cfg, st, out['all_done'], None, seed=1234, step=2 * t + 2)
         dt = time.perf_counter() - t0
         return n_envs * steps / dt, dt
+    if env_name == 'SimpleGridworld':
+        start = (S // 2, S // 2)
+        state = np.zeros((n_envs, 2, S, S), np.float32)
+        orc.grid_reset(state, np.ones(n_envs, np.uint8), start, None, seed=1234, step=0)
+        pool = [rng.integers(0, 4, n_envs).astype(np.int64) for _ in range(ACTION_POOL)]
+        t0 = None
+        for t in range(warmup + steps):
+            if t == warmup:
+                t0 = time.perf_counter()
+            r, d = orc.grid_step(state, pool[t % ACTION_POOL], None, seed=1234, step=2 * t + 1)
+            obs = orc.grid_observe(state, mode)
+            orc.grid_reset(state, d, start, None, seed=1234, step=2 * t + 2)
+        dt = time.perf_counter() - t0
+        return n_envs * steps / dt, dt
     state = np.zeros((n_envs, 3, S, S), np.float32)
     orc.single_reset(state, np.ones(n_envs, np.uint8), None, seed=1234, step=0)
     pool = [rng.integers(0, 4, n_envs).astype(np.int64) for _ in range(ACTION_POOL)]
@@ -300,13 +337,13 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput (value) + per-launch step-kernel time (roofline) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()                         # nvidia-smi takes a moment to produce its first row: start before the warm-up
     for t in range(W):
         obs, reward, done = ad.step(t)
         ad.reset(done)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     t_wall0 = time.time()
     start.record()
@@ -327,7 +364,7 @@ def run_gpu(args):
 
     # ---- supplementary: the fused step+reset fast path (one launch per step; SingleSnake) ----
     fused_ms = None
-    if hasattr(ad, 'fused_step'):
+    if getattr(ad, 'fused_step', None) is not None:
         for t in range(W):
             ad.fused_step(t)
         f_start, f_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -436,7 +473,7 @@ def main():
     ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='wurm_b200', choices=['wurm_b200', 'reference'])
-    ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))    # C1..C5 = BASELINE.json configs
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -29,3 +29,12 @@ def test_rollout_driver_gridworld():
     summary = main(['--env', 'gridworld', '--num-envs', '256', '--size', '7', '--agent', 'feedforward', '--observation',
                     'default', '--total-steps', str(256 * 100), '--seed', '3'])
     assert summary['steps'] == 256 * 100 and summary['episodes'] > 0
+
+
+def test_multiagent_rollout_driver_with_annealing():
+    """The reference's multiagent.py defaults (random_rate food, respawn any) with food-rate annealing."""
+    from experiments.multiagent import main
+    summary = main(['--n-envs', '256', '--n-agents', '4', '--size', '25', '--obs', 'partial_4', '--total-steps',
+                    str(256 * 120), '--food-rate', '3e-3', '--food-rate-min', '1e-3', '--seed', '2'])
+    assert summary['steps'] == 256 * 120 and summary['edge_collisions'] > 0 and summary['food'] > 0
+    assert abs(summary['food_rate'] - 1e-3) < 1e-4

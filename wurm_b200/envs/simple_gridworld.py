@@ -94,8 +94,13 @@ class SimpleGridworld(object):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.envs.device).cuda_stream)
 
-    def stats(self):
-        return dict(zip(_lib.STAT_NAMES, self._stats.sum(dim=0).tolist()))
+    def stats(self, reduce_group=None):
+        """Episode statistics accumulated on the device (env_steps, episodes, reward, edge_collisions)."""
+        totals = self._stats.sum(dim=0)
+        if reduce_group is not None:
+            from ..distributed import all_reduce_stats
+            all_reduce_stats(totals, None if reduce_group is True else reduce_group)
+        return dict(zip(_lib.STAT_NAMES, totals.tolist()))
 
     def check_status(self):
         """Raises if a kernel met a state outside the supported set since the last check (one sync)."""
