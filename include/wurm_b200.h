@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WURM_ABI_VERSION 2
+#define WURM_ABI_VERSION 3
 
 /* return codes */
 #define WURM_OK 0
@@ -86,12 +86,16 @@ int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg);
  *   obs      per cfg->obs_mode, may be NULL with       = 2/4/8), sanitised IN PLACE like :222
  *            WURM_OBS_NONE                            reward (N,) f32, done/self_col/edge_col (N,) u8
  *   food_cell_replay (N,) int32 or NULL: cell index y*S+x of the respawned food for envs that eat
- *            this step (-1: none); NULL -> uniform over free interior cells from Philox.        */
+ *            this step (-1: none); NULL -> uniform over free interior cells from Philox.
+ *   hints    (N,2) int16 or NULL: scratch owned by the caller in which the kernels leave each env's
+ *            (head cell, snake size) for their next call.  Pure accelerator: every hint is verified
+ *            against `envs` before use, so stale or garbage hints (the caller edited `envs`) only
+ *            cost the scans they would have saved.                                               */
 int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                      const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                      float* obs, float* reward,
                      uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status,
-                     int64_t* stats /* nullable */, void* stream);
+                     int64_t* stats /* nullable */, int16_t* hints /* nullable */, void* stream);
 
 /* Fused fast path: wurm_single_step followed by wurm_single_reset(done) in ONE launch -- the pair the
  * reference's driver issues every iteration (experiments/main.py:212-227).  Outputs are those of the
@@ -102,13 +106,14 @@ int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int a
 int wurm_single_step_reset(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                            const int32_t* food_cell_replay, const int32_t* spawn_replay, uint64_t seed, uint64_t step,
                            const uint64_t* step_dev, float* obs, float* reward, uint8_t* done, uint8_t* self_col,
-                           uint8_t* edge_col, int32_t* status, int64_t* stats /* nullable */, void* stream);
+                           uint8_t* edge_col, int32_t* status, int64_t* stats /* nullable */, int16_t* hints /* nullable */,
+                           void* stream);
 
 /* Replaces the state update of SingleSnake.reset / _create_envs (single_snake.py:322-337, 344-387):
  * envs whose done_mask byte is non-zero are re-created, all others untouched.
  *   spawn_replay (N,4) int32 or NULL: rows (y, x, dir, food_cell), read for done envs only.     */
 int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* spawn_replay,
-                      uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream);
+                      uint64_t seed, uint64_t step, const uint64_t* step_dev, int16_t* hints /* nullable */, void* stream);
 
 /* Replaces SingleSnake._observe (single_snake.py:130-195) on the current state. */
 int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream);

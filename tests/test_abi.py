@@ -45,7 +45,7 @@ def test_obs_elems():
 def test_bad_config_is_rejected_on_the_host(cfg, code):
     L = _lib.lib()
     c = _lib.WurmSingleCfg(*cfg)
-    rc = L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None, None)
+    rc = L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None, None, None)
     assert rc == code
     assert L.wurm_last_error()
     with pytest.raises(_lib.WurmError):
@@ -55,10 +55,10 @@ def test_bad_config_is_rejected_on_the_host(cfg, code):
 def test_null_pointers_are_rejected():
     L = _lib.lib()
     c = _lib.WurmSingleCfg(4, 9, 0, 0)
-    assert L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None, None) == _lib.E_INVALID
+    assert L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None, None, None) == _lib.E_INVALID
     assert L.wurm_single_observe(ctypes.byref(c), None, None, None, None) == _lib.E_INVALID
     assert L.wurm_single_step(ctypes.byref(c), None, None, 8, None, 0, 0, None, None, None, None, None, None, None,
-                              None, None) == _lib.E_INVALID
+                              None, None, None) == _lib.E_INVALID
 
 
 def test_env_refuses_to_run_without_cuda_device():

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
 ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP = 1, 2, 4, 8
@@ -102,11 +102,11 @@ def lib():
     L.wurm_single_obs_elems.restype = ctypes.c_int64
     L.wurm_single_obs_elems.argtypes = [cfg]
     L.wurm_single_step.restype = i32
-    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.wurm_single_step_reset.restype = i32
-    L.wurm_single_step_reset.argtypes = [cfg, vp, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_step_reset.argtypes = [cfg, vp, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.wurm_single_reset.restype = i32
-    L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp, vp]
+    L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp, vp, vp]
     L.wurm_single_observe.restype = i32
     L.wurm_single_observe.argtypes = [cfg, vp, vp, vp, vp]
     mcfg, mst = ctypes.POINTER(WurmMultiCfg), ctypes.POINTER(WurmMultiState)

@@ -42,6 +42,7 @@ struct SingleParams {
     const unsigned long long* step_dev;   // nullable: added to `step` on the device (CUDA-graph replays)
     int auto_reset;       // fused step+reset: envs that end this step are re-created by the same launch
     const int32_t* spawn; // (N,4) replayed (y, x, dir, food_cell) of the fused / stand-alone reset, or NULL
+    short* hints;         // (N,2) nullable: (head cell, snake size) left by the previous call -- hints only, always verified
     int N, S, C;          // envs, grid side, cells per channel
     int T;                // envs per tile (= per CTA)
     int action_bytes;     // 2 / 4 / 8
@@ -167,7 +168,8 @@ __device__ __forceinline__ float new_env_value(int i, int C, int tail, int mid, 
 
 // single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
 template <int G>
-__device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e, int l, int* cnt_s) {
+__device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e, int l, int* cnt_s, long long a_in,
+                                        int hint_head, int hint_sz) {
     const unsigned gm = group_mask<G>();
     const int S = p.S, C = p.C;
     float* food = env;
@@ -181,28 +183,56 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
     float* ghead = gfood + C;
     float* gbody = gfood + 2 * C;
 
-    // snake size (:210) and head cell
-    float m = -INFINITY;
+    // Snake size (:210), head cell, and the (size, size-1) cell counts the orientation rule needs.
+    // The previous call left (head cell, size) HINTS per env.  They are never trusted: the head hint is
+    // used only if that cell really holds a head, the size hint only if the scan finds the same maximum --
+    // then the counts taken against the hinted size in the SAME pass are the true ones and the second pass
+    // over the body, as well as the scan of the head channel, are skipped.  Stale hints (caller edited
+    // `envs`, first step, hints disabled) fall back to the full scans.
     int hp = -1, hc = 0;
+    float hint_size = -1.0f;
+    if (p.hints) {
+        hint_size = (float)hint_sz;
+        if (hint_head >= 0 && hint_head < C && head[hint_head] != 0.0f) { hp = hint_head; hc = 1; }
+    }
+    const bool scan_head = hc == 0;
+    float m = -INFINITY;
+    int c1 = 0, c2 = 0, p1 = -1, p2 = -1;
+    const float hint_sm1 = hint_size - 1.0f;
+    if (scan_head) {
 #pragma unroll 4
-    for (int q = l; q < C; q += G) {
-        m = fmaxf(m, body[q]);
-        if (head[q] != 0.0f) { hp = q; ++hc; }
+        for (int q = l; q < C; q += G) {
+            const float v = body[q];
+            m = fmaxf(m, v);
+            if (v == hint_size) { ++c1; p1 = q; }
+            if (v == hint_sm1) { ++c2; p2 = q; }
+            if (head[q] != 0.0f) { hp = q; ++hc; }
+        }
+        hp = group_max<G>(hp, gm);
+        hc = group_sum<G>(hc, gm);
+    } else {
+#pragma unroll 4
+        for (int q = l; q < C; q += G) {
+            const float v = body[q];
+            m = fmaxf(m, v);
+            if (v == hint_size) { ++c1; p1 = q; }
+            if (v == hint_sm1) { ++c2; p2 = q; }
+        }
     }
     const float size = group_max<G>(m, gm);
-    hp = group_max<G>(hp, gm);
-    hc = group_sum<G>(hc, gm);
 
     // orientation (:212).  Canonical case: exactly one cell == size (head) and one == size-1
     // (neck): the response of filter k peaks at 2 iff head = neck + OFF[k]; otherwise all four
     // filters tie at 1 and argmax returns 0.
-    int c1 = 0, c2 = 0, p1 = -1, p2 = -1;
-    const float sm1 = size - 1.0f;
+    if (size != hint_size) {                                         // stale size hint: count against the true size
+        c1 = c2 = 0; p1 = p2 = -1;
+        const float sm1 = size - 1.0f;
 #pragma unroll 4
-    for (int q = l; q < C; q += G) {
-        const float v = body[q];
-        if (v == size) { ++c1; p1 = q; }
-        if (v == sm1) { ++c2; p2 = q; }
+        for (int q = l; q < C; q += G) {
+            const float v = body[q];
+            if (v == size) { ++c1; p1 = q; }
+            if (v == sm1) { ++c2; p2 = q; }
+        }
     }
     c1 = group_sum<G>(c1, gm);
     c2 = group_sum<G>(c2, gm);
@@ -221,10 +251,6 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
     }
 
     // action sanitisation, written back into the caller's tensor (:221-222)
-    long long a_in;
-    if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
-    else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
-    else a_in = ((const short*)p.actions)[e];
     const long long a = (a_in + ((long long)k == a_in ? 2 : 0)) % 4;
     if (l == 0 && a != a_in) {
         if (p.action_bytes == 8) ((long long*)p.actions)[e] = a;
@@ -289,6 +315,10 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
         p.edge_col[e] = !interior;                                   // :290-293 no head in the interior
         p.done[e] = sc || !interior;
         if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+        if (p.hints) {                                               // for the next call: head cell and size now
+            p.hints[2 * (size_t)e] = (short)np;
+            p.hints[2 * (size_t)e + 1] = (short)((np >= 0) ? (int)(size + ov) : -1);
+        }
         if (p.stats) {                                               // episode statistics, per-CTA partials
             if (sc || !interior) atomicAdd(cnt_s + 0, 1);
             if (ov != 0.0f) atomicAdd(cnt_s + 1, (int)ov);
@@ -308,6 +338,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
             const float nv = new_env_value(i, C, tail, mid, hd, cell);
             if (env[i] != nv) gfood[i] = nv;
         }
+        if (l == 0 && p.hints) { p.hints[2 * (size_t)e] = (short)hd; p.hints[2 * (size_t)e + 1] = 3; }
     }
     return np;
 }
@@ -433,14 +464,24 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
         for (int i = threadIdx.x; i < nfloats; i += blockDim.x) tile[i] = p.envs[goff + i];
     }
     if (threadIdx.x < 4) cnt_s[threadIdx.x] = 0;
+    // per-env scalars (action, hints) are fetched while the tile is still in flight
+    const int t = threadIdx.x / G, l = threadIdx.x % G;
+    long long a_in = 0;
+    int hint_head = -1, hint_sz = -1;
+    if (STEP && t < nvalid) {
+        const size_t e = (size_t)(env0 + t);
+        if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
+        else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
+        else a_in = ((const short*)p.actions)[e];
+        if (p.hints) { hint_head = p.hints[2 * e]; hint_sz = p.hints[2 * e + 1]; }
+    }
     __syncthreads();                        // mbarrier init / fallback tile visible
     if (bulk) mbar_wait(bar, 0);
 
-    const int t = threadIdx.x / G, l = threadIdx.x % G;
     if (t < nvalid) {
         float* env = tile + (size_t)t * 3 * p.C;
         int hp = -1;
-        if (STEP) hp = step_env<G>(p, env, env0 + t, l, cnt_s);
+        if (STEP) hp = step_env<G>(p, env, env0 + t, l, cnt_s, a_in, hint_head, hint_sz);
         else if (partial) hp = find_head<G>(p, env, l);
         if (partial) render_partial<G>(p, env, hp, stage + (size_t)t * E, l);
     }
@@ -495,6 +536,7 @@ __global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p,
         new_env_layout(p, spawn, call_counter(p), e, tail, mid, hd, cell);
         float* env = p.envs + (size_t)e * 3 * C;
         for (int i = lane; i < 3 * C; i += 32) env[i] = new_env_value(i, C, tail, mid, hd, cell);
+        if (lane == 0 && p.hints) { p.hints[2 * (size_t)e] = (short)hd; p.hints[2 * (size_t)e + 1] = 3; }
     }
 }
 
@@ -639,7 +681,8 @@ extern "C" int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg) {
 static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                             const int32_t* food_cell_replay, int auto_reset, const int32_t* spawn_replay, uint64_t seed,
                             uint64_t step, const uint64_t* step_dev, float* obs, float* reward, uint8_t* done,
-                            uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, void* stream) {
+                            uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, int16_t* hints,
+                            void* stream) {
     SingleParams p = {};
     SingleLaunch L;
     if (int rc = plan_single(cfg, &p, &L)) return rc;
@@ -647,7 +690,7 @@ static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions
     if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
     if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
-    p.auto_reset = auto_reset; p.spawn = spawn_replay;
+    p.auto_reset = auto_reset; p.spawn = spawn_replay; p.hints = hints;
     p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
     p.edge_col = edge_col; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
@@ -658,17 +701,18 @@ static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions
 extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                                 const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                                 float* obs, float* reward, uint8_t* done, uint8_t* self_col, uint8_t* edge_col,
-                                int32_t* status, int64_t* stats, void* stream) {
+                                int32_t* status, int64_t* stats, int16_t* hints, void* stream) {
     return single_step_impl(cfg, envs, actions, action_bytes, food_cell_replay, 0, nullptr, seed, step, step_dev, obs, reward,
-                            done, self_col, edge_col, status, stats, stream);
+                            done, self_col, edge_col, status, stats, hints, stream);
 }
 
 extern "C" int wurm_single_step_reset(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                                       const int32_t* food_cell_replay, const int32_t* spawn_replay, uint64_t seed,
                                       uint64_t step, const uint64_t* step_dev, float* obs, float* reward, uint8_t* done,
-                                      uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, void* stream) {
+                                      uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, int16_t* hints,
+                                      void* stream) {
     return single_step_impl(cfg, envs, actions, action_bytes, food_cell_replay, 1, spawn_replay, seed, step, step_dev, obs,
-                            reward, done, self_col, edge_col, status, stats, stream);
+                            reward, done, self_col, edge_col, status, stats, hints, stream);
 }
 
 extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream) {
@@ -683,11 +727,12 @@ extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, 
 }
 
 extern "C" int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* spawn_replay,
-                                 uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream) {
+                                 uint64_t seed, uint64_t step, const uint64_t* step_dev, int16_t* hints, void* stream) {
     SingleParams p = {};
     SingleLaunch L;
     if (int rc = plan_single(cfg, &p, &L)) return rc;
     if (!envs || !done_mask) return fail(WURM_E_INVALID, "NULL pointer");
+    p.hints = hints;
     p.envs = envs; p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     const int warps_per_block = 8;
     const int blocks = (p.N + 32 * warps_per_block - 1) / (32 * warps_per_block);

@@ -45,6 +45,7 @@ class SingleSnake(object):
         'render.modes': ['rgb_array'],
         'video.frames_per_second': 12
     }
+    supports_fused_reset = True     # step(..., auto_reset=True): wurm_single_step_reset
 
     def __init__(self,
                  num_envs: int,
@@ -85,6 +86,9 @@ class SingleSnake(object):
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         # episode statistics accumulated by the step kernel (see `stats`)
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
+        # (head cell, snake size) per env left by one kernel call for the next: verified hints that let the step
+        # kernel skip two of its scans; never trusted, so editing `envs` behind the env's back stays safe
+        self._hints = torch.full((num_envs, 2), -1, dtype=torch.short, device=self.device)
 
         self.envs = torch.zeros((num_envs, 3, size, size), device=self.device)
         self.t = 0
@@ -226,13 +230,15 @@ class SingleSnake(object):
                 _lib.check(self._lib.wurm_single_step_reset(
                     ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                     _ptr(spawn_replay), self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
-                    _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
+                    _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), _ptr(self._hints),
+                    self._stream()))
                 self._draws += 1            # the fused reset consumed the next counter value
             else:
                 _lib.check(self._lib.wurm_single_step(
                     ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                     self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
-                    _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), self._stream()))
+                    _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), _ptr(self._hints),
+                    self._stream()))
         if host_actions is not None:
             host_actions.copy_(actions, non_blocking=True)      # the sanitised actions (reference :222)
         info = {'self_collision': self_collision, 'edge_collision': edge_collision}
@@ -277,7 +283,9 @@ class SingleSnake(object):
         self._draws += 1
         with torch.cuda.device(envs.device):
             _lib.check(self._lib.wurm_single_reset(ctypes.byref(cfg), _ptr(envs), _ptr(mask), _ptr(spawn_replay),
-                                                   self.seed, self._draws, _ptr(self._draws_dev), self._stream()))
+                                                   self.seed, self._draws, _ptr(self._draws_dev),
+                                                   _ptr(self._hints) if envs.shape[0] == self.num_envs else None,
+                                                   self._stream()))
 
     def _create_envs(self, num_envs: int, *, spawn_replay: torch.Tensor = None):
         """Vectorised environment creation (reference :344-387)."""

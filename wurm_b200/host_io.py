@@ -106,7 +106,7 @@ class HostStepper(object):
         else:
             # below ~64K envs the step is launch-bound and the fused step+reset launch wins; above it the
             # (instruction-bound) step kernel is better left alone and the cheap reset kernel follows it
-            fused = self.auto_reset and self.env.num_envs <= FUSED_RESET_MAX_ENVS and hasattr(self.env, 'check_consistency')
+            fused = self.auto_reset and self.env.num_envs <= FUSED_RESET_MAX_ENVS and getattr(self.env, 'supports_fused_reset', False)
             obs, reward_t, done_t, info = self.env.step(dev_actions, auto_reset=True) if fused else self.env.step(dev_actions)
             env_done = done_t
         stepped = torch.cuda.Event()
