@@ -527,15 +527,35 @@ __global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p,
     const int e_base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
     if (e_base >= p.N) return;
     const int e_mine = e_base + lane;
-    unsigned todo = __ballot_sync(0xffffffffu, e_mine < p.N && done_mask[e_mine] != 0);
-    const int C = p.C;
+    const bool mine = e_mine < p.N && done_mask[e_mine] != 0;
+    unsigned todo = __ballot_sync(0xffffffffu, mine);
+    if (todo == 0u) return;
+    const int C = p.C, n = 3 * C;
+    // every lane draws the layout of ITS env (one Philox evaluation per warp instead of one per finished env)
+    int my_tail = 0, my_mid = 0, my_hd = 0, my_cell = -1;
+    if (mine) new_env_layout(p, spawn, call_counter(p), e_mine, my_tail, my_mid, my_hd, my_cell);
     while (todo) {
-        const int e = e_base + __ffs(todo) - 1;
+        const int src = __ffs(todo) - 1, e = e_base + src;
         todo &= todo - 1;
-        int tail, mid, hd, cell;
-        new_env_layout(p, spawn, call_counter(p), e, tail, mid, hd, cell);
-        float* env = p.envs + (size_t)e * 3 * C;
-        for (int i = lane; i < 3 * C; i += 32) env[i] = new_env_value(i, C, tail, mid, hd, cell);
+        const int tail = __shfl_sync(0xffffffffu, my_tail, src), mid = __shfl_sync(0xffffffffu, my_mid, src);
+        const int hd = __shfl_sync(0xffffffffu, my_hd, src), cell = __shfl_sync(0xffffffffu, my_cell, src);
+        float* env = p.envs + (size_t)e * n;
+        // the new env is zeros plus five cells: 128-bit zero stores over the aligned middle, then (ordered by the
+        // warp barrier) the five cells of the LENGTH_3_SNAKES stamp, head and food (:372-385)
+        int lead = (4 - (int)((reinterpret_cast<uintptr_t>(env) >> 2) & 3)) & 3;
+        if (lead > n) lead = n;
+        if (lane < lead) env[lane] = 0.0f;
+        const int nvec = (n - lead) >> 2;
+        float4* vb = reinterpret_cast<float4*>(env + lead);
+        for (int j = lane; j < nvec; j += 32) vb[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int tail0 = lead + 4 * nvec;
+        if (lane < n - tail0) env[tail0 + lane] = 0.0f;
+        __syncwarp();
+        if (lane < 5) {
+            const int idx = lane == 0 ? cell : lane == 1 ? C + hd : lane == 2 ? 2 * C + tail : lane == 3 ? 2 * C + mid : 2 * C + hd;
+            const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
+            if (idx >= 0) env[idx] = val;
+        }
         if (lane == 0 && p.hints) { p.hints[2 * (size_t)e] = (short)hd; p.hints[2 * (size_t)e + 1] = 3; }
     }
 }
