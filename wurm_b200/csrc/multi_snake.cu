@@ -309,10 +309,12 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
 }
 
 // One CTA = one environment.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
-// THREADS = 128 for small grids (S*S <= 1024; register budget capped so that 12 CTAs stay resident per SM:
-// these envs are latency-bound, more envs in flight is what hides the load and barrier latencies), 256 otherwise.
+// THREADS = 32 for small grids (S*S <= 1024): one warp per env, so the ~12 barriers of the step cost nothing,
+// no warp idles while lane-per-snake logic runs, and 32 envs stay resident per SM (measured on B200 at K=4,
+// S=25: 0.466 ms per launch against 0.489 / 0.533 ms with 64 / 128 threads; staging the raw env through
+// shared memory with TMA was tried and lost to the occupancy it costs).  256 threads otherwise.
 template <bool STEP, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 12 : 4) multi_env_kernel(const MultiParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 32) multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MultiSmem s = carve(smem_raw, p.C);
     const int C = p.C, K = p.K, S = p.S;
@@ -320,8 +322,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 12 : 4) multi_env_ke
 
     // per-snake scalars (action, orientation, boost-cost draw) are fetched by warp 0 before the env is streamed
     // in, so that their latency hides behind the load instead of heading the serial per-snake logic
-    // (measured on B200: +2 % at K=16,S=64 with 256 threads; -6 % at K=4,S=25 with 128 threads and a 40-register
-    // budget, where the values are fetched right before use instead)
+    // (measured on B200: +2 % at K=16,S=64 with 256 threads; a loss for the small-grid variant, where the values are
+    // fetched right before use instead)
     constexpr bool kPrefetch = THREADS == 256;
     long long pre_action = 0, pre_orient = 0;
     float pre_cost = 0.0f;
@@ -886,7 +888,7 @@ static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
 
 template <bool STEP>
 static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
-    return p.C <= 1024 ? launch_multi_env_t<STEP, 128>(p, stream) : launch_multi_env_t<STEP, 256>(p, stream);
+    return p.C <= 1024 ? launch_multi_env_t<STEP, 32>(p, stream) : launch_multi_env_t<STEP, 256>(p, stream);
 }
 
 }  // namespace wurm
