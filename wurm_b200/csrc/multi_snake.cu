@@ -28,6 +28,7 @@
 // without boosting agents the phase changes nothing) -- except in replay mode, where the flag
 // recorded from the reference is followed literally.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/wurm_b200.h"
 #include "common.cuh"
@@ -309,12 +310,14 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
 }
 
 // One CTA = one environment.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
-// THREADS = 32 for small grids (S*S <= 1024): one warp per env, so the ~12 barriers of the step cost nothing,
-// no warp idles while lane-per-snake logic runs, and 32 envs stay resident per SM (measured on B200 at K=4,
-// S=25: 0.466 ms per launch against 0.489 / 0.533 ms with 64 / 128 threads; staging the raw env through
-// shared memory with TMA was tried and lost to the occupancy it costs).  256 threads otherwise.
+// THREADS grows with the grid (~24 cells per thread at most, measured sweep in profiles/r01_sweep_multi.txt): for
+// small grids one warp per env, so that the ~12 barriers of the step cost nothing, no warp idles while the
+// lane-per-snake logic runs and 32 envs stay resident per SM (K=4, S=25: 0.466 ms per launch against 0.489 /
+// 0.533 ms with 64 / 128 threads; staging the raw env through shared memory with TMA was tried and lost to the
+// occupancy it costs); 256 threads for S=64, where streaming 540 KB per env wants the loads of many threads in flight.
 template <bool STEP, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 32) multi_env_kernel(const MultiParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? 12 : THREADS == 64 ? 20 : 32)
+multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MultiSmem s = carve(smem_raw, p.C);
     const int C = p.C, K = p.K, S = p.S;
@@ -888,7 +891,16 @@ static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
 
 template <bool STEP>
 static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
-    return p.C <= 1024 ? launch_multi_env_t<STEP, 32>(p, stream) : launch_multi_env_t<STEP, 256>(p, stream);
+    // ~24 cells per thread at most (profiles/r01_sweep_multi.txt): 32 threads up to S=31, 64 to S=39, 128 to S=55, 256 above
+    int threads = 32;
+    while (threads < 256 && p.C > 24 * threads) threads <<= 1;
+    if (const char* v = getenv("WURM_MULTI_THREADS")) threads = atoi(v);       // tuning override: 32, 64, 128, 256
+    switch (threads) {
+        case 32: return launch_multi_env_t<STEP, 32>(p, stream);
+        case 64: return launch_multi_env_t<STEP, 64>(p, stream);
+        case 128: return launch_multi_env_t<STEP, 128>(p, stream);
+        default: return launch_multi_env_t<STEP, 256>(p, stream);
+    }
 }
 
 }  // namespace wurm
