@@ -1,8 +1,8 @@
 // SimpleGridworld (wurm/envs/simple_gridworld.py) for B200 (sm_100a): the reference's two-channel debug
 // env -- an agent pixel and one food pixel, the same move / eat / respawn / edge machinery as SingleSnake
 // without a body.  An env is 2*S*S floats (392 B at the reference's size 7), far too small to stage:
-// one warp per env works straight on global memory with coalesced strided loads, finds the agent with a
-// ballot, and stores only the two or three cells a step changes.
+// a small lane group per env (8 lanes at size 7: four envs per warp) works straight on global memory with
+// strided loads, finds the agent with shuffles, and stores only the two or three cells a step changes.
 #include <math.h>
 
 #include "../../include/wurm_b200.h"
@@ -51,13 +51,15 @@ __device__ __forceinline__ int grid_pick_free(const GridParams& p, const float* 
     return -1;
 }
 
-// simple_gridworld.py:88-133 for env e by one warp (reads through L2: the step's own stores are visible)
+// simple_gridworld.py:88-133 for env e by a group of G lanes (reads through L2: the step's own stores are visible)
+template <int G>
 __device__ __forceinline__ void grid_observe_env(const GridParams& p, int e, int lane) {
+    const unsigned gm = group_mask<G>();
     const int S = p.S, C = p.C;
     const float* env = p.envs + (size_t)e * 2 * C;
     if (p.obs_mode == WURM_OBS_DEFAULT) {                            // black background (:90), agent green, food red
         float* o = p.obs + (size_t)e * 3 * C;
-        for (int q = lane; q < C; q += 32) {
+        for (int q = lane; q < C; q += G) {
             const int y = (int)__umulhi((uint32_t)q, p.magic_S), x = q - y * S;
             float r = 0.0f, g = 0.0f;
             if (__ldcg(env + C + q) > kEps) { r = 0.0f; g = 1.0f; }
@@ -66,19 +68,19 @@ __device__ __forceinline__ void grid_observe_env(const GridParams& p, int e, int
             o[q] = r; o[C + q] = g; o[2 * C + q] = 0.0f;
         }
     } else if (p.obs_mode == WURM_OBS_RAW) {
-        for (int i = lane; i < 2 * C; i += 32) p.obs[(size_t)e * 2 * C + i] = __ldcg(env + i);
+        for (int i = lane; i < 2 * C; i += G) p.obs[(size_t)e * 2 * C + i] = __ldcg(env + i);
     } else if (p.obs_mode == WURM_OBS_POSITIONS) {                   // first argmax of agent / food (:119-130)
         int idx[2];
         for (int ch = 0; ch < 2; ++ch) {
             const float* v = env + (ch == 0 ? C : 0);
             float bv = -INFINITY;
             int bq = 0;
-            for (int q = lane; q < C; q += 32) {
+            for (int q = lane; q < C; q += G) {
                 const float x = __ldcg(v + q);
                 if (x > bv) { bv = x; bq = q; }
             }
-            const float gv = group_max<32>(bv, 0xffffffffu);
-            idx[ch] = -group_max<32>(bv == gv ? -bq : -(1 << 30), 0xffffffffu);
+            const float gv = group_max<G>(bv, gm);
+            idx[ch] = -group_max<G>(bv == gv ? -bq : -(1 << 30), gm);
         }
         if (lane == 0) {
             float* o = p.obs + (size_t)e * 4;
@@ -87,21 +89,27 @@ __device__ __forceinline__ void grid_observe_env(const GridParams& p, int e, int
     }
 }
 
-// simple_gridworld.py:135-201, one warp per env
-template <bool STEP>
+// simple_gridworld.py:135-201: G consecutive lanes per env (G = 8 at the reference's size 7: four envs per warp)
+template <int G, bool STEP>
 __global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= p.N) return;
-    if (STEP) {
+    __shared__ int cnt_s[4];                                          // per-CTA episode statistics
+    const unsigned gm = group_mask<G>();
+    const int lane = threadIdx.x % G;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = e < p.N;
+    if (STEP && p.stats) {
+        if (threadIdx.x < 4) cnt_s[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    if (STEP && active) {
         const int S = p.S, C = p.C;
         float* food = p.envs + (size_t)e * 2 * C;
         float* head = food + C;
         int hp = -1, hc = 0;
-        for (int q = lane; q < C; q += 32)
+        for (int q = lane; q < C; q += G)
             if (head[q] != 0.0f) { hp = q; ++hc; }
-        hp = group_max<32>(hp, 0xffffffffu);
-        hc = group_sum<32>(hc, 0xffffffffu);
+        hp = group_max<G>(hp, gm);
+        hc = group_sum<G>(hc, gm);
         long long a;
         if (p.action_bytes == 8) a = ((const long long*)p.actions)[e];
         else if (p.action_bytes == 4) a = ((const int*)p.actions)[e];
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
             if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
         }
         const float ov = np >= 0 ? food[np] : 0.0f;                   // :169 agent-food overlap
-        __syncwarp();
+        __syncwarp(gm);
         if (lane == 0 && hp >= 0) {
             head[hp] = 0.0f;
             if (np >= 0) {
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
                 if (ov != 0.0f) food[np] = ov + ov * -1.0f;           // :171
             }
         }
-        __syncwarp();
+        __syncwarp(gm);
         if (ov != 0.0f) {                                             // :176-181 respawn
             const int cell = p.food_replay ? p.food_replay[e]
                                            : grid_pick_free(p, food, call_counter(p), e, kStreamGridStepFood);
@@ -133,15 +141,32 @@ __global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
             p.done[e] = !interior;                                    // :189-194 edge collision is the only way to end
             if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
             if (p.stats) {
-                unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
-                atomicAdd(slot + WURM_STAT_ENV_STEPS, 1ull);
-                if (!interior) { atomicAdd(slot + WURM_STAT_EPISODES, 1ull); atomicAdd(slot + WURM_STAT_EDGE_COLLISIONS, 1ull); }
-                if (ov != 0.0f) atomicAdd(slot + WURM_STAT_REWARD, 1ull);
+                atomicAdd(&cnt_s[0], 1);
+                if (!interior) atomicAdd(&cnt_s[1], 1);
+                if (ov != 0.0f) atomicAdd(&cnt_s[2], 1);
             }
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
-    if (p.obs_mode >= 0) grid_observe_env(p, e, lane);
+    if (active && p.obs_mode >= 0) grid_observe_env<G>(p, e, lane);
+    if (STEP && p.stats) {                                            // one striped slot per CTA: no hot address in L2
+        __syncthreads();
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        if (threadIdx.x == 0 && cnt_s[0]) atomicAdd(slot + WURM_STAT_ENV_STEPS, (unsigned long long)cnt_s[0]);
+        if (threadIdx.x == 1 && cnt_s[1]) {
+            atomicAdd(slot + WURM_STAT_EPISODES, (unsigned long long)cnt_s[1]);
+            atomicAdd(slot + WURM_STAT_EDGE_COLLISIONS, (unsigned long long)cnt_s[1]);
+        }
+        if (threadIdx.x == 2 && cnt_s[2]) atomicAdd(slot + WURM_STAT_REWARD, (unsigned long long)cnt_s[2]);
+    }
+}
+
+template <bool STEP>
+static int launch_grid_env(const GridParams& p, cudaStream_t stream) {
+    const long long threads_g8 = (long long)p.N * 8, threads_g32 = (long long)p.N * 32;
+    if (p.C <= 64) grid_env_kernel<8, STEP><<<(unsigned)((threads_g8 + 255) / 256), 256, 0, stream>>>(p);
+    else grid_env_kernel<32, STEP><<<(unsigned)((threads_g32 + 255) / 256), 256, 0, stream>>>(p);
+    return check_launch("grid_env_kernel");
 }
 
 // simple_gridworld.py:222-262: done envs get the agent at the start location and one food
@@ -192,8 +217,7 @@ extern "C" int wurm_grid_step(const WurmGridCfg* cfg, float* envs, const void* a
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
     p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
     p.obs = obs; p.reward = reward; p.done = done; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
-    grid_env_kernel<true><<<(p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
-    return check_launch("grid_env_kernel");
+    return launch_grid_env<true>(p, (cudaStream_t)stream);
 }
 
 extern "C" int wurm_grid_observe(const WurmGridCfg* cfg, const float* envs, float* obs, void* stream) {
@@ -202,8 +226,7 @@ extern "C" int wurm_grid_observe(const WurmGridCfg* cfg, const float* envs, floa
     if (!envs || !obs) return fail(WURM_E_INVALID, "NULL pointer");
     if (cfg->obs_mode == WURM_OBS_NONE) return WURM_OK;
     p.envs = const_cast<float*>(envs); p.obs = obs;
-    grid_env_kernel<false><<<(p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
-    return check_launch("grid_env_kernel");
+    return launch_grid_env<false>(p, (cudaStream_t)stream);
 }
 
 extern "C" int wurm_grid_reset(const WurmGridCfg* cfg, float* envs, const uint8_t* done_mask, const int32_t* food_cell_replay,
