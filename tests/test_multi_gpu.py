@@ -416,3 +416,42 @@ def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
         assert_same(stack_dict(dones, K), stack_dict(dones2, K), f'step {t}: dones')
         plain.reset(dones2['__all__'], return_observations=False)
         check_state(graphed, env_state(plain), f'step {t}: state after reset')
+
+
+def test_only_one_food_on_a_nearly_full_board():
+    """MultiSnake only_one food respawn with 0..5 free interior cells: rejection misses, ranking fallback, none free."""
+    S, K = 9, 2
+    cells = []
+    for r in range(1, S - 1):
+        cols = range(1, S - 1) if r % 2 == 1 else range(S - 2, 0, -1)
+        cells += [(r, c) for c in cols]
+    lengths = [40, 41, 42, 43, 44, 45] * 30                          # snake 0 covers path[0:L], snake 1 the last 3 cells
+    E = len(lengths)
+    env = make_env(E, K, S, 'partial_2', manual_setup=True, seed=77)
+    st = orc.MultiState(E, K, S)
+    acts = np.zeros((E, K), np.int64)
+    delta = {(1, 0): 0, (0, -1): 1, (-1, 0): 2, (0, 1): 3}
+    for e, L in enumerate(lengths):
+        for v, (y, x) in enumerate(cells[:L], 1):
+            st.bodies[e * K, 0, y, x] = v
+        hy, hx = cells[L - 1]
+        st.heads[e * K, 0, hy, hx] = 1
+        ny, nx = cells[L]
+        acts[e, 0] = delta[(ny - hy, nx - hx)]
+        st.orientations[e * K] = (acts[e, 0] + 2) % 4                 # facing where it is about to go
+        for v, (y, x) in enumerate(reversed(cells[46:49]), 1):       # snake 1: cells 48,47,46 hold 1,2,3; head on cell 46
+            st.bodies[e * K + 1, 0, y, x] = v
+        y, x = cells[46]
+        st.heads[e * K + 1, 0, y, x] = 1
+        acts[e, 1] = 7                                                # arbitrary: it will collide or move, both fine
+    for name in ('foods', 'heads', 'bodies'):
+        setattr(env, name, torch.from_numpy(getattr(st, name).copy()).to(DEV))
+    env.orientations = torch.from_numpy(st.orientations.copy()).to(DEV)
+    st.agent_colours[:] = np_(env.agent_colours)
+    cfg = orc.multi_cfg(E, K, S)
+    dev_acts = torch.from_numpy(acts).to(DEV)
+    obs, rewards, dones, info = env.step({f'agent_{k}': dev_acts[:, k].contiguous() for k in range(K)})
+    out = orc.multi_step(cfg, st, acts, None, seed=77, step=env._draws)
+    check_state(env, st, 'state after a step on a nearly full board')
+    assert_same(stack_dict(rewards, K), out['rewards'], 'rewards')
+    env.check_status()

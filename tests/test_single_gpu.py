@@ -371,3 +371,44 @@ def test_obs_out_renders_into_a_trajectory_buffer():
         assert_same(np_(ring[t]), np_(obs), f'step {t}')
     with pytest.raises(RuntimeError):
         b.step(acts[0].clone(), obs_out=torch.zeros((N, 74), device=DEV))
+
+
+def boustrophedon(S):
+    """Interior cells of an S x S grid in snake order (row 1 left to right, row 2 right to left, ...)."""
+    cells = []
+    for r in range(1, S - 1):
+        cols = range(1, S - 1) if r % 2 == 1 else range(S - 2, 0, -1)
+        cells += [(r, c) for c in cols]
+    return cells
+
+
+def test_nearly_full_board_food_respawn_and_no_free_cell():
+    """A snake that fills almost the whole interior eats: the respawn has 0..6 free cells to choose from, which
+    exercises the rejection-sampling misses, the explicit ranking fallback and the 'no free cell' case
+    (the reference places nothing then, single_snake.py:306-320)."""
+    S, path = 9, boustrophedon(9)
+    delta = {(1, 0): 0, (0, -1): 1, (-1, 0): 2, (0, 1): 3}            # head displacement -> action
+    lengths = [42, 43, 44, 45, 46, 47, 48] * 40                       # interior = 49 cells; food takes one more
+    N = len(lengths)
+    state = np.zeros((N, 3, S, S), np.float32)
+    actions = np.zeros(N, np.int64)
+    for e, L in enumerate(lengths):
+        for v, (y, x) in enumerate(path[:L], 1):
+            state[e, 2, y, x] = v
+        hy, hx = path[L - 1]
+        fy, fx = path[L]
+        state[e, 1, hy, hx] = 1
+        state[e, 0, fy, fx] = 1
+        actions[e] = delta[(fy - hy, fx - hx)]
+    env = make_env(N, S, 'partial_2', manual_setup=True, seed=2024)
+    env.envs = torch.from_numpy(state.copy()).to(DEV)
+    a = torch.from_numpy(actions.copy()).to(DEV)
+    obs, reward, done, info = env.step(a)
+    r, d, sc, ec = orc.single_step(state, actions, None, seed=2024, step=env._draws)
+    assert (r == 1).all() and not d.any()
+    assert_same(np_(env.envs), state, 'state after eating on a nearly full board')
+    assert_same(np_(reward).reshape(-1), r, 'reward')
+    assert_same(np_(obs), orc.single_observe(state, 'partial_2')[0], 'observation')
+    food_left = state[:, 0].reshape(N, -1).sum(-1)
+    assert (food_left[np.array(lengths) == 48] == 0).all()            # 49 body cells: nowhere to put the food
+    assert (food_left[np.array(lengths) < 48] == 1).all()
