@@ -219,6 +219,16 @@ int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const 
                     const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                     const WurmMultiStepOut* out, int32_t* status, int64_t* stats /* nullable */, void* stream);
 
+/* Fused fast path: wurm_multi_step followed by wurm_multi_reset(dones['__all__']) in ONE launch -- the pair the
+ * reference's driver issues every iteration (experiments/multiagent.py:375-377).  Outputs (and the
+ * observations) are those of the step; the state left behind is the one after the reset.  The reset's
+ * draws use call counter `step` + 1: bit-identical to the two calls in sequence.  reset_draws: replay tape of
+ * the reset or NULL. */
+int wurm_multi_step_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions, int action_bytes,
+                          const WurmMultiStepDraws* draws, const WurmMultiResetDraws* reset_draws, uint64_t seed,
+                          uint64_t step, const uint64_t* step_dev, const WurmMultiStepOut* out, int32_t* status,
+                          int64_t* stats /* nullable */, void* stream);
+
 /* Replaces the state update of MultiSnake.reset (multi_snake.py:771-831) incl. _create_envs,
  * _add_snake, _get_snake_addition and get_n_colours.  env_done (E): envs to re-create. */
 int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const uint8_t* env_done,

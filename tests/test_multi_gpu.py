@@ -455,3 +455,58 @@ def test_only_one_food_on_a_nearly_full_board():
     check_state(env, st, 'state after a step on a nearly full board')
     assert_same(stack_dict(rewards, K), out['rewards'], 'rewards')
     env.check_status()
+
+
+FUSED_CASES = [
+    (300, 4, 25, 'partial_4', dict()),
+    (200, 4, 25, 'partial_3', dict(food_mode='random_rate', food_rate=3e-3, respawn_mode='any', food_on_death_prob=0.33,
+                                   boost_cost_prob=0.25)),
+    (96, 3, 12, 'full', dict(respawn_mode='any', food_on_death_prob=1.0, agent_colours='fixed')),
+    (24, 16, 64, 'partial_4', dict(respawn_mode='any')),
+]
+
+
+@pytest.mark.parametrize('E,K,S,mode,rules', FUSED_CASES)
+def test_fused_step_reset_equals_step_then_reset(E, K, S, mode, rules):
+    """step(a, auto_reset=True) == step(a); reset(dones['__all__'], return_observations=False): same outputs, same
+    state afterwards (re-created envs, recoloured and respawned snakes), same draws."""
+    two_calls = make_env(E, K, S, mode, seed=91, **rules)
+    fused = make_env(E, K, S, mode, seed=91, **rules)
+    fused.agent_colours = two_calls.agent_colours.clone()
+    g = torch.Generator().manual_seed(3)
+    for t in range(50):
+        acts = torch.randint(0, 8, (K, E), generator=g).to(DEV)
+        obs, rewards, dones, info = two_calls.step({f'agent_{k}': acts[k] for k in range(K)})
+        two_calls.reset(dones['__all__'], return_observations=False)
+        obs_f, rewards_f, dones_f, info_f = fused.step({f'agent_{k}': acts[k] for k in range(K)}, auto_reset=True)
+        tag = f'step {t}: '
+        for k in range(K):
+            assert_same(np_(obs_f[f'agent_{k}']), np_(obs[f'agent_{k}']), tag + f'observation {k}')
+        assert_same(stack_dict(rewards_f, K), stack_dict(rewards, K), tag + 'rewards')
+        assert_same(stack_dict(dones_f, K), stack_dict(dones, K), tag + 'dones')
+        assert_same(np_(dones_f['__all__']), np_(dones['__all__']), tag + '__all__')
+        check_state(fused, env_state(two_calls), tag + 'state after reset')
+    fused.check_consistency()
+    assert fused._draws == two_calls._draws
+
+
+@pytest.mark.parametrize('i', range(len(MULTI)))
+def test_fused_step_reset_golden_replay(i):
+    """The fused launch against the reference's recorded step+reset trajectories (both tapes replayed)."""
+    tr = MULTI[i]
+    E, K, S, mode = int(tr['E']), int(tr['K']), int(tr['S']), str(tr['mode'])
+    env = make_env(E, K, S, mode, manual_setup=True, **multi_rules(tr))
+    init = multi_state_arrays(tr, 'init')
+    env.agent_colours = torch.from_numpy(init['agent_colours']).to(DEV)
+    env._create_all(draws=dict(create=tr['init/create'], respawn=np.full((E, 2), -1, np.int32), colours=init['agent_colours']))
+    for t in range(int(tr['steps'])):
+        tag = f'trajectory {i} step {t}'
+        acts = torch.from_numpy(tr[f'{t}/actions']).to(DEV)
+        obs, rewards, dones, info = env.step({f'agent_{k}': acts[:, k].contiguous() for k in range(K)}, auto_reset=True,
+                                             draws=multi_step_draws(tr, t, dense_rate=True),
+                                             reset_draws=multi_group(tr, f'{t}/reset_draws', ('create', 'respawn', 'colours')))
+        expect = {k: tr[f'{t}/{k}'] for k in ('rewards', 'dones', 'all_done', 'snake_collision', 'edge_collision', 'food',
+                                              'boost', 'size', 'obs')}
+        check_step_outputs(env, K, obs, rewards, dones, info, expect, tag)
+        check_state(env, multi_state_arrays(tr, f'{t}/reset_state'), tag + ' after the fused reset')
+    env.check_status()

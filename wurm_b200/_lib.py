@@ -20,7 +20,7 @@ OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1
 # every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_step_reset',
            'wurm_single_reset',
-           'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_reset', 'wurm_multi_observe',
+           'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_step_reset', 'wurm_multi_reset', 'wurm_multi_observe',
            'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check', 'wurm_grid_step', 'wurm_grid_reset',
            'wurm_grid_observe']
 CHECK_REPORT = 4
@@ -115,6 +115,10 @@ def lib():
     L.wurm_multi_step.restype = i32
     L.wurm_multi_step.argtypes = [mcfg, mst, ctypes.POINTER(vp), i32, ctypes.POINTER(WurmMultiStepDraws), u64, u64, vp,
                                   ctypes.POINTER(WurmMultiStepOut), vp, vp, vp]
+    L.wurm_multi_step_reset.restype = i32
+    L.wurm_multi_step_reset.argtypes = [mcfg, mst, ctypes.POINTER(vp), i32, ctypes.POINTER(WurmMultiStepDraws),
+                                        ctypes.POINTER(WurmMultiResetDraws), u64, u64, vp, ctypes.POINTER(WurmMultiStepOut),
+                                        vp, vp, vp]
     L.wurm_multi_reset.restype = i32
     L.wurm_multi_reset.argtypes = [mcfg, mst, vp, ctypes.POINTER(WurmMultiResetDraws), u64, u64, vp, vp, vp]
     L.wurm_multi_observe.restype = i32

@@ -82,6 +82,7 @@ struct MultiParams {
     int* status;
     unsigned long long* stats;
     uint32_t magic_S, magic_C, magic_W;
+    int auto_reset;       // fused step+reset: the env's reset runs in the step's launch, with call counter + 1
 };
 
 __device__ __forceinline__ uint64_t call_counter(const MultiParams& p) { return p.step + (p.step_dev ? *p.step_dev : 0ull); }
@@ -181,6 +182,7 @@ struct MultiSmem {
     int* sum;         // sum of body values per snake (invariant check)
     int* misc;        // [0] food cells, [2] run_boost, [3] force full write-back
     short* col;       // K*3
+    unsigned char* reset;   // ResetScratch of the fused step+reset path
 };
 
 __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
@@ -190,11 +192,13 @@ __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
     s.size = s.hp + 32; s.hcnt = s.size + 32; s.done = s.hcnt + 32; s.decay = s.done + 32; s.cost = s.decay + 32;
     s.boost = s.cost + 32; s.sum = s.boost + 32; s.misc = s.sum + 32;
     s.col = reinterpret_cast<short*>(s.misc + 8);
+    s.reset = reinterpret_cast<unsigned char*>(s.col + 96);
     return s;
 }
 
 static size_t multi_smem_bytes(int C, int W, int obs_mode) {
-    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + 16;
+    // records + per-snake arrays + misc + colours + the fused reset's scratch (occupancy bytes, picks)
+    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4 + 32;
 }
 
 // Food transitions keep the env's food-cell count (misc[0]) current, so _add_food needs no counting pass.
@@ -306,6 +310,189 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
             env_pixel(p, s, q, y, x, rgb);
             for (int c = 0; c < 3; ++c) p.img[((size_t)e * 3 + c) * C + q] = (short)rgb[c];
         }
+    }
+}
+
+// Block-wide uniform choice among the cells q < C with pred(q), in raster order: every thread counts its
+// contiguous chunk, a shuffle scan ranks the chunks, `rnd` picks a rank and the owning thread finds the
+// cell (written to *out).  Returns the number of candidate cells.  `counts`: >= 33 ints of shared scratch.
+template <typename P>
+__device__ __forceinline__ int block_pick(int C, int* counts, uint32_t rnd, int* out, P&& pred) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int chunk = (C + nthr - 1) / nthr, q0 = tid * chunk, q1 = min(C, q0 + chunk);
+    int mine = 0;
+    for (int q = q0; q < q1; ++q) mine += pred(q) ? 1 : 0;
+    int incl = mine;                                                  // inclusive scan within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) counts[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = counts[w];
+        if (w < warp) before += c;
+        total += c;
+    }
+    const int first = before + incl - mine;                           // rank of this thread's first candidate
+    if (total > 0) {
+        const int r = (int)bounded(rnd, (uint32_t)total);
+        if (r >= first && r < first + mine) {
+            int left = r - first;
+            for (int q = q0; q < q1; ++q)
+                if (pred(q) && left-- == 0) { *out = q; break; }
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+// ---- pieces of the reset shared by the stand-alone kernel and the fused step+reset path ----
+struct ResetScratch {
+    uint8_t* occ;      // C occupancy bytes
+    int* counts;       // block_pick scratch (one int per warp)
+    int* pick;         // [0] chosen cell
+    int* snake_cell;   // K seed cells of a re-created env
+    int* snake_dir;    // K directions
+};
+
+static size_t reset_scratch_bytes(int C) { return (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4; }
+
+__device__ __forceinline__ ResetScratch carve_reset(unsigned char* base, int C) {
+    ResetScratch r;
+    r.occ = base;
+    r.counts = reinterpret_cast<int*>(base + ((C + 15) & ~15));
+    r.pick = r.counts + 16;
+    r.snake_cell = r.pick + 4;
+    r.snake_dir = r.snake_cell + 32;
+    return r;
+}
+
+// :846-858 / :927-941: a snake may be seeded on cell q if q is at least two cells from the wall and nothing
+// occupies its 3x3 neighbourhood
+__device__ __forceinline__ bool spawnable(const MultiParams& p, const uint8_t* occ, int q) {
+    const int S = p.S, y = fdiv(q, p.magic_S), x = q - y * S;
+    if (y < 2 || y > S - 3 || x < 2 || x > S - 3) return false;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+            if (occ[(y + dy) * S + x + dx]) return false;
+    return true;
+}
+
+// cells of a length-3 snake seeded at `cell` facing d (LENGTH_3_SNAKES): tail 1, seed 2, head 3
+__device__ __forceinline__ void snake_cells(const MultiParams& p, int cell, int d, int& tl, int& hd) {
+    const int S = p.S, y = fdiv(cell, p.magic_S), x = cell - y * S;
+    hd = (y + off_y(d)) * S + (x + off_x(d));
+    tl = (y - off_y(d)) * S + (x - off_x(d));
+}
+
+// _create_envs (:996-1019): K snakes placed one after the other (_add_snake :911-994) and one food, decided on a
+// fresh occupancy map; results in sc.snake_cell / sc.snake_dir and the returned food cell.  Whole CTA.
+__device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
+    const int C = p.C, K = p.K, S = p.S, tid = threadIdx.x, nthr = blockDim.x;
+    for (int q = tid; q < C; q += nthr) sc.occ[q] = 0;
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        if (tid == 0) sc.pick[0] = -1;
+        __syncthreads();
+        int d;
+        if (p.create) {
+            if (tid == 0) sc.pick[0] = p.create[((size_t)e * (K + 1) + k) * 2];
+            d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
+            __syncthreads();
+        } else {
+            const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
+            block_pick(C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(p, sc.occ, q); });
+            d = (int)(r.y >> 30);
+        }
+        const int cell = sc.pick[0];
+        __syncthreads();
+        if (tid == 0) {
+            sc.snake_cell[k] = cell; sc.snake_dir[k] = d;
+            if (cell >= 0) {
+                int tl, hd;
+                snake_cells(p, cell, d, tl, hd);
+                sc.occ[tl] = 1; sc.occ[cell] = 1; sc.occ[hd] = 1;
+            } else {
+                atomicOr(p.status, WURM_ST_NO_SPAWN);                 // the reference raises (:947)
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) sc.pick[0] = -1;
+    __syncthreads();
+    if (p.create) {
+        if (tid == 0) sc.pick[0] = p.create[((size_t)e * (K + 1) + K) * 2];
+        __syncthreads();
+    } else {                                                          // :1016 one food on a free interior cell
+        block_pick(C, sc.counts, draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateFood).x, sc.pick, [&](int q) {
+            const int y = fdiv(q, p.magic_S), x = q - y * S;
+            return y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && !sc.occ[q];
+        });
+    }
+    return sc.pick[0];
+}
+
+// Stores the cells of the re-created env's snakes and food and revives its agents (:790-798).  Whole CTA; the
+// caller has zeroed (or is zeroing, to the same values) whatever else the tensors held.
+__device__ __forceinline__ void write_recreated(const MultiParams& p, int e, const ResetScratch& sc, int fcell) {
+    const int C = p.C, K = p.K, tid = threadIdx.x;
+    if (tid == 0 && fcell >= 0) p.foods[(size_t)e * C + fcell] = 1.0f;
+    if (tid < K) {
+        const size_t n = (size_t)e * K + tid;
+        if (sc.snake_cell[tid] >= 0) {
+            int tl, hd;
+            snake_cells(p, sc.snake_cell[tid], sc.snake_dir[tid], tl, hd);
+            p.heads[n * C + hd] = 1.0f;
+            p.bodies[n * C + hd] = 3.0f; p.bodies[n * C + sc.snake_cell[tid]] = 2.0f; p.bodies[n * C + tl] = 1.0f;
+            p.orientations[n] = sc.snake_dir[tid];                    // :793
+        }
+        p.dones[n] = 0;                                               // :798
+    }
+}
+
+// :805-829 + _get_snake_addition :838-909: seed cell (or -1) and direction for the env's first dead snake, on the
+// occupancy map the caller prepared.  Whole CTA.
+__device__ __forceinline__ int decide_respawn(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc, int& d) {
+    if (threadIdx.x == 0) sc.pick[0] = -1;
+    __syncthreads();
+    if (p.respawn) {
+        if (threadIdx.x == 0) sc.pick[0] = p.respawn[2 * (size_t)e];
+        d = p.respawn[2 * (size_t)e + 1];
+        __syncthreads();
+    } else {
+        const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiRespawn);
+        block_pick(p.C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(p, sc.occ, q); });
+        d = (int)(r.y >> 30);
+    }
+    return sc.pick[0];
+}
+
+// one thread: the respawned snake's cells, orientation and done flag (:826-829)
+__device__ __forceinline__ void write_respawned(const MultiParams& p, int e, int k, int cell, int d) {
+    const size_t n = (size_t)e * p.K + k;
+    if (cell >= 0) {
+        int tl, hd;
+        snake_cells(p, cell, d, tl, hd);
+        p.heads[n * p.C + hd] = 1.0f;
+        p.bodies[n * p.C + hd] = 3.0f; p.bodies[n * p.C + cell] = 2.0f; p.bodies[n * p.C + tl] = 1.0f;
+    }
+    p.orientations[n] = d;                                            // :828 even when the spawn failed
+    p.dones[n] = cell < 0;                                            // :829
+}
+
+// get_n_colours (:163-169) for one dead snake (:800-803)
+__device__ __forceinline__ void recolour(const MultiParams& p, int e, int k, uint64_t ctr) {
+    short* col = p.colours + 3 * ((size_t)e * p.K + k);
+    if (p.colours_replay) {
+        for (int c = 0; c < 3; ++c) col[c] = p.colours_replay[3 * ((size_t)e * p.K + k) + c];
+    } else {
+        const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiColour | ((uint32_t)k << 4));
+        const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
+        const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+        col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f); col[2] = (short)(c2 / norm * 192.0f);
     }
 }
 
@@ -581,6 +768,37 @@ multi_env_kernel(const MultiParams p) {
         }
     }
     write_multi_obs(p, s, e);
+
+    if (STEP && p.auto_reset) {
+        // ---- fused reset (multi_snake.py:771-831), bit-identical to wurm_multi_reset called right after this
+        // step: same draws (call counter + 1), same result.  The compact form already knows what the stand-alone
+        // kernel has to scan the tensors for: which cells are occupied, which snakes are dead.
+        __syncthreads();                                              // the observation is done with the records
+        const ResetScratch sc = carve_reset(reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15), C);
+        const uint64_t ctr = call_counter(p) + 1;
+        int first_dead = -1;
+        for (int kk = K - 1; kk >= 0; --kk)
+            if (s.done[kk]) first_dead = kk;
+        bool all_dead = true;
+        for (int kk = 0; kk < K; ++kk) all_dead &= s.done[kk] != 0;
+        if (all_dead) {                                               // :787-798 re-create the env
+            const int fcell = decide_recreate(p, e, ctr, sc);
+            // all snakes are dead, so their tensors are already zero (the step deleted them); only food is left
+            for (int q = tid; q < C; q += nthr)
+                if (s.cell[q] & kFood) p.foods[(size_t)e * C + q] = 0.0f;
+            __syncthreads();
+            write_recreated(p, e, sc, fcell);
+        } else if (first_dead >= 0) {
+            if (p.colour_random && tid < K && s.done[tid]) recolour(p, e, tid, ctr);     // :800-803
+            if (p.respawn_any) {                                      // :805-829
+                for (int q = tid; q < C; q += nthr) sc.occ[q] = (s.cell[q] & (kLive | kFood)) != 0u;
+                __syncthreads();
+                int d;
+                const int cell = decide_respawn(p, e, ctr, sc, d);
+                if (tid == 0) write_respawned(p, e, first_dead, cell, d);
+            }
+        }
+    }
 }
 
 // MultiSnake.check_consistency (multi_snake.py:733-769) on the compact form: one CTA per env streams the
@@ -624,51 +842,11 @@ __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, i
 // ---------------------------------------------------------------------------------------------
 // reset (multi_snake.py:771-831)
 // ---------------------------------------------------------------------------------------------
-// Block-wide uniform choice among the cells q < C with pred(q), in raster order: every thread counts its
-// contiguous chunk, a shuffle scan ranks the chunks, `rnd` picks a rank and the owning thread finds the
-// cell (written to *out).  Returns the number of candidate cells.  `counts`: >= 33 ints of shared scratch.
-template <typename P>
-__device__ __forceinline__ int block_pick(int C, int* counts, uint32_t rnd, int* out, P&& pred) {
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const int chunk = (C + nthr - 1) / nthr, q0 = tid * chunk, q1 = min(C, q0 + chunk);
-    int mine = 0;
-    for (int q = q0; q < q1; ++q) mine += pred(q) ? 1 : 0;
-    int incl = mine;                                                  // inclusive scan within the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) counts[warp] = incl;
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < nwarps; ++w) {
-        const int c = counts[w];
-        if (w < warp) before += c;
-        total += c;
-    }
-    const int first = before + incl - mine;                           // rank of this thread's first candidate
-    if (total > 0) {
-        const int r = (int)bounded(rnd, (uint32_t)total);
-        if (r >= first && r < first + mine) {
-            int left = r - first;
-            for (int q = q0; q < q1; ++q)
-                if (pred(q) && left-- == 0) { *out = q; break; }
-        }
-    }
-    __syncthreads();
-    return total;
-}
-
-// The reset of ONE env by the whole CTA (every thread calls it with the same e).
+// The CTA-wide part of the stand-alone reset of ONE env (every thread calls it with the same e).
 __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned char* smem_raw, int e) {
-    const int C = p.C, K = p.K, S = p.S;
-    uint8_t* occ = smem_raw;                                          // C occupancy bytes
-    int* counts = reinterpret_cast<int*>(smem_raw + ((C + 15) & ~15)); // blockDim.x + 1
-    int* pick = counts + blockDim.x + 1;                              // [0] chosen cell
-    int* snake_cell = pick + 4;                                       // K
-    int* snake_dir = snake_cell + 32;                                 // K
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
+    const ResetScratch sc = carve_reset(smem_raw, C);
+    const uint64_t ctr = call_counter(p);
 
     const bool recreate = p.env_done[e] != 0;
     int first_dead = -1, ndead = 0;
@@ -676,128 +854,40 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         if (p.dones[(size_t)e * K + k]) { first_dead = k; ++ndead; }
     if (!recreate && (ndead == 0 || !p.respawn_any)) return;          // nothing to do for this env
 
-    auto inner = [&](int q) {
-        const int y = fdiv(q, p.magic_S), x = q - y * S;
-        return y >= 2 && y <= S - 3 && x >= 2 && x <= S - 3;
-    };
-    auto spawnable = [&](int q) {                                      // :846-858 / :927-941
-        if (!inner(q)) return false;
-        const int y = fdiv(q, p.magic_S), x = q - y * S;
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx)
-                if (occ[(y + dy) * S + x + dx]) return false;
-        return true;
-    };
-    auto stamp = [&](int cell, int d) {                                // LENGTH_3_SNAKES
-        const int y = fdiv(cell, p.magic_S), x = cell - y * S;
-        occ[(y - off_y(d)) * S + (x - off_x(d))] = 1; occ[cell] = 1; occ[(y + off_y(d)) * S + (x + off_x(d))] = 1;
-    };
-    auto snake_value = [&](int cell, int d, int q, bool head) -> float {
-        const int y = fdiv(cell, p.magic_S), x = cell - y * S;
-        const int hd = (y + off_y(d)) * S + (x + off_x(d)), tl = (y - off_y(d)) * S + (x - off_x(d));
-        if (head) return q == hd ? 1.0f : 0.0f;
-        return q == hd ? 3.0f : q == cell ? 2.0f : q == tl ? 1.0f : 0.0f;
-    };
-
-    if (recreate) {                                                   // :787-798 + _create_envs :996-1019
-        for (int q = tid; q < C; q += nthr) occ[q] = 0;
+    float* gfood = p.foods + (size_t)e * C;
+    float* ghead = p.heads + (size_t)e * K * C;
+    float* gbody = p.bodies + (size_t)e * K * C;
+    if (recreate) {                                                   // :787-798
+        const int fcell = decide_recreate(p, e, ctr, sc);
+        // An env is re-created when all its snakes are dead, i.e. (on a consistent state) its head and body grids
+        // are already all-zero: instead of storing (1+2K)*S*S values, the old tensors are scanned (cheap 128-bit
+        // loads) and only non-zero leftovers are cleared, then the 4K+1 cells of the new env are stored.
+        scan_nonzero(gfood, C, [&](int i, float) { gfood[i] = 0.0f; });
+        scan_nonzero(ghead, K * C, [&](int i, float) { ghead[i] = 0.0f; });
+        scan_nonzero(gbody, K * C, [&](int i, float) { gbody[i] = 0.0f; });
         __syncthreads();
-        for (int k = 0; k < K; ++k) {                                 // _add_snake, one snake after the other
-            if (tid == 0) pick[0] = -1;
-            __syncthreads();
-            int d;
-            if (p.create) {
-                if (tid == 0) pick[0] = p.create[((size_t)e * (K + 1) + k) * 2];
-                d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
-                __syncthreads();
-            } else {
-                const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
-                block_pick(C, counts, r.x, pick, spawnable);
-                d = (int)(r.y >> 30);
-            }
-            const int cell = pick[0];
-            __syncthreads();
-            if (tid == 0) {
-                snake_cell[k] = cell; snake_dir[k] = d;
-                if (cell >= 0) stamp(cell, d);
-                else atomicOr(p.status, WURM_ST_NO_SPAWN);            // the reference raises (:947)
-            }
-            __syncthreads();
-        }
-        if (tid == 0) pick[0] = -1;
-        __syncthreads();
-        auto free_interior = [&](int q) {
-            const int y = fdiv(q, p.magic_S), x = q - y * S;
-            return y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && !occ[q];
-        };
-        if (p.create) {
-            if (tid == 0) pick[0] = p.create[((size_t)e * (K + 1) + K) * 2];
-            __syncthreads();
-        } else {                                                      // :1016 one food on a free interior cell
-            block_pick(C, counts, draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiCreateFood).x, pick, free_interior);
-        }
-        const int fcell = pick[0];
-        // Write the new env.  An env is re-created when all its snakes are dead, i.e. (on a consistent state)
-        // its head and body grids are already all-zero: instead of storing (1+2K)*S*S values, the old tensors
-        // are scanned (cheap 128-bit loads) and only non-zero leftovers that differ from the new env are
-        // overwritten, then the 4K+1 cells of the new snakes and the new food are stored.
-        float* gfood = p.foods + (size_t)e * C;
-        float* ghead = p.heads + (size_t)e * K * C;
-        float* gbody = p.bodies + (size_t)e * K * C;
-        scan_nonzero(gfood, C, [&](int i, float v) { if (i != fcell) gfood[i] = 0.0f; (void)v; });
-        scan_nonzero(ghead, K * C, [&](int i, float v) {
-            const int kk = fdiv(i, p.magic_C);
-            const float nv = snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, true) : 0.0f;
-            if (nv != v) ghead[i] = nv;
-        });
-        scan_nonzero(gbody, K * C, [&](int i, float v) {
-            const int kk = fdiv(i, p.magic_C);
-            const float nv = snake_cell[kk] >= 0 ? snake_value(snake_cell[kk], snake_dir[kk], i - kk * C, false) : 0.0f;
-            if (nv != v) gbody[i] = nv;
-        });
-        if (tid == 0 && fcell >= 0) gfood[fcell] = 1.0f;
-        if (tid < K && snake_cell[tid] >= 0) {
-            const int cell = snake_cell[tid], d = snake_dir[tid];
-            const int y = fdiv(cell, p.magic_S), x = cell - y * S;
-            const int hd = (y + off_y(d)) * S + (x + off_x(d)), tl = (y - off_y(d)) * S + (x - off_x(d));
-            ghead[(size_t)tid * C + hd] = 1.0f;
-            gbody[(size_t)tid * C + hd] = 3.0f; gbody[(size_t)tid * C + cell] = 2.0f; gbody[(size_t)tid * C + tl] = 1.0f;
-        }
-        if (tid < K) {
-            if (snake_cell[tid] >= 0) p.orientations[(size_t)e * K + tid] = snake_dir[tid];   // :793
-            p.dones[(size_t)e * K + tid] = 0;                                                 // :798
-        }
-        return;                                                       // every agent alive: no colours, no respawn
+        write_recreated(p, e, sc, fcell);
+        return;                                                       // every agent alive: no respawn
     }
-
-    if (!p.respawn_any) return;
 
     // :805-829 respawn the first dead snake of the env where there is room
-    for (int q = tid; q < C; q += nthr) occ[q] = 0;
-    if (tid == 0) pick[0] = -1;
+    for (int q = tid; q < C; q += nthr) sc.occ[q] = 0;
     __syncthreads();
-    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float) { occ[i] = 1; });
-    scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float) { occ[i - fdiv(i, p.magic_C) * C] = 1; });
-    scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float) { occ[i - fdiv(i, p.magic_C) * C] = 1; });
+    scan_nonzero(gfood, C, [&](int i, float) { sc.occ[i] = 1; });
+    scan_nonzero(ghead, K * C, [&](int i, float) {
+        const int kk = fdiv(i, p.magic_C);
+        sc.occ[i - kk * C] = 1;
+        if (kk == first_dead) ghead[i] = 0.0f;                        // leftovers of the dead snake (none on a consistent state)
+    });
+    scan_nonzero(gbody, K * C, [&](int i, float) {
+        const int kk = fdiv(i, p.magic_C);
+        sc.occ[i - kk * C] = 1;
+        if (kk == first_dead) gbody[i] = 0.0f;
+    });
     __syncthreads();
     int d;
-    if (p.respawn) {
-        if (tid == 0) pick[0] = p.respawn[2 * (size_t)e];
-        d = p.respawn[2 * (size_t)e + 1];
-        __syncthreads();
-    } else {
-        const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiRespawn);
-        block_pick(C, counts, r.x, pick, spawnable);
-        d = (int)(r.y >> 30);
-    }
-    const int cell = pick[0];
-    const size_t n = (size_t)e * K + first_dead;
-    store_floats(p.heads + n * C, C, [&](int i) { return cell >= 0 ? snake_value(cell, d, i, true) : 0.0f; });    // :826-827
-    store_floats(p.bodies + n * C, C, [&](int i) { return cell >= 0 ? snake_value(cell, d, i, false) : 0.0f; });
-    if (tid == 0) {
-        p.orientations[n] = d;                                        // :828 even when the spawn failed
-        p.dones[n] = cell < 0;                                        // :829
-    }
+    const int cell = decide_respawn(p, e, ctr, sc, d);
+    if (tid == 0) write_respawned(p, e, first_dead, cell, d);
 }
 
 // One CTA looks at 32 consecutive envs: lane i of warp 0 reads env i's flags (coalesced), a ballot gives
@@ -817,18 +907,7 @@ __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
                 for (int k = 0; k < K; ++k) {
                     if (!p.dones[(size_t)e * K + k]) continue;
                     any_dead = true;
-                    if (p.colour_random) {                            // :800-803 a new colour for every dead snake
-                        short* col = p.colours + 3 * ((size_t)e * K + k);
-                        if (p.colours_replay) {
-                            for (int c = 0; c < 3; ++c) col[c] = p.colours_replay[3 * ((size_t)e * K + k) + c];
-                        } else {                                      // get_n_colours :163-169
-                            const uint4 r = draw(p.seed, call_counter(p), (uint32_t)e, kStreamMultiColour | ((uint32_t)k << 4));
-                            const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
-                            const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
-                            col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f);
-                            col[2] = (short)(c2 / norm * 192.0f);
-                        }
-                    }
+                    if (p.colour_random) recolour(p, e, k, call_counter(p));   // :800-803 a new colour for every dead snake
                 }
             work = recreate || (any_dead && p.respawn_any);          // CTA-wide work: re-creation or a respawn
         }
@@ -913,10 +992,10 @@ extern "C" int64_t wurm_multi_obs_elems(const WurmMultiCfg* cfg) {
     return cfg->obs_mode == WURM_MOBS_FULL ? 3 * C : cfg->obs_mode == WURM_MOBS_PARTIAL ? 3 * W * W : 0;
 }
 
-extern "C" int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions,
-                               int action_bytes, const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step,
-                               const uint64_t* step_dev, const WurmMultiStepOut* out, int32_t* status, int64_t* stats,
-                               void* stream) {
+static int multi_step_impl(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions, int action_bytes,
+                           const WurmMultiStepDraws* draws, int auto_reset, const WurmMultiResetDraws* reset_draws, uint64_t seed,
+                           uint64_t step, const uint64_t* step_dev, const WurmMultiStepOut* out, int32_t* status, int64_t* stats,
+                           void* stream) {
     MultiParams p = {};
     if (int rc = plan_multi(cfg, state, &p)) return rc;
     if (!actions || !out || !status) return fail(WURM_E_INVALID, "NULL pointer");
@@ -945,7 +1024,28 @@ extern "C" int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* st
     p.food_cons = out->food; p.sizes = out->size; p.all_done = out->all_done; p.obs = out->obs;
     p.dones_out = out->dones; p.boost_out = out->boost;
     p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
+    p.auto_reset = auto_reset;
+    if (auto_reset && reset_draws) {
+        p.create = reset_draws->create; p.respawn = reset_draws->respawn; p.colours_replay = reset_draws->colours;
+        if (!p.create || (p.respawn_any && !p.respawn) || (p.colour_random && !p.colours_replay))
+            return fail(WURM_E_INVALID, "replay: NULL reset draw array");
+    }
     return launch_multi_env<true>(p, (cudaStream_t)stream);
+}
+
+extern "C" int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions,
+                               int action_bytes, const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step,
+                               const uint64_t* step_dev, const WurmMultiStepOut* out, int32_t* status, int64_t* stats,
+                               void* stream) {
+    return multi_step_impl(cfg, state, actions, action_bytes, draws, 0, nullptr, seed, step, step_dev, out, status, stats, stream);
+}
+
+extern "C" int wurm_multi_step_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions,
+                                     int action_bytes, const WurmMultiStepDraws* draws, const WurmMultiResetDraws* reset_draws,
+                                     uint64_t seed, uint64_t step, const uint64_t* step_dev, const WurmMultiStepOut* out,
+                                     int32_t* status, int64_t* stats, void* stream) {
+    return multi_step_impl(cfg, state, actions, action_bytes, draws, 1, reset_draws, seed, step, step_dev, out, status, stats,
+                           stream);
 }
 
 extern "C" int wurm_multi_observe(const WurmMultiCfg* cfg, const WurmMultiState* state, float* obs, int32_t* status,
@@ -981,7 +1081,7 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
             return fail(WURM_E_INVALID, "replay: NULL draw array");
     }
     const int threads = p.C <= 1024 ? 128 : 256;
-    const size_t smem = ((p.C + 15) & ~15) + (size_t)(threads + 1 + 4 + 64) * 4 + 16;
+    const size_t smem = reset_scratch_bytes(p.C) + 16;
     multi_reset_kernel<<<(p.E + 31) / 32, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
 }

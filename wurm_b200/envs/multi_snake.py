@@ -42,6 +42,7 @@ class MultiSnake(object):
         'render.modes': ['rgb_array'],
         'video.frames_per_second': 12
     }
+    supports_fused_reset = True     # step(..., auto_reset=True): wurm_multi_step_reset
 
     def __init__(self,
                  num_envs: int,
@@ -268,7 +269,12 @@ class MultiSnake(object):
     # ------------------------------------------------------------------------------------------
     # step
     # ------------------------------------------------------------------------------------------
-    def step(self, actions: Dict[str, torch.Tensor], *, draws: dict = None):
+    def step(self, actions: Dict[str, torch.Tensor], *, draws: dict = None, auto_reset: bool = False,
+             reset_draws: dict = None):
+        """reference :462-731.  `auto_reset=True` (an extension) fuses the `reset(dones['__all__'],
+        return_observations=False)` the reference's driver issues right after every step
+        (experiments/multiagent.py:377) into the same launch; outputs and observations are the step's, the
+        state afterwards is the one after the reset; bit-identical to the two calls."""
         if len(actions) != self.num_snakes:
             raise RuntimeError('Must have a Tensor of actions for each snake')
 
@@ -313,13 +319,28 @@ class MultiSnake(object):
             dr = _lib.WurmMultiStepDraws(int(bool(draws['boost_phase_ran'])), dev_t('u_boost', torch.float32),
                                          dev_t('u_cost', torch.float32), dev_t('u_reg', torch.float32),
                                          dev_t('food_cell', torch.int32), dev_t('u_rate', torch.float32))
+        rdr = None
+        if auto_reset and reset_draws is not None:
+            def dev_r(key, dt):
+                t = torch.as_tensor(reset_draws[key]).to(device=dev, dtype=dt).contiguous()
+                keep.append(t)
+                return t.data_ptr()
+            rdr = _lib.WurmMultiResetDraws(dev_r('create', torch.int32), dev_r('respawn', torch.int32),
+                                           dev_r('colours', torch.short))
         self._draws += 1
         with torch.cuda.device(dev):
-            _lib.check(self._lib.wurm_multi_step(
-                ctypes.byref(cfg), ctypes.byref(st), act_ptrs, _ACTION_BYTES[dtype],
-                ctypes.byref(dr) if dr is not None else None, self.seed, self._draws, _ptr(self._draws_dev),
-                ctypes.byref(out),
-                _ptr(self._status), _ptr(self._stats), self._stream()))
+            if auto_reset:
+                _lib.check(self._lib.wurm_multi_step_reset(
+                    ctypes.byref(cfg), ctypes.byref(st), act_ptrs, _ACTION_BYTES[dtype],
+                    ctypes.byref(dr) if dr is not None else None, ctypes.byref(rdr) if rdr is not None else None,
+                    self.seed, self._draws, _ptr(self._draws_dev), ctypes.byref(out), _ptr(self._status), _ptr(self._stats),
+                    self._stream()))
+                self._draws += 1            # the fused reset consumed the next counter value
+            else:
+                _lib.check(self._lib.wurm_multi_step(
+                    ctypes.byref(cfg), ctypes.byref(st), act_ptrs, _ACTION_BYTES[dtype],
+                    ctypes.byref(dr) if dr is not None else None, self.seed, self._draws, _ptr(self._draws_dev),
+                    ctypes.byref(out), _ptr(self._status), _ptr(self._stats), self._stream()))
 
         self.rewards = rewards.view(E * K)
         self._step_dones = flags[2]          # (E,K) copy of the done flags owned by this step's outputs

@@ -43,16 +43,15 @@ class GraphedStepper(object):
 
     def _one(self, capturing):
         env = self.env
-        fused = False
+        fused = self.auto_reset and getattr(env, 'supports_fused_reset', False)
         if self.multi:
-            obs, rewards, dones, info = env.step(self.actions)
+            obs, rewards, dones, info = env.step(self.actions, auto_reset=fused)
             out = (obs, rewards, dones, info)
             done = dones['__all__']
         else:
-            fused = self.auto_reset and getattr(env, 'supports_fused_reset', False)
             obs, reward, done, info = env.step(self.actions, auto_reset=True) if fused else env.step(self.actions)
             out = (obs, reward, done, info)
-        if self.auto_reset and (self.multi or not fused):
+        if self.auto_reset and not fused:
             env.reset(done, return_observations=False)
         if capturing:
             env._draws_dev.add_(2 if self.auto_reset else 1)      # one tick per step, one per reset

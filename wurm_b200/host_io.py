@@ -99,7 +99,8 @@ class HostStepper(object):
         compute.wait_event(uploaded)
         fused = False
         if self.multi:
-            obs, rewards, dones, info = self.env.step(dev_actions)
+            fused = self.auto_reset and self.env.num_envs <= FUSED_RESET_MAX_ENVS
+            obs, rewards, dones, info = self.env.step(dev_actions, auto_reset=fused)
             reward_t = self.env.rewards.view(self.env.num_envs, self.env.num_snakes)
             done_t = self.env._step_dones
             env_done = dones['__all__']
@@ -111,7 +112,7 @@ class HostStepper(object):
             env_done = done_t
         stepped = torch.cuda.Event()
         stepped.record(compute)
-        if self.auto_reset and (self.multi or not fused):
+        if self.auto_reset and not fused:
             self.env.reset(env_done, return_observations=False)
         self.d2h.wait_event(stepped)
         with torch.cuda.stream(self.d2h):
