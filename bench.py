@@ -145,6 +145,9 @@ class MultiAdapter(object):
     def reset(self, done):
         self.env.reset(done, return_observations=False)
 
+    def fused_step(self, t):
+        return self.env.step(self.pool[t % ACTION_POOL], auto_reset=True)
+
     def obs_elems(self, obs):
         return sum(o[0].numel() for o in obs.values())
 
@@ -464,7 +467,7 @@ def run_gpu(args):
         if fused_ms:
             line['fused_step_reset'] = {'value': world * N * K / (fused_ms * 1e-3), 'unit': 'env-steps/s',
                                         'ms_per_step': fused_ms / K, 'gpu_launches': K,
-                                        'loop': 'obs,reward,done,info = env.step(a, auto_reset=True)  (one launch per step)'}
+                                        'loop': 'env.step(actions, auto_reset=True)  (one launch per step)'}
         if world == 1 and not args.no_cpu_baseline:
             n = cpu_sample_size(key)
             threads = os.cpu_count() or 1

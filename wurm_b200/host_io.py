@@ -99,7 +99,7 @@ class HostStepper(object):
         compute.wait_event(uploaded)
         fused = False
         if self.multi:
-            fused = self.auto_reset and self.env.num_envs <= FUSED_RESET_MAX_ENVS
+            fused = self.auto_reset                  # MultiSnake: the fused launch never loses (profiles/r01_final_*.json)
             obs, rewards, dones, info = self.env.step(dev_actions, auto_reset=fused)
             reward_t = self.env.rewards.view(self.env.num_envs, self.env.num_snakes)
             done_t = self.env._step_dones
