@@ -259,3 +259,17 @@ def grid_observe(envs, mode):
     obs = np.zeros(shape, np.float32)
     lib().wurm_oracle_grid_observe(N, S, _p(envs), m, _p(obs))
     return obs
+
+
+# ------------------------------------------------------------------------------------------------
+# A2C returns (wurm/rl/a2c.py:49-63)
+# ------------------------------------------------------------------------------------------------
+def a2c_returns(bootstrap, rewards, values, dones, gamma, gae_lambda=None):
+    """(T,N) fp32 returns; gae_lambda None -> n-step returns."""
+    rewards = _c(rewards, np.float32); values = _c(values, np.float32); dones = _c(dones, np.uint8)
+    bootstrap = _c(bootstrap, np.float32)
+    T, N = rewards.shape
+    out = np.zeros((T, N), np.float32)
+    lib().wurm_oracle_a2c_returns(T, N, ctypes.c_float(gamma), ctypes.c_float(-1.0 if gae_lambda is None else gae_lambda),
+                                  _p(bootstrap), _p(rewards), _p(values), _p(dones), _p(out))
+    return out

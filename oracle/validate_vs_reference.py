@@ -190,6 +190,34 @@ def validate_grid(ref, tally, N, S, mode, steps, seed):
     return N * steps
 
 
+def validate_a2c(ref_path, tally):
+    """A2C.loss of the reference (wurm/rl/a2c.py:32-79) against losses computed from the oracle's returns with
+    the reference's own two closing lines (:70-73).  The reference's `return_returns` is broken (`tuple += Tensor`),
+    so the returns are pinned through the two losses, compared bit for bit."""
+    sys.path.insert(0, ref_path)
+    from wurm.rl.a2c import A2C
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    n = 0
+    for T, N in [(20, 512), (5, 33), (64, 1000)]:
+        for gae_lambda in (None, 0.95):
+            gamma = 0.99
+            rewards = (torch.rand(T, N, 1, generator=g) < 0.1).float() - (torch.rand(T, N, 1, generator=g) < 0.05).float()
+            values = torch.randn(T, N, 1, generator=g)
+            log_probs = -torch.rand(T, N, 1, generator=g)
+            dones = torch.rand(T, N, 1, generator=g) < 0.08
+            bootstrap = torch.randn(N, 1, generator=g)
+            a2c = A2C(gamma=gamma, use_gae=gae_lambda is not None, gae_lambda=gae_lambda)
+            value_loss, policy_loss = a2c.loss(bootstrap, rewards, values, log_probs, dones)
+            ret = torch.from_numpy(orc.a2c_returns(bootstrap.numpy().reshape(N), rewards.numpy().reshape(T, N),
+                                                   values.numpy().reshape(T, N), dones.numpy().reshape(T, N), gamma,
+                                                   gae_lambda)).reshape(T, N, 1)
+            tally.check(f'a2c/T{T}N{N}/gae{gae_lambda}/value_loss', value_loss.numpy(), F.smooth_l1_loss(values, ret).mean().numpy())
+            tally.check(f'a2c/T{T}N{N}/gae{gae_lambda}/policy_loss', policy_loss.numpy(), (-((ret - values).detach() * log_probs).mean()).numpy())
+            n += T * N
+    return n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
@@ -205,6 +233,12 @@ def main():
     for mode in ['default', 'raw', 'one_channel', 'positions']:
         total += validate_single(ref, tally, 32 * scale, 9, mode, 42 * scale, seed=7, reset_every_step=False)
     print(f'single: {total} env-steps, {tally.checks} tensor comparisons, {len(tally.fails)} mismatches')
+    if tally.fails:
+        print('first failures:', tally.fails[:10])
+        sys.exit(1)
+    tally = Tally()
+    total = validate_a2c(rl.REFERENCE_PATH, tally)
+    print(f'a2c returns: {total} (t, env) pairs through both losses, {tally.checks} comparisons, {len(tally.fails)} mismatches')
     if tally.fails:
         print('first failures:', tally.fails[:10])
         sys.exit(1)

@@ -1008,3 +1008,32 @@ void wurm_oracle_grid_observe(int N, int S, const float* envs, int mode, float* 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A2C return scan (wurm/rl/a2c.py:49-63), fp32, the reference's operation order.                */
+/* rewards, values, dones, returns: (T,N) row-major; bootstrap: (N).  lambda < 0: n-step returns  */
+/* (:58-61), else generalised advantage estimation (:50-57).                                     */
+/* ------------------------------------------------------------------------------------------ */
+void wurm_oracle_a2c_returns(int T, int N, float gamma, float lambda, const float* bootstrap, const float* rewards,
+                             const float* values, const uint8_t* dones, float* returns) {
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < N; ++n) {
+        if (lambda < 0.0f) {
+            float R = bootstrap[n] * (dones[(size_t)(T - 1) * N + n] ? 0.0f : 1.0f);                 /* :58 */
+            for (int t = T - 1; t >= 0; --t) {
+                float m = dones[(size_t)t * N + n] ? 0.0f : 1.0f;
+                R = rewards[(size_t)t * N + n] + gamma * R * m;                                      /* :60 */
+                returns[(size_t)t * N + n] = R;
+            }
+        } else {
+            float gae = 0.0f;
+            for (int t = T - 1; t >= 0; --t) {
+                float m = dones[(size_t)t * N + n] ? 0.0f : 1.0f;
+                float next = t == T - 1 ? bootstrap[n] : values[(size_t)(t + 1) * N + n];
+                float delta = rewards[(size_t)t * N + n] + gamma * next * m - values[(size_t)t * N + n];   /* :52-55 */
+                gae = delta + gamma * lambda * m * gae;                                              /* :56 */
+                returns[(size_t)t * N + n] = gae + values[(size_t)t * N + n];                        /* :57 */
+            }
+        }
+    }
+}

@@ -208,3 +208,24 @@ def test_gridworld_golden(i):
         assert_same(orc.grid_observe(state, mode), tr[f'{t}/obs'], tag + 'observation')
         orc.grid_reset(state, d, start, tr[f'{t}/reset_food'])
         assert_same(state, tr[f'{t}/reset_envs'].astype(np.float32), tag + 'envs after reset')
+
+
+def test_a2c_returns_known_answers():
+    """Hand-checked recurrences (reference wurm/rl/a2c.py:49-63): n-step R_t = r_t + g R_{t+1} (1 - d_t), and GAE."""
+    rewards = np.array([[1.0], [0.0], [2.0]], np.float32)
+    dones = np.array([[0], [1], [0]], np.uint8)
+    values = np.array([[0.5], [0.25], [1.0]], np.float32)
+    boot = np.array([4.0], np.float32)
+    g = np.float32(0.5)
+    got = orc.a2c_returns(boot, rewards, values, dones, 0.5)
+    R2 = np.float32(2.0) + g * np.float32(4.0)          # 4.0
+    R1 = np.float32(0.0)                                 # done at t=1 cuts the bootstrap
+    R0 = np.float32(1.0) + g * R1
+    assert_same(got.reshape(-1), np.array([R0, R1, R2], np.float32), 'n-step returns')
+    lam = np.float32(0.5)
+    d2 = np.float32(2.0) + g * np.float32(4.0) - np.float32(1.0); gae2 = d2
+    d1 = np.float32(0.0) - np.float32(0.25); gae1 = d1   # done: no bootstrap, no carried advantage
+    d0 = np.float32(1.0) + g * np.float32(0.25) - np.float32(0.5); gae0 = d0 + g * lam * gae1
+    got = orc.a2c_returns(boot, rewards, values, dones, 0.5, 0.5)
+    assert_same(got.reshape(-1), np.array([gae0 + np.float32(0.5), gae1 + np.float32(0.25), gae2 + np.float32(1.0)], np.float32),
+                'GAE returns')

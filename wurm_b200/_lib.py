@@ -22,7 +22,7 @@ SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm
            'wurm_single_reset',
            'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_step_reset', 'wurm_multi_reset', 'wurm_multi_observe',
            'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check', 'wurm_grid_step', 'wurm_grid_reset',
-           'wurm_grid_observe']
+           'wurm_grid_observe', 'wurm_a2c_returns']
 CHECK_REPORT = 4
 # WURM_CHK_* bits in the order the reference tests them, with the reference's messages
 CHECK_MESSAGES = [
@@ -132,6 +132,8 @@ def lib():
     L.wurm_grid_reset.argtypes = [gcfg, vp, vp, vp, u64, u64, vp, vp]
     L.wurm_grid_observe.restype = i32
     L.wurm_grid_observe.argtypes = [gcfg, vp, vp, vp]
+    L.wurm_a2c_returns.restype = i32
+    L.wurm_a2c_returns.argtypes = [i32, i32, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     L.wurm_single_check.restype = i32
     L.wurm_single_check.argtypes = [cfg, vp, vp, vp, vp]
     L.wurm_multi_check.restype = i32
