@@ -4,8 +4,9 @@ Own copy of the *rollout* half of the reference's `experiments/main.py` (its cal
 :252-320, and the CLI flags that concern the env, :30-54), with the three defects of the shipped driver
 repaired (trap 2: `A2C(model, ...)` signature, `RandomAgent` on flat
 observations, log-prob/value broadcasting).  The env comes from `wurm_b200.envs`; the policy stand-ins
-(uniform random, 2x64 feed-forward) are plain torch -- policies and the A2C learner are outside this
-repository's scope.
+(uniform random, 2x64 feed-forward) are plain torch.  `--train true` runs the reference's A2C update
+(main.py:232-246) with the return scan on the device (`wurm_b200.rl.A2C`); the
+reference's conv / recurrent agents, model saving, video and CSV logging stay outside this repository's scope.
 
     python -m experiments.main --env snake --num-envs 512 --size 9 --agent random --observation partial_2 \
         --total-steps 1e6
@@ -24,8 +25,11 @@ from torch import nn
 from torch.distributions import Categorical
 
 from wurm_b200.envs import SingleSnake, SimpleGridworld
+from wurm_b200.rl import A2C
+from wurm_b200.trajectory_store import TrajectoryStore
 
 LOG_INTERVAL = 100
+MAX_GRAD_NORM = 0.5          # reference main.py:27
 
 
 def boolean(x):
@@ -78,12 +82,16 @@ def main(argv=None):
                         help='run env_consistency on the live envs every step, as the reference driver does')
     parser.add_argument('--device', default='cuda', type=str)
     parser.add_argument('--seed', default=None, type=int)
+    parser.add_argument('--lr', default=1e-3, type=float)
+    parser.add_argument('--gamma', default=0.99, type=float)
+    parser.add_argument('--update-steps', default=20, type=int)
+    parser.add_argument('--entropy', default=0.0, type=float)
     args = parser.parse_args(argv)
 
     if args.env not in ('snake', 'gridworld'):
         raise ValueError('Unrecognised environment')
-    if args.train:
-        raise NotImplementedError('the A2C learner is outside the scope of wurm_b200 (DESIGN.md section 7); use --train false')
+    if args.train and args.agent == 'random':
+        raise ValueError('--train true needs a trainable agent')
 
     render_args = {'size': args.render_window_size, 'num_rows': args.render_rows, 'num_cols': args.render_cols}
     if args.env == 'gridworld':                          # reference main.py:166-168
@@ -101,23 +109,50 @@ def main(argv=None):
     else:
         raise ValueError('Unrecognised agent (this driver covers random and feedforward)')
 
+    train = bool(args.train)
+    if train:
+        optimizer = torch.optim.Adam(model.parameters(), lr=args.lr)
+        a2c = A2C(gamma=args.gamma)
+        trajectories = TrajectoryStore()
+
     num_steps = num_episodes = 0
     t0 = time()
-    summary = {}
+    summary, losses = {}, {}
     for i_step in count(1):
         if args.render:
             env.render()
 
-        with torch.no_grad():
+        with torch.set_grad_enabled(train):
             probs, state_value = model(state)
-        action = Categorical(probs).sample().clone().long()
+        action_distribution = Categorical(probs)
+        action = action_distribution.sample().clone().long()
 
         state, reward, done, info = env.step(action)
+        # NB `action` was sanitised in place by step() (single_snake.py:222), after sampling -- the log-prob below is that
+        # of the action actually taken, as in the reference (main.py:218).
 
         if args.check_consistency and args.env == 'snake':
             env.check_consistency(skip=done)      # == env_consistency(env.envs[~done.squeeze(-1)]) (main.py:215), fused
 
+        if train:
+            trajectories.append(action=action, log_prob=action_distribution.log_prob(action).unsqueeze(-1),
+                                value=state_value.reshape(-1, 1), reward=reward, done=done,
+                                entropy=action_distribution.entropy().mean())
+
         env.reset(done, return_observations=False)
+
+        if train and i_step % args.update_steps == 0:                 # reference main.py:232-246
+            with torch.no_grad():
+                _, bootstrap_values = model(state)
+            value_loss, policy_loss = a2c.loss(bootstrap_values.reshape(-1, 1), trajectories.rewards, trajectories.values,
+                                               trajectories.log_probs, trajectories.dones)
+            entropy_loss = - trajectories.entropies.mean()
+            optimizer.zero_grad()
+            (value_loss + policy_loss + args.entropy * entropy_loss).backward()
+            nn.utils.clip_grad_norm_(model.parameters(), MAX_GRAD_NORM)
+            optimizer.step()
+            trajectories.clear()
+            losses = dict(value_loss=value_loss.item(), policy_loss=policy_loss.item())
 
         num_steps += args.num_envs
         if i_step % LOG_INTERVAL == 0 or num_steps >= args.total_steps:
@@ -127,7 +162,7 @@ def main(argv=None):
             summary = dict(steps=num_steps, episodes=num_episodes, reward_rate=stats['reward'] / max(stats['env_steps'], 1),
                            edge_collisions=stats['edge_collisions'], self_collisions=stats['self_collisions'],
                            avg_size=env.envs[:, -1].reshape(args.num_envs, -1).max(dim=-1)[0].mean().item(),
-                           steps_per_second=num_steps / dt)
+                           steps_per_second=num_steps / dt, **losses)
             print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
 
         if num_steps >= args.total_steps or num_episodes >= args.total_episodes:

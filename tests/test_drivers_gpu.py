@@ -38,3 +38,25 @@ def test_multiagent_rollout_driver_with_annealing():
                     str(256 * 120), '--food-rate', '3e-3', '--food-rate-min', '1e-3', '--seed', '2'])
     assert summary['steps'] == 256 * 120 and summary['edge_collisions'] > 0 and summary['food'] > 0
     assert abs(summary['food_rate'] - 1e-3) < 1e-4
+
+
+def test_rollout_driver_trains_with_a2c():
+    """`--train true`: the reference's A2C update (main.py:232-246) on the device return scan; losses stay finite and
+    the trajectory store behaves like the reference's (stacked (T, N, 1) tensors)."""
+    import math
+    import torch
+    from experiments import main as driver
+    from wurm_b200.trajectory_store import TrajectoryStore
+    torch.manual_seed(0)
+    summary = driver.main(['--env', 'snake', '--num-envs', '256', '--size', '9', '--agent', 'feedforward', '--observation',
+                           'partial_2', '--train', 'true', '--update-steps', '10', '--total-steps', str(256 * 200),
+                           '--seed', '3'])
+    assert summary['steps'] == 256 * 200
+    assert math.isfinite(summary['value_loss']) and math.isfinite(summary['policy_loss'])
+
+    store = TrajectoryStore()
+    for t in range(3):
+        store.append(reward=torch.full((4, 1), float(t)), done=torch.zeros(4, 1, dtype=torch.bool))
+    assert store.rewards.shape == (3, 4, 1) and store.dones.dtype == torch.bool and len(store) == 3
+    store.clear()
+    assert len(store) == 0
