@@ -9,7 +9,7 @@ pat = re.compile(r'^(gpu__time_duration.sum|dram__bytes_(read|write).sum|gpu__dr
                  r'smsp__issue_active.avg.pct_of_peak_sustained_active|sm__throughput.avg.pct_of_peak_sustained_elapsed|'
                  r'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum|lts__t_sectors_op_write.sum|lts__t_sectors_op_read.sum|'
                  r'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active|'
-                 r'smsp__warp_issue_stalled_(barrier|long_scoreboard|short_scoreboard|lg_throttle|mio_throttle|membar|wait|not_selected|no_instruction|math_pipe_throttle|sleeping|dispatch_stall|branch_resolving|drain|imc_miss|tex_throttle)_per_warp_active.pct)$')
+                 r'smsp__average_warps_issue_stalled_\w+_per_issue_active.ratio|smsp__warp_issue_stalled_(barrier|long_scoreboard|short_scoreboard|lg_throttle|mio_throttle|membar|wait|not_selected|no_instruction|math_pipe_throttle|sleeping|dispatch_stall|branch_resolving|drain|imc_miss|tex_throttle)_per_warp_active.pct)$')
 name = [v for h, v in zip(hdr, vals) if h == 'Kernel Name']
 print('#', ' '.join(sys.argv[2:]) or rep)
 if name: print('kernel,', name[0])

@@ -169,7 +169,7 @@ __device__ __forceinline__ float new_env_value(int i, int C, int tail, int mid, 
 // single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
 template <int G>
 __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e, int l, int* cnt_s, long long a_in,
-                                        int hint_head, int hint_sz) {
+                                        int hint_head, int hint_sz, bool& ended) {
     const unsigned gm = group_mask<G>();
     const int S = p.S, C = p.C;
     float* food = env;
@@ -327,19 +327,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
         }
     }
     __syncwarp(gm);                                                  // lane 0's cell updates -> the group's render
-    if (p.auto_reset && (sc || !interior)) {
-        // Fused reset (:322-337): the env ended, re-create it in HBM right away.  The shared copy keeps the
-        // terminal state (the observation returned by step is the terminal one, and it is what the
-        // reference's driver feeds its policy next, main.py:227); HBM holds exactly that state at this
-        // point, so only the cells whose value differs in the new env are written.
-        int tail, mid, hd, cell;
-        new_env_layout(p, p.spawn, call_counter(p) + 1, e, tail, mid, hd, cell);
-        for (int i = l; i < 3 * C; i += G) {
-            const float nv = new_env_value(i, C, tail, mid, hd, cell);
-            if (env[i] != nv) gfood[i] = nv;
-        }
-        if (l == 0 && p.hints) { p.hints[2 * (size_t)e] = (short)hd; p.hints[2 * (size_t)e + 1] = 3; }
-    }
+    ended = sc || !interior;
     return np;
 }
 
@@ -372,7 +360,7 @@ __device__ __forceinline__ void render_partial(const SingleParams& p, const floa
         const int i = (int)__umulhi((uint32_t)ij, p.magic_W), j = ij - i * W;
         const int y = hy - n + i, x = hx - n + j;
         float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
-        if (y >= 0 && y < S && x >= 0 && x < S && !(y == 0 || x == 0 || y == S - 1 || x == S - 1)) {
+        if ((unsigned)(y - 1) < (unsigned)(S - 2) && (unsigned)(x - 1) < (unsigned)(S - 2)) {   // inside the grid, not on its border
             const int q = y * S + x;
             v0 = v1 = v2 = 1.0f;                                     // empty cell: white
             if (env[2 * C + q] > kEps) { v0 = 0.0f; v1 = kHalf; v2 = 0.0f; }
@@ -438,6 +426,7 @@ __device__ __forceinline__ void write_obs(const SingleParams& p, const float* ti
 // One CTA = one tile of T envs.  STEP: load -> step -> store -> observe.  !STEP: load -> observe.
 template <int G, bool STEP>
 __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) {
+    const int KC = p.C;                              // cells per channel
     extern __shared__ __align__(128) unsigned char smem[];
     float* tile = reinterpret_cast<float*>(smem);
     float* stage = reinterpret_cast<float*>(smem + p.tile_bytes_padded);
@@ -446,8 +435,8 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
 
     const int env0 = blockIdx.x * p.T;
     const int nvalid = min(p.T, p.N - env0);
-    const size_t goff = (size_t)env0 * 3 * p.C;
-    const int nfloats = nvalid * 3 * p.C;
+    const size_t goff = (size_t)env0 * 3 * KC;
+    const int nfloats = nvalid * 3 * KC;
     const uint32_t bytes = (uint32_t)nfloats * 4u;
     const bool bulk = p.bulk_ok && (bytes % 16u == 0u);
     const bool partial = p.obs_mode == WURM_OBS_PARTIAL;
@@ -478,12 +467,45 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     __syncthreads();                        // mbarrier init / fallback tile visible
     if (bulk) mbar_wait(bar, 0);
 
+    bool ended = false;
     if (t < nvalid) {
-        float* env = tile + (size_t)t * 3 * p.C;
+        float* env = tile + (size_t)t * 3 * KC;
         int hp = -1;
-        if (STEP) hp = step_env<G>(p, env, env0 + t, l, cnt_s, a_in, hint_head, hint_sz);
+        if (STEP) hp = step_env<G>(p, env, env0 + t, l, cnt_s, a_in, hint_head, hint_sz, ended);
         else if (partial) hp = find_head<G>(p, env, l);
         if (partial) render_partial<G>(p, env, hp, stage + (size_t)t * E, l);
+    }
+    if (STEP && p.auto_reset) {
+        // Fused reset (:322-337): envs that ended are re-created in HBM right away, one after another by the WHOLE
+        // warp (a lane group doing it alone would stall the warp's other envs for 3C/G iterations).  The shared
+        // copy keeps the terminal state -- the observation returned by step is the terminal one, and it is what
+        // the reference's driver feeds its policy next (main.py:227) -- and HBM holds exactly that state at this
+        // point, so only its non-zero cells are cleared before the five cells of the new env are written.
+        const int lane = threadIdx.x & 31;
+        int my_tail = 0, my_mid = 0, my_hd = 0, my_cell = -1;
+        const bool mine = ended && l == 0;
+        __syncwarp();                       // every group's updates of the shared tile -> visible to the whole warp
+        if (mine) new_env_layout(p, p.spawn, call_counter(p) + 1, env0 + t, my_tail, my_mid, my_hd, my_cell);
+        unsigned todo = __ballot_sync(0xffffffffu, mine);
+        const int C = KC, n = 3 * C;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int tail = __shfl_sync(0xffffffffu, my_tail, src), mid = __shfl_sync(0xffffffffu, my_mid, src);
+            const int hd = __shfl_sync(0xffffffffu, my_hd, src), cell = __shfl_sync(0xffffffffu, my_cell, src);
+            const int ts = ((threadIdx.x & ~31) + src) / G;
+            const float* old = tile + (size_t)ts * n;
+            float* g = p.envs + (size_t)(env0 + ts) * n;
+            for (int i = lane; i < n; i += 32)
+                if (old[i] != 0.0f) g[i] = 0.0f;
+            __syncwarp();
+            if (lane < 5) {
+                const int idx = lane == 0 ? cell : lane == 1 ? C + hd : lane == 2 ? 2 * C + tail : lane == 3 ? 2 * C + mid : 2 * C + hd;
+                const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
+                if (idx >= 0) g[idx] = val;
+            }
+            if (lane == 0 && p.hints) { p.hints[2 * (size_t)(env0 + ts)] = (short)hd; p.hints[2 * (size_t)(env0 + ts) + 1] = 3; }
+        }
     }
     fence_proxy_async();                    // generic-proxy writes -> visible to the bulk stores
     __syncthreads();

@@ -19,7 +19,6 @@ un-pipelined form of the same thing.
 import torch
 
 
-FUSED_RESET_MAX_ENVS = 1 << 16      # measured on B200: profiles/r01_small_batch.txt, r01_bench_C2_v5.json
 
 
 class Ticket(object):
@@ -105,9 +104,9 @@ class HostStepper(object):
             done_t = self.env._step_dones
             env_done = dones['__all__']
         else:
-            # below ~64K envs the step is launch-bound and the fused step+reset launch wins; above it the
-            # (instruction-bound) step kernel is better left alone and the cheap reset kernel follows it
-            fused = self.auto_reset and self.env.num_envs <= FUSED_RESET_MAX_ENVS and getattr(self.env, 'supports_fused_reset', False)
+            # one fused step+reset launch: the warp re-creates its finished envs while their sectors are still in L2;
+            # far ahead where the pair is launch-bound, a little ahead at 2^20 envs (profiles/r01_final_*.json)
+            fused = self.auto_reset and getattr(self.env, 'supports_fused_reset', False)
             obs, reward_t, done_t, info = self.env.step(dev_actions, auto_reset=True) if fused else self.env.step(dev_actions)
             env_done = done_t
         stepped = torch.cuda.Event()
