@@ -1,8 +1,9 @@
 // SimpleGridworld (wurm/envs/simple_gridworld.py) for B200 (sm_100a): the reference's two-channel debug
 // env -- an agent pixel and one food pixel, the same move / eat / respawn / edge machinery as SingleSnake
-// without a body.  An env is 2*S*S floats (392 B at the reference's size 7), far too small to stage:
-// a small lane group per env (8 lanes at size 7: four envs per warp) works straight on global memory with
-// strided loads, finds the agent with shuffles, and stores only the two or three cells a step changes.
+// without a body.  An env is 2*S*S floats (392 B at the reference's size 7), far too small to stage: a lane
+// group per env works straight on global memory.  Up to 64 cells (grid_small_kernel): 8 lanes per env with the
+// env held in registers; larger grids (grid_env_kernel): 32 lanes per env, strided loads, the agent found with
+// shuffles.  Either way only the two or three cells a step changes are stored.
 #include <math.h>
 
 #include "../../include/wurm_b200.h"
@@ -161,10 +162,155 @@ __global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
     }
 }
 
+// Envs of at most 64 cells (the reference's size 7: 392 B of state, 588 B of observation): 8 lanes per env,
+// each lane keeps its <= 8 cells of both channels in REGISTERS -- all loads of the env are issued at once (one
+// DRAM round trip), the step edits registers and stores only the two or three cells it changes, and the
+// observation is rendered from the registers instead of re-reading the env through L2.
+template <bool STEP>
+// 128 threads, >= 8 CTAs per SM (<= 64 registers): best of the measured launch shapes (profiles/r01_sweep_grid.txt)
+#ifndef WURM_GRID_MINB
+#define WURM_GRID_MINB 8
+#endif
+#ifndef WURM_GRID_THREADS
+#define WURM_GRID_THREADS 128
+#endif
+__global__ void __launch_bounds__(WURM_GRID_THREADS, WURM_GRID_MINB) grid_small_kernel(const GridParams p) {
+    constexpr int G = 8, R = 8;
+    __shared__ int cnt_s[4];                                          // per-CTA episode statistics
+    const unsigned gm = group_mask<G>();
+    const int lane = threadIdx.x % G;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = e < p.N;
+    const int S = p.S, C = p.C;
+    if (STEP && p.stats && threadIdx.x < 4) cnt_s[threadIdx.x] = 0;
+    float f[R], h[R];
+    long long a = 0;
+    float* food = p.envs + (size_t)(active ? e : 0) * 2 * C;
+    float* head = food + C;
+#pragma unroll
+    for (int it = 0; it < R; ++it) {
+        const int q = lane + G * it;
+        const bool in = active && q < C;
+        f[it] = in ? food[q] : 0.0f;
+        h[it] = in ? head[q] : 0.0f;
+    }
+    if (STEP && active) {
+        if (p.action_bytes == 8) a = ((const long long*)p.actions)[e];
+        else if (p.action_bytes == 4) a = ((const int*)p.actions)[e];
+        else a = ((const short*)p.actions)[e];
+    }
+    if (STEP && p.stats) __syncthreads();
+    if (STEP && active) {
+        int hp = -1, hc = 0;
+#pragma unroll
+        for (int it = 0; it < R; ++it)
+            if (h[it] != 0.0f) { hp = lane + G * it; ++hc; }
+        hp = group_max<G>(hp, gm);
+        hc = group_sum<G>(hc, gm);
+        int np = -1, ny = -1, nx = -1;                                // :149-158 the conv2d translates the agent by -OFF[a]
+        if (hp >= 0) {
+            const int hy = (int)__umulhi((uint32_t)hp, p.magic_S), hx = hp - hy * S;
+            ny = hy - off_y((int)a); nx = hx - off_x((int)a);
+            if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
+        }
+        float ov = 0.0f;                                              // :169 agent-food overlap: food[np], owned by one lane
+#pragma unroll
+        for (int it = 0; it < R; ++it)
+            if (lane + G * it == np) ov = f[it];
+        ov = group_sum<G>(ov, gm);                                    // one non-zero term at most: exact
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            const int q = lane + G * it;
+            if (q == hp) { h[it] = 0.0f; head[q] = 0.0f; }
+        }
+        __syncwarp(gm);                                               // hp == np cannot happen, but keep the stores ordered
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            const int q = lane + G * it;
+            if (q == np) {
+                h[it] = 1.0f; head[q] = 1.0f;
+                if (ov != 0.0f) { f[it] = ov + ov * -1.0f; food[q] = f[it]; }   // :171
+            }
+        }
+        if (ov != 0.0f) {                                             // :176-181 respawn (reads the env through L2)
+            __syncwarp(gm);
+            const int cell = p.food_replay ? p.food_replay[e]
+                                           : grid_pick_free(p, food, call_counter(p), e, kStreamGridStepFood);
+#pragma unroll
+            for (int it = 0; it < R; ++it) {
+                const int q = lane + G * it;
+                if (q == cell) { f[it] += 1.0f; food[q] = f[it]; }
+            }
+        }
+        const bool interior = np >= 0 && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
+        if (lane == 0) {
+            p.reward[e] = 0.0f - ov * -1.0f;
+            p.done[e] = !interior;                                    // :189-194 edge collision is the only way to end
+            if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+            if (p.stats) {
+                atomicAdd(&cnt_s[0], 1);
+                if (!interior) atomicAdd(&cnt_s[1], 1);
+                if (ov != 0.0f) atomicAdd(&cnt_s[2], 1);
+            }
+        }
+    }
+    if (active && p.obs_mode == WURM_OBS_DEFAULT) {                   // :88-133 black background (:90), agent green, food red
+        float* o = p.obs + (size_t)e * 3 * C;
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            const int q = lane + G * it;
+            if (q < C) {
+                const int y = (int)__umulhi((uint32_t)q, p.magic_S), x = q - y * S;
+                float r = 0.0f, g = 0.0f;
+                if (h[it] > kEps) { r = 0.0f; g = 1.0f; }
+                if (f[it] > kEps) { r = 1.0f; g = 0.0f; }
+                if (y == 0 || x == 0 || y == S - 1 || x == S - 1) r = g = 0.0f;
+                o[q] = r; o[C + q] = g; o[2 * C + q] = 0.0f;
+            }
+        }
+    } else if (active && p.obs_mode == WURM_OBS_RAW) {
+        float* o = p.obs + (size_t)e * 2 * C;
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            const int q = lane + G * it;
+            if (q < C) { o[q] = f[it]; o[C + q] = h[it]; }
+        }
+    } else if (active && p.obs_mode == WURM_OBS_POSITIONS) {          // first argmax of agent / food (:119-130)
+        int idx[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float bv = -INFINITY;
+            int bq = 0;
+#pragma unroll
+            for (int it = 0; it < R; ++it) {
+                const int q = lane + G * it;
+                const float x = ch == 0 ? h[it] : f[it];
+                if (q < C && x > bv) { bv = x; bq = q; }
+            }
+            const float gv = group_max<G>(bv, gm);
+            idx[ch] = -group_max<G>(bv == gv ? -bq : -(1 << 30), gm);
+        }
+        if (lane == 0) {
+            float* o = p.obs + (size_t)e * 4;
+            o[0] = (float)(idx[0] / S); o[1] = (float)(idx[0] % S); o[2] = (float)(idx[1] / S); o[3] = (float)(idx[1] % S);
+        }
+    }
+    if (STEP && p.stats) {                                            // one striped slot per CTA: no hot address in L2
+        __syncthreads();
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        if (threadIdx.x == 0 && cnt_s[0]) atomicAdd(slot + WURM_STAT_ENV_STEPS, (unsigned long long)cnt_s[0]);
+        if (threadIdx.x == 1 && cnt_s[1]) {
+            atomicAdd(slot + WURM_STAT_EPISODES, (unsigned long long)cnt_s[1]);
+            atomicAdd(slot + WURM_STAT_EDGE_COLLISIONS, (unsigned long long)cnt_s[1]);
+        }
+        if (threadIdx.x == 2 && cnt_s[2]) atomicAdd(slot + WURM_STAT_REWARD, (unsigned long long)cnt_s[2]);
+    }
+}
+
 template <bool STEP>
 static int launch_grid_env(const GridParams& p, cudaStream_t stream) {
     const long long threads_g8 = (long long)p.N * 8, threads_g32 = (long long)p.N * 32;
-    if (p.C <= 64) grid_env_kernel<8, STEP><<<(unsigned)((threads_g8 + 255) / 256), 256, 0, stream>>>(p);
+    if (p.C <= 64) grid_small_kernel<STEP><<<(unsigned)((threads_g8 + WURM_GRID_THREADS - 1) / WURM_GRID_THREADS), WURM_GRID_THREADS, 0, stream>>>(p);
     else grid_env_kernel<32, STEP><<<(unsigned)((threads_g32 + 255) / 256), 256, 0, stream>>>(p);
     return check_launch("grid_env_kernel");
 }
