@@ -182,7 +182,10 @@ struct MultiSmem {
     int* sum;         // sum of body values per snake (invariant check)
     int* misc;        // [0] food cells, [2] run_boost, [3] force full write-back
     short* col;       // K*3
-    unsigned char* reset;   // ResetScratch of the fused step+reset path
+    unsigned char* reset;   // ResetScratch of the fused step+reset path (>= 768 bytes)
+    float* tab;       // 2*32*3: rendered colour of snake o's body (2o) / head (2o+1) cell, see build_colour_table; ALIASES
+                      // the reset scratch, which is only used after the observation is written -- shared memory per
+                      // CTA decides how many envs are resident per SM, and 768 bytes more cost 9 % at K=4, S=25
 };
 
 __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
@@ -193,12 +196,14 @@ __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
     s.boost = s.cost + 32; s.sum = s.boost + 32; s.misc = s.sum + 32;
     s.col = reinterpret_cast<short*>(s.misc + 8);
     s.reset = reinterpret_cast<unsigned char*>(s.col + 96);
+    s.tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15);
     return s;
 }
 
 static size_t multi_smem_bytes(int C, int W, int obs_mode) {
     // records + per-snake arrays + misc + colours + the fused reset's scratch (occupancy bytes, picks)
-    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4 + 32;
+    const size_t scratch = (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;     // fused reset; the colour table aliases it
+    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + (scratch > 768 ? scratch : 768) + 32;
 }
 
 // Food transitions keep the env's food-cell count (misc[0]) current, so _add_food needs no counting pass.
@@ -240,20 +245,38 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
     if (overlap || odd) s.misc[3] = 1;
 }
 
+// multi_snake.py:197-206: int16 colour of a body (or, is_head, head) cell of snake o
+__device__ __forceinline__ void snake_rgb(const MultiSmem& s, int o, bool is_head, int rgb[3]) {
+    float inten = 1.0f * 1.0f / 3.0f + (is_head ? 1.0f : 0.0f) * 1.0f / 3.0f;                  // :197
+    inten *= 1.0f + 0.5f * (s.boost[o] ? 1.0f : 0.0f);                                      // :198
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = (int)(short)(inten * (float)s.col[3 * o + c]);      // :201-206
+}
+
 // multi_snake.py:194-227 _get_env_images: int16 colour of cell q (canonical state: one owner per cell)
 __device__ __forceinline__ void env_pixel(const MultiParams& p, const MultiSmem& s, int q, int y, int x, int rgb[3]) {
     const uint32_t rec = s.cell[q];
     rgb[0] = rgb[1] = rgb[2] = 0;
     if (rec_body(rec)) {
         const int o = rec_owner(rec);
-        float inten = 1.0f * 1.0f / 3.0f + (s.hp[o] == q ? 1.0f : 0.0f) * 1.0f / 3.0f;      // :197
-        inten *= 1.0f + 0.5f * (s.boost[o] ? 1.0f : 0.0f);                                  // :198
-#pragma unroll
-        for (int c = 0; c < 3; ++c) rgb[c] = (int)(short)(inten * (float)s.col[3 * o + c]);  // :201-206
+        snake_rgb(s, o, s.hp[o] == q, rgb);
     }
     if (rec & kFood) rgb[0] += 255;                                                          // :208-209
     if (rgb[0] == 0 && rgb[1] == 0 && rgb[2] == 0) rgb[0] = rgb[1] = rgb[2] = 255;           // :214-219
     if (y == 0 || x == 0 || y == p.S - 1 || x == p.S - 1) rgb[0] = rgb[1] = rgb[2] = 0;      // :225
+}
+
+// The partial observation shows, for almost every window cell, one of a handful of colours: black (border /
+// outside), white (empty), red (food), or a snake's body / head colour.  The 2K snake colours are rendered once
+// per env -- through the same expressions as env_pixel, so bit-identical -- and the per-cell work is a look-up.
+__device__ __forceinline__ void build_colour_table(const MultiParams& p, const MultiSmem& s) {
+    for (int t = threadIdx.x; t < 2 * p.K; t += blockDim.x) {
+        int rgb[3];
+        snake_rgb(s, t >> 1, (t & 1) != 0, rgb);
+        if (rgb[0] == 0 && rgb[1] == 0 && rgb[2] == 0) rgb[0] = rgb[1] = rgb[2] = 255;       // :214-219
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s.tab[3 * t + c] = div255(rgb[c]);
+    }
 }
 
 // multi_snake.py:283-334 from the compact form into the per-agent buffers obs[k][e].
@@ -262,6 +285,8 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (p.obs_mode == WURM_MOBS_PARTIAL) {                           // :289-332
         const int n = p.obs_n, W = p.W, WW = W * W;
+        build_colour_table(p, s);
+        __syncthreads();
         for (int k = warp; k < K; k += nwarps) {
             float* o = p.obs + ((size_t)k * p.E + e) * 3 * WW;
             const int hp = s.hp[k];
@@ -273,11 +298,24 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
             for (int ij = lane; ij < WW; ij += 32) {                  // one window cell per lane, three channel rows
                 const int i = fdiv(ij, p.magic_W), j = ij - i * W;
                 const int y = hy - n + i, x = hx - n + j;
-                float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;                // zero padding :301-302
-                if (y >= 0 && y < S && x >= 0 && x < S) {
-                    int rgb[3];
-                    env_pixel(p, s, y * S + x, y, x, rgb);
-                    v0 = div255(rgb[0]); v1 = div255(rgb[1]); v2 = div255(rgb[2]);        // :296
+                float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;                // zero padding :301-302, black border :225
+                if ((unsigned)(y - 1) < (unsigned)(S - 2) && (unsigned)(x - 1) < (unsigned)(S - 2)) {
+                    const int q = y * S + x;
+                    const uint32_t rec = s.cell[q];
+                    if (!(rec & kFood)) {
+                        v0 = v1 = v2 = 1.0f;                          // empty: white (255 / 255)
+                        if (rec_body(rec)) {
+                            const int ow = rec_owner(rec);
+                            const float* t = s.tab + 3 * (2 * ow + (s.hp[ow] == q ? 1 : 0));
+                            v0 = t[0]; v1 = t[1]; v2 = t[2];
+                        }
+                    } else if (!rec_body(rec)) {
+                        v0 = 1.0f;                                    // food: (255, 0, 0)
+                    } else {                                          // food under a body: the general expression
+                        int rgb[3];
+                        env_pixel(p, s, q, y, x, rgb);
+                        v0 = div255(rgb[0]); v1 = div255(rgb[1]); v2 = div255(rgb[2]);        // :296
+                    }
                 }
                 o[ij] = v0; o[WW + ij] = v1; o[2 * WW + ij] = v2;
             }
