@@ -93,8 +93,12 @@ __device__ __forceinline__ int fdiv(int q, uint32_t magic) { return (int)__umulh
 //   bits  0-15  body value            bits 16-21  owner snake + 1      (together: the "live" body, 0 = none)
 //   bits 22-27  owner + 1 when loaded bit 28      body modified since the load
 //   bit  29     food                  bit 30      food when loaded
+//   bit  31     the cell is on the env's live list
 // so that the write-back can tell exactly which cells of which tensors changed.
-constexpr uint32_t kLive = 0x003FFFFFu, kDirty = 1u << 28, kFood = 1u << 29, kFood0 = 1u << 30;
+// The LIVE LIST holds every cell whose record ever became non-zero (a body or food at load time, a new head cell,
+// spawned food): ~1 % of the grid.  The per-cell passes of a step (decay, deaths, boost cost, write-back) walk the
+// list -- a couple of iterations with every lane busy -- instead of all S*S records.
+constexpr uint32_t kLive = 0x003FFFFFu, kDirty = 1u << 28, kFood = 1u << 29, kFood0 = 1u << 30, kListed = 1u << 31;
 __device__ __forceinline__ uint32_t make_rec(int owner, int value) { return ((uint32_t)(owner + 1) << 16) | (uint32_t)value; }
 __device__ __forceinline__ int rec_owner(uint32_t r) { return (int)((r >> 16) & 63u) - 1; }
 __device__ __forceinline__ int rec_owner0(uint32_t r) { return (int)((r >> 22) & 63u) - 1; }
@@ -180,9 +184,10 @@ struct MultiSmem {
     int* cost;
     int* boost;
     int* sum;         // sum of body values per snake (invariant check)
-    int* misc;        // [0] food cells, [2] run_boost, [3] force full write-back
+    int* misc;        // [0] food cells, [1] live-list length, [2] run_boost, [3] force full write-back
     short* col;       // K*3
     unsigned char* reset;   // ResetScratch of the fused step+reset path (>= 768 bytes)
+    unsigned short* list;   // live list (<= C entries); ALIASES the reset scratch too: it is dead once the state is written back
     float* tab;       // 2*32*3: rendered colour of snake o's body (2o) / head (2o+1) cell, see build_colour_table; ALIASES
                       // the reset scratch, which is only used after the observation is written -- shared memory per
                       // CTA decides how many envs are resident per SM, and 768 bytes more cost 9 % at K=4, S=25
@@ -197,18 +202,25 @@ __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
     s.col = reinterpret_cast<short*>(s.misc + 8);
     s.reset = reinterpret_cast<unsigned char*>(s.col + 96);
     s.tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15);
+    s.list = reinterpret_cast<unsigned short*>(s.tab);
     return s;
 }
 
 static size_t multi_smem_bytes(int C, int W, int obs_mode) {
     // records + per-snake arrays + misc + colours + the fused reset's scratch (occupancy bytes, picks)
-    const size_t scratch = (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;     // fused reset; the colour table aliases it
-    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + (scratch > 768 ? scratch : 768) + 32;
+    // one region serves, in turn, the live list (2C bytes), the colour table (768) and the fused reset's scratch
+    size_t scratch = (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;
+    if (scratch < 768) scratch = 768;
+    if (scratch < 2 * (size_t)C) scratch = 2 * (size_t)C;
+    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + scratch + 32;
 }
 
 // Food transitions keep the env's food-cell count (misc[0]) current, so _add_food needs no counting pass.
+__device__ __forceinline__ void list_push(const MultiSmem& s, int q) { s.list[atomicAdd(&s.misc[1], 1)] = (unsigned short)q; }
 __device__ __forceinline__ void set_food(const MultiSmem& s, int q) {
-    if (!(atomicOr(&s.cell[q], kFood) & kFood)) atomicAdd(&s.misc[0], 1);
+    const uint32_t old = atomicOr(&s.cell[q], kFood | kListed);
+    if (!(old & kFood)) atomicAdd(&s.misc[0], 1);
+    if (!(old & kListed)) list_push(s, q);
 }
 __device__ __forceinline__ void clear_food(const MultiSmem& s, int q) {
     if (atomicAnd(&s.cell[q], ~kFood) & kFood) atomicSub(&s.misc[0], 1);
@@ -222,7 +234,7 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
     // is then written back in full (which normalises it) instead of cell by cell.
     bool overlap = false, odd = false;
     scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float v) {
-        atomicOr(&s.cell[i], kFood | kFood0);
+        if (!(atomicOr(&s.cell[i], kFood | kFood0 | kListed) & kListed)) list_push(s, i);
         atomicAdd(&s.misc[0], 1);
         odd |= v != 1.0f;
         if (CHECK && v != 1.0f) s.misc[5] = 1;                       // a food pixel that is neither 0 nor 1
@@ -236,7 +248,9 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
     scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float v) {
         const int k = fdiv(i, p.magic_C), val = (int)v;
         const uint32_t owner = (uint32_t)(k + 1);
-        if (atomicOr(&s.cell[i - k * C], (owner << 22) | (owner << 16) | ((uint32_t)val & 0xffffu)) & kLive) overlap = true;
+        const uint32_t old = atomicOr(&s.cell[i - k * C], (owner << 22) | (owner << 16) | ((uint32_t)val & 0xffffu) | kListed);
+        if (old & kLive) overlap = true;
+        if (!(old & kListed)) list_push(s, i - k * C);
         atomicMax(&s.size[k], val);
         if (CHECK) atomicAdd(&s.sum[k], val);
         odd |= (float)val != v || val < 1 || val > 65535;
@@ -285,6 +299,7 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (p.obs_mode == WURM_MOBS_PARTIAL) {                           // :289-332
         const int n = p.obs_n, W = p.W, WW = W * W;
+        __syncthreads();                                              // the live list (same memory) is dead from here on
         build_colour_table(p, s);
         __syncthreads();
         for (int k = warp; k < K; k += nwarps) {
@@ -563,7 +578,11 @@ multi_env_kernel(const MultiParams p) {
         pre_orient = p.orientations[n];
         if (p.replay && p.u_cost) pre_cost = p.u_cost[n];
     }
-    for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
+    {
+        uint4* c4 = reinterpret_cast<uint4*>(s.cell);                 // 16-byte aligned: the start of the dynamic shared memory
+        for (int j = tid; j < (C >> 2); j += nthr) c4[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < (C & 3)) s.cell[(C & ~3) + tid] = 0u;
+    }
     if (tid < 32) {
         s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.decay[tid] = 0; s.cost[tid] = 0; s.sum[tid] = 0;
         s.done[tid] = (tid < K) ? (p.dones[(size_t)e * K + tid] != 0) : 1;
@@ -630,7 +649,8 @@ multi_env_kernel(const MultiParams p) {
                 if (active && ov) { a_reward += 1.0f; a_foodc += 1.0f; }   // :527-529 / :629-631
             }
             __syncthreads();
-            for (int q = tid; q < C; q += nthr) {                     // _decay_bodies :362-363
+            for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {  // _decay_bodies :362-363
+                const int q = s.list[n];
                 const uint32_t rec = s.cell[q];
                 if (rec_body(rec) && s.decay[rec_owner(rec)])
                     s.cell[q] = ((rec_value(rec) == 1) ? (rec & ~kLive) : rec - 1u) | kDirty;
@@ -647,7 +667,10 @@ multi_env_kernel(const MultiParams p) {
                 if (active && a_hp >= 0) {                            // :553 / :650 growth at the head cell
                     const uint32_t add = (uint32_t)(a_size + (ov ? 1 : 0));
                     const uint32_t cur = s.cell[a_hp];
-                    if (!rec_body(cur)) atomicCAS(&s.cell[a_hp], cur, cur | make_rec(k, (int)add) | kDirty);   // head-on: first claim wins
+                    if (!rec_body(cur)) {                             // head-on: first claim wins
+                        if (atomicCAS(&s.cell[a_hp], cur, cur | make_rec(k, (int)add) | kDirty | kListed) == cur && !(cur & kListed))
+                            list_push(s, a_hp);
+                    }
                     else if (rec_owner(cur) == k) s.cell[a_hp] = (cur + add) | kDirty;   // self collision: values add up
                     // a collider's head value on ANOTHER snake's cell is dropped: the collider is
                     // deleted below and that cell counts as covered by the other body either way
@@ -672,7 +695,8 @@ multi_env_kernel(const MultiParams p) {
             {   // food from dead bodies (:416-428), boost cost on the bodies (:583-589), deletion (:595 / :676)
                 const float* U = p.replay ? (boost_phase ? p.u_boost : p.u_reg) : nullptr;
                 const uint32_t stream = boost_phase ? kStreamMultiDeathBoost : kStreamMultiDeathRegular;
-                for (int q = tid; q < C; q += nthr) {
+                for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {
+                    const int q = s.list[n];
                     uint32_t rec = s.cell[q];
                     if (!rec_body(rec)) continue;
                     const int o = rec_owner(rec);
@@ -733,7 +757,7 @@ multi_env_kernel(const MultiParams p) {
                     if (y < 1 || y > S - 2 || x < 1 || x > S - 2 || !cell_free(q)) continue;
                     const float u = p.replay ? p.u_rate[(size_t)e * C + q]
                                              : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodRate, (uint32_t)q));
-                    if (u < p.food_rate) s.cell[q] |= kFood;            // (the count is not needed any more)
+                    if (u < p.food_rate) set_food(s, q);
                 }
             }
         }
@@ -789,7 +813,8 @@ multi_env_kernel(const MultiParams p) {
             // touches O(snake length) cells of an S*S grid: write traffic drops from the full state
             // to a few sectors per snake.
             float* bodies = p.bodies + (size_t)e * K * C;
-            for (int q = tid; q < C; q += nthr) {
+            for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {
+                const int q = s.list[n];
                 const uint32_t rec = s.cell[q];
                 if (rec & kDirty) {
                     const int ko = rec_owner0(rec), kn = rec_body(rec) ? rec_owner(rec) : -1;
