@@ -99,6 +99,8 @@ ROLLOUTS = [
     (40, 10, 36, 'partial_2', 40, dict(respawn_mode='any'), torch.long),   # experiments/speeds.py geometry
     (3, 32, 40, 'partial_1', 20, DEFAULT_RULES, torch.long),           # the maximum number of snakes
     (1, 1, 7, 'full', 20, DEFAULT_RULES, torch.long),                  # the smallest env
+    (20, 12, 20, 'partial_2', 30, dict(respawn_mode='any'), torch.long),   # one warp per env with 3K colours > 32 lanes
+    (4, 6, 30, 'partial_3', 60, dict(food_on_death_prob=1.0), torch.long),  # long snakes: the load scan's hit queue overflows
 ]
 
 

@@ -111,40 +111,37 @@ __device__ __forceinline__ float4 ld_stream(const float4* ptr) {
     return v;
 }
 
-// Calls f(i, v) for every non-zero base[i], i < n.  128-bit streaming loads, four in flight per thread.
+// Calls f(i, v) for every non-zero base[i], i < n.  128-bit streaming loads, four in flight per thread; loads past
+// the end are clamped to the last vector instead of predicated (their hits are dropped by the index test).
 template <typename F>
 __device__ __forceinline__ void scan_nonzero(const float* base, int n, F&& f) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     int lead = (4 - (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3)) & 3;
     if (lead > n) lead = n;
-    if (tid < lead) {
-        const float v = base[tid];
-        if (v != 0.0f) f(tid, v);
-    }
     const int nvec = (n - lead) >> 2;
+    const int tail0 = lead + 4 * nvec;
+    if (tid < lead + (n - tail0)) {                                  // the (at most 3 + 3) unaligned edge elements
+        const int i = tid < lead ? tid : tail0 + (tid - lead);
+        const float v = base[i];
+        if (v != 0.0f) f(i, v);
+    }
     const float4* vb = reinterpret_cast<const float4*>(base + lead);
     for (int j0 = tid; j0 < nvec; j0 += 4 * nthr) {
         float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * nthr;
-            v[u] = (j < nvec) ? ld_stream(vb + j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream(vb + min(j0 + u * nthr, nvec - 1));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (v[u].x != 0.0f || v[u].y != 0.0f || v[u].z != 0.0f || v[u].w != 0.0f) {
-                const int i = lead + 4 * (j0 + u * nthr);
-                if (v[u].x != 0.0f) f(i, v[u].x);
-                if (v[u].y != 0.0f) f(i + 1, v[u].y);
-                if (v[u].z != 0.0f) f(i + 2, v[u].z);
-                if (v[u].w != 0.0f) f(i + 3, v[u].w);
+                const int j = j0 + u * nthr, i = lead + 4 * j;
+                if (j < nvec) {
+                    if (v[u].x != 0.0f) f(i, v[u].x);
+                    if (v[u].y != 0.0f) f(i + 1, v[u].y);
+                    if (v[u].z != 0.0f) f(i + 2, v[u].z);
+                    if (v[u].w != 0.0f) f(i + 3, v[u].w);
+                }
             }
         }
-    }
-    const int tail0 = lead + 4 * nvec;
-    if (tid < n - tail0) {
-        const float v = base[tail0 + tid];
-        if (v != 0.0f) f(tail0 + tid, v);
     }
 }
 
@@ -184,7 +181,9 @@ struct MultiSmem {
     int* cost;
     int* boost;
     int* sum;         // sum of body values per snake (invariant check)
-    int* misc;        // [0] food cells, [1] live-list length, [2] run_boost, [3] force full write-back
+    int* misc;        // [0] food cells, [1] live-list length, [2] run_boost, [3] force full write-back, [6] queued hits
+    int2* queue;      // non-zero elements found by the load scan: (tensor << 30 | index, value bits), see load_env
+    int qcap;
     short* col;       // K*3
     unsigned char* reset;   // ResetScratch of the fused step+reset path (>= 768 bytes)
     unsigned short* list;   // live list (<= C entries); ALIASES the reset scratch too: it is dead once the state is written back
@@ -193,26 +192,35 @@ struct MultiSmem {
                       // CTA decides how many envs are resident per SM, and 768 bytes more cost 9 % at K=4, S=25
 };
 
-__device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C) {
+// Shared memory per CTA decides how many small envs are resident per SM (K=4, S=25: 768 bytes more cost 9 %), so the
+// per-snake arrays are sized by K (rounded up to 4), not by the 32-snake maximum.
+__host__ __device__ __forceinline__ int snakes_padded(int K) { return (K + 3) & ~3; }
+__host__ __device__ __forceinline__ int queue_capacity(int K) { return 16 * K + 64; }
+
+__device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C, int K) {
     MultiSmem s;
+    const int KP = snakes_padded(K);
     s.cell = reinterpret_cast<uint32_t*>(smem);
-    s.hp = reinterpret_cast<int*>(s.cell + C);
-    s.size = s.hp + 32; s.hcnt = s.size + 32; s.done = s.hcnt + 32; s.decay = s.done + 32; s.cost = s.decay + 32;
-    s.boost = s.cost + 32; s.sum = s.boost + 32; s.misc = s.sum + 32;
+    s.queue = reinterpret_cast<int2*>(s.cell + ((C + 1) & ~1));        // 8-byte aligned
+    s.qcap = queue_capacity(K);
+    s.hp = reinterpret_cast<int*>(s.queue + s.qcap);
+    s.size = s.hp + KP; s.hcnt = s.size + KP; s.done = s.hcnt + KP; s.decay = s.done + KP; s.cost = s.decay + KP;
+    s.boost = s.cost + KP; s.sum = s.boost + KP; s.misc = s.sum + KP;
     s.col = reinterpret_cast<short*>(s.misc + 8);
-    s.reset = reinterpret_cast<unsigned char*>(s.col + 96);
+    s.reset = reinterpret_cast<unsigned char*>(s.col + 3 * KP);
     s.tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15);
     s.list = reinterpret_cast<unsigned short*>(s.tab);
     return s;
 }
 
-static size_t multi_smem_bytes(int C, int W, int obs_mode) {
+static size_t multi_smem_bytes(int C, int K) {
     // records + per-snake arrays + misc + colours + the fused reset's scratch (occupancy bytes, picks)
     // one region serves, in turn, the live list (2C bytes), the colour table (768) and the fused reset's scratch
     size_t scratch = (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;
     if (scratch < 768) scratch = 768;
     if (scratch < 2 * (size_t)C) scratch = 2 * (size_t)C;
-    return (size_t)C * 4 + 8 * 32 * 4 + 8 * 4 + 96 * 2 + scratch + 32;
+    const size_t KP = (size_t)snakes_padded(K);
+    return (size_t)((C + 1) & ~1) * 4 + (size_t)queue_capacity(K) * 8 + 8 * KP * 4 + 8 * 4 + 3 * KP * 2 + scratch + 32;
 }
 
 // Food transitions keep the env's food-cell count (misc[0]) current, so _add_food needs no counting pass.
@@ -226,37 +234,64 @@ __device__ __forceinline__ void clear_food(const MultiSmem& s, int q) {
     if (atomicAnd(&s.cell[q], ~kFood) & kFood) atomicSub(&s.misc[0], 1);
 }
 
-// Streams env e's tensors from HBM into the compact shared-memory form.
-template <bool CHECK = false>
-__device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e) {
-    const int C = p.C, K = p.K;
-    // `odd`: a value the compact form cannot carry exactly (food/head != 1, non-integral body): the env
-    // is then written back in full (which normalises it) instead of cell by cell.
-    bool overlap = false, odd = false;
-    scan_nonzero(p.foods + (size_t)e * C, C, [&](int i, float v) {
+// Folds one non-zero element of env e's tensors into the compact form (what: 0 food, 1 head, 2 body).  A value the
+// compact form cannot carry exactly (food / head != 1, non-integral body) or two bodies on one cell set misc[3]: the
+// env is then written back in full (which normalises it) instead of cell by cell.
+template <bool CHECK>
+__device__ __forceinline__ void fold_nonzero(const MultiSmem& s, int C, uint32_t magic_C, int32_t* status, int what, int i, float v) {
+    bool odd;
+    if (what == 0) {
         if (!(atomicOr(&s.cell[i], kFood | kFood0 | kListed) & kListed)) list_push(s, i);
         atomicAdd(&s.misc[0], 1);
-        odd |= v != 1.0f;
-        if (CHECK && v != 1.0f) s.misc[5] = 1;                       // a food pixel that is neither 0 nor 1
-    });
-    scan_nonzero(p.heads + (size_t)e * K * C, K * C, [&](int i, float v) {
-        const int k = fdiv(i, p.magic_C);
+        odd = v != 1.0f;
+        if (CHECK && odd) s.misc[5] = 1;                             // a food pixel that is neither 0 nor 1
+    } else if (what == 1) {
+        const int k = fdiv(i, magic_C);
         atomicMax(&s.hp[k], i - k * C);
         atomicAdd(&s.hcnt[k], v == 1.0f ? 1 : 2);                    // a head value other than 1 counts as "not one head"
-        odd |= v != 1.0f;
-    });
-    scan_nonzero(p.bodies + (size_t)e * K * C, K * C, [&](int i, float v) {
-        const int k = fdiv(i, p.magic_C), val = (int)v;
+        odd = v != 1.0f;
+    } else {
+        const int k = fdiv(i, magic_C), val = (int)v;
         const uint32_t owner = (uint32_t)(k + 1);
         const uint32_t old = atomicOr(&s.cell[i - k * C], (owner << 22) | (owner << 16) | ((uint32_t)val & 0xffffu) | kListed);
-        if (old & kLive) overlap = true;
+        odd = (float)val != v || val < 1 || val > 65535;
+        if (old & kLive) { atomicOr(status, WURM_ST_OVERLAP); odd = true; }
         if (!(old & kListed)) list_push(s, i - k * C);
         atomicMax(&s.size[k], val);
         if (CHECK) atomicAdd(&s.sum[k], val);
-        odd |= (float)val != v || val < 1 || val > 65535;
-    });
-    if (overlap) atomicOr(p.status, WURM_ST_OVERLAP);
-    if (overlap || odd) s.misc[3] = 1;
+    }
+    if (odd) s.misc[3] = 1;
+}
+
+// (plain arguments: a reference to the kernel's parameter struct would force a copy of it onto the stack)
+template <bool CHECK>
+__device__ __noinline__ void fold_nonzero_overflow(unsigned char* smem, int C, int K, uint32_t magic_C, int32_t* status, int what,
+                                                   int i, float v) {
+    fold_nonzero<CHECK>(carve(smem, C, K), C, magic_C, status, what, i, v);
+}
+
+// Streams env e's tensors from HBM into the compact shared-memory form.  ONE copy of the scan loop runs over the
+// three tensors; the ~1 % non-zero elements it meets are only QUEUED (a counter bump and one 8-byte store, whichever
+// lane meets them), and folded afterwards with every lane busy -- handling each hit where it is found would run the
+// whole fold with one or two lanes active per hit.  Hits beyond the queue's capacity are folded on the spot.
+template <bool CHECK = false>
+__device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e) {
+    const int C = p.C, K = p.K;
+#pragma unroll 1
+    for (int what = 0; what < 3; ++what) {
+        const float* base = what == 0 ? p.foods + (size_t)e * C : (what == 1 ? p.heads : p.bodies) + (size_t)e * K * C;
+        scan_nonzero(base, what == 0 ? C : K * C, [&](int i, float v) {
+            const int n = atomicAdd(&s.misc[6], 1);
+            if (n < s.qcap) s.queue[n] = make_int2((int)((unsigned)i | ((unsigned)what << 30)), __float_as_int(v));
+            else fold_nonzero_overflow<CHECK>(reinterpret_cast<unsigned char*>(s.cell), C, K, p.magic_C, p.status, what, i, v);
+        });
+    }
+    __syncthreads();
+    const int nq = min(s.misc[6], s.qcap);
+    for (int n = threadIdx.x; n < nq; n += blockDim.x) {
+        const int2 h = s.queue[n];
+        fold_nonzero<CHECK>(s, C, p.magic_C, p.status, (int)((unsigned)h.x >> 30), h.x & 0x3fffffff, __int_as_float(h.y));
+    }
 }
 
 // multi_snake.py:197-206: int16 colour of a body (or, is_head, head) cell of snake o
@@ -559,7 +594,7 @@ template <bool STEP, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? 12 : THREADS == 64 ? 20 : 32)
 multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const MultiSmem s = carve(smem_raw, p.C);
+    const MultiSmem s = carve(smem_raw, p.C, p.K);
     const int C = p.C, K = p.K, S = p.S;
     const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
 
@@ -583,13 +618,13 @@ multi_env_kernel(const MultiParams p) {
         for (int j = tid; j < (C >> 2); j += nthr) c4[j] = make_uint4(0u, 0u, 0u, 0u);
         if (tid < (C & 3)) s.cell[(C & ~3) + tid] = 0u;
     }
-    if (tid < 32) {
+    if (tid < K) {
         s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.decay[tid] = 0; s.cost[tid] = 0; s.sum[tid] = 0;
-        s.done[tid] = (tid < K) ? (p.dones[(size_t)e * K + tid] != 0) : 1;
-        s.boost[tid] = (!STEP && tid < K) ? (p.boost_this_step[(size_t)e * K + tid] != 0) : 0;
+        s.done[tid] = p.dones[(size_t)e * K + tid] != 0;
+        s.boost[tid] = !STEP ? (p.boost_this_step[(size_t)e * K + tid] != 0) : 0;
     }
     if (tid < 8) s.misc[tid] = 0;
-    if (tid < 3 * K) s.col[tid] = p.colours[(size_t)e * K * 3 + tid];
+    for (int t = tid; t < 3 * K; t += nthr) s.col[t] = p.colours[(size_t)e * K * 3 + t];
     __syncthreads();
     load_env(p, s, e);
     __syncthreads();
@@ -645,7 +680,7 @@ multi_env_kernel(const MultiParams p) {
                 ov = valid && a_hp >= 0 && (s.cell[a_hp] & kFood);    // :514 / :618 overlap of ALL heads
                 __syncwarp();
                 if (ov) clear_food(s, a_hp);                          // :517 / :622
-                if (k < 32) s.decay[k] = active && !ov;               // :523-526 / :627-628
+                if (valid) s.decay[k] = active && !ov;                // :523-526 / :627-628
                 if (active && ov) { a_reward += 1.0f; a_foodc += 1.0f; }   // :527-529 / :629-631
             }
             __syncthreads();
@@ -687,7 +722,7 @@ multi_env_kernel(const MultiParams p) {
                                                  : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiBoostCost, (uint32_t)k));
                         cost = u < p.boost_cost_prob;
                     }
-                    if (k < 32) s.cost[k] = cost;
+                    if (valid) s.cost[k] = cost;
                     if (cost) { a_reward -= 1.0f; a_size -= 1; }      // :590-591
                 }
             }
@@ -868,12 +903,12 @@ multi_env_kernel(const MultiParams p) {
 // state once; the per-snake verdicts come from the head index, body maximum / sum and the cell records.
 __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, int* report) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const MultiSmem s = carve(smem_raw, p.C);
+    const MultiSmem s = carve(smem_raw, p.C, p.K);
     const int C = p.C, K = p.K, e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
-    if (tid < 32) {
+    if (tid < K) {
         s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.sum[tid] = 0;
-        s.done[tid] = (tid < K) ? (p.dones[(size_t)e * K + tid] != 0) : 1;
+        s.done[tid] = p.dones[(size_t)e * K + tid] != 0;
     }
     if (tid < 8) s.misc[tid] = 0;
     __syncthreads();
@@ -1019,7 +1054,7 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
 template <bool STEP, int THREADS>
 static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
     auto kern = multi_env_kernel<STEP, THREADS>;
-    const size_t smem = multi_smem_bytes(p.C, p.W, p.obs_mode);
+    const size_t smem = multi_smem_bytes(p.C, p.K);
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
@@ -1153,7 +1188,7 @@ extern "C" int wurm_multi_check(const WurmMultiCfg* cfg, const WurmMultiState* s
     MultiParams p = {};
     if (int rc = plan_multi(cfg, state, &p)) return rc;
     if (!report) return fail(WURM_E_INVALID, "NULL pointer");
-    const size_t smem = multi_smem_bytes(p.C, p.W, p.obs_mode);
+    const size_t smem = multi_smem_bytes(p.C, p.K);
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(multi_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
