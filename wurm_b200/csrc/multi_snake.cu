@@ -195,7 +195,7 @@ struct MultiSmem {
 // Shared memory per CTA decides how many small envs are resident per SM (K=4, S=25: 768 bytes more cost 9 %), so the
 // per-snake arrays are sized by K (rounded up to 4), not by the 32-snake maximum.
 __host__ __device__ __forceinline__ int snakes_padded(int K) { return (K + 3) & ~3; }
-__host__ __device__ __forceinline__ int queue_capacity(int K) { return 16 * K + 64; }
+__host__ __device__ __forceinline__ int queue_capacity(int K) { return 12 * K + 32; }
 
 __device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C, int K) {
     MultiSmem s;
