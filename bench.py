@@ -15,8 +15,9 @@ episode-statistics counters after the timed region.  Rank 0 prints ONE JSON line
 
   value      whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed, max over ranks
   e2e        same loop through the public host-buffer API (wurm_b200.HostStepper): every step copies that step's
-             actions from pinned host memory, and copies the sanitised actions, rewards and done flags back to
-             pinned host memory, all inside the timed region (copies of neighbouring steps overlap the kernels)
+             actions from pinned host memory, and copies that step's results (rewards and done flags) back to
+             pinned host memory, all inside the timed region (copies of neighbouring steps overlap the kernels;
+             observations stay on the device: they are the policy's input)
   roofline   for the dominant kernel (the step kernel): algorithmic bytes per launch (SURVEY.md section 8d:
              read state + write state + write observation + per-env vectors) / its average launch duration,
              measured live with CUDA events around every step launch of the timed region, against the
@@ -393,7 +394,7 @@ def run_gpu(args):
 
     # ---- end to end through the public API with host buffers (wurm_b200.HostStepper) ----
     # every step: H2D copy of that step's actions from pinned host memory, step + reset kernels, D2H copy of
-    # the step's results (rewards, done flags, sanitised actions) into pinned host memory; the copies of
+    # the step's results (rewards, done flags) into pinned host memory; the copies of
     # neighbouring steps overlap the kernels (double-buffered, one copy stream per direction)
     from wurm_b200 import HostStepper
     stepper = HostStepper(env, depth=2)
@@ -451,7 +452,8 @@ def run_gpu(args):
                        'parallelism': f'{world} independent env slices, NCCL all-reduce of episode stats only'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': Ke, 'ms_per_step': e2e_ms / Ke},
+                    'steps': Ke, 'ms_per_step': e2e_ms / Ke,
+                    'copies': 'H2D actions; D2H rewards (f32) + done flags per env / agent; fused step+reset launch'},
             'gpu_launches': 2 * K,
             'roofline': {'bound': 'hbm', 'kernel': ad.kernel, 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': profiled_traffic(key),

@@ -266,7 +266,7 @@ def test_host_stepper_matches_direct_stepping():
     a = torch.randint(0, 4, (steps, N), generator=torch.Generator().manual_seed(3))
     direct = make_env(N, S, 'partial_2', seed=77)
     piped = make_env(N, S, 'partial_2', seed=77)
-    stepper = HostStepper(piped, depth=2)
+    stepper = HostStepper(piped, depth=2, return_actions=True)
     expect = []
     for t in range(steps):
         acts = a[t].to(DEV)

@@ -1,17 +1,19 @@
 """Stepping an env from HOST action buffers with results delivered to HOST buffers.
 
 The env state lives on the GPU; what crosses PCIe every step is the actions (host -> device) and the
-per-env results a host-side consumer needs (device -> host: rewards, done flags and, for
-SingleSnake, the sanitised actions the reference writes back into the caller's tensor,
-single_snake.py:222).  `HostStepper` double-buffers both directions in pinned memory and puts each
-direction on its own copy stream, so the copies of step t+1 / t-1 overlap the kernels of step t:
+per-env results a host-side consumer needs (device -> host: rewards and done flags; on request
+(`return_actions=True`) also SingleSnake's sanitised actions -- the reference sanitises the DEVICE tensor it
+is given in place, single_snake.py:222, and so does the kernel with the uploaded copy; bringing that back
+costs 8 of 13.6 MB per step at 2^20 envs and makes two GPUs behind one PCIe switch copy-bound).
+`HostStepper` double-buffers both directions in pinned memory and puts each direction on its own copy
+stream, so the copies of step t+1 / t-1 overlap the kernels of step t:
 
     stepper = HostStepper(env)
     tickets = []
     for actions in host_action_batches:          # pinned CPU tensors (or dicts of them for MultiSnake)
         tickets.append(stepper.submit(actions))  # H2D copy, step kernel, reset kernel, D2H copies: all async
         if len(tickets) > stepper.depth:
-            result = tickets.pop(0).wait()       # .reward / .done (/.actions) are pinned host tensors
+            result = tickets.pop(0).wait()       # .reward / .done (/.actions) are pinned host tensors, .obs stays on the device
 
 Calling `env.step(host_tensor)` directly also works (the env copies on the compute stream); it is the
 un-pipelined form of the same thing.
@@ -40,10 +42,11 @@ class Ticket(object):
 
 
 class HostStepper(object):
-    def __init__(self, env, depth: int = 2, auto_reset: bool = True):
+    def __init__(self, env, depth: int = 2, auto_reset: bool = True, return_actions: bool = False):
         self.env = env
         self.depth = depth
         self.auto_reset = auto_reset
+        self.return_actions = return_actions
         self.multi = hasattr(env, 'num_snakes')
         self.device = torch.device(env.device) if not isinstance(env.device, torch.device) else env.device
         if self.device.index is None:
@@ -72,11 +75,12 @@ class HostStepper(object):
             else:
                 self._dev_actions[slot] = torch.empty_like(actions, device=self.device)
                 self._host_out[slot] = dict(reward=torch.empty((N, 1), dtype=torch.float32, **pin),
-                                            done=torch.empty((N, 1), dtype=torch.bool, **pin),
-                                            actions=torch.empty_like(actions, **pin))
+                                            done=torch.empty((N, 1), dtype=torch.bool, **pin))
                 act = actions.numel() * actions.element_size()
+                if self.return_actions:
+                    self._host_out[slot]['actions'] = torch.empty_like(actions, **pin)
                 self.h2d_bytes_per_step = act
-                self.d2h_bytes_per_step = act + N * 5
+                self.d2h_bytes_per_step = N * 5 + (act if self.return_actions else 0)
         return self._dev_actions[slot], self._host_out[slot]
 
     def submit(self, actions) -> Ticket:
@@ -121,7 +125,8 @@ class HostStepper(object):
                 host_out['all_done'].copy_(env_done, non_blocking=True)
             else:
                 host_out['done'].copy_(done_t, non_blocking=True)
-                host_out['actions'].copy_(dev_actions, non_blocking=True)      # sanitised in place by the kernel
+                if self.return_actions:
+                    host_out['actions'].copy_(dev_actions, non_blocking=True)  # sanitised in place by the kernel
             done_ev = torch.cuda.Event()
             done_ev.record(self.d2h)
         for t in (reward_t, done_t, env_done):
