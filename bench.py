@@ -51,6 +51,7 @@ WORKLOADS = {
     'G1': ('SimpleGridworld', 7, 1 << 20, 'default', 1),      # next-row env, reference test size
 }
 ACTION_POOL = 16        # pre-generated action tensors cycled through by the timed loop
+GRAPHED_E2E_MAX_ENVS = 16384   # at or below: e2e goes through GraphedStepper(host_io=True), the API for launch-bound sizes
 
 
 def workload_name(key, n_envs=None):
@@ -396,28 +397,59 @@ def run_gpu(args):
     # every step: H2D copy of that step's actions from pinned host memory, step + reset kernels, D2H copy of
     # the step's results (rewards, done flags) into pinned host memory; the copies of
     # neighbouring steps overlap the kernels (double-buffered, one copy stream per direction)
-    from wurm_b200 import HostStepper
-    stepper = HostStepper(env, depth=2)
+    from wurm_b200 import HostStepper, GraphedStepper
     host_pool = ad.host_pool()
     Ke = max(10, K // 2)
-    tickets = []
-    for t in range(4):
-        tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
-    while tickets:
-        tickets.pop(0).wait()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e_start.record()
-    for t in range(Ke):
-        tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
-        if len(tickets) > stepper.depth:
+    graphed_e2e = N <= GRAPHED_E2E_MAX_ENVS and getattr(env, 'supports_fused_reset', False)
+    if graphed_e2e:
+        # launch-bound sizes: the copies ride inside the CUDA graph (GraphedStepper(host_io=True)); per step the host
+        # writes that step's actions into the graph's pinned input, replays, synchronises and reads the results
+        first = ad.pool[0]
+        static = {a: t.clone() for a, t in first.items()} if isinstance(first, dict) else first.clone()
+        stepper = GraphedStepper(env, static, host_io=True)
+
+        def put(src):
+            if isinstance(src, dict):
+                for a, t in src.items():
+                    stepper.host_actions[a].copy_(t)
+            else:
+                stepper.host_actions.copy_(src)
+        for t in range(4):
+            put(host_pool[t % ACTION_POOL]); stepper.step_host()
+        barrier()
+        e_start.record()
+        checksum = 0.0
+        for t in range(Ke):
+            put(host_pool[t % ACTION_POOL])
+            stepper.step_host()
+            checksum += float(stepper.host_reward[0].sum())      # the host reads the step's result
+        e_stop.record()
+        barrier()
+        e2e_ms = e_start.elapsed_time(e_stop)
+        h2d = sum(t.numel() * t.element_size() for t in (first.values() if isinstance(first, dict) else [first]))
+        d2h = stepper.host_reward.numel() * 4 + stepper.host_done.numel() + (stepper.host_all_done.numel() if hasattr(stepper, 'host_all_done') else 0)
+        e2e_api = 'GraphedStepper(host_io=True): one CUDA-graph launch per step carrying H2D actions, fused step+reset, D2H rewards + done flags'
+    else:
+        stepper = HostStepper(env, depth=2)
+        tickets = []
+        for t in range(4):
+            tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
+        while tickets:
             tickets.pop(0).wait()
-    while tickets:
-        last = tickets.pop(0).wait()
-    e_stop.record(stepper.d2h)
-    barrier()
-    e2e_ms = e_start.elapsed_time(e_stop)
-    h2d, d2h = stepper.h2d_bytes_per_step, stepper.d2h_bytes_per_step
+        barrier()
+        e_start.record()
+        for t in range(Ke):
+            tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
+            if len(tickets) > stepper.depth:
+                tickets.pop(0).wait()
+        while tickets:
+            last = tickets.pop(0).wait()
+        e_stop.record(stepper.d2h)
+        barrier()
+        e2e_ms = e_start.elapsed_time(e_stop)
+        h2d, d2h = stepper.h2d_bytes_per_step, stepper.d2h_bytes_per_step
+        e2e_api = 'HostStepper: pinned double-buffered H2D actions / D2H rewards + done flags on copy streams around the fused step+reset launch'
 
     # ---- max over ranks, episode statistics (the only collective on this path) ----
     times = torch.tensor([ms_total, e2e_ms, step_kernel_ms, fused_ms or 0.0], dtype=torch.float64, device=dev)
@@ -453,7 +485,7 @@ def run_gpu(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': Ke, 'ms_per_step': e2e_ms / Ke,
-                    'copies': 'H2D actions; D2H rewards (f32) + done flags per env / agent; fused step+reset launch'},
+                    'api': e2e_api},
             'gpu_launches': 2 * K,
             'roofline': {'bound': 'hbm', 'kernel': ad.kernel, 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': profiled_traffic(key),

@@ -412,3 +412,30 @@ def test_nearly_full_board_food_respawn_and_no_free_cell():
     food_left = state[:, 0].reshape(N, -1).sum(-1)
     assert (food_left[np.array(lengths) == 48] == 0).all()            # 49 body cells: nowhere to put the food
     assert (food_left[np.array(lengths) < 48] == 1).all()
+
+
+def test_graphed_stepper_with_host_io():
+    """GraphedStepper(host_io=True): the graph carries H2D actions and D2H rewards / done flags; results in the pinned
+    host buffers equal call-by-call stepping of a twin env."""
+    from wurm_b200 import GraphedStepper
+    N, S, steps = 512, 9, 25
+    plain = make_env(N, S, 'partial_2', seed=77)
+    graphed = make_env(N, S, 'partial_2', seed=77)
+    acts = torch.randint(0, 4, (steps + 1, N), generator=torch.Generator().manual_seed(5))
+    static_actions = acts[0].to(DEV)
+    stepper = GraphedStepper(graphed, static_actions, warmup=2, host_io=True)
+    a0 = acts[0].to(DEV)
+    for _ in range(2):
+        _, _, done, _ = plain.step(a0)
+        plain.reset(done, return_observations=False)
+    for t in range(1, steps + 1):
+        stepper.host_actions.copy_(acts[t])
+        obs, _, _, _ = stepper.step_host()
+        obs2, reward2, done2, _ = plain.step(acts[t].to(DEV))
+        assert_same(stepper.host_reward.numpy(), np_(reward2), f'step {t}: host reward')
+        assert_same(stepper.host_done.numpy(), np_(done2), f'step {t}: host done')
+        assert_same(np_(obs), np_(obs2), f'step {t}: obs')
+        plain.reset(done2, return_observations=False)
+        assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')
+    with pytest.raises(RuntimeError):
+        GraphedStepper(plain, a0, warmup=1).step_host()
