@@ -66,3 +66,36 @@ def test_env_refuses_to_run_without_cuda_device():
     from wurm_b200.envs import SingleSnake
     with pytest.raises(RuntimeError):
         SingleSnake(num_envs=2, size=9, device='cpu')
+
+
+def test_a2c_returns_rejects_bad_arguments():
+    L = _lib.lib()
+    assert L.wurm_a2c_returns(0, 4, 0.99, -1.0, None, None, None, None, None, None) == _lib.E_INVALID
+    assert L.wurm_a2c_returns(5, 4, 0.99, -1.0, None, None, None, None, None, None) == _lib.E_INVALID
+
+
+def test_trajectory_store_mirrors_the_reference():
+    """wurm/rl/trajectory_store.py:4-89: append() keeps what it is given, properties stack to (T, N, ...), clear() empties."""
+    import torch
+    from wurm_b200.trajectory_store import TrajectoryStore
+    store = TrajectoryStore()
+    for t in range(3):
+        store.append(action=torch.full((4,), t), log_prob=torch.zeros(4, 1, requires_grad=True), reward=torch.full((4, 1), float(t)),
+                     value=torch.ones(4, 1), done=torch.zeros(4, 1, dtype=torch.bool), entropy=torch.tensor(0.5))
+    assert store.rewards.shape == (3, 4, 1) and store.actions.shape == (3, 4) and store.entropies.shape == (3,)
+    assert store.log_probs.requires_grad and store.dones.dtype == torch.bool and len(store) == 3
+    assert float(store.rewards[2, 0, 0]) == 2.0
+    with pytest.raises(RuntimeError):
+        store.states                      # nothing appended: torch.stack of an empty list, as in the reference
+    store.clear()
+    assert len(store) == 0
+
+
+def test_a2c_has_no_cpu_fallback():
+    """The return scan runs on the device only: CPU tensors are refused (the CPU implementation is the reference itself)."""
+    import torch
+    from wurm_b200.rl import A2C
+    T, N = 3, 4
+    with pytest.raises(RuntimeError):
+        A2C(gamma=0.99).loss(torch.zeros(N, 1), torch.zeros(T, N, 1), torch.zeros(T, N, 1), torch.zeros(T, N, 1),
+                             torch.zeros(T, N, 1, dtype=torch.bool))

@@ -26,6 +26,8 @@ def returns(bootstrap_values: torch.Tensor, rewards: torch.Tensor, values: torch
     """Returns of shape rewards.shape ((T, N) or (T, N, 1)), no gradient."""
     T, N = rewards.shape[0], rewards.shape[1]
     dev = rewards.device
+    if dev.type != 'cuda':
+        raise RuntimeError('wurm_b200.rl runs on CUDA tensors only (there is no CPU fallback; the CPU implementation is the reference)')
     r = rewards.detach().reshape(T, N).to(torch.float32).contiguous()
     v = values.detach().reshape(T, N).to(torch.float32).contiguous()
     d = dones.reshape(T, N).to(torch.bool).contiguous()
