@@ -459,14 +459,30 @@ __device__ __forceinline__ ResetScratch carve_reset(unsigned char* base, int C) 
 }
 
 // :846-858 / :927-941: a snake may be seeded on cell q if q is at least two cells from the wall and nothing
-// occupies its 3x3 neighbourhood
-__device__ __forceinline__ bool spawnable(const MultiParams& p, const uint8_t* occ, int q) {
+// occupies its 3x3 neighbourhood.  The occupancy bytes carry that test precomputed: bit 0 = the cell is occupied,
+// bit 1 = "no seed here" (too close to the wall, or an occupied cell in the 3x3 neighbourhood), so that the
+// candidate scans of block_pick read one byte per cell instead of nine.
+constexpr uint8_t kOccupied = 1, kNoSeed = 2;
+__device__ __forceinline__ bool spawnable(const uint8_t* occ, int q) { return !(occ[q] & kNoSeed); }
+__device__ __forceinline__ bool seed_margin(const MultiParams& p, int q) {
     const int S = p.S, y = fdiv(q, p.magic_S), x = q - y * S;
-    if (y < 2 || y > S - 3 || x < 2 || x > S - 3) return false;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx)
-            if (occ[(y + dy) * S + x + dx]) return false;
-    return true;
+    return y < 2 || y > S - 3 || x < 2 || x > S - 3;
+}
+// marks the 3x3 neighbourhood of occupied cell q (callers keep q off the outermost ring or check bounds here)
+__device__ __forceinline__ void block_around(const MultiParams& p, uint8_t* occ, int q, int nb) {
+    const int S = p.S, y = fdiv(q, p.magic_S) + nb / 3 - 1, x = q - fdiv(q, p.magic_S) * S + nb % 3 - 1;
+    if (y >= 0 && y < S && x >= 0 && x < S) occ[y * S + x] |= kNoSeed;
+}
+// completes an occupancy map whose bytes hold bit 0 only: wall margin and 3x3 dilation into bit 1.  Whole CTA.
+// (Every writer only ever ORs bit 1 in and bit 0 is constant here, so racing byte updates agree.)
+__device__ __forceinline__ void finish_occupancy(const MultiParams& p, uint8_t* occ) {
+    for (int q = threadIdx.x; q < p.C; q += blockDim.x) {
+        const uint8_t v = occ[q];
+        if (seed_margin(p, q)) occ[q] = v | kNoSeed;
+        if (v & kOccupied)
+            for (int nb = 0; nb < 9; ++nb) block_around(p, occ, q, nb);
+    }
+    __syncthreads();
 }
 
 // cells of a length-3 snake seeded at `cell` facing d (LENGTH_3_SNAKES): tail 1, seed 2, head 3
@@ -480,7 +496,7 @@ __device__ __forceinline__ void snake_cells(const MultiParams& p, int cell, int 
 // fresh occupancy map; results in sc.snake_cell / sc.snake_dir and the returned food cell.  Whole CTA.
 __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
     const int C = p.C, K = p.K, S = p.S, tid = threadIdx.x, nthr = blockDim.x;
-    for (int q = tid; q < C; q += nthr) sc.occ[q] = 0;
+    for (int q = tid; q < C; q += nthr) sc.occ[q] = seed_margin(p, q) ? kNoSeed : 0;
     __syncthreads();
     for (int k = 0; k < K; ++k) {
         if (tid == 0) sc.pick[0] = -1;
@@ -492,20 +508,21 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
             __syncthreads();
         } else {
             const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
-            block_pick(C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(p, sc.occ, q); });
+            block_pick(C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(sc.occ, q); });
             d = (int)(r.y >> 30);
         }
         const int cell = sc.pick[0];
         __syncthreads();
         if (tid == 0) {
             sc.snake_cell[k] = cell; sc.snake_dir[k] = d;
-            if (cell >= 0) {
-                int tl, hd;
-                snake_cells(p, cell, d, tl, hd);
-                sc.occ[tl] = 1; sc.occ[cell] = 1; sc.occ[hd] = 1;
-            } else {
-                atomicOr(p.status, WURM_ST_NO_SPAWN);                 // the reference raises (:947)
-            }
+            if (cell < 0) atomicOr(p.status, WURM_ST_NO_SPAWN);       // the reference raises (:947)
+        }
+        if (cell >= 0) {                                              // the new snake's three cells and their surroundings
+            int tl, hd;
+            snake_cells(p, cell, d, tl, hd);
+            if (tid < 3) sc.occ[tid == 0 ? tl : tid == 1 ? cell : hd] |= kOccupied | kNoSeed;
+            __syncthreads();                                          // bit 0 is settled before the racing ORs of bit 1
+            for (int j = tid; j < 27; j += nthr) block_around(p, sc.occ, j < 9 ? tl : j < 18 ? cell : hd, j % 9);
         }
         __syncthreads();
     }
@@ -517,7 +534,7 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
     } else {                                                          // :1016 one food on a free interior cell
         block_pick(C, sc.counts, draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateFood).x, sc.pick, [&](int q) {
             const int y = fdiv(q, p.magic_S), x = q - y * S;
-            return y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && !sc.occ[q];
+            return y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && !(sc.occ[q] & kOccupied);
         });
     }
     return sc.pick[0];
@@ -551,8 +568,9 @@ __device__ __forceinline__ int decide_respawn(const MultiParams& p, int e, uint6
         d = p.respawn[2 * (size_t)e + 1];
         __syncthreads();
     } else {
+        finish_occupancy(p, sc.occ);
         const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiRespawn);
-        block_pick(p.C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(p, sc.occ, q); });
+        block_pick(p.C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(sc.occ, q); });
         d = (int)(r.y >> 30);
     }
     return sc.pick[0];
