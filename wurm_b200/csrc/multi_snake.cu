@@ -468,18 +468,22 @@ __device__ __forceinline__ bool seed_margin(const MultiParams& p, int q) {
     const int S = p.S, y = fdiv(q, p.magic_S), x = q - y * S;
     return y < 2 || y > S - 3 || x < 2 || x > S - 3;
 }
-// marks the 3x3 neighbourhood of occupied cell q (callers keep q off the outermost ring or check bounds here)
+// ORs bits into occupancy byte q; several threads may hit one byte (or its word) at once: a shared-memory atomic on
+// the enclosing 32-bit word (the map starts 16-byte aligned)
+__device__ __forceinline__ void occ_or(uint8_t* occ, int q, uint8_t bits) {
+    atomicOr(reinterpret_cast<unsigned*>(occ + (q & ~3)), (unsigned)bits << (8 * (q & 3)));
+}
+// marks neighbour nb (0..8, row-major 3x3) of occupied cell q
 __device__ __forceinline__ void block_around(const MultiParams& p, uint8_t* occ, int q, int nb) {
     const int S = p.S, y = fdiv(q, p.magic_S) + nb / 3 - 1, x = q - fdiv(q, p.magic_S) * S + nb % 3 - 1;
-    if (y >= 0 && y < S && x >= 0 && x < S) occ[y * S + x] |= kNoSeed;
+    if (y >= 0 && y < S && x >= 0 && x < S) occ_or(occ, y * S + x, kNoSeed);
 }
 // completes an occupancy map whose bytes hold bit 0 only: wall margin and 3x3 dilation into bit 1.  Whole CTA.
-// (Every writer only ever ORs bit 1 in and bit 0 is constant here, so racing byte updates agree.)
 __device__ __forceinline__ void finish_occupancy(const MultiParams& p, uint8_t* occ) {
     for (int q = threadIdx.x; q < p.C; q += blockDim.x) {
-        const uint8_t v = occ[q];
-        if (seed_margin(p, q)) occ[q] = v | kNoSeed;
-        if (v & kOccupied)
+        // (the byte is read through the atomic too: neighbours may be ORing into the same word right now)
+        const unsigned w = atomicOr(reinterpret_cast<unsigned*>(occ + (q & ~3)), seed_margin(p, q) ? (unsigned)kNoSeed << (8 * (q & 3)) : 0u);
+        if ((w >> (8 * (q & 3))) & kOccupied)
             for (int nb = 0; nb < 9; ++nb) block_around(p, occ, q, nb);
     }
     __syncthreads();
@@ -520,9 +524,11 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
         if (cell >= 0) {                                              // the new snake's three cells and their surroundings
             int tl, hd;
             snake_cells(p, cell, d, tl, hd);
-            if (tid < 3) sc.occ[tid == 0 ? tl : tid == 1 ? cell : hd] |= kOccupied | kNoSeed;
-            __syncthreads();                                          // bit 0 is settled before the racing ORs of bit 1
-            for (int j = tid; j < 27; j += nthr) block_around(p, sc.occ, j < 9 ? tl : j < 18 ? cell : hd, j % 9);
+            for (int j = tid; j < 27; j += nthr) {
+                const int c = j < 9 ? tl : j < 18 ? cell : hd;
+                if (j % 9 == 4) occ_or(sc.occ, c, kOccupied);
+                block_around(p, sc.occ, c, j % 9);
+            }
         }
         __syncthreads();
     }
