@@ -402,6 +402,27 @@ def run_gpu(args):
     Ke = max(10, K // 2)
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     graphed_e2e = N <= GRAPHED_E2E_MAX_ENVS and getattr(env, 'supports_fused_reset', False)
+    graphed_ms = None
+    if graphed_e2e:
+        # supplementary: the same step+reset through one CUDA-graph launch per step, actions resident on the device
+        first = ad.pool[0]
+        static_dev = {a: t.clone() for a, t in first.items()} if isinstance(first, dict) else first.clone()
+        gs = GraphedStepper(env, static_dev)
+        g_start, g_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g_start.record()
+        for t in range(K):
+            src = ad.pool[t % ACTION_POOL]
+            if isinstance(src, dict):
+                for a, v in src.items():
+                    static_dev[a].copy_(v)
+            else:
+                static_dev.copy_(src)
+            gs.step()
+        g_stop.record()
+        barrier()
+        graphed_ms = g_start.elapsed_time(g_stop)
+        del gs
     if graphed_e2e:
         # launch-bound sizes: the copies ride inside the CUDA graph (GraphedStepper(host_io=True)); per step the host
         # writes that step's actions into the graph's pinned input, replays, synchronises and reads the results
@@ -502,6 +523,11 @@ def run_gpu(args):
             line['fused_step_reset'] = {'value': world * N * K / (fused_ms * 1e-3), 'unit': 'env-steps/s',
                                         'ms_per_step': fused_ms / K, 'gpu_launches': K,
                                         'loop': 'env.step(actions, auto_reset=True)  (one launch per step)'}
+        if graphed_ms:
+            line['graphed_step_reset'] = {'value': world * N * K / (graphed_ms * 1e-3), 'unit': 'env-steps/s',
+                                          'ms_per_step': graphed_ms / K,
+                                          'loop': 'GraphedStepper(env, actions).step()  (one CUDA-graph launch per step; plus '
+                                                  'the device-side copy of the step\'s actions into the static input)'}
         if world == 1 and not args.no_cpu_baseline:
             n = cpu_sample_size(key)
             threads = os.cpu_count() or 1
