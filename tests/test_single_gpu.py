@@ -439,3 +439,39 @@ def test_graphed_stepper_with_host_io():
         assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')
     with pytest.raises(RuntimeError):
         GraphedStepper(plain, a0, warmup=1).step_host()
+
+
+def test_state_edited_between_calls_makes_hints_stale_not_wrong():
+    """`envs` is a plain tensor the caller may write between calls (the reference's tests do).  The kernels keep
+    (head cell, size) hints per env from one call to the next; after the caller shuffles, grows or replaces envs the
+    hints no longer match and must only cost the fast path, never the result."""
+    N, S, seed = 512, 9, 99
+    env = make_env(N, S, 'partial_2', seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    for t in range(6):                                   # populate the hints
+        _, _, done, _ = env.step(torch.randint(0, 4, (N,), generator=g).to(DEV))
+        env.reset(done, return_observations=False)
+    fresh = make_env(N, S, 'partial_2', seed=seed + 1)
+    for edit in ('roll', 'grow', 'replace', 'roll'):
+        if edit == 'roll':
+            env.envs.copy_(env.envs.roll(1, dims=0))     # every env now sits under its neighbour's hints
+        elif edit == 'grow':
+            env.envs[:, 2].mul_(2.0)                     # body values 2, 4, 6, ...: sizes differ from the hinted ones
+        else:
+            env.envs.copy_(fresh.envs)                   # brand-new envs under the old hints
+        for t in range(3):
+            state = np_(env.envs).copy()
+            a_cpu = torch.randint(0, 4, (N,), generator=g)
+            a = a_cpu.to(DEV)
+            obs, reward, done, info = env.step(a)
+            a_orc = a_cpu.numpy().astype(np.int64)
+            r, d, sc, ec = orc.single_step(state, a_orc, None, seed=seed, step=env._draws)
+            tag = f'{edit} step {t}: '
+            assert_same(np_(env.envs), state, tag + 'envs')
+            assert_same(np_(a).astype(np.int64), a_orc, tag + 'sanitised actions')
+            assert_same(np_(reward).reshape(-1), r, tag + 'reward')
+            assert_same(np_(done).reshape(-1).astype(np.uint8), d, tag + 'done')
+            if edit != 'grow':                           # (doubled bodies have no head on them: partial obs would flag it)
+                o, _ = orc.single_observe(state, 'partial_2')
+                assert_same(np_(obs), o, tag + 'observation')
+            env.reset(done, return_observations=False)
