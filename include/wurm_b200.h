@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WURM_ABI_VERSION 3
+#define WURM_ABI_VERSION 4
 
 /* return codes */
 #define WURM_OK 0
@@ -176,6 +176,13 @@ typedef struct WurmMultiState {
     int64_t* orientations;  /* (E*K)       */
     uint8_t* boost_this_step; /* (E*K)     */
     int16_t* agent_colours; /* (E*K,3)     */
+    /* Optional (E*K) scratch owned by the library between calls, NULL to disable: the head cell each snake was left on
+     * by the previous call (-1 dead, -2 unknown; initialise to -2).  The heads tensor is 44-48 % of the state bytes and
+     * holds one non-zero per snake: a call that finds every live snake's hinted cell still holding a head (and every
+     * dead snake still flagged done) skips streaming it.  Hints are verified, never trusted: after the caller edits the
+     * tensors they only cost the scan back.  (What is not re-verified is the absence of a SECOND head of a snake: such
+     * states are outside the supported set, as for the reference's own check_consistency.) */
+    int16_t* head_hints;
 } WurmMultiState;
 
 /* Replayed random draws of one step, dense per env (NULL struct pointer -> Philox).

@@ -516,3 +516,66 @@ def test_fused_step_reset_golden_replay(i):
         check_step_outputs(env, K, obs, rewards, dones, info, expect, tag)
         check_state(env, multi_state_arrays(tr, f'{t}/reset_state'), tag + ' after the fused reset')
     env.check_status()
+
+
+@pytest.mark.parametrize('E,K,S,mode', [(96, 4, 25, 'partial_4'), (24, 16, 64, 'partial_4'), (48, 3, 12, 'full')])
+def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mode):
+    """The kernels keep each snake's head cell from one call to the next and skip streaming the heads tensor when every
+    hint still verifies.  Rolling the envs along the batch (every env now sits under its neighbour's hints), replacing
+    the tensors wholesale and killing snakes by hand must only cost the scan back, never the result."""
+    seed = 99 + E
+    rules = dict(respawn_mode='any')
+    env = make_env(E, K, S, mode, seed=seed, **rules)
+    cfg = orc.multi_cfg(E, K, S, **rules)
+    st = orc.MultiState(E, K, S)
+    assert orc.multi_reset(cfg, st, np.ones(E, np.uint8), None, seed=seed, step=env._draws) == 0
+    st.agent_colours[:] = np_(env.agent_colours)
+    g = torch.Generator().manual_seed(seed)
+
+    def run(steps, tag):
+        for t in range(steps):
+            acts = torch.randint(0, 8, (E, K), generator=g)
+            obs, rewards, dones, info = env.step({f'agent_{k}': acts[:, k].contiguous().to(DEV) for k in range(K)})
+            out = orc.multi_step(cfg, st, acts.numpy(), None, seed=seed, step=env._draws)
+            check_state(env, st, f'{tag} step {t}')
+            o, _ = orc.multi_observe(cfg, st, mode)
+            assert_same(np.stack([np_(obs[f'agent_{k}']) for k in range(K)]), o, f'{tag} step {t}: obs')
+            assert_same(stack_dict(rewards, K), out['rewards'], f'{tag} step {t}: rewards')
+            env.reset(dones['__all__'], return_observations=False)
+            orc.multi_reset(cfg, st, out['all_done'], None, seed=seed, step=env._draws)
+            check_state(env, st, f'{tag} step {t} after reset')
+
+    run(8, 'warm')                                         # hints populated
+    # 1. roll every tensor by one env: consistent states, foreign hints
+    for name, per_env in (('foods', 1), ('heads', K), ('bodies', K), ('dones', K), ('orientations', K), ('boost_this_step', K),
+                          ('agent_colours', K)):
+        t = getattr(env, name)
+        t.copy_(t.roll(per_env, dims=0))
+        a = getattr(st, name)
+        a[...] = np.roll(a, per_env, axis=0)
+    run(4, 'rolled')
+    # 2. the caller replaces the tensors by new objects holding another env's state (hints now describe the old tensors)
+    env.heads = env.heads.view(E, K, 1, S, S).flip(0).reshape(E * K, 1, S, S).contiguous()      # env order reversed
+    env.bodies = env.bodies.view(E, K, 1, S, S).flip(0).reshape(E * K, 1, S, S).contiguous()
+    env.foods = env.foods.flip(0).contiguous()
+    for name in ('dones', 'orientations', 'boost_this_step'):
+        setattr(env, name, getattr(env, name).view(E, K).flip(0).reshape(E * K).contiguous())
+    env.agent_colours = env.agent_colours.view(E, K, 3).flip(0).reshape(E * K, 3).contiguous()
+    st.heads[...] = st.heads.reshape(E, K, 1, S, S)[::-1].reshape(E * K, 1, S, S)
+    st.bodies[...] = st.bodies.reshape(E, K, 1, S, S)[::-1].reshape(E * K, 1, S, S)
+    st.foods[...] = st.foods[::-1]
+    for name in ('dones', 'orientations', 'boost_this_step'):
+        a = getattr(st, name)
+        a[...] = a.reshape(E, K)[::-1].reshape(E * K)
+    st.agent_colours[...] = st.agent_colours.reshape(E, K, 3)[::-1].reshape(E * K, 3)
+    run(4, 'replaced')
+    # 3. kill one live snake per env by hand (tensors zeroed, flag set): its hint must not resurrect a head
+    alive = (~env.dones.view(E, K)).float()
+    victim = alive.argmax(dim=1)                           # first live snake of each env (all have one after a reset)
+    rows = torch.arange(E, device=DEV) * K + victim
+    has_live = alive.sum(dim=1) > 0
+    rows = rows[has_live]
+    env.heads[rows] = 0; env.bodies[rows] = 0; env.dones[rows] = True
+    r = rows.cpu().numpy()
+    st.heads[r] = 0; st.bodies[r] = 0; st.dones[r] = 1
+    run(4, 'killed')

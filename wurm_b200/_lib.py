@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
 ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP = 1, 2, 4, 8
@@ -61,7 +61,7 @@ class WurmMultiCfg(ctypes.Structure):
 
 class WurmMultiState(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step',
-                                               'agent_colours')]
+                                               'agent_colours', 'head_hints')]
 
 
 class WurmMultiStepDraws(ctypes.Structure):

@@ -47,6 +47,7 @@ struct MultiParams {
     long long* orientations;
     uint8_t* boost_this_step;
     short* colours;
+    short* head_hints;    // (E*K) nullable: head cell left by the previous call (-1 dead, -2 unknown), verified before use
     // step inputs
     const void* actions[kMaxK];
     int action_bytes;
@@ -274,11 +275,30 @@ __device__ __noinline__ void fold_nonzero_overflow(unsigned char* smem, int C, i
 // three tensors; the ~1 % non-zero elements it meets are only QUEUED (a counter bump and one 8-byte store, whichever
 // lane meets them), and folded afterwards with every lane busy -- handling each hit where it is found would run the
 // whole fold with one or two lanes active per hit.  Hits beyond the queue's capacity are folded on the spot.
+// `use_hints`: thread k < K brings snake k's head hint, the value of the heads tensor at that cell and the snake's done
+// flag (loaded by the caller before the scans start, looked at only after the foods / bodies streams so that their
+// latency hides behind them).  A live snake's hint verifies if the cell holds a head, a dead snake's if it is still
+// flagged done; if every snake's does, the heads tensor -- one non-zero per snake in 44-48 % of the state's bytes --
+// is not streamed at all.
 template <bool CHECK = false>
-__device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e) {
+__device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e, bool use_hints = false, int hint_h = -1,
+                                         float hint_val = 0.0f, bool hint_dead = false) {
     const int C = p.C, K = p.K;
 #pragma unroll 1
-    for (int what = 0; what < 3; ++what) {
+    for (int pass = 0; pass < 3; ++pass) {
+        const int what = pass == 0 ? 0 : pass == 1 ? 2 : 1;            // foods, bodies, heads
+        if (what == 1 && use_hints) {
+            if (threadIdx.x < 32) {
+                const bool mine_ok = threadIdx.x >= K || ((hint_h >= 0 && hint_h < C) ? (!hint_dead && hint_val == 1.0f)
+                                                                                     : (hint_h == -1 && hint_dead));
+                const bool all_ok = __all_sync(0xffffffffu, mine_ok);
+                if (all_ok && threadIdx.x < K) { s.hp[threadIdx.x] = hint_h; s.hcnt[threadIdx.x] = hint_h >= 0 ? 1 : 0; }
+                __syncwarp();
+                if (threadIdx.x == 0) s.misc[7] = all_ok;
+            }
+            __syncthreads();
+            if (s.misc[7]) break;
+        }
         const float* base = what == 0 ? p.foods + (size_t)e * C : (what == 1 ? p.heads : p.bodies) + (size_t)e * K * C;
         scan_nonzero(base, what == 0 ? C : K * C, [&](int i, float v) {
             const int n = atomicAdd(&s.misc[6], 1);
@@ -559,6 +579,9 @@ __device__ __forceinline__ void write_recreated(const MultiParams& p, int e, con
             p.heads[n * C + hd] = 1.0f;
             p.bodies[n * C + hd] = 3.0f; p.bodies[n * C + sc.snake_cell[tid]] = 2.0f; p.bodies[n * C + tl] = 1.0f;
             p.orientations[n] = sc.snake_dir[tid];                    // :793
+            if (p.head_hints) p.head_hints[n] = (short)hd;
+        } else if (p.head_hints) {
+            p.head_hints[n] = -2;
         }
         p.dones[n] = 0;                                               // :798
     }
@@ -593,6 +616,11 @@ __device__ __forceinline__ void write_respawned(const MultiParams& p, int e, int
     }
     p.orientations[n] = d;                                            // :828 even when the spawn failed
     p.dones[n] = cell < 0;                                            // :829
+    if (p.head_hints) {
+        int tl, hd = -1;
+        if (cell >= 0) snake_cells(p, cell, d, tl, hd);
+        p.head_hints[n] = (short)hd;
+    }
 }
 
 // get_n_colours (:163-169) for one dead snake (:800-803)
@@ -626,6 +654,15 @@ multi_env_kernel(const MultiParams p) {
     // in, so that their latency hides behind the load instead of heading the serial per-snake logic
     // (measured on B200: +2 % at K=16,S=64 with 256 threads; a loss for the small-grid variant, where the values are
     // fetched right before use instead)
+    // Head hints (see load_env): this thread's snake's hint and done flag, fetched before anything else so that the
+    // dependent look-up into the heads tensor can be issued ahead of the scans
+    int hint_h = -1;
+    bool hint_dead = false;
+    const bool use_hints = p.head_hints != nullptr;
+    if (use_hints && tid < K) {
+        hint_h = p.head_hints[(size_t)e * K + tid];
+        hint_dead = p.dones[(size_t)e * K + tid] != 0;
+    }
     constexpr bool kPrefetch = THREADS == 256;
     long long pre_action = 0, pre_orient = 0;
     float pre_cost = 0.0f;
@@ -649,8 +686,11 @@ multi_env_kernel(const MultiParams p) {
     }
     if (tid < 8) s.misc[tid] = 0;
     for (int t = tid; t < 3 * K; t += nthr) s.col[t] = p.colours[(size_t)e * K * 3 + t];
+    // Head hints: the heads tensor's value at this thread's snake's hinted cell (the hint itself was fetched first thing)
+    float hint_val = 0.0f;
+    if (use_hints && tid < K && hint_h >= 0 && hint_h < C) hint_val = p.heads[((size_t)e * K + tid) * C + hint_h];
     __syncthreads();
-    load_env(p, s, e);
+    load_env(p, s, e, use_hints, hint_h, hint_val, hint_dead);
     __syncthreads();
 
     if (STEP) {
@@ -833,6 +873,7 @@ multi_env_kernel(const MultiParams p) {
                 p.sizes[n] = (float)a_size;
                 p.dones[n] = a_done;
                 p.dones_out[n] = a_done;
+                if (p.head_hints) p.head_hints[n] = (short)(a_done ? -1 : a_hp);
                 p.boost_out[n] = a_boosted;
             }
             const unsigned alive = __ballot_sync(0xffffffffu, valid && !a_done);
@@ -1063,6 +1104,7 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     p->foods = st->foods; p->heads = st->heads; p->bodies = st->bodies; p->dones = st->dones;
     p->orientations = reinterpret_cast<long long*>(st->orientations); p->boost_this_step = st->boost_this_step;
     p->colours = st->agent_colours;
+    p->head_hints = (cfg->size * cfg->size <= 32767) ? st->head_hints : nullptr;
     p->E = cfg->num_envs; p->K = cfg->num_snakes; p->S = cfg->size; p->C = cfg->size * cfg->size;
     p->boost = cfg->boost; p->food_on_death = cfg->food_on_death; p->food_mode = cfg->food_mode;
     p->respawn_any = cfg->respawn_any; p->colour_random = cfg->colour_random;

@@ -97,6 +97,9 @@ class MultiSnake(object):
         self._draws = 0
         # device-side addend of the call counter: stays 0 in normal use, bumped between CUDA-graph replays
         self._draws_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # head cell per snake left by one kernel call for the next (-1 dead, -2 unknown): verified hints that let a call
+        # skip streaming the heads tensor (include/wurm_b200.h, WurmMultiState.head_hints)
+        self._head_hints = torch.full((num_envs * num_snakes,), -2, dtype=torch.short, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
 
@@ -201,7 +204,7 @@ class MultiSnake(object):
             _ptr(self._norm('foods', torch.float32, (E, 1, S, S))), _ptr(self._norm('heads', torch.float32, (E * K, 1, S, S))),
             _ptr(self._norm('bodies', torch.float32, (E * K, 1, S, S))), _ptr(self._norm('dones', torch.bool, (E * K,))),
             _ptr(self._norm('orientations', torch.long, (E * K,))), _ptr(self._norm('boost_this_step', torch.bool, (E * K,))),
-            _ptr(self._norm('agent_colours', torch.short, (E * K, 3))))
+            _ptr(self._norm('agent_colours', torch.short, (E * K, 3))), _ptr(self._head_hints))
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.foods.device).cuda_stream)
