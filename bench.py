@@ -513,8 +513,10 @@ def run_gpu(args):
                          'peak_source': peak_src, 'bytes_per_launch': bytes_per_launch,
                          'kernel_ms': step_kernel_ms, 'frac_of_nominal_8TBs': achieved / 8000.0,
                          'note': 'achieved = ALGORITHMIC bytes (dense fp32 state read + write + obs) / kernel time; the '
-                                 'kernels write back only the cells a step changed, so the DRAM traffic ncu measures '
-                                 '(traffic) is below the algorithmic count and frac can exceed 1',
+                                 'kernels write back only the cells a step changed and (MultiSnake) do not stream the '
+                                 'heads tensor when every head hint verifies, so the DRAM traffic ncu measures (traffic) '
+                                 'is below the algorithmic count and frac can exceed 1; dram_gbs_from_traffic is the '
+                                 'physical rate',
                          'dram_gbs_from_traffic': (profiled_traffic(key) / (step_kernel_ms * 1e-3) / 1e9)
                          if profiled_traffic(key) else None},
             'episode_stats': stats,
