@@ -87,10 +87,13 @@ int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg);
  *            WURM_OBS_NONE                            reward (N,) f32, done/self_col/edge_col (N,) u8
  *   food_cell_replay (N,) int32 or NULL: cell index y*S+x of the respawned food for envs that eat
  *            this step (-1: none); NULL -> uniform over free interior cells from Philox.
- *   hints    (N,2) int16 or NULL: scratch owned by the caller in which the kernels leave each env's
- *            (head cell, snake size) for their next call.  Pure accelerator: every hint is verified
- *            against `envs` before use, so stale or garbage hints (the caller edited `envs`) only
- *            cost the scans they would have saved.                                               */
+ *   hints    (N,4) int16 or NULL (initialise to -1): scratch owned by the caller in which the kernels leave each
+ *            env's (head cell, snake size, food cell, unused) for their next call.  Pure accelerator: every hint
+ *            is verified against `envs` before use -- the head cell must hold a head, the food cell food, the
+ *            body channel's maximum and its (size, size-1) cells must be what the hints say -- so stale or garbage
+ *            hints (the caller edited `envs`) only cost the work they would have saved: a scan of the body channel
+ *            and, for even grid sides from 16 up, reading the food and head channels at all.  (Not re-verified:
+ *            the absence of a second head or food cell, i.e. states the reference's env_consistency rejects.)  */
 int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                      const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                      float* obs, float* reward,

@@ -71,6 +71,9 @@ ROLLOUTS = [
     (400, 9, 'default', 28, 7, torch.long),         # dead envs stepped again: heads leave the grid
     (400, 11, 'positions', 28, 7, torch.long),
     (1, 9, 'partial_2', 20, 1, torch.long),
+    (333, 16, 'partial_2', 40, 1, torch.long),      # body-only tiles (even sizes from 16 up), ragged last tile
+    (200, 18, 'default', 30, 7, torch.int),         # ... with dead envs stepped again (general step on global memory)
+    (77, 24, 'one_channel', 30, 3, torch.long),
 ]
 
 
@@ -315,7 +318,8 @@ def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
         assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')
 
 
-@pytest.mark.parametrize('N,S,mode', [(1000, 9, 'partial_2'), (300, 12, 'default'), (130, 36, 'one_channel')])
+@pytest.mark.parametrize('N,S,mode', [(1000, 9, 'partial_2'), (300, 12, 'default'), (130, 36, 'one_channel'), (257, 16, 'partial_3'),
+                                      (65, 36, 'default'), (40, 20, 'positions')])
 def test_fused_step_reset_equals_step_then_reset(N, S, mode):
     """step(a, auto_reset=True) == step(a); reset(done): same outputs, same state afterwards, same draws."""
     two_calls = make_env(N, S, mode, seed=55)
@@ -441,11 +445,12 @@ def test_graphed_stepper_with_host_io():
         GraphedStepper(plain, a0, warmup=1).step_host()
 
 
-def test_state_edited_between_calls_makes_hints_stale_not_wrong():
+@pytest.mark.parametrize('S', [9, 16])
+def test_state_edited_between_calls_makes_hints_stale_not_wrong(S):
     """`envs` is a plain tensor the caller may write between calls (the reference's tests do).  The kernels keep
     (head cell, size) hints per env from one call to the next; after the caller shuffles, grows or replaces envs the
     hints no longer match and must only cost the fast path, never the result."""
-    N, S, seed = 512, 9, 99
+    N, seed = 512, 99
     env = make_env(N, S, 'partial_2', seed=seed)
     g = torch.Generator().manual_seed(seed)
     for t in range(6):                                   # populate the hints

@@ -42,7 +42,7 @@ struct SingleParams {
     const unsigned long long* step_dev;   // nullable: added to `step` on the device (CUDA-graph replays)
     int auto_reset;       // fused step+reset: envs that end this step are re-created by the same launch
     const int32_t* spawn; // (N,4) replayed (y, x, dir, food_cell) of the fused / stand-alone reset, or NULL
-    short* hints;         // (N,2) nullable: (head cell, snake size) left by the previous call -- hints only, always verified
+    short* hints;         // (N,4) nullable: (head cell, snake size, food cell, -) left by the previous call -- hints only, always verified
     int N, S, C;          // envs, grid side, cells per channel
     int T;                // envs per tile (= per CTA)
     int action_bytes;     // 2 / 4 / 8
@@ -308,6 +308,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
                                          draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
         }
         if (l == 0 && cell >= 0) { const float f = food[cell] + 1.0f; food[cell] = f; gfood[cell] = f; }
+        if (l == 0 && p.hints) p.hints[4 * (size_t)e + 2] = (short)cell;
     }
     if (l == 0) {
         p.reward[e] = 0.0f - ov * -1.0f;                             // :271
@@ -316,8 +317,8 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
         p.done[e] = sc || !interior;
         if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
         if (p.hints) {                                               // for the next call: head cell and size now
-            p.hints[2 * (size_t)e] = (short)np;
-            p.hints[2 * (size_t)e + 1] = (short)((np >= 0) ? (int)(size + ov) : -1);
+            p.hints[4 * (size_t)e] = (short)np;
+            p.hints[4 * (size_t)e + 1] = (short)((np >= 0) ? (int)(size + ov) : -1);
         }
         if (p.stats) {                                               // episode statistics, per-CTA partials
             if (sc || !interior) atomicAdd(cnt_s + 0, 1);
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
         if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
         else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
         else a_in = ((const short*)p.actions)[e];
-        if (p.hints) { hint_head = p.hints[2 * e]; hint_sz = p.hints[2 * e + 1]; }
+        if (p.hints) { hint_head = p.hints[4 * e]; hint_sz = p.hints[4 * e + 1]; }
     }
     __syncthreads();                        // mbarrier init / fallback tile visible
     if (bulk) mbar_wait(bar, 0);
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
                 const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
                 if (idx >= 0) g[idx] = val;
             }
-            if (lane == 0 && p.hints) { p.hints[2 * (size_t)(env0 + ts)] = (short)hd; p.hints[2 * (size_t)(env0 + ts) + 1] = 3; }
+            if (lane == 0 && p.hints) { short* h = p.hints + 4 * (size_t)(env0 + ts); h[0] = (short)hd; h[1] = 3; h[2] = (short)cell; }
         }
     }
     fence_proxy_async();                    // generic-proxy writes -> visible to the bulk stores
@@ -538,6 +539,349 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     if (((bulk && raw) || obs_bulk) && threadIdx.x == 0) {
         bulk_commit();
         bulk_wait_read_all();               // shared memory must outlive the bulk stores' reads
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Body-only tiles: the steady-state path for larger grids
+// ---------------------------------------------------------------------------------------------
+// In steady state the previous call left every env's head cell, snake size and food cell.  If the head cell still
+// holds a head, the food cell still holds food, and the body channel's maximum and its (size, size-1) cells are what
+// the hints say, the step needs NOTHING else from the food and head channels: two thirds of the state are not read.
+// For even grid sides a channel is a 16-byte-aligned span, so the tile is loaded as one bulk copy PER ENV of its body
+// channel only (all on one mbarrier).  Observations are rendered from the body tile plus the known head and food
+// cells.  An env whose hints do not verify takes the general step straight on global memory (the tile kernel's code
+// with `env` pointing at HBM): slow, rare, and it re-derives the hints.  Measured on B200 this pays for large envs
+// (size 36: 15.5 KB of state) and loses for tiny ones (size 9: scattered sectors, sparse stores into sectors that are
+// no longer in L2, two DRAM round trips instead of one), so the host uses it from size 16 up.
+template <int G>
+__device__ __noinline__ int pick_free_cell_body(const float* body, int head_cell, int S, int C, uint32_t magic, uint32_t rnd, int l,
+                                                unsigned gm) {
+    const unsigned shift = (G == 32) ? 0u : ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+    const unsigned low = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    auto free_bits = [&](int base) {
+        const int q = base + l;
+        bool f = false;
+        if (q < C) {
+            const int y = div_S(q, magic), x = q - y * S;
+            f = y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && (body[q] + (q == head_cell ? 1.0f : 0.0f) < kEps);
+        }
+        return (__ballot_sync(gm, f) >> shift) & low;
+    };
+    int nfree = 0;
+    for (int base = 0; base < C; base += G) nfree += __popc(free_bits(base));
+    if (nfree == 0) return -1;
+    int r = (int)bounded(rnd, (uint32_t)nfree);
+    for (int base = 0; base < C; base += G) {
+        const unsigned bits = free_bits(base);
+        const int cnt = __popc(bits);
+        if (r < cnt) return base + (int)__fns(bits, 0, r + 1);
+        r -= cnt;
+    }
+    return -1;
+}
+
+// The general step for one env straight on global memory, out of line and with the parameters BY VALUE (a reference
+// would pin the kernel's parameter struct to every thread's stack).  Returns (new head cell, food cell, ended).
+template <int G>
+__device__ __noinline__ int3 slow_step_on_global(const SingleParams p, int e, int l, int* cnt_s, long long a_in, int hint_head,
+                                                 int hint_sz, float* partial_out) {
+    const unsigned gm = group_mask<G>();
+    const int C = p.C;
+    float* genv = p.envs + (size_t)e * 3 * C;
+    bool ended = false;
+    const int np = step_env<G>(p, genv, e, l, cnt_s, a_in, hint_head, hint_sz, ended);
+    __syncwarp(gm);
+    int fc = 0, fq = -1;
+    for (int q = l; q < C; q += G)
+        if (genv[q] == 1.0f) { ++fc; fq = q; }
+    fc = group_sum<G>(fc, gm);
+    fq = group_max<G>(fq, gm);
+    const int food_now = fc == 1 ? fq : -1;
+    if (l == 0) p.hints[4 * (size_t)e + 2] = (short)food_now;
+    // the observation of this env is rendered here, before a fused reset can overwrite the terminal state in HBM
+    if (p.obs_mode == WURM_OBS_PARTIAL) render_partial<G>(p, genv, np, partial_out, l);
+    if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
+        const int S = p.S;
+        for (int q = l; q < C; q += G) {
+            const int y = div_S(q, p.magic_S), x = q - y * S;
+            const bool border = y == 0 || x == 0 || y == S - 1 || x == S - 1;
+            const float f = genv[q], h = genv[C + q], b = genv[2 * C + q];
+            if (p.obs_mode == WURM_OBS_DEFAULT) {
+                float* o = p.obs + (size_t)e * 3 * C;
+                o[q] = rgb_channel(f, h, b, border, 0);
+                o[C + q] = rgb_channel(f, h, b, border, 1);
+                o[2 * C + q] = rgb_channel(f, h, b, border, 2);
+            } else {
+                float v = (b > kEps ? 1.0f : 0.0f) * 0.5f;
+                v += h * 0.5f;
+                v += f * 1.5f;
+                p.obs[(size_t)e * C + q] = border ? -1.0f : v;
+            }
+        }
+    }
+    return make_int3(np, food_now, ended ? 1 : 0);
+}
+
+// 64 threads (two size-36 envs) and >= 12 CTAs per SM measured best on B200 (profiles/r01_sweep_single_body.txt)
+#ifndef WURM_BODY_MINB
+#define WURM_BODY_MINB 12
+#endif
+#ifndef WURM_BODY_THREADS
+#define WURM_BODY_THREADS 64
+#endif
+template <int G>
+__global__ void __launch_bounds__(WURM_BODY_THREADS, WURM_BODY_MINB) single_body_kernel(const SingleParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int C = p.C, S = p.S;
+    float* body_all = reinterpret_cast<float*>(smem);
+    float* stage = reinterpret_cast<float*>(smem + p.tile_bytes_padded);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.tile_bytes_padded + p.stage_bytes);
+    int* cnt_s = reinterpret_cast<int*>(bar + 1);                     // 4 counters, then per env: fast, head cell, food cell
+    int* env_s = cnt_s + 4;
+    const int tid = threadIdx.x, lane = tid & 31, t = tid / G, l = tid % G;
+    const unsigned gm = group_mask<G>();
+    const int env0 = blockIdx.x * p.T, nvalid = min(p.T, p.N - env0);
+    const bool valid = t < nvalid;
+    const int e = env0 + (valid ? t : 0);
+    const bool partial = p.obs_mode == WURM_OBS_PARTIAL;
+    const int E = 3 * p.W * p.W;
+    float* gfood = p.envs + (size_t)e * 3 * C;
+    float* ghead = gfood + C;
+    float* gbody = gfood + 2 * C;
+    float* body = body_all + (size_t)t * C;
+
+    if (tid == 0) {                                                   // one bulk copy per env: its body channel
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * C) * 4u);
+        for (int i = 0; i < nvalid; ++i)
+            bulk_load(body_all + (size_t)i * C, p.envs + ((size_t)(env0 + i) * 3 + 2) * C, (uint32_t)C * 4u, bar);
+    }
+    if (tid < 4) cnt_s[tid] = 0;
+    long long a_in = 0;
+    int hint_head = -1, hint_sz = -1, hint_food = -1;
+    if (valid) {
+        if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
+        else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
+        else a_in = ((const short*)p.actions)[e];
+        const short4 h = *reinterpret_cast<const short4*>(p.hints + 4 * (size_t)e);
+        hint_head = h.x; hint_sz = h.y; hint_food = h.z;
+    }
+    float hv = 0.0f, fv = 0.0f;                                       // the two verification loads
+    if (valid && hint_head >= 0 && hint_head < C) hv = ghead[hint_head];
+    if (valid && hint_food >= 0 && hint_food < C) fv = gfood[hint_food];
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    float m = -INFINITY;
+    int c1 = 0, c2 = 0, p1 = -1, p2 = -1;
+    const float hint_size = (float)hint_sz, hint_sm1 = hint_size - 1.0f;
+    if (valid) {
+#pragma unroll 4
+        for (int q = l; q < C; q += G) {
+            const float v = body[q];
+            m = fmaxf(m, v);
+            if (v == hint_size) { ++c1; p1 = q; }
+            if (v == hint_sm1) { ++c2; p2 = q; }
+        }
+    }
+    const float size = group_max<G>(m, gm);
+    c1 = group_sum<G>(c1, gm);
+    c2 = group_sum<G>(c2, gm);
+    p1 = group_max<G>(p1, gm);
+    p2 = group_max<G>(p2, gm);
+    const bool fast = valid && hv != 0.0f && fv == 1.0f && hint_sz >= 1 && size == hint_size && c1 == 1 && c2 == 1;
+
+    int np = -1, food_now = hint_food;
+    bool ended = false;
+    if (valid && !fast) {
+        const int3 res = slow_step_on_global<G>(p, e, l, cnt_s, a_in, hint_head, hint_sz, stage + (size_t)t * E);
+        np = res.x; food_now = res.y; ended = res.z != 0;
+    }
+    if (fast) {
+        const int hp = hint_head;
+        int k = 0;                                                    // orientation (:212), canonical case
+        {
+            const int d = p1 - p2;
+            const int x2 = p2 - div_S(p2, p.magic_S) * S;
+            if (d == -S) k = 0;
+            else if (d == 1 && x2 != S - 1) k = 1;
+            else if (d == S) k = 2;
+            else if (d == -1 && x2 != 0) k = 3;
+        }
+        const long long a = (a_in + ((long long)k == a_in ? 2 : 0)) % 4;     // :221-222
+        if (l == 0 && a != a_in) {
+            if (p.action_bytes == 8) ((long long*)p.actions)[e] = a;
+            else if (p.action_bytes == 4) ((int*)p.actions)[e] = (int)a;
+            else ((short*)p.actions)[e] = (short)a;
+        }
+        int ny, nx;
+        {
+            const int hy = div_S(hp, p.magic_S), hx = hp - hy * S;       // :225-233
+            ny = hy - (a >= 0 ? off_y((int)a) : 0);
+            nx = hx - (a >= 0 ? off_x((int)a) : 0);
+            if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
+        }
+        const float ov = (np >= 0 && np == hint_food) ? fv : 0.0f;    // :242 the only food is on the hinted cell
+        if (ov == 0.0f) {                                            // :246-249 decay unless it ate
+#pragma unroll 4
+            for (int q = l; q < C; q += G) {
+                const float v = body[q], nv = fmaxf(v - 1.0f, 0.0f);
+                if (nv != v) { body[q] = nv; gbody[q] = nv; }
+            }
+        }
+        __syncwarp(gm);
+        const bool sc = (np >= 0) && (body[np] > kEps);              // :252
+        const bool interior = (np >= 0) && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
+        __syncwarp(gm);
+        if (l == 0) {
+            ghead[hp] = 0.0f;
+            if (np >= 0) {
+                ghead[np] = 1.0f;
+                const float grown = body[np] + (size + ov);          // :258-262
+                body[np] = grown; gbody[np] = grown;
+                if (ov != 0.0f) gfood[np] = fv + ov * -1.0f;         // :270-272
+            }
+        }
+        __syncwarp(gm);
+        if (ov != 0.0f) {                                            // :277-282 respawn
+            int cell;
+            if (p.food_replay) cell = p.food_replay[e];
+            else {
+                const int I = S - 2;
+                cell = -1;
+                for (uint32_t tr = 0; tr < kRejectionTries && cell < 0; ++tr) {
+                    const int cand = (int)bounded(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamSingleStepFood, tr), (uint32_t)(I * I));
+                    const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
+                    if (body[q] + (q == np ? 1.0f : 0.0f) < kEps) cell = q;    // the eaten food is gone: the food channel is all zero
+                }
+                if (cell < 0)
+                    cell = pick_free_cell_body<G>(body, np, S, C, p.magic_S,
+                                                  draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
+            }
+            if (l == 0 && cell >= 0) gfood[cell] = (cell == np ? fv + ov * -1.0f : 0.0f) + 1.0f;
+            food_now = cell;
+        }
+        if (l == 0) {
+            p.reward[e] = 0.0f - ov * -1.0f;                             // :271
+            p.self_col[e] = sc;
+            p.edge_col[e] = !interior;                                   // :290-293
+            p.done[e] = sc || !interior;
+            short4 h;
+            h.x = (short)np; h.y = (short)((np >= 0) ? (int)(size + ov) : -1); h.z = (short)food_now; h.w = 0;
+            *reinterpret_cast<short4*>(p.hints + 4 * (size_t)e) = h;
+            if (p.stats) {
+                if (sc || !interior) atomicAdd(cnt_s + 0, 1);
+                if (ov != 0.0f) atomicAdd(cnt_s + 1, (int)ov);
+                if (sc) atomicAdd(cnt_s + 2, 1);
+                if (!interior) atomicAdd(cnt_s + 3, 1);
+            }
+        }
+        ended = sc || !interior;
+        __syncwarp(gm);
+        if (partial) {                                               // :166-193 the crop around the new head
+            float* out = stage + (size_t)t * E;
+            const int W = p.W, WW = W * W, n = p.obs_n;
+            if (np < 0) {
+                for (int q = l; q < 3 * WW; q += G) out[q] = 0.0f;
+                if (l == 0) atomicOr(p.status, WURM_ST_NO_HEAD_PARTIAL);
+            } else {
+                constexpr float kHalf = 127.0f / 255.0f;
+                for (int ij = l; ij < WW; ij += G) {
+                    const int i = (int)__umulhi((uint32_t)ij, p.magic_W), j = ij - i * W;
+                    const int y = ny - n + i, x = nx - n + j;
+                    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+                    if ((unsigned)(y - 1) < (unsigned)(S - 2) && (unsigned)(x - 1) < (unsigned)(S - 2)) {
+                        const int q = y * S + x;
+                        v0 = v1 = v2 = 1.0f;
+                        if (body[q] > kEps) { v0 = 0.0f; v1 = kHalf; v2 = 0.0f; }
+                        if (q == np) { v0 = 0.0f; v1 = 1.0f; v2 = 0.0f; }
+                        if (q == food_now) { v0 = 1.0f; v1 = 0.0f; v2 = 0.0f; }
+                    }
+                    out[ij] = v0; out[WW + ij] = v1; out[2 * WW + ij] = v2;
+                }
+            }
+        }
+    }
+    if (valid && l == 0) { env_s[3 * t] = fast; env_s[3 * t + 1] = np; env_s[3 * t + 2] = food_now; }
+
+    if (p.auto_reset) {                                              // fused reset, see single_tile_kernel
+        int my_tail = 0, my_mid = 0, my_hd = 0, my_cell = -1;
+        const bool mine = ended && l == 0;
+        __syncwarp();
+        if (mine) new_env_layout(p, p.spawn, call_counter(p) + 1, e, my_tail, my_mid, my_hd, my_cell);
+        unsigned todo = __ballot_sync(0xffffffffu, mine);
+        const int n = 3 * C;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int tail = __shfl_sync(0xffffffffu, my_tail, src), mid = __shfl_sync(0xffffffffu, my_mid, src);
+            const int hd = __shfl_sync(0xffffffffu, my_hd, src), cell = __shfl_sync(0xffffffffu, my_cell, src);
+            const int was_fast = __shfl_sync(0xffffffffu, (int)fast, src);
+            const int old_head = __shfl_sync(0xffffffffu, np, src), old_food = __shfl_sync(0xffffffffu, food_now, src);
+            const int ts = ((tid & ~31) + src) / G;
+            float* g = p.envs + (size_t)(env0 + ts) * n;
+            if (was_fast) {                                          // the terminal state's non-zero cells are known
+                const float* ob = body_all + (size_t)ts * C;
+                for (int i = lane; i < C; i += 32)
+                    if (ob[i] != 0.0f) g[2 * C + i] = 0.0f;
+                if (lane == 0 && old_head >= 0) g[C + old_head] = 0.0f;
+                if (lane == 1 && old_food >= 0) g[old_food] = 0.0f;
+            } else {
+                for (int i = lane; i < n; i += 32)
+                    if (g[i] != 0.0f) g[i] = 0.0f;
+            }
+            __syncwarp();
+            if (lane < 5) {
+                const int idx = lane == 0 ? cell : lane == 1 ? C + hd : lane == 2 ? 2 * C + tail : lane == 3 ? 2 * C + mid : 2 * C + hd;
+                const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
+                if (idx >= 0) g[idx] = val;
+            }
+            if (lane == 0) { short* h = p.hints + 4 * (size_t)(env0 + ts); h[0] = (short)hd; h[1] = 3; h[2] = (short)cell; }
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (p.stats && tid < WURM_STATS_FIELDS) {
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        const int v = tid == 0 ? nvalid : cnt_s[tid - 1];
+        if (v) atomicAdd(slot + tid, (unsigned long long)v);
+    }
+    if (partial) {
+        float* dst = p.obs + (size_t)env0 * E;
+        const uint32_t obytes = (uint32_t)(nvalid * E) * 4u;
+        const bool obs_bulk = (obytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+        if (obs_bulk) {
+            if (tid == 0) { bulk_store(dst, stage, obytes); bulk_commit(); bulk_wait_read_all(); }
+        } else {
+            for (int i = tid; i < nvalid * E; i += blockDim.x) dst[i] = stage[i];
+        }
+    } else if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
+        // single_snake.py:131-151 from the body tile and the known head / food cells (general-path envs have
+        // rendered theirs already)
+        const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+        for (int tt = warp; tt < nvalid; tt += nwarps) {
+            if (env_s[3 * tt] == 0) continue;
+            const int hcell = env_s[3 * tt + 1], fcell = env_s[3 * tt + 2];
+            const float* bt = body_all + (size_t)tt * C;
+            for (int q = lane; q < C; q += 32) {
+                const int y = div_S(q, p.magic_S), x = q - y * S;
+                const bool border = y == 0 || x == 0 || y == S - 1 || x == S - 1;
+                const float f = q == fcell ? 1.0f : 0.0f, h = q == hcell ? 1.0f : 0.0f, b = bt[q];
+                if (p.obs_mode == WURM_OBS_DEFAULT) {
+                    float* o = p.obs + (size_t)(env0 + tt) * 3 * C;
+                    o[q] = rgb_channel(f, h, b, border, 0);
+                    o[C + q] = rgb_channel(f, h, b, border, 1);
+                    o[2 * C + q] = rgb_channel(f, h, b, border, 2);
+                } else {
+                    float v = (b > kEps ? 1.0f : 0.0f) * 0.5f;
+                    v += h * 0.5f;
+                    v += f * 1.5f;
+                    p.obs[(size_t)(env0 + tt) * C + q] = border ? -1.0f : v;
+                }
+            }
+        }
     }
 }
 
@@ -578,7 +922,7 @@ __global__ void __launch_bounds__(256) single_reset_kernel(const SingleParams p,
             const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
             if (idx >= 0) env[idx] = val;
         }
-        if (lane == 0 && p.hints) { p.hints[2 * (size_t)e] = (short)hd; p.hints[2 * (size_t)e + 1] = 3; }
+        if (lane == 0 && p.hints) { short* h = p.hints + 4 * (size_t)e; h[0] = (short)hd; h[1] = 3; h[2] = (short)cell; }
     }
 }
 
@@ -703,6 +1047,52 @@ static int dispatch_tile(const SingleParams& p, const SingleLaunch& L, cudaStrea
 
 static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
 
+template <int G>
+static int launch_body_t(const SingleParams& p, int blocks, int threads, int smem, cudaStream_t stream) {
+    auto kern = single_body_kernel<G>;
+    static int configured_smem = -1;                   // per instantiation
+    if (smem > configured_smem) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(single_body_kernel)");
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured_smem = smem;
+    }
+    kern<<<blocks, threads, smem, stream>>>(p);
+    return check_launch("single_body_kernel");
+}
+
+// The body-only path (single_body_kernel) applies to steps with hints, an even grid side from 16 up (a channel is then
+// a 16-byte-aligned span worth skipping) and an observation that can be rendered from the body tile; -1 if it does not.
+static int try_launch_body(SingleParams p, int G, cudaStream_t stream) {
+    const int min_size = getenv("WURM_SINGLE_BODY_MIN_SIZE") ? atoi(getenv("WURM_SINGLE_BODY_MIN_SIZE")) : 16;
+    if (!p.hints || (p.S & 1) || p.S < min_size || !aligned16(p.envs) || getenv("WURM_SINGLE_NO_BODY_PATH")) return -1;
+    if (p.obs_mode != WURM_OBS_PARTIAL && p.obs_mode != WURM_OBS_NONE && p.obs_mode != WURM_OBS_DEFAULT &&
+        p.obs_mode != WURM_OBS_ONE_CHANNEL)
+        return -1;
+    const int per_warp = 32 / G;
+    const int chan_bytes = p.C * 4, stage_env_bytes = p.obs_mode == WURM_OBS_PARTIAL ? 3 * p.W * p.W * 4 : 0;
+    int max_threads = stage_env_bytes ? 32 : WURM_BODY_THREADS;
+    int T = max_threads / G;
+    const int budget = 48 * 1024;
+    if (T * (chan_bytes + stage_env_bytes) > budget) T = budget / (chan_bytes + stage_env_bytes);
+    T = (T / per_warp) * per_warp;
+    if (T < per_warp) T = per_warp;
+    if (T > 64) T = 64;
+    p.T = T;
+    p.tile_bytes_padded = (T * chan_bytes + 15) & ~15;
+    p.stage_bytes = (T * stage_env_bytes + 15) & ~15;
+    const int smem = p.tile_bytes_padded + p.stage_bytes + 8 + 16 + 3 * T * 4 + 16;
+    if (smem > 200 * 1024) return -1;
+    const int blocks = (p.N + T - 1) / T, threads = T * G;
+    switch (G) {
+        case 4: return launch_body_t<4>(p, blocks, threads, smem, stream);
+        case 8: return launch_body_t<8>(p, blocks, threads, smem, stream);
+        case 16: return launch_body_t<16>(p, blocks, threads, smem, stream);
+        case 32: return launch_body_t<32>(p, blocks, threads, smem, stream);
+        default: return -1;
+    }
+}
+
 }  // namespace wurm
 
 using namespace wurm;
@@ -737,6 +1127,10 @@ static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions
     p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
     p.edge_col = edge_col; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
+    {
+        const int rc = try_launch_body(p, L.G, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     return dispatch_tile<true>(p, L, (cudaStream_t)stream);
 }
 

@@ -86,9 +86,9 @@ class SingleSnake(object):
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         # episode statistics accumulated by the step kernel (see `stats`)
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
-        # (head cell, snake size) per env left by one kernel call for the next: verified hints that let the step
+        # (head cell, snake size, food cell, -) per env left by one kernel call for the next: verified hints that let the step
         # kernel skip two of its scans; never trusted, so editing `envs` behind the env's back stays safe
-        self._hints = torch.full((num_envs, 2), -1, dtype=torch.short, device=self.device)
+        self._hints = torch.full((num_envs, 4), -1, dtype=torch.short, device=self.device)
 
         self.envs = torch.zeros((num_envs, 3, size, size), device=self.device)
         self.t = 0
