@@ -11,8 +11,9 @@ DEV = 'cuda'
 def single_env(n=64, S=12):
     from wurm_b200.envs import SingleSnake
     env = SingleSnake(num_envs=n, size=S, observation_mode='one_channel', device=DEV, seed=5)
+    g = torch.Generator().manual_seed(5)                 # a fixed rollout: the corruptions below must not depend on luck
     for _ in range(10):
-        _, _, done, _ = env.step(torch.randint(0, 4, (n,), device=DEV))
+        _, _, done, _ = env.step(torch.randint(0, 4, (n,), generator=g).to(DEV))
         env.reset(done, return_observations=False)
     return env
 
@@ -68,8 +69,9 @@ def test_single_checker_messages_match_the_torch_path(fragment, corrupt):
 def multi_env():
     from wurm_b200.envs import MultiSnake
     env = MultiSnake(num_envs=32, num_snakes=3, size=14, observation_mode='partial_2', device=DEV, seed=9)
+    g = torch.Generator().manual_seed(9)                 # a fixed rollout: the corruptions below must not depend on luck
     for _ in range(15):
-        actions = {f'agent_{k}': torch.randint(0, 8, (32,), device=DEV) for k in range(3)}
+        actions = {f'agent_{k}': torch.randint(0, 8, (32,), generator=g).to(DEV) for k in range(3)}
         _, _, dones, _ = env.step(actions)
         env.reset(dones['__all__'], return_observations=False)
     return env
@@ -77,6 +79,12 @@ def multi_env():
 
 def living_agent(env):
     return int((~env.dones).nonzero()[0])
+
+
+def cell_away_from_head(env, a):
+    """An interior cell that is neither the head of snake `a` nor next to it."""
+    hy, hx = divmod(int(env.heads[a, 0].flatten().argmax()), env.size)
+    return (2, 2) if abs(hy - 2) + abs(hx - 2) > 2 else (env.size - 3, env.size - 3)
 
 
 def test_multi_checker():
@@ -100,8 +108,9 @@ def test_multi_checker():
     # head not at the end of the body
     env3 = multi_env()
     a = living_agent(env3)
+    y, x = cell_away_from_head(env3, a)
     env3.heads[a].zero_()
-    env3.heads[a, 0, 1, 1] = 1
+    env3.heads[a, 0, y, x] = 1
     with pytest.raises(RuntimeError, match='head not at the end'):
         env3.check_consistency()
     # dead snake with leftovers
@@ -114,6 +123,7 @@ def test_multi_checker():
     # two heads
     env5 = multi_env()
     a = living_agent(env5)
-    env5.heads[a, 0, 2, 2] = 1
+    y, x = cell_away_from_head(env5, a)
+    env5.heads[a, 0, y, x] = 1
     with pytest.raises(RuntimeError, match='num_heads'):
         env5.check_consistency()
