@@ -146,6 +146,7 @@ size = 12
 def get_test_env(num_envs=1, **kw):
     """The reference's two-snake fixture (:21-47)."""
     from wurm_b200.utils import determine_orientations
+    kw.setdefault('seed', 20)                    # scenarios assert exact sizes: the food respawns must not depend on luck
     env = make_env(num_envs, 2, size, 'full', manual_setup=True, **kw)
     for i in range(num_envs):
         env.heads[2 * i, 0, 5, 5] = 1

@@ -152,7 +152,7 @@ def head_position(env):
 
 
 def run_actions(actions, orientation='up'):
-    env = make_env(1, size, 'one_channel', manual_setup=True)
+    env = make_env(1, size, 'one_channel', manual_setup=True, seed=20)
     env.envs = get_test_env(orientation).to(DEV)
     for a in actions:
         yield env, env.step(torch.tensor([a], device=DEV))
