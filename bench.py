@@ -109,7 +109,7 @@ class SingleAdapter(object):
 
 
 class GridAdapter(SingleAdapter):
-    kernel = 'grid_env_kernel<STEP=true>'
+    kernel = 'grid_small_kernel<STEP=true>'    # grids up to 64 cells; larger: grid_env_kernel<32,true>
 
     def __init__(self, key, dev, seed, rank):
         import torch
