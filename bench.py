@@ -84,7 +84,7 @@ class SingleAdapter(object):
         _, S, N, mode, _ = WORKLOADS[key]
         self.N, self.torch = N, torch
         self.env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=seed)
-        if S % 2 == 0 and S >= 16 and (mode in ('default', 'one_channel', 'none') or mode.startswith('partial')):
+        if S % 2 == 0 and S >= 16 and (mode in ('default', 'one_channel') or not 20 < S < 32):
             self.kernel = 'single_body_kernel<G>'       # even sizes from 16 up step on body-only tiles
         g = torch.Generator(device=dev).manual_seed(4321 + rank)
         self.pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]

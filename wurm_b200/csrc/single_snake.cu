@@ -1069,6 +1069,12 @@ static int try_launch_body(SingleParams p, int G, cudaStream_t stream) {
     if (p.obs_mode != WURM_OBS_PARTIAL && p.obs_mode != WURM_OBS_NONE && p.obs_mode != WURM_OBS_DEFAULT &&
         p.obs_mode != WURM_OBS_ONE_CHANNEL)
         return -1;
+    // measured (profiles/r01_body_path_sizes.txt): with a full-grid observation the path wins from size 16 up; with a
+    // partial (or no) observation it wins while several envs share a warp (sizes 16-20) and again once the env is large
+    // (size 36: 15.5 KB), but loses in between (size 24: one 2.3 KB env per warp and two DRAM round trips)
+    if ((p.obs_mode == WURM_OBS_PARTIAL || p.obs_mode == WURM_OBS_NONE) && p.S > 20 && p.S < 32 &&
+        !getenv("WURM_SINGLE_BODY_MIN_SIZE"))
+        return -1;
     const int per_warp = 32 / G;
     const int chan_bytes = p.C * 4, stage_env_bytes = p.obs_mode == WURM_OBS_PARTIAL ? 3 * p.W * p.W * 4 : 0;
     int max_threads = stage_env_bytes ? 32 : WURM_BODY_THREADS;
