@@ -5,8 +5,11 @@ env :47-93, env construction :247-251, hyper-parameter annealing by attribute as
 call sequence :350-378): per step every agent samples an action from its policy's probabilities,
 `observations, reward, done, info = env.step(actions)`, `env.reset(done['__all__'],
 return_observations=False)`, `env.check_consistency()`.  The env comes from `wurm_b200.envs`; the policy
-stand-in is a uniform random agent over the 8 actions (4 moves x boost) -- policies, species, DIAYN
-and the A2C learner are outside this repository's scope.
+stand-ins are a uniform random agent over the 8 actions (4 moves x boost) and one shared 2x64 feed-forward
+network (`--agent feedforward`).  `--train true` runs the reference's A2C update (:424-463: per-agent
+trajectories flattened agent-major, one bootstrap pass, Adam, gradient clipping) with the return scan on the
+device (`wurm_b200.rl.A2C`); species, shared backbones, recurrent agents and DIAYN stay outside this
+repository's scope.
 
     python -m experiments.multiagent --n-envs 4096 --n-agents 4 --size 25 --obs partial_4 --total-steps 1e6
 """
@@ -15,11 +18,17 @@ from itertools import count
 from time import time
 
 import torch
+from torch import nn
 from torch.distributions import Categorical
 
+from experiments.main import FeedforwardAgent
 from wurm_b200.envs import MultiSnake
+from wurm_b200.rl import A2C
+from wurm_b200.trajectory_store import TrajectoryStore
 
 LOG_INTERVAL = 100
+MAX_GRAD_NORM = 0.5          # reference multiagent.py:31-32
+VALUE_LOSS_COEFF = 0.5
 
 
 def boolean(x):
@@ -50,13 +59,18 @@ def main(argv=None):
     parser.add_argument('--colour-mode', type=str, default='random')
     parser.add_argument('--check-consistency', default=True, type=boolean)
     parser.add_argument('--seed', default=None, type=int)
+    parser.add_argument('--lr', default=1e-3, type=float)
+    parser.add_argument('--gamma', default=0.99, type=float)
+    parser.add_argument('--update-steps', default=5, type=int)
+    parser.add_argument('--entropy', default=0.0, type=float)
     args = parser.parse_args(argv)
 
     if args.env != 'snake':
         raise ValueError('Unrecognised environment')
-    if args.train or args.agent != ['random']:
-        raise NotImplementedError('policies and the A2C learner are outside the scope of wurm_b200 (DESIGN.md section 7); '
-                                  'use --agent random --train false')
+    agent_type = args.agent[0]
+    if agent_type not in ('random', 'feedforward'):
+        raise ValueError('Unrecognised agent (this driver covers random and feedforward)')
+    train = bool(args.train) and agent_type != 'random'
 
     env = MultiSnake(num_envs=args.n_envs, num_snakes=args.n_agents, size=args.size, device=args.device,
                      observation_mode=args.obs, boost=args.boost, boost_cost_prob=args.boost_cost,
@@ -64,8 +78,21 @@ def main(argv=None):
                      food_rate=args.food_rate, respawn_mode=args.respawn_mode, agent_colours=args.colour_mode, seed=args.seed)
 
     num_actions = 8 if args.boost else 4
-    uniform = torch.full((args.n_envs, num_actions), 1.0 / num_actions, device=args.device)
+    K, E = args.n_agents, args.n_envs
+    agents = [f'agent_{k}' for k in range(K)]
+    uniform = torch.full((K * E, num_actions), 1.0 / num_actions, device=args.device)
     observations = env.reset()
+    model = None
+    if agent_type == 'feedforward':
+        model = FeedforwardAgent(num_actions, 2, 64, num_inputs=observations['agent_0'][0].numel()).to(args.device)
+    if train:
+        optimizer = torch.optim.Adam(model.parameters(), lr=args.lr)
+        a2c = A2C(gamma=args.gamma)
+        trajectories = TrajectoryStore()
+    losses = {}
+
+    def flat(d):                                     # the reference's flatten_dict: agent-major (K*E, 1)
+        return torch.stack([d[a] for a in agents]).reshape(K * E, 1)
     num_steps = 0
     t0 = time()
     summary = {}
@@ -76,13 +103,37 @@ def main(argv=None):
         if args.food_on_death_min is not None:
             env.food_on_death_prob -= (args.food_on_death - args.food_on_death_min) / args.total_steps * args.n_envs
 
-        actions = {agent: Categorical(uniform).sample().clone().long() for agent, obs in observations.items()}
+        if model is None:
+            dist = Categorical(uniform)
+        else:
+            with torch.set_grad_enabled(train):
+                probs, values = model(torch.cat([observations[a] for a in agents]))       # one pass for all agents
+            dist = Categorical(probs)
+        sampled = dist.sample().clone().long()
+        actions = {a: sampled[k * E:(k + 1) * E].clone() for k, a in enumerate(agents)}
 
         observations, reward, done, info = env.step(actions)
+
+        if train:
+            trajectories.append(action=sampled, log_prob=dist.log_prob(sampled).unsqueeze(-1), value=values.reshape(-1, 1),
+                                reward=flat(reward), done=flat(done), entropy=dist.entropy().mean())
 
         env.reset(done['__all__'], return_observations=False)
         if args.check_consistency:
             env.check_consistency()
+
+        if train and i_step % args.update_steps == 0:                 # reference multiagent.py:424-463
+            with torch.no_grad():
+                _, bootstrap_values = model(torch.cat([observations[a] for a in agents]))
+            value_loss, policy_loss = a2c.loss(bootstrap_values.reshape(-1, 1), trajectories.rewards, trajectories.values,
+                                               trajectories.log_probs, trajectories.dones)
+            entropy_loss = - trajectories.entropies.mean()
+            optimizer.zero_grad()
+            (VALUE_LOSS_COEFF * value_loss + policy_loss + args.entropy * entropy_loss).backward()
+            nn.utils.clip_grad_norm_(model.parameters(), MAX_GRAD_NORM)
+            optimizer.step()
+            trajectories.clear()
+            losses = dict(value_loss=value_loss.item(), policy_loss=policy_loss.item())
 
         num_steps += args.n_envs
         if i_step % LOG_INTERVAL == 0 or num_steps >= args.total_steps:
@@ -90,7 +141,7 @@ def main(argv=None):
             summary = dict(steps=num_steps, episodes=stats['episodes'], food=stats['reward'],
                            snake_collisions=stats['self_collisions'], edge_collisions=stats['edge_collisions'],
                            food_rate=env.food_rate, food_on_death_prob=env.food_on_death_prob,
-                           fps=num_steps / (time() - t0))
+                           fps=num_steps / (time() - t0), **losses)
             print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
         if num_steps >= args.total_steps or summary.get('episodes', 0) >= args.total_episodes:
             break

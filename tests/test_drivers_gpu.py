@@ -60,3 +60,16 @@ def test_rollout_driver_trains_with_a2c():
     assert store.rewards.shape == (3, 4, 1) and store.dones.dtype == torch.bool and len(store) == 3
     store.clear()
     assert len(store) == 0
+
+
+def test_multiagent_driver_trains_with_a2c():
+    """`--agent feedforward --train true`: the reference's multi-agent A2C update (multiagent.py:424-463) on the device
+    return scan; finite losses, consistent envs throughout."""
+    import math
+    import torch
+    from experiments import multiagent as driver
+    torch.manual_seed(0)
+    summary = driver.main(['--n-envs', '64', '--n-agents', '4', '--size', '25', '--obs', 'partial_4', '--agent', 'feedforward',
+                           '--train', 'true', '--update-steps', '5', '--total-steps', str(64 * 100), '--seed', '3'])
+    assert summary['steps'] == 64 * 100
+    assert math.isfinite(summary['value_loss']) and math.isfinite(summary['policy_loss'])
