@@ -112,9 +112,10 @@ __device__ __forceinline__ float4 ld_stream(const float4* ptr) {
     return v;
 }
 
-// Calls f(i, v) for every non-zero base[i], i < n.  128-bit streaming loads, four in flight per thread; loads past
-// the end are clamped to the last vector instead of predicated (their hits are dropped by the index test).
-template <typename F>
+// Calls f(i, v) for every non-zero base[i], i < n.  128-bit streaming loads, U in flight per thread (4 for the small
+// CTAs, whose registers decide how many envs are resident; 8 for the 256-thread CTAs of large grids: C5 1.65 -> 1.58 ms);
+// loads past the end are clamped to the last vector instead of predicated (their hits are dropped by the index test).
+template <int U = 4, typename F>
 __device__ __forceinline__ void scan_nonzero(const float* base, int n, F&& f) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     int lead = (4 - (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3)) & 3;
@@ -127,12 +128,12 @@ __device__ __forceinline__ void scan_nonzero(const float* base, int n, F&& f) {
         if (v != 0.0f) f(i, v);
     }
     const float4* vb = reinterpret_cast<const float4*>(base + lead);
-    for (int j0 = tid; j0 < nvec; j0 += 4 * nthr) {
-        float4 v[4];
+    for (int j0 = tid; j0 < nvec; j0 += U * nthr) {
+        float4 v[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_stream(vb + min(j0 + u * nthr, nvec - 1));
+        for (int u = 0; u < U; ++u) v[u] = ld_stream(vb + min(j0 + u * nthr, nvec - 1));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (v[u].x != 0.0f || v[u].y != 0.0f || v[u].z != 0.0f || v[u].w != 0.0f) {
                 const int j = j0 + u * nthr, i = lead + 4 * j;
                 if (j < nvec) {
@@ -280,7 +281,7 @@ __device__ __noinline__ void fold_nonzero_overflow(unsigned char* smem, int C, i
 // latency hides behind them).  A live snake's hint verifies if the cell holds a head, a dead snake's if it is still
 // flagged done; if every snake's does, the heads tensor -- one non-zero per snake in 44-48 % of the state's bytes --
 // is not streamed at all.
-template <bool CHECK = false>
+template <bool CHECK = false, int U = 4>
 __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& s, int e, bool use_hints = false, int hint_h = -1,
                                          float hint_val = 0.0f, bool hint_dead = false) {
     const int C = p.C, K = p.K;
@@ -300,7 +301,7 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
             if (s.misc[7]) break;
         }
         const float* base = what == 0 ? p.foods + (size_t)e * C : (what == 1 ? p.heads : p.bodies) + (size_t)e * K * C;
-        scan_nonzero(base, what == 0 ? C : K * C, [&](int i, float v) {
+        scan_nonzero<U>(base, what == 0 ? C : K * C, [&](int i, float v) {
             const int n = atomicAdd(&s.misc[6], 1);
             if (n < s.qcap) s.queue[n] = make_int2((int)((unsigned)i | ((unsigned)what << 30)), __float_as_int(v));
             else fold_nonzero_overflow<CHECK>(reinterpret_cast<unsigned char*>(s.cell), C, K, p.magic_C, p.status, what, i, v);
@@ -690,7 +691,7 @@ multi_env_kernel(const MultiParams p) {
     float hint_val = 0.0f;
     if (use_hints && tid < K && hint_h >= 0 && hint_h < C) hint_val = p.heads[((size_t)e * K + tid) * C + hint_h];
     __syncthreads();
-    load_env(p, s, e, use_hints, hint_h, hint_val, hint_dead);
+    load_env<false, (THREADS >= 256 ? 8 : 4)>(p, s, e, use_hints, hint_h, hint_val, hint_dead);
     __syncthreads();
 
     if (STEP) {
