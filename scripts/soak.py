@@ -31,8 +31,7 @@ while time.time() - t0 < budget:
         steps = rng.choice([10, 25, 40])
         rules = rng.choice([dict(), dict(respawn_mode='any'), dict(respawn_mode='any', food_on_death_prob=1.0, boost_cost_prob=1.0),
                             dict(boost=False, food_on_death_prob=0.0, reward_on_death=-2),
-                            dict(food_mode='random_rate', food_rate=3e-3, respawn_mode='any', food_on_death_prob=0.33, boost_cost_prob=0.25),
-                            dict(agent_colours='fixed', respawn_mode='any')])
+                            dict(food_mode='random_rate', food_rate=3e-3, respawn_mode='any', food_on_death_prob=0.33, boost_cost_prob=0.25)])
         desc = f'multi E={E} K={K} S={S} {mode} steps={steps} {rules}'
         if K > max(1, (S - 4) ** 2 // 25):           # leave room to place every snake
             continue
