@@ -22,7 +22,11 @@ while time.time() - t0 < budget:
         every = rng.choice([1, 1, 1, 3, 6])
         adt = rng.choice([torch.long, torch.int, torch.short])
         desc = f'single N={N} S={S} {mode} steps={steps} reset_every={every} {adt}'
-        ts.test_rollout_matches_oracle(N, S, mode, steps, every, adt)
+        if rng.random() < 0.25 and every == 1:       # the fused step+reset launch against step-then-reset
+            desc += ' (fused vs two calls)'
+            ts.test_fused_step_reset_equals_step_then_reset(N, S, mode)
+        else:
+            ts.test_rollout_matches_oracle(N, S, mode, steps, every, adt)
     else:
         K = rng.choice([1, 2, 3, 4, 6, 8, 12, 16])
         S = rng.choice([8, 10, 12, 14, 20, 25, 30, 36, 48])
@@ -35,7 +39,11 @@ while time.time() - t0 < budget:
         desc = f'multi E={E} K={K} S={S} {mode} steps={steps} {rules}'
         if K > max(1, (S - 4) ** 2 // 25):           # leave room to place every snake
             continue
-        tm.test_rollout_matches_oracle(E, K, S, mode, steps, rules, torch.long)
+        if rng.random() < 0.25:
+            desc += ' (fused vs two calls)'
+            tm.test_fused_step_reset_equals_step_then_reset(E, K, S, mode, rules)
+        else:
+            tm.test_rollout_matches_oracle(E, K, S, mode, steps, rules, torch.long)
     runs += 1
     print(f'ok {runs}: {desc}', flush=True)
 print(f'soak finished: {runs} rollouts in {time.time() - t0:.0f} s, no mismatch')
