@@ -278,8 +278,9 @@ int wurm_grid_observe(const WurmGridCfg* cfg, const float* envs, float* obs, voi
 
 /* A2C return scan (wurm/rl/a2c.py:49-63): the backward recurrence over a (T,N) trajectory
  * in one launch, fp32 in the reference's operation order.  rewards / values / dones / returns (T,N) row-major, bootstrap
- * (N).  gae_lambda < 0: n-step returns R_t = r_t + gamma R_{t+1} (1 - d_t) (:58-61); otherwise GAE (:50-57). */
-int wurm_a2c_returns(int32_t num_steps, int32_t num_envs, float gamma, float gae_lambda, const float* bootstrap,
+ * (N).  gae_lambda < 0: n-step returns R_t = r_t + gamma R_{t+1} (1 - d_t) (:58-61); otherwise GAE (:50-57).  gamma and
+ * gae_lambda are DOUBLES, as in the reference (Python floats): :56 multiplies them in double before the product meets fp32. */
+int wurm_a2c_returns(int32_t num_steps, int32_t num_envs, double gamma, double gae_lambda, const float* bootstrap,
                      const float* rewards, const float* values, const uint8_t* dones, float* returns, void* stream);
 
 /* MultiSnake.check_consistency (multi_snake.py:733-769): living snakes against snake_consistency,

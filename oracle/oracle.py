@@ -270,6 +270,6 @@ def a2c_returns(bootstrap, rewards, values, dones, gamma, gae_lambda=None):
     bootstrap = _c(bootstrap, np.float32)
     T, N = rewards.shape
     out = np.zeros((T, N), np.float32)
-    lib().wurm_oracle_a2c_returns(T, N, ctypes.c_float(gamma), ctypes.c_float(-1.0 if gae_lambda is None else gae_lambda),
+    lib().wurm_oracle_a2c_returns(T, N, ctypes.c_double(gamma), ctypes.c_double(-1.0 if gae_lambda is None else gae_lambda),
                                   _p(bootstrap), _p(rewards), _p(values), _p(dones), _p(out))
     return out

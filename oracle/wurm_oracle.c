@@ -1014,11 +1014,15 @@ void wurm_oracle_grid_observe(int N, int S, const float* envs, int mode, float* 
 /* rewards, values, dones, returns: (T,N) row-major; bootstrap: (N).  lambda < 0: n-step returns  */
 /* (:58-61), else generalised advantage estimation (:50-57).                                     */
 /* ------------------------------------------------------------------------------------------ */
-void wurm_oracle_a2c_returns(int T, int N, float gamma, float lambda, const float* bootstrap, const float* rewards,
+void wurm_oracle_a2c_returns(int T, int N, double gamma_d, double lambda_d, const float* bootstrap, const float* rewards,
                              const float* values, const uint8_t* dones, float* returns) {
+    /* the reference's scalars are Python doubles: each meets an fp32 tensor as its own fp32 rounding, and
+       `self.gamma * self.gae_lambda` (:56) is multiplied in double BEFORE it is rounded */
+    const float gamma = (float)gamma_d, gamma_lambda = (float)(gamma_d * lambda_d);
+    const int use_gae = lambda_d >= 0.0;
 #pragma omp parallel for schedule(static)
     for (int n = 0; n < N; ++n) {
-        if (lambda < 0.0f) {
+        if (!use_gae) {
             float R = bootstrap[n] * (dones[(size_t)(T - 1) * N + n] ? 0.0f : 1.0f);                 /* :58 */
             for (int t = T - 1; t >= 0; --t) {
                 float m = dones[(size_t)t * N + n] ? 0.0f : 1.0f;
@@ -1031,7 +1035,7 @@ void wurm_oracle_a2c_returns(int T, int N, float gamma, float lambda, const floa
                 float m = dones[(size_t)t * N + n] ? 0.0f : 1.0f;
                 float next = t == T - 1 ? bootstrap[n] : values[(size_t)(t + 1) * N + n];
                 float delta = rewards[(size_t)t * N + n] + gamma * next * m - values[(size_t)t * N + n];   /* :52-55 */
-                gae = delta + gamma * lambda * m * gae;                                              /* :56 */
+                gae = delta + gamma_lambda * m * gae;                                                /* :56 */
                 returns[(size_t)t * N + n] = gae + values[(size_t)t * N + n];                        /* :57 */
             }
         }

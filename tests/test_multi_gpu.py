@@ -407,15 +407,17 @@ def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
     graphed.agent_colours = plain.agent_colours.clone()
     acts = torch.randint(0, 8, (steps + 1, K, E), generator=torch.Generator().manual_seed(2)).to(DEV)
     static = {f'agent_{k}': acts[0, k].clone() for k in range(K)}
-    stepper = GraphedStepper(graphed, static, warmup=2)
-    for _ in range(2):
-        _, _, dones, _ = plain.step({f'agent_{k}': acts[0, k] for k in range(K)})
-        plain.reset(dones['__all__'], return_observations=False)
-    check_state(graphed, env_state(plain), 'state after warm-up')
+    stepper = GraphedStepper(graphed, static, warmup=2)       # warms up with real steps, then restores the env
+    check_state(graphed, env_state(plain), 'state after construction')
+    assert graphed._draws == plain._draws
     for t in range(1, steps + 1):
-        for k in range(K):
-            static[f'agent_{k}'].copy_(acts[t, k])
-        obs, rewards, dones, info = stepper.step()
+        if t % 6 == 2:                                          # a direct call interleaved with the replays
+            obs, rewards, dones, info = graphed.step({f'agent_{k}': acts[t, k].clone() for k in range(K)})
+            graphed.reset(dones['__all__'], return_observations=False)
+        else:
+            for k in range(K):
+                static[f'agent_{k}'].copy_(acts[t, k])
+            obs, rewards, dones, info = stepper.step()
         obs2, rewards2, dones2, info2 = plain.step({f'agent_{k}': acts[t, k] for k in range(K)})
         for k in range(K):
             assert_same(np_(obs[f'agent_{k}']), np_(obs2[f'agent_{k}']), f'step {t}: obs {k}')
@@ -523,7 +525,9 @@ def test_fused_step_reset_golden_replay(i):
 def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mode):
     """The kernels keep each snake's head cell from one call to the next and skip streaming the heads tensor when every
     hint still verifies.  Rolling the envs along the batch (every env now sits under its neighbour's hints), replacing
-    the tensors wholesale and killing snakes by hand must only cost the scan back, never the result."""
+    the tensors wholesale and killing snakes by hand must only cost the scan back, never the result.  The Python class
+    drops the hints by itself when it sees such edits (tensor identity / version); `_adopt_state()` after every edit
+    hides them from it -- as a raw-pointer writer would -- so that what is tested is the KERNEL's own verification."""
     seed = 99 + E
     rules = dict(respawn_mode='any')
     env = make_env(E, K, S, mode, seed=seed, **rules)
@@ -554,6 +558,7 @@ def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mo
         t.copy_(t.roll(per_env, dims=0))
         a = getattr(st, name)
         a[...] = np.roll(a, per_env, axis=0)
+    env._adopt_state()
     run(4, 'rolled')
     # 2. the caller replaces the tensors by new objects holding another env's state (hints now describe the old tensors)
     env.heads = env.heads.view(E, K, 1, S, S).flip(0).reshape(E * K, 1, S, S).contiguous()      # env order reversed
@@ -569,6 +574,7 @@ def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mo
         a = getattr(st, name)
         a[...] = a.reshape(E, K)[::-1].reshape(E * K)
     st.agent_colours[...] = st.agent_colours.reshape(E, K, 3)[::-1].reshape(E * K, 3)
+    env._adopt_state()
     run(4, 'replaced')
     # 3. kill one live snake per env by hand (tensors zeroed, flag set): its hint must not resurrect a head
     alive = (~env.dones.view(E, K)).float()
@@ -579,4 +585,30 @@ def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mo
     env.heads[rows] = 0; env.bodies[rows] = 0; env.dones[rows] = True
     r = rows.cpu().numpy()
     st.heads[r] = 0; st.bodies[r] = 0; st.dones[r] = 1
+    env._adopt_state()
     run(4, 'killed')
+
+
+def test_second_head_written_by_the_caller_is_reported_not_ignored():
+    """A second head cell of a snake is outside the supported set (the reference's check_consistency rejects it too).
+    In steady state the kernels run on verified head hints and do not stream the heads tensor, so they would never
+    SEE it: a write through `env.heads` must drop the hints so that the next call scans the tensor and raises
+    WURM_ST_MULTI_HEAD instead of silently stepping a different state."""
+    E, K, S = 32, 4, 25
+    env = make_env(E, K, S, 'partial_4', seed=5)
+    g = torch.Generator().manual_seed(5)
+    for t in range(3):
+        acts = torch.randint(0, 4, (E, K), generator=g)
+        env.step({f'agent_{k}': acts[:, k].contiguous().to(DEV) for k in range(K)}, auto_reset=True)
+    env.check_status()
+    assert int((env._head_hints >= 0).sum()) > 0
+    live = int((~env.dones).nonzero()[0])
+    free = (env.heads[live, 0] == 0).nonzero()[0]
+    env.heads[live, 0, free[0], free[1]] = 1.0
+    acts = torch.randint(0, 4, (E, K), generator=g)
+    env.step({f'agent_{k}': acts[:, k].contiguous().to(DEV) for k in range(K)})
+    with pytest.raises(RuntimeError, match='more than one head'):
+        env.check_status()
+    # by hand, for raw-pointer writers
+    env.invalidate_hints()
+    assert int((env._head_hints != -2).sum()) == 0

@@ -297,25 +297,33 @@ def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
     graphed = make_env(N, S, 'partial_2', seed=123)
     acts = torch.randint(0, 4, (steps + 2, N), generator=torch.Generator().manual_seed(1)).to(DEV)
     static_actions = torch.zeros(N, dtype=torch.long, device=DEV)
-    # the stepper warms up with 2 real steps before capturing: replay them on the twin
+    # the stepper warms up with 2 real steps before capturing and then RESTORES the env (state, hints, statistics,
+    # call counter): construction has no visible side effect
     static_actions.copy_(acts[0])
+    stats_before = graphed.stats()
     stepper = GraphedStepper(graphed, static_actions, warmup=2)
-    a0 = acts[0].clone()                # both warm-up steps reuse (and re-sanitise) the same action tensor
-    for _ in range(2):
-        _, _, done, _ = plain.step(a0)
-        plain.reset(done, return_observations=False)
-    assert_same(np_(graphed.envs), np_(plain.envs), 'state after warm-up')
+    assert_same(np_(graphed.envs), np_(plain.envs), 'state after construction')
+    assert graphed._draws == plain._draws and graphed.stats() == stats_before
     for t in range(1, steps + 1):
-        static_actions.copy_(acts[t])
-        obs, reward, done, info = stepper.step()
         a = acts[t].clone()
+        if t % 7 == 3:
+            # a DIRECT call interleaved with the replays: both paths keep drawing from one counter sequence
+            a_direct = acts[t].clone()
+            obs, reward, done, info = graphed.step(a_direct)
+            graphed.reset(done, return_observations=False)
+            sanitised = a_direct
+        else:
+            static_actions.copy_(acts[t])
+            obs, reward, done, info = stepper.step()
+            sanitised = static_actions
         obs2, reward2, done2, info2 = plain.step(a)
         assert_same(np_(obs), np_(obs2), f'step {t}: obs')
         assert_same(np_(reward), np_(reward2), f'step {t}: reward')
         assert_same(np_(done), np_(done2), f'step {t}: done')
-        assert_same(np_(static_actions), np_(a), f'step {t}: sanitised actions')
+        assert_same(np_(sanitised), np_(a), f'step {t}: sanitised actions')
         plain.reset(done2, return_observations=False)
         assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')
+        assert graphed._draws == plain._draws
 
 
 @pytest.mark.parametrize('N,S,mode', [(1000, 9, 'partial_2'), (300, 12, 'default'), (130, 36, 'one_channel'), (257, 16, 'partial_3'),
@@ -427,11 +435,8 @@ def test_graphed_stepper_with_host_io():
     graphed = make_env(N, S, 'partial_2', seed=77)
     acts = torch.randint(0, 4, (steps + 1, N), generator=torch.Generator().manual_seed(5))
     static_actions = acts[0].to(DEV)
-    stepper = GraphedStepper(graphed, static_actions, warmup=2, host_io=True)
-    a0 = acts[0].to(DEV)
-    for _ in range(2):
-        _, _, done, _ = plain.step(a0)
-        plain.reset(done, return_observations=False)
+    stepper = GraphedStepper(graphed, static_actions, warmup=2, host_io=True)    # construction leaves the env untouched
+    assert_same(np_(graphed.envs), np_(plain.envs), 'state after construction')
     for t in range(1, steps + 1):
         stepper.host_actions.copy_(acts[t])
         obs, _, _, _ = stepper.step_host()
@@ -480,3 +485,70 @@ def test_state_edited_between_calls_makes_hints_stale_not_wrong(S):
                 o, _ = orc.single_observe(state, 'partial_2')
                 assert_same(np_(obs), o, tag + 'observation')
             env.reset(done, return_observations=False)
+
+
+@pytest.mark.parametrize('S,mode', [(36, 'default'), (16, 'partial_2'), (9, 'partial_2'), (24, 'one_channel')])
+def test_second_food_cell_written_by_the_caller_is_eaten_like_in_the_reference(S, mode):
+    """The reference's step handles any number of food cells (single_snake.py:242,270-272; only env_consistency
+    rejects them).  In steady state the kernels run on verified hints (body-only tiles from size 16 up) that do not
+    re-check that the hinted food cell is the ONLY one: a write through `env.envs` must drop the hints, so that a
+    second food cell placed right in front of the head is eaten exactly as the oracle eats it."""
+    N, seed = 96, 99
+    env = make_env(N, S, mode, seed=seed)
+    state = np.zeros((N, 3, S, S), np.float32)
+    orc.single_reset(state, np.ones(N, np.uint8), None, seed=seed, step=env._draws)
+    g = torch.Generator().manual_seed(3)
+
+    def both(a_cpu, tag):
+        a = a_cpu.to(DEV)
+        obs, reward, done, info = env.step(a)
+        a_np = a_cpu.numpy().copy()
+        r, d, sc, ec = orc.single_step(state, a_np, None, seed=seed, step=env._draws)
+        assert_same(np_(env.envs), state, tag + 'envs')
+        assert_same(np_(reward).reshape(-1), r, tag + 'reward')
+        assert_same(np_(done).reshape(-1).astype(np.uint8), d, tag + 'done')
+        assert_same(np_(obs), orc.single_observe(state, mode)[0], tag + 'observation')
+        return r, d
+
+    for t in range(3):                                   # steady state: hints valid
+        r, d = both(torch.randint(0, 4, (N,), generator=g), f'warm step {t}: ')
+        env.reset(torch.from_numpy(d != 0).to(DEV), return_observations=False)
+        orc.single_reset(state, d, None, seed=seed, step=env._draws)
+    # second food cell on the cell the head will enter when it keeps going straight (action = 2-opposite of the
+    # orientation is sanitised to "straight on": use the direction head - neck)
+    body = state[:, 2].reshape(N, -1)
+    head_cell = body.argmax(1)
+    size = body.max(1)
+    neck_cell = (body == (size - 1)[:, None]).argmax(1)
+    step_to = 2 * head_cell - neck_cell                    # head + (head - neck)
+    hy, hx = head_cell // S, head_cell % S
+    ty, tx = step_to // S, step_to % S
+    ok = (np.abs(ty - hy) + np.abs(tx - hx) == 1) & (ty >= 1) & (ty <= S - 2) & (tx >= 1) & (tx <= S - 2)
+    ok &= state[:, 0].reshape(N, -1)[np.arange(N), np.clip(step_to, 0, S * S - 1)] == 0
+    assert ok.sum() > N // 4
+    rows = np.flatnonzero(ok)
+    state[rows, 0, ty[rows], tx[rows]] = 1.0
+    env.envs[torch.from_numpy(rows).to(DEV), 0, torch.from_numpy(ty[rows]).to(DEV), torch.from_numpy(tx[rows]).to(DEV)] = 1.0
+    # the action that moves head -> step_to: DELTA[a] = [(+1,0),(0,-1),(-1,0),(0,+1)]
+    dy, dx = ty - hy, tx - hx
+    a = np.where(dy == 1, 0, np.where(dx == -1, 1, np.where(dy == -1, 2, 3))).astype(np.int64)
+    r, d = both(torch.from_numpy(a), 'step onto the second food cell: ')
+    assert (r[rows] == 1).all()
+    for t in range(4):                                   # and the env carries on with two food cells on the board
+        r, d = both(torch.randint(0, 4, (N,), generator=g), f'after step {t}: ')
+
+
+def test_raw_pointer_writers_can_invalidate_hints_by_hand():
+    """`invalidate_hints()` is the documented escape hatch for writes torch's version counter cannot see."""
+    N, S, seed = 64, 36, 5
+    env = make_env(N, S, 'default', seed=seed)
+    a = torch.zeros(N, dtype=torch.long, device=DEV)
+    env.step(a)
+    assert int((env._hints[:, 0] >= 0).sum()) > 0
+    env.invalidate_hints()
+    assert int((env._hints >= 0).sum()) == 0
+    key = env._hint_key
+    env.step(a)
+    assert env._hint_key == key                          # the env's own launches do not look like caller edits
+    env.envs[0, 0, 1, 1] = 0.0                           # a torch write does
+    assert (env.envs.data_ptr(), env.envs._version) != env._hint_key

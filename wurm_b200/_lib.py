@@ -133,7 +133,7 @@ def lib():
     L.wurm_grid_observe.restype = i32
     L.wurm_grid_observe.argtypes = [gcfg, vp, vp, vp]
     L.wurm_a2c_returns.restype = i32
-    L.wurm_a2c_returns.argtypes = [i32, i32, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
+    L.wurm_a2c_returns.argtypes = [i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp, vp]
     L.wurm_single_check.restype = i32
     L.wurm_single_check.argtypes = [cfg, vp, vp, vp, vp]
     L.wurm_multi_check.restype = i32

@@ -15,9 +15,10 @@
 //     that compact form: the per-snake logic on one lane per snake of warp 0 (collisions are
 //     look-ups at the new head cell, head-to-head clashes a K-wide compare), the per-cell work
 //     (decay, food from dead bodies, deletion) as CTA-wide passes over the records;
-//   * the new state is expanded back to the reference's fp32 tensors with coalesced 128-bit
-//     stores, and the observations are rendered from the compact form straight into the policy's
-//     per-agent input buffers;
+//   * a step changes O(snake length) cells: the records carry "modified since the load" bits and only
+//     those cells are stored back into the reference's fp32 tensors (sparse write-back; a state the
+//     compact form cannot carry exactly is expanded densely instead), and the observations are rendered
+//     from the compact form straight into the policy's per-agent input buffers;
 //   * no tensor cores: nothing here is a dense contraction.
 //
 // Supported states: the reference's own invariant (MultiSnake.check_consistency, :733-769) --
@@ -89,6 +90,13 @@ struct MultiParams {
 __device__ __forceinline__ uint64_t call_counter(const MultiParams& p) { return p.step + (p.step_dev ? *p.step_dev : 0ull); }
 
 __device__ __forceinline__ int fdiv(int q, uint32_t magic) { return (int)__umulhi((uint32_t)q, magic); }
+// i / C for i < K*C (up to 32 * 181^2): with magic = ceil(2^32 / C) the multiply-shift estimate is exact only while
+// i * (C * magic - 2^32) < 2^32, which large K and S exceed for the last cells of a snake's grid; the estimate is
+// never more than one too high, so one compare corrects it.
+__device__ __forceinline__ int fdiv_C(int i, int C, uint32_t magic_C) {
+    const int q = (int)__umulhi((uint32_t)i, magic_C);
+    return q * C > i ? q - 1 : q;
+}
 
 // One 32-bit record per cell holds everything the step needs to know about it:
 //   bits  0-15  body value            bits 16-21  owner snake + 1      (together: the "live" body, 0 = none)
@@ -248,12 +256,12 @@ __device__ __forceinline__ void fold_nonzero(const MultiSmem& s, int C, uint32_t
         odd = v != 1.0f;
         if (CHECK && odd) s.misc[5] = 1;                             // a food pixel that is neither 0 nor 1
     } else if (what == 1) {
-        const int k = fdiv(i, magic_C);
+        const int k = fdiv_C(i, C, magic_C);
         atomicMax(&s.hp[k], i - k * C);
         atomicAdd(&s.hcnt[k], v == 1.0f ? 1 : 2);                    // a head value other than 1 counts as "not one head"
         odd = v != 1.0f;
     } else {
-        const int k = fdiv(i, magic_C), val = (int)v;
+        const int k = fdiv_C(i, C, magic_C), val = (int)v;
         const uint32_t owner = (uint32_t)(k + 1);
         const uint32_t old = atomicOr(&s.cell[i - k * C], (owner << 22) | (owner << 16) | ((uint32_t)val & 0xffffu) | kListed);
         odd = (float)val != v || val < 1 || val > 65535;
@@ -900,11 +908,11 @@ multi_env_kernel(const MultiParams p) {
             // non-canonical input: expand the whole compact form into the reference's tensors
             store_floats(p.foods + (size_t)e * C, C, [&](int i) { return (s.cell[i] & kFood) ? 1.0f : 0.0f; });
             store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
-                const int kk = fdiv(i, p.magic_C);
+                const int kk = fdiv_C(i, C, p.magic_C);
                 return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
             });
             store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
-                const int kk = fdiv(i, p.magic_C);
+                const int kk = fdiv_C(i, C, p.magic_C);
                 const uint32_t rec = s.cell[i - kk * C];
                 return (rec_body(rec) && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
             });
@@ -1039,12 +1047,12 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
     __syncthreads();
     scan_nonzero(gfood, C, [&](int i, float) { sc.occ[i] = 1; });
     scan_nonzero(ghead, K * C, [&](int i, float) {
-        const int kk = fdiv(i, p.magic_C);
+        const int kk = fdiv_C(i, C, p.magic_C);
         sc.occ[i - kk * C] = 1;
         if (kk == first_dead) ghead[i] = 0.0f;                        // leftovers of the dead snake (none on a consistent state)
     });
     scan_nonzero(gbody, K * C, [&](int i, float) {
-        const int kk = fdiv(i, p.magic_C);
+        const int kk = fdiv_C(i, C, p.magic_C);
         sc.occ[i - kk * C] = 1;
         if (kk == first_dead) gbody[i] = 0.0f;
     });
@@ -1123,12 +1131,8 @@ static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
     auto kern = multi_env_kernel<STEP, THREADS>;
     const size_t smem = multi_smem_bytes(p.C, p.K);
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(multi_env_kernel)");
-        configured = smem;
-    }
+    static SmemOptIn opt_in;                           // per instantiation, per device inside
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, (int)smem, false, "cudaFuncSetAttribute(multi_env_kernel)")) return rc;
     kern<<<p.E, THREADS, smem, stream>>>(p);
     return check_launch("multi_env_kernel");
 }
@@ -1256,12 +1260,8 @@ extern "C" int wurm_multi_check(const WurmMultiCfg* cfg, const WurmMultiState* s
     if (int rc = plan_multi(cfg, state, &p)) return rc;
     if (!report) return fail(WURM_E_INVALID, "NULL pointer");
     const size_t smem = multi_smem_bytes(p.C, p.K);
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(multi_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(multi_check_kernel)");
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(multi_check_kernel), &opt_in, (int)smem, false, "cudaFuncSetAttribute(multi_check_kernel)")) return rc;
     multi_check_kernel<<<p.E, p.C <= 1024 ? 128 : 256, smem, (cudaStream_t)stream>>>(p, report);
     return check_launch("multi_check_kernel");
 }

@@ -1022,13 +1022,8 @@ static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* 
 template <int G, bool STEP>
 static int launch_tile(const SingleParams& p, const SingleLaunch& L, cudaStream_t stream) {
     auto kern = single_tile_kernel<G, STEP>;
-    static int configured_smem = -1;                   // per instantiation
-    if (L.smem > configured_smem) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem);
-        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(single_tile_kernel)");
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured_smem = L.smem;
-    }
+    static SmemOptIn opt_in;                           // per instantiation, per device inside
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, L.smem, true, "cudaFuncSetAttribute(single_tile_kernel)")) return rc;
     kern<<<L.blocks, L.threads, L.smem, stream>>>(p);
     return check_launch("single_tile_kernel");
 }
@@ -1050,13 +1045,8 @@ static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr
 template <int G>
 static int launch_body_t(const SingleParams& p, int blocks, int threads, int smem, cudaStream_t stream) {
     auto kern = single_body_kernel<G>;
-    static int configured_smem = -1;                   // per instantiation
-    if (smem > configured_smem) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (err != cudaSuccess) return fail_cuda(err, "cudaFuncSetAttribute(single_body_kernel)");
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured_smem = smem;
-    }
+    static SmemOptIn opt_in;                           // per instantiation, per device inside
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, smem, true, "cudaFuncSetAttribute(single_body_kernel)")) return rc;
     kern<<<blocks, threads, smem, stream>>>(p);
     return check_launch("single_body_kernel");
 }

@@ -152,8 +152,10 @@ class MultiSnake(object):
         self.edge_locations_mask[:, :, -1:, :] = 1
         self.edge_locations_mask[:, :, :, -1:] = 1
 
+        self._hint_key = None
         if not manual_setup:
             self._create_all()
+        self._adopt_state()
 
     # ------------------------------------------------------------------------------------------
     # plumbing
@@ -197,12 +199,33 @@ class MultiSnake(object):
             raise RuntimeError(f'{name} has shape {tuple(t.shape)}, expected {shape}')
         return t
 
+    def _hint_identity(self):
+        return tuple((t.data_ptr(), t._version) for t in (self.heads, self.bodies, self.foods, self.dones))
+
+    def _adopt_state(self):
+        """Records the identity of the state tensors as what the head hints describe (after this env's own kernels)."""
+        self._hint_key = self._hint_identity()
+
+    def invalidate_hints(self):
+        """Drops the per-snake head-cell hints: the next call streams the heads tensor again.  Called automatically
+        when a state tensor was replaced or written through torch since this env's last own call (the kernels verify
+        that a hinted cell still holds a head, not that it is the snake's ONLY head cell); call it by hand after
+        writing the state through a raw pointer, which torch's version counter cannot see."""
+        self._head_hints.fill_(-2)
+        self._adopt_state()
+
     def _state(self):
-        """The state attributes may have been replaced by the caller (tests assign them): normalise."""
+        """The state attributes may have been replaced by the caller (tests assign them): normalise.  Also where the
+        head hints are dropped if the caller touched a state tensor since this env's last own call."""
         E, K, S = self.num_envs, self.num_snakes, self.size
+        foods = self._norm('foods', torch.float32, (E, 1, S, S))
+        heads = self._norm('heads', torch.float32, (E * K, 1, S, S))
+        bodies = self._norm('bodies', torch.float32, (E * K, 1, S, S))
+        dones = self._norm('dones', torch.bool, (E * K,))
+        if self._hint_identity() != self._hint_key:
+            self.invalidate_hints()
         return _lib.WurmMultiState(
-            _ptr(self._norm('foods', torch.float32, (E, 1, S, S))), _ptr(self._norm('heads', torch.float32, (E * K, 1, S, S))),
-            _ptr(self._norm('bodies', torch.float32, (E * K, 1, S, S))), _ptr(self._norm('dones', torch.bool, (E * K,))),
+            _ptr(foods), _ptr(heads), _ptr(bodies), _ptr(dones),
             _ptr(self._norm('orientations', torch.long, (E * K,))), _ptr(self._norm('boost_this_step', torch.bool, (E * K,))),
             _ptr(self._norm('agent_colours', torch.short, (E * K, 3))), _ptr(self._head_hints))
 
@@ -430,33 +453,6 @@ class MultiSnake(object):
         self.check_status()
 
     def render(self, mode: str = 'human', env: int = None):
-        """Human display (reference :229-266); host-side, outside the hot path."""
-        img = self._get_env_images().cpu().numpy()
-
-        if self.num_envs == 1 or env is not None:
-            num_cols = num_rows = 1
-            img = np.transpose(img[env or 0], (1, 2, 0))
-        else:
-            num_rows = self.render_args['num_rows']
-            num_cols = self.render_args['num_cols']
-            output = np.zeros((self.size * num_rows, self.size * num_cols, 3))
-            for i in range(num_rows):
-                for j in range(num_cols):
-                    output[i * self.size:(i + 1) * self.size, j * self.size:(j + 1) * self.size, :] = \
-                        np.transpose(img[i * num_cols + j], (1, 2, 0))
-            img = output
-
-        from PIL import Image
-        img = np.array(Image.fromarray(img.astype(np.uint8)).resize(
-            (self.render_args['size'] * num_cols, self.render_args['size'] * num_rows)))
-
-        if mode == 'human':
-            if self.viewer is None:
-                from gym.envs.classic_control import rendering
-                self.viewer = rendering.SimpleImageViewer()
-            self.viewer.imshow(img)
-            return self.viewer.isopen
-        elif mode == 'rgb_array':
-            return img
-        else:
-            raise ValueError('Render mode not recognised.')
+        """Human display of `_get_env_images()` (reference :229-266); host-side convenience, outside the hot path."""
+        from ._display import show
+        return show(self, self._get_env_images(), mode, env)

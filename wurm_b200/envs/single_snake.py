@@ -17,7 +17,6 @@ from collections import namedtuple
 from time import time
 import ctypes
 
-import numpy as np
 import torch
 
 from .. import _lib
@@ -95,6 +94,8 @@ class SingleSnake(object):
 
         if not manual_setup:
             self.envs = self._create_envs(self.num_envs)
+        self._hint_key = None
+        self._adopt_state()
 
         self.done = torch.zeros(num_envs, dtype=torch.bool, device=self.device)
 
@@ -127,14 +128,32 @@ class SingleSnake(object):
                 _lib.OBS_POSITIONS: (n, 4), _lib.OBS_PARTIAL: (n, 3 * w * w)}[cfg.obs_mode]
 
     def _state(self):
-        """`envs` may have been replaced or sliced by the caller (tests assign it): normalise."""
+        """`envs` may have been replaced or sliced by the caller (tests assign it): normalise.  Also where the hints
+        are dropped if the caller touched the tensor since this env's last own call: the kernels verify that the
+        hinted head / food cells still hold a head / food, but not that they are the ONLY such cells, so a state
+        edited behind the env's back (a second food cell, say -- which the reference's step handles like any other)
+        must not be stepped on stale hints.  torch bumps `_version` on every in-place write through the tensor or
+        any view of it, and an assignment changes `data_ptr()`; two integer compares per call."""
         e = self.envs
         if e.dtype != torch.float32 or not e.is_contiguous() or e.device.type != 'cuda':
             e = e.to(device=self.device, dtype=torch.float32).contiguous()
             self.envs = e
         if tuple(e.shape) != (self.num_envs, 3, self.size, self.size):
             raise RuntimeError(f'envs has shape {tuple(e.shape)}, expected {(self.num_envs, 3, self.size, self.size)}')
+        if (e.data_ptr(), e._version) != self._hint_key:
+            self.invalidate_hints()
         return e
+
+    def _adopt_state(self):
+        """Records the identity of `envs` as the state the hints describe (after this env's own kernels wrote it)."""
+        self._hint_key = (self.envs.data_ptr(), self.envs._version)
+
+    def invalidate_hints(self):
+        """Drops the per-env (head cell, size, food cell) hints: the next step re-derives everything from `envs`.
+        Called automatically when `envs` was replaced or written through torch; call it by hand after writing the
+        state through a raw pointer (a custom kernel, `.data_ptr()`), which torch's version counter cannot see."""
+        self._hints.fill_(-1)
+        self._adopt_state()
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.envs.device).cuda_stream)
@@ -300,33 +319,6 @@ class SingleSnake(object):
         return envs
 
     def render(self, mode: str = 'human'):
-        """Human display (reference :389-428); host-side, outside the hot path."""
-        img = self._get_rgb().cpu().numpy()
-
-        if self.num_envs == 1:
-            num_cols = num_rows = 1
-            img = np.transpose(img[0], (1, 2, 0))
-        else:
-            num_rows = self.render_args['num_rows']
-            num_cols = self.render_args['num_cols']
-            output = np.zeros((self.size * num_rows, self.size * num_cols, 3))
-            for i in range(num_rows):
-                for j in range(num_cols):
-                    output[i * self.size:(i + 1) * self.size, j * self.size:(j + 1) * self.size, :] = \
-                        np.transpose(img[i * num_cols + j], (1, 2, 0))
-            img = output
-
-        from PIL import Image
-        img = np.array(Image.fromarray(img.astype(np.uint8)).resize(
-            (self.render_args['size'] * num_cols, self.render_args['size'] * num_rows)))
-
-        if mode == 'human':
-            if self.viewer is None:
-                from gym.envs.classic_control import rendering
-                self.viewer = rendering.SimpleImageViewer()
-            self.viewer.imshow(img)
-            return self.viewer.isopen
-        elif mode == 'rgb_array':
-            return img
-        else:
-            raise ValueError('Render mode not recognised.')
+        """Human display of `_get_rgb()` (reference :389-428); host-side convenience, outside the hot path."""
+        from ._display import show
+        return show(self, self._get_rgb(), mode)

@@ -8,9 +8,11 @@ allocations, the Python between them).  `GraphedStepper` captures
 
 once into a CUDA graph and replays it: one `cudaGraphLaunch` per env step (for SingleSnake the pair is
 additionally fused into a single kernel, `wurm_single_step_reset`).  The kernels read their
-Philox call counter as `step + *step_dev` (include/wurm_b200.h); the graph bumps the device word
-after every replay, so replays draw fresh random numbers and a graphed rollout is bit-identical to the
-same rollout stepped call by call.
+Philox call counter as `step + *step_dev` (include/wurm_b200.h); the graph bumps a device word private to the
+stepper after every replay (and the env's host counter moves with it), so replays draw fresh random numbers, a
+graphed rollout is bit-identical to the same rollout stepped call by call, and direct `env.step()` / `env.reset()`
+calls may be interleaved with replays without ever reusing a (seed, counter, env) triple.  Construction warms the
+kernels up with real steps but restores the env (state, statistics, counters) afterwards.
 
     stepper = GraphedStepper(env, actions)      # `actions`: device tensor (dict of tensors for MultiSnake)
     for t in range(T):
@@ -57,18 +59,45 @@ class GraphedStepper(object):
                 self.host_actions.copy_(actions)
                 self.host_reward = torch.empty((N, 1), dtype=torch.float32, **pin)
                 self.host_done = torch.empty((N, 1), dtype=torch.bool, **pin)
+        # Warm-up outside the capture (first-launch work: function attributes, allocator pools) runs REAL steps, so the
+        # env's state, statistics, hints and call counter are snapshotted before and restored after: constructing a
+        # GraphedStepper leaves the env exactly as it found it.
+        names = ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards',
+                 '_head_hints', '_stats', '_status') if self.multi else ('envs', 'done', '_hints', '_stats', '_status')
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):                 # first-launch work (function attributes, allocator pools)
-                self._one(capturing=False)
+            if warmup > 0:
+                saved = {n: getattr(env, n).clone() for n in names if hasattr(env, n)}
+                saved_draws = env._draws
+                for _ in range(warmup):
+                    self._one(capturing=False)
+                for n, t in saved.items():
+                    getattr(env, n).copy_(t)
+                env._draws = saved_draws
+                if hasattr(env, '_adopt_state'):
+                    env._adopt_state()              # the restored hints describe the restored state
+                del saved
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.outputs = self._one(capturing=True)
-        # The capture enqueued nothing: the first replay IS the step whose host-side counters were baked in,
-        # and every replay ends by moving the device-side addend on by the ticks one replay consumes.
+        # Call counters.  The captured launches carry the host counter of the capture moment baked in (`_base`) and add
+        # a device word to it -- PRIVATE to this stepper, so direct env.step()/reset() calls (which add the env's own,
+        # always-zero word) are unaffected by replays.  Every replay leaves the device word advanced by the ticks it
+        # consumed and advances the env's host counter by the same amount, so a graphed rollout draws exactly what the
+        # same rollout stepped call by call draws; if direct calls were made in between, the device word is re-aimed
+        # at the env's counter before the next replay (one tiny fill), so the two paths never share a (seed, counter, env).
+        self._ticks = 2 if auto_reset else 1
+        self._addend = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._mirror = 0                            # host mirror of the device word
+        self._base = env._draws + 1                 # the counter the captured step uses
+        env_word, env._draws_dev = env._draws_dev, self._addend
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.outputs = self._one(capturing=True)
+        finally:
+            env._draws_dev = env_word
+        env._draws = self._base - 1                 # the capture enqueued nothing: its host ticks are handed back
         self.obs = self.outputs[0]
 
     def _one(self, capturing):
@@ -98,18 +127,28 @@ class GraphedStepper(object):
                 self.host_reward.copy_(reward, non_blocking=True)
                 self.host_done.copy_(done, non_blocking=True)
         if capturing:
-            env._draws_dev.add_(2 if self.auto_reset else 1)      # one tick per step, one per reset
+            self._addend.add_(self._ticks)          # one tick per step, one per reset
         return out
+
+    def _replay(self):
+        env = self.env
+        want = env._draws + 1 - self._base          # the captured step must run with the env's next counter value
+        if want != self._mirror:                    # direct env.step()/reset() calls were made since the last replay
+            self._addend.fill_(want)
+            self._mirror = want
+        self.graph.replay()
+        self._mirror += self._ticks
+        env._draws += self._ticks
 
     def step(self):
         """One env step (+ reset of finished envs).  Returns the static output tensors of the captured step."""
-        self.graph.replay()
+        self._replay()
         return self.outputs
 
     def step_host(self):
         """host_io=True: one env step fed from `host_actions`; returns once `host_reward` / `host_done` are valid."""
         if not self.host_io:
             raise RuntimeError('GraphedStepper was built without host_io=True')
-        self.graph.replay()
+        self._replay()
         torch.cuda.current_stream(self._dev).synchronize()
         return self.outputs
