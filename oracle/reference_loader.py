@@ -1,8 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference (oscarknagg/wurm) for pinning the oracle.
 
-This module is used only by `oracle/gen_golden.py` and `oracle/validate_vs_reference.py`, in the
-build container where the read-only reference tree exists (default `/root/reference`, override
-with `WURM_REFERENCE_PATH`).  It never runs on the GPU box and nothing in `wurm_b200/` imports it.
+Used by `oracle/gen_golden.py` and `oracle/validate_vs_reference.py` (pinning the oracle), by
+`bench.py --impl reference` / its `cpu_baseline` and `reference_cuda` legs (timing the reference's own
+PyTorch implementation beside the CUDA path) and by `tests/test_reference_suite_gpu.py`; nothing in
+`wurm_b200/` imports it.  The reference tree is looked for at `$WURM_REFERENCE_PATH`, then
+`/root/reference` (the build container's read-only copy), then `baseline/_ref/` in this repo -- a
+git-ignored verbatim copy that `__graft_entry__.build()` makes whenever `/root/reference` is present, so
+that it travels to the GPU box with the snapshot (the reference has no setup.py / pyproject, so
+`pip install --target baseline/_ref` is not possible: the tree is copied instead).
 
 The reference was written for torch 1.1 / python 3.6.  It is imported *unmodified*; what is patched
 is the interpreter around it, restoring the semantics the reference was written against
@@ -30,7 +35,41 @@ import types
 
 import torch
 
-REFERENCE_PATH = os.environ.get('WURM_REFERENCE_PATH', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIPPED_PATH = os.path.join(_REPO, 'baseline', '_ref')
+
+
+def find_reference():
+    """Path of the reference tree, or None."""
+    for cand in (os.environ.get('WURM_REFERENCE_PATH'), '/root/reference', SHIPPED_PATH):
+        if cand and os.path.isfile(os.path.join(cand, 'wurm', 'envs', 'single_snake.py')):
+            return cand
+    return None
+
+
+REFERENCE_PATH = find_reference() or '/root/reference'
+
+
+def ship(dest=SHIPPED_PATH, source='/root/reference'):
+    """Copies the reference's Python tree (wurm/, tests/, experiments/, config.py) verbatim into the git-ignored
+    baseline/_ref/ so that it exists on the GPU box.  No-op when the source is absent (the GPU box) or unchanged."""
+    import filecmp
+    import shutil
+    if not os.path.isdir(source):
+        return os.path.isdir(dest)
+    for name in ('wurm', 'tests', 'experiments'):
+        src, dst = os.path.join(source, name), os.path.join(dest, name)
+        if os.path.isdir(dst):
+            cmp = filecmp.dircmp(src, dst)
+            if not (cmp.left_only or cmp.right_only or cmp.diff_files):
+                continue
+            shutil.rmtree(dst)
+        shutil.copytree(src, dst, ignore=shutil.ignore_patterns('__pycache__', '*.pyc'))
+    os.makedirs(dest, exist_ok=True)
+    for name in ('config.py', 'README.md', 'requirements.txt'):
+        if os.path.isfile(os.path.join(source, name)):
+            shutil.copyfile(os.path.join(source, name), os.path.join(dest, name))
+    return True
 
 TAPE = []          # list of (kind, lineno, payload) appended by the recording proxies
 _loaded = {}
@@ -97,23 +136,25 @@ class _TorchProxy(object):
         return out
 
 
-def load():
-    """Returns a namespace with the reference's SingleSnake, MultiSnake, utils and config modules."""
+def load(record=True, device='cpu'):
+    """Returns a namespace with the reference's SingleSnake, MultiSnake, utils and config modules.
+    `record=False` leaves the reference's random draws unrecorded (the timing runs: the recording proxies clone
+    every draw and walk the interpreter stack).  `device`: what config.DEFAULT_DEVICE is patched to."""
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not os.path.isdir(REFERENCE_PATH):
-        raise RuntimeError(f'reference tree not found at {REFERENCE_PATH} (container-only tooling)')
+        raise RuntimeError(f'reference tree not found at {REFERENCE_PATH} (nor under $WURM_REFERENCE_PATH or baseline/_ref)')
     _install_shims()
     sys.path.insert(0, REFERENCE_PATH)
     import config as ref_config                      # (3) patch before wurm.* is imported
     assert os.path.realpath(ref_config.__file__).startswith(os.path.realpath(REFERENCE_PATH))
-    ref_config.DEFAULT_DEVICE = 'cpu'
+    ref_config.DEFAULT_DEVICE = device
     import wurm.utils as ref_utils
     import wurm.envs.single_snake as ref_single
     import wurm.envs.multi_snake as ref_multi
     import wurm.envs.simple_gridworld as ref_grid
 
-    for mod in (ref_single, ref_multi, ref_grid):
+    for mod in (ref_single, ref_multi, ref_grid) if record else ():
         orig = mod.drop_duplicates
 
         def recording_drop_duplicates(tensor, column, random=True, _orig=orig):

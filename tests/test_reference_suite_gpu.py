@@ -1,0 +1,56 @@
+"""GPU: the reference's OWN test files (tests/test_single_snake_env.py, test_multi_snake_env.py,
+test_simple_gridworld.py of oscarknagg/wurm), UNMODIFIED, run against the drop-in: `wurm.envs`, `wurm.utils` and `config`
+are bound to `wurm_b200.envs`, `wurm_b200.utils`, `wurm_b200.config` (tests/reference_suite.py) and the files are loaded
+from where the reference lies (baseline/_ref on the GPU box, shipped by __graft_entry__.build()).  One pytest case per
+reference test so that each shows up by name."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# every test method of the three reference files (names only; the bodies stay in the reference tree)
+REFERENCE_TESTS = [
+    'test_single_snake_env.py::' + n for n in (
+        'test_multiple_envs', 'test_setup', 'test_reset', 'test_loop_movement', 'test_basic_movement', 'test_eat_food',
+        'test_hit_boundary', 'test_hit_self', 'test_cannot_move_backwards')
+] + [
+    'test_multi_snake_env.py::' + n for n in (
+        'test_random_actions', 'test_random_actions_with_boost', 'test_basic_movement', 'test_edge_collision',
+        'test_self_collision', 'test_other_snake_collision', 'test_eat_food', 'test_create_envs', 'test_reset',
+        'test_agent_observations', 'test_boost_through_food', 'test_boost_leaves_food', 'test_cant_boost_until_size_4',
+        'test_boost_cost', 'test_many_snakes', 'test_boost_rendering', 'test_respawn_mode_any', 'test_partial_observations')
+] + [
+    'test_simple_gridworld.py::' + n for n in ('test_basic_movement', 'test_eat_food', 'test_edge_collision')
+]
+
+
+def run_suite(target):
+    out = subprocess.run([sys.executable, os.path.join(HERE, 'reference_suite.py'), '--target', target],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert lines, f'reference_suite.py produced no result (rc {out.returncode}): {out.stderr[-2000:]}'
+    return json.loads(lines[-1])
+
+
+@pytest.fixture(scope='module')
+def results():
+    res = run_suite('dropin')
+    if 'error' in res:
+        pytest.skip(res['error'])
+    return res
+
+
+@pytest.mark.parametrize('name', REFERENCE_TESTS)
+def test_reference_test_passes_against_the_dropin(results, name):
+    assert name in results, f'{name} was not collected: {sorted(results)}'
+    assert results[name] == 'ok', results[name]
+
+
+def test_no_reference_test_went_unlisted(results):
+    assert sorted(results) == sorted(REFERENCE_TESTS)

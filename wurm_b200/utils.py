@@ -36,6 +36,29 @@ def determine_orientations(envs: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# (orientation, body cells tail..head, food cell) of the reference's four hand-made single-snake fixtures
+_TEST_ENVS = {
+    'up': ([(3, 3), (3, 4), (4, 4), (5, 4)], (6, 6)),
+    'right': ([(3, 3), (3, 4), (4, 4), (4, 5)], (6, 9)),
+    'down': ([(8, 8), (7, 8), (6, 8), (5, 8)], (7, 2)),
+    'left': ([(8, 7), (7, 7), (6, 7), (6, 6)], (1, 2)),
+}
+
+
+def get_test_env(size: int, orientation: str = 'up') -> torch.Tensor:
+    """The reference's predetermined single-snake environments (wurm/utils.py:68-110): a CPU (1,3,size,size) tensor with
+    a length-4 snake and one food cell, which its tests move to the device and assign to `env.envs`."""
+    if orientation not in _TEST_ENVS:
+        raise Exception
+    cells, food_cell = _TEST_ENVS[orientation]
+    env = torch.zeros((1, 3, size, size))
+    for value, (y, x) in enumerate(cells, start=1):
+        env[0, BODY_CHANNEL, y, x] = value
+    env[0, HEAD_CHANNEL, cells[-1][0], cells[-1][1]] = 1
+    env[0, FOOD_CHANNEL, food_cell[0], food_cell[1]] = 1
+    return env
+
+
 def _fused_check(envs: torch.Tensor, skip=None):
     """One launch of wurm_single_check on a contiguous fp32 CUDA batch; returns the 3-int report (one sync)."""
     import ctypes
