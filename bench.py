@@ -123,7 +123,8 @@ class SingleAdapter(object):
         return obs[0].numel()
 
     def host_pool(self):
-        return [p.cpu().pin_memory() for p in self.pool]
+        # what a host-side policy hands over: uint8 actions in pinned memory (one byte per env-step over PCIe)
+        return [p.to(self.torch.uint8).cpu().pin_memory() for p in self.pool]
 
 
 class GridAdapter(SingleAdapter):
@@ -174,7 +175,7 @@ class MultiAdapter(object):
         return sum(o[0].numel() for o in obs.values())
 
     def host_pool(self):
-        return [{a: t.cpu().pin_memory() for a, t in d.items()} for d in self.pool]
+        return [{a: t.to(self.torch.uint8).cpu().pin_memory() for a, t in d.items()} for d in self.pool]
 
 
 def make_adapter(key, dev, seed, rank):
@@ -600,7 +601,8 @@ def measure_config(ctx, key, K, W, min_seconds, exact_steps):
         del gs
         # launch-bound sizes: the copies ride inside the CUDA graph (GraphedStepper(host_io=True)); per step the host
         # writes that step's actions into the graph's pinned input, replays, synchronises and reads the results
-        static = {a: t.clone() for a, t in first.items()} if isinstance(first, dict) else first.clone()
+        first = host_pool[0]
+        static = {a: t.to(dev) for a, t in first.items()} if isinstance(first, dict) else first.to(dev)
         stepper = GraphedStepper(env, static, host_io=True)
 
         def put(src):

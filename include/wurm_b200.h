@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WURM_ABI_VERSION 4
+#define WURM_ABI_VERSION 5
 
 /* return codes */
 #define WURM_OK 0
@@ -83,8 +83,11 @@ int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg);
  * food respawn (_get_food_addition :306-320 + drop_duplicates wurm/utils.py:205-232) and
  * _observe/_get_rgb (:104-195) in ONE launch.
  *   envs     (N,3,S,S) f32, updated in place          actions (N,) int16/int32/int64 (action_bytes
- *   obs      per cfg->obs_mode, may be NULL with       = 2/4/8), sanitised IN PLACE like :222
+ *   obs      per cfg->obs_mode, may be NULL with       = 2/4/8) or uint8 (= 1), sanitised IN PLACE like :222
  *            WURM_OBS_NONE                            reward (N,) f32, done/self_col/edge_col (N,) u8
+ *   packed   (N,) u8 or NULL: the step's per-env results once more as ONE byte (WURM_PACKED_*), for consumers
+ *            on the far side of PCIe -- with uint8 actions a host-side policy moves 2 bytes per env-step
+ *            instead of the 13 of int64 actions + fp32 reward + done flag.
  *   food_cell_replay (N,) int32 or NULL: cell index y*S+x of the respawned food for envs that eat
  *            this step (-1: none); NULL -> uniform over free interior cells from Philox.
  *   hints    (N,4) int16 or NULL (initialise to -1): scratch owned by the caller in which the kernels leave each
@@ -94,11 +97,17 @@ int64_t wurm_single_obs_elems(const WurmSingleCfg* cfg);
  *            hints (the caller edited `envs`) only cost the work they would have saved: a scan of the body channel
  *            and, for even grid sides from 16 up, reading the food and head channels at all.  (Not re-verified:
  *            the absence of a second head or food cell, i.e. states the reference's env_consistency rejects.)  */
+#define WURM_PACKED_DONE 1         /* bit 0: done                                                  */
+#define WURM_PACKED_SELF 2         /* bit 1: info['self_collision']                                */
+#define WURM_PACKED_EDGE 4         /* bit 2: info['edge_collision']                                */
+#define WURM_PACKED_REWARD_SHIFT 3 /* bits 3-4: the reward as an integer 0..3 (:271: 0 or 1 on every
+                                      state the reference's env_consistency accepts)               */
 int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                      const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                      float* obs, float* reward,
                      uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status,
-                     int64_t* stats /* nullable */, int16_t* hints /* nullable */, void* stream);
+                     int64_t* stats /* nullable */, int16_t* hints /* nullable */, uint8_t* packed /* nullable */,
+                     void* stream);
 
 /* Fused fast path: wurm_single_step followed by wurm_single_reset(done) in ONE launch -- the pair the
  * reference's driver issues every iteration (experiments/main.py:212-227).  Outputs are those of the
@@ -110,7 +119,7 @@ int wurm_single_step_reset(const WurmSingleCfg* cfg, float* envs, void* actions,
                            const int32_t* food_cell_replay, const int32_t* spawn_replay, uint64_t seed, uint64_t step,
                            const uint64_t* step_dev, float* obs, float* reward, uint8_t* done, uint8_t* self_col,
                            uint8_t* edge_col, int32_t* status, int64_t* stats /* nullable */, int16_t* hints /* nullable */,
-                           void* stream);
+                           uint8_t* packed /* nullable */, void* stream);
 
 /* Replaces the state update of SingleSnake.reset / _create_envs (single_snake.py:322-337, 344-387):
  * envs whose done_mask byte is non-zero are re-created, all others untouched.
@@ -223,8 +232,8 @@ int64_t wurm_multi_obs_elems(const WurmMultiCfg* cfg); /* floats per (agent, env
 
 /* Replaces MultiSnake.step (multi_snake.py:462-731) incl. _move_heads, _get_food_overlap,
  * _decay_bodies, _check_collisions, _check_edges, _food_from_death, _add_food, _get_env_images and
- * _observe, in ONE launch.  actions: host array of K device pointers, each (E,) of action_bytes
- * integers in [0,8) (agents in dict order). */
+ * _observe, in ONE launch.  actions: host array of K device pointers, each (E,) of action_bytes (8/4/2: int64/int32/
+ * int16 as in the reference; 1: uint8) integers in [0,8) (agents in dict order). */
 int wurm_multi_step(const WurmMultiCfg* cfg, const WurmMultiState* state, const void* const* actions, int action_bytes,
                     const WurmMultiStepDraws* draws, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                     const WurmMultiStepOut* out, int32_t* status, int64_t* stats /* nullable */, void* stream);

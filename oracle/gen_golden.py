@@ -147,8 +147,32 @@ def save(name, trajectories):
     print(path, os.path.getsize(path) // 1024, 'KiB')
 
 
+def baseline_geometries(ref):
+    """The BASELINE.json geometries themselves: C3 (size 36 `default`), the even sizes from 16
+    up on which the CUDA side steps on body-only tiles, C5 (16 snakes, size 64) in both observation modes, and the
+    32-snake maximum.  Kept in files of their own so that the round-1 fixtures stay byte-identical."""
+    trs = [single_trajectory(ref, 10, 36, 'default', 14, seed=800),
+           single_trajectory(ref, 8, 36, 'partial_2', 14, seed=801),
+           single_trajectory(ref, 24, 16, 'partial_2', 20, seed=802),
+           single_trajectory(ref, 12, 24, 'partial_2', 16, seed=803),
+           single_trajectory(ref, 12, 24, 'one_channel', 16, seed=804),
+           single_trajectory(ref, 12, 20, 'default', 21, seed=805, reset_every=7)]
+    save('single_baseline.npz', trs)
+    driver_rules = dict(food_mode='random_rate', food_rate=3e-4, respawn_mode='any', food_on_death_prob=0.33, boost_cost_prob=0.25)
+    trs = [multi_trajectory(ref, 3, 16, 64, 'partial_4', 12, seed=900),
+           multi_trajectory(ref, 2, 16, 64, 'full', 5, seed=901),
+           multi_trajectory(ref, 2, 16, 64, 'partial_4', 10, seed=902, **driver_rules),
+           multi_trajectory(ref, 2, 32, 48, 'partial_3', 8, seed=903),
+           multi_trajectory(ref, 4, 4, 25, 'partial_4', 16, seed=904),
+           multi_trajectory(ref, 4, 4, 25, 'partial_4', 16, seed=905, **driver_rules)]
+    save('multi_baseline.npz', trs)
+
+
 def main():
     ref = rl.load()
+    if '--baseline-only' in sys.argv:
+        baseline_geometries(ref)
+        return
     trs = []
     for i, mode in enumerate(['partial_2', 'partial_3', 'default', 'raw', 'one_channel', 'positions']):
         trs.append(single_trajectory(ref, 24, 9, mode, 24, seed=100 + i))
@@ -187,6 +211,7 @@ def main():
         trs.append(multi_trajectory(ref, 6, 2, 12, 'full', 18, seed=500 + i, **rules))
         trs.append(multi_trajectory(ref, 4, 4, 14, 'partial_3', 18, seed=600 + i, **rules))
     save('multi.npz', trs)
+    baseline_geometries(ref)
 
 
 if __name__ == '__main__':

@@ -90,6 +90,9 @@ def _install_shims():
         if name not in sys.modules:
             _stub(name)
     sys.modules['gym.envs.classic_control'].rendering = sys.modules['gym.envs.classic_control.rendering']
+    # MultiSnake.render constructs a viewer even for mode='rgb_array' (multi_snake.py:229-231): an inert one
+    sys.modules['gym.envs.classic_control.rendering'].SimpleImageViewer = type(
+        'SimpleImageViewer', (), {'imshow': lambda self, img: None, 'isopen': True})
     sys.modules['gym.wrappers.monitoring.video_recorder'].VideoRecorder = type('VideoRecorder', (), {})
     # (2)
     if not hasattr(collections, 'Iterable'):

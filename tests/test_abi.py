@@ -58,7 +58,7 @@ def test_null_pointers_are_rejected():
     assert L.wurm_single_reset(ctypes.byref(c), None, None, None, 0, 0, None, None, None) == _lib.E_INVALID
     assert L.wurm_single_observe(ctypes.byref(c), None, None, None, None) == _lib.E_INVALID
     assert L.wurm_single_step(ctypes.byref(c), None, None, 8, None, 0, 0, None, None, None, None, None, None, None,
-                              None, None, None) == _lib.E_INVALID
+                              None, None, None, None) == _lib.E_INVALID
 
 
 def test_env_refuses_to_run_without_cuda_device():

@@ -15,7 +15,7 @@ from golden_util import (load, assert_same, multi_rules, multi_group, multi_step
 
 pytestmark = pytest.mark.gpu
 
-MULTI = load('multi.npz')
+MULTI = load('multi.npz') + load('multi_baseline.npz')        # round-1 fixtures + the BASELINE.json geometries
 DEV = 'cuda'
 
 

@@ -10,8 +10,8 @@ from oracle import oracle as orc
 from golden_util import (load, assert_same, multi_rules, multi_group, multi_step_draws, multi_state_arrays,
                          STATE_FIELDS)
 
-SINGLE = load('single.npz')
-MULTI = load('multi.npz')
+SINGLE = load('single.npz') + load('single_baseline.npz')      # round-1 fixtures + the BASELINE.json geometries
+MULTI = load('multi.npz') + load('multi_baseline.npz')        # round-1 fixtures + the BASELINE.json geometries
 GRID = load('gridworld.npz')
 
 

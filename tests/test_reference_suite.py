@@ -3,10 +3,7 @@ oracle/reference_loader.py -- the evidence that the shims restore the semantics 
 pass set the drop-in is held to in tests/test_reference_suite_gpu.py).  Skipped where no reference tree exists."""
 import pytest
 
-from test_reference_suite_gpu import REFERENCE_TESTS, run_suite
-
-# needs gym's SimpleImageViewer even for mode='rgb_array' (multi_snake.py:229-231); gym is not installed
-NEEDS_GYM = {'test_multi_snake_env.py::test_boost_rendering'}
+from test_reference_suite_gpu import REFERENCE_TESTS, FAILS_ON_THE_REFERENCE_TOO, run_suite
 
 
 @pytest.fixture(scope='module')
@@ -17,6 +14,13 @@ def results():
     return run_suite('reference')
 
 
-@pytest.mark.parametrize('name', [n for n in REFERENCE_TESTS if n not in NEEDS_GYM])
+@pytest.mark.parametrize('name', [n for n in REFERENCE_TESTS if n not in FAILS_ON_THE_REFERENCE_TOO])
 def test_reference_passes_its_own_test_under_the_shims(results, name):
     assert results.get(name) == 'ok', results.get(name)
+
+
+@pytest.mark.parametrize('name', sorted(FAILS_ON_THE_REFERENCE_TOO))
+def test_known_failure_of_the_reference_against_itself(results, name):
+    """Pins WHY the drop-in is not asked to pass this test: the reference does not pass it either (gym is not installed:
+    reference_loader puts an inert SimpleImageViewer in its place, so the failure is the test's own assertion)."""
+    assert FAILS_ON_THE_REFERENCE_TOO[name] in results.get(name, ''), results.get(name)

@@ -46,9 +46,18 @@ def results():
     return res
 
 
+# test_boost_rendering compares the brightness of one rendered pixel between two steps; it FAILS against the reference
+# itself (tests/test_reference_suite.py pins that: "203.3 not greater than 328.2" -- gym absent, an inert viewer stands
+# in), so the drop-in is held to the same verdict: the same assertion must fail, nothing may crash.
+FAILS_ON_THE_REFERENCE_TOO = {'test_multi_snake_env.py::test_boost_rendering': 'not greater than'}
+
+
 @pytest.mark.parametrize('name', REFERENCE_TESTS)
 def test_reference_test_passes_against_the_dropin(results, name):
     assert name in results, f'{name} was not collected: {sorted(results)}'
+    if name in FAILS_ON_THE_REFERENCE_TOO:
+        assert results[name] == 'ok' or FAILS_ON_THE_REFERENCE_TOO[name] in results[name], results[name]
+        return
     assert results[name] == 'ok', results[name]
 
 

@@ -14,7 +14,7 @@ from golden_util import load, assert_same
 
 pytestmark = pytest.mark.gpu
 
-SINGLE = load('single.npz')
+SINGLE = load('single.npz') + load('single_baseline.npz')      # round-1 fixtures + the BASELINE.json geometries
 DEV = 'cuda'
 
 
@@ -262,29 +262,64 @@ def test_full_size_invariants_and_food_uniformity():
     env.check_status()
 
 
-def test_host_stepper_matches_direct_stepping():
-    """wurm_b200.HostStepper (pinned host buffers, pipelined copies) == stepping with device tensors."""
+
+@pytest.mark.parametrize('compact,adtype', [(True, torch.uint8), (True, torch.long), (False, torch.long)])
+def test_host_stepper_matches_direct_stepping(compact, adtype):
+    """wurm_b200.HostStepper (pinned host buffers, pipelined copies) == stepping with device tensors; with
+    `compact=True` the results cross PCIe as one packed byte per env and are decoded on the host, and uint8 actions
+    upload one byte per env."""
     from wurm_b200 import HostStepper
     N, S, steps = 3000, 9, 12
     a = torch.randint(0, 4, (steps, N), generator=torch.Generator().manual_seed(3))
     direct = make_env(N, S, 'partial_2', seed=77)
     piped = make_env(N, S, 'partial_2', seed=77)
-    stepper = HostStepper(piped, depth=2, return_actions=True)
+    stepper = HostStepper(piped, depth=2, return_actions=True, compact=compact, return_obs=True)
     expect = []
     for t in range(steps):
         acts = a[t].to(DEV)
         obs, reward, done, info = direct.step(acts)
         direct.reset(done, return_observations=False)
-        expect.append((np_(obs), np_(reward), np_(done), np_(acts)))
-    tickets = [stepper.submit(a[t].clone().pin_memory()) for t in range(steps)]      # far ahead of the waits
+        expect.append((np_(obs), np_(reward), np_(done), np_(acts), np_(info['self_collision']), np_(info['edge_collision'])))
+    tickets = [stepper.submit(a[t].to(adtype).pin_memory()) for t in range(steps)]      # far ahead of the waits
     for t, ticket in enumerate(tickets):
         ticket.wait()
         if t >= steps - 3:              # the slots of the last `depth + 1` tickets have not been recycled
+            assert ticket.reward.shape == (N, 1) and ticket.done.shape == (N, 1) and ticket.done.dtype == torch.bool
             assert_same(ticket.reward.numpy(), expect[t][1], f'step {t}: reward')
             assert_same(ticket.done.numpy(), expect[t][2], f'step {t}: done')
-            assert_same(ticket.actions.numpy(), expect[t][3], f'step {t}: sanitised actions')
+            assert_same(ticket.actions.numpy().astype(np.int64), expect[t][3], f'step {t}: sanitised actions')
+            assert_same(ticket.obs_host.numpy(), expect[t][0], f'step {t}: observation on the host')
+            if compact:
+                assert_same(ticket.self_collision.numpy(), expect[t][4], f'step {t}: self collision')
+                assert_same(ticket.edge_collision.numpy(), expect[t][5], f'step {t}: edge collision')
     assert_same(np_(piped.envs), np_(direct.envs), 'final state')
-    assert stepper.h2d_bytes_per_step == N * 8 and stepper.d2h_bytes_per_step == N * 13
+    width = {torch.uint8: 1, torch.long: 8}[adtype]
+    assert stepper.h2d_bytes_per_step == N * width
+    assert stepper.d2h_bytes_per_step == N * ((1 if compact else 5) + width + 300)
+
+
+def test_packed_result_byte_and_uint8_actions():
+    """The packed byte carries done / self / edge / reward of every env, and uint8 actions step (and are sanitised)
+    exactly like int64 ones -- on the tile kernel (size 9) and on the body-only kernel (size 36)."""
+    for N, S, mode in [(777, 9, 'partial_2'), (130, 36, 'default')]:
+        wide = make_env(N, S, mode, seed=5)
+        narrow = make_env(N, S, mode, seed=5)
+        g = torch.Generator().manual_seed(9)
+        packed = torch.empty(N, dtype=torch.uint8, device=DEV)
+        for t in range(25):
+            a64 = torch.randint(0, 4, (N,), generator=g).to(DEV)
+            a8 = a64.to(torch.uint8)
+            o1, r1, d1, i1 = wide.step(a64, auto_reset=True)
+            o2, r2, d2, i2 = narrow.step(a8, auto_reset=True, packed_out=packed)
+            assert_same(np_(o2), np_(o1), f'{S} step {t}: obs')
+            assert_same(np_(a8).astype(np.int64), np_(a64), f'{S} step {t}: sanitised actions')
+            assert_same(np_(narrow.envs), np_(wide.envs), f'{S} step {t}: state')
+            p = np_(packed)
+            assert_same((p & 1) != 0, np_(d1).reshape(-1), 'packed done')
+            assert_same((p & 2) != 0, np_(i1['self_collision']), 'packed self collision')
+            assert_same((p & 4) != 0, np_(i1['edge_collision']), 'packed edge collision')
+            assert_same(((p >> 3) & 3).astype(np.float32), np_(r1).reshape(-1), 'packed reward')
+            assert not (p >> 5).any()
 
 
 def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():

@@ -9,12 +9,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
 ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP = 1, 2, 4, 8
 STATS_SLOTS, STATS_FIELDS = 32, 5
 STAT_NAMES = ['env_steps', 'episodes', 'reward', 'self_collisions', 'edge_collisions']
+PACKED_DONE, PACKED_SELF, PACKED_EDGE, PACKED_REWARD_SHIFT = 1, 2, 4, 3
 OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1, 0, 1, 2, 3, 4
 
 # every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
@@ -102,9 +103,9 @@ def lib():
     L.wurm_single_obs_elems.restype = ctypes.c_int64
     L.wurm_single_obs_elems.argtypes = [cfg]
     L.wurm_single_step.restype = i32
-    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_step.argtypes = [cfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.wurm_single_step_reset.restype = i32
-    L.wurm_single_step_reset.argtypes = [cfg, vp, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.wurm_single_step_reset.argtypes = [cfg, vp, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.wurm_single_reset.restype = i32
     L.wurm_single_reset.argtypes = [cfg, vp, vp, vp, u64, u64, vp, vp, vp]
     L.wurm_single_observe.restype = i32

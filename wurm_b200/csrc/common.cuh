@@ -56,6 +56,31 @@ __device__ __forceinline__ float unit_float(uint32_t r) { return (float)(r >> 8)
 __device__ __forceinline__ uint32_t bounded(uint32_t r, uint32_t n) { return __umulhi(r, n); }
 
 // ---------------------------------------------------------------------------------------------
+// Action vectors: int64 / int32 / int16 as in the reference (single_snake.py:198-200), plus uint8 (action_bytes 1), the
+// width a host-side policy uploads when PCIe bytes matter (8 -> 1 byte per env-step).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long load_action(const void* actions, int action_bytes, size_t e) {
+    if (action_bytes == 8) return ((const long long*)actions)[e];
+    if (action_bytes == 4) return ((const int*)actions)[e];
+    if (action_bytes == 2) return ((const short*)actions)[e];
+    return ((const unsigned char*)actions)[e];
+}
+__device__ __forceinline__ void store_action(void* actions, int action_bytes, size_t e, long long a) {
+    if (action_bytes == 8) ((long long*)actions)[e] = a;
+    else if (action_bytes == 4) ((int*)actions)[e] = (int)a;
+    else if (action_bytes == 2) ((short*)actions)[e] = (short)a;
+    else ((unsigned char*)actions)[e] = (unsigned char)a;
+}
+__host__ __device__ __forceinline__ bool valid_action_bytes(int b) { return b == 1 || b == 2 || b == 4 || b == 8; }
+
+// One byte per env-step carrying everything a host-side consumer needs back (WURM_PACKED_* in the header):
+// bit 0 done, bit 1 self collision, bit 2 edge collision, bits 3-4 the reward as a small integer (0..3).
+__device__ __forceinline__ unsigned char pack_result(bool done, bool self_col, bool edge_col, float reward) {
+    const int r = reward <= 0.0f ? 0 : reward >= 3.0f ? 3 : (int)reward;
+    return (unsigned char)((done ? 1 : 0) | (self_col ? 2 : 0) | (edge_col ? 4 : 0) | (r << 3));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bulk asynchronous copies (TMA 1-D, SASS UBLKCP) between global memory and a CTA's shared tile,
 // completion tracked by an mbarrier (loads) or a bulk async-group (stores).
 // Addresses and byte counts must be multiples of 16.

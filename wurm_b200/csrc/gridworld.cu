@@ -112,9 +112,7 @@ __global__ void __launch_bounds__(256) grid_env_kernel(const GridParams p) {
         hp = group_max<G>(hp, gm);
         hc = group_sum<G>(hc, gm);
         long long a;
-        if (p.action_bytes == 8) a = ((const long long*)p.actions)[e];
-        else if (p.action_bytes == 4) a = ((const int*)p.actions)[e];
-        else a = ((const short*)p.actions)[e];
+        a = load_action(p.actions, p.action_bytes, (size_t)e);
         int np = -1, ny = -1, nx = -1;                                // :149-158 the conv2d translates the agent by -OFF[a]
         if (hp >= 0) {
             const int hy = (int)__umulhi((uint32_t)hp, p.magic_S), hx = hp - hy * S;
@@ -195,9 +193,7 @@ __global__ void __launch_bounds__(WURM_GRID_THREADS, WURM_GRID_MINB) grid_small_
         h[it] = in ? head[q] : 0.0f;
     }
     if (STEP && active) {
-        if (p.action_bytes == 8) a = ((const long long*)p.actions)[e];
-        else if (p.action_bytes == 4) a = ((const int*)p.actions)[e];
-        else a = ((const short*)p.actions)[e];
+        a = load_action(p.actions, p.action_bytes, (size_t)e);
     }
     if (STEP && p.stats) __syncthreads();
     if (STEP && active) {
@@ -358,7 +354,7 @@ extern "C" int wurm_grid_step(const WurmGridCfg* cfg, float* envs, const void* a
     GridParams p = {};
     if (int rc = plan_grid(cfg, &p)) return rc;
     if (!envs || !actions || !reward || !done || !status) return fail(WURM_E_INVALID, "NULL pointer");
-    if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
+    if (!valid_action_bytes(action_bytes)) return fail(WURM_E_INVALID, "action_bytes must be 1, 2, 4 or 8");
     if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
     p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);

@@ -677,9 +677,7 @@ multi_env_kernel(const MultiParams p) {
     float pre_cost = 0.0f;
     if (STEP && kPrefetch && tid < K) {
         const size_t n = (size_t)e * K + tid;
-        if (p.action_bytes == 8) pre_action = ((const long long*)p.actions[tid])[e];
-        else if (p.action_bytes == 4) pre_action = ((const int*)p.actions[tid])[e];
-        else pre_action = ((const short*)p.actions[tid])[e];
+        pre_action = load_action(p.actions[tid], p.action_bytes, (size_t)e);
         pre_orient = p.orientations[n];
         if (p.replay && p.u_cost) pre_cost = p.u_cost[n];
     }
@@ -714,9 +712,7 @@ multi_env_kernel(const MultiParams p) {
             if (valid) {
                 const size_t n = (size_t)e * K + k;
                 if (!kPrefetch) {
-                    if (p.action_bytes == 8) pre_action = ((const long long*)p.actions[k])[e];
-                    else if (p.action_bytes == 4) pre_action = ((const int*)p.actions[k])[e];
-                    else pre_action = ((const short*)p.actions[k])[e];
+                    pre_action = load_action(p.actions[k], p.action_bytes, (size_t)e);
                     pre_orient = p.orientations[n];
                 }
                 const long long a = pre_action;
@@ -1168,7 +1164,7 @@ static int multi_step_impl(const WurmMultiCfg* cfg, const WurmMultiState* state,
     MultiParams p = {};
     if (int rc = plan_multi(cfg, state, &p)) return rc;
     if (!actions || !out || !status) return fail(WURM_E_INVALID, "NULL pointer");
-    if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
+    if (!valid_action_bytes(action_bytes)) return fail(WURM_E_INVALID, "action_bytes must be 1, 2, 4 or 8");
     for (int k = 0; k < p.K; ++k) {
         if (!actions[k]) return fail(WURM_E_INVALID, "NULL action pointer");
         p.actions[k] = actions[k];

@@ -36,6 +36,7 @@ struct SingleParams {
     uint8_t* done;
     uint8_t* self_col;
     uint8_t* edge_col;
+    uint8_t* packed;             // nullable: one result byte per env (pack_result)
     int32_t* status;
     unsigned long long* stats;   // nullable: WURM_STATS_SLOTS x WURM_STATS_FIELDS counters
     uint64_t seed, step;
@@ -252,11 +253,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
 
     // action sanitisation, written back into the caller's tensor (:221-222)
     const long long a = (a_in + ((long long)k == a_in ? 2 : 0)) % 4;
-    if (l == 0 && a != a_in) {
-        if (p.action_bytes == 8) ((long long*)p.actions)[e] = a;
-        else if (p.action_bytes == 4) ((int*)p.actions)[e] = (int)a;
-        else ((short*)p.actions)[e] = (short)a;
-    }
+    if (l == 0 && a != a_in) store_action(p.actions, p.action_bytes, (size_t)e, a);
 
     // head move (:225-233): the conv2d with filter a translates the head channel by -OFF[a];
     // a head that leaves the grid vanishes.
@@ -315,6 +312,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
         p.self_col[e] = sc;
         p.edge_col[e] = !interior;                                   // :290-293 no head in the interior
         p.done[e] = sc || !interior;
+        if (p.packed) p.packed[e] = pack_result(sc || !interior, sc, !interior, ov);
         if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
         if (p.hints) {                                               // for the next call: head cell and size now
             p.hints[4 * (size_t)e] = (short)np;
@@ -460,9 +458,7 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
     int hint_head = -1, hint_sz = -1;
     if (STEP && t < nvalid) {
         const size_t e = (size_t)(env0 + t);
-        if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
-        else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
-        else a_in = ((const short*)p.actions)[e];
+        a_in = load_action(p.actions, p.action_bytes, e);
         if (p.hints) { hint_head = p.hints[4 * e]; hint_sz = p.hints[4 * e + 1]; }
     }
     __syncthreads();                        // mbarrier init / fallback tile visible
@@ -662,9 +658,7 @@ __global__ void __launch_bounds__(WURM_BODY_THREADS, WURM_BODY_MINB) single_body
     long long a_in = 0;
     int hint_head = -1, hint_sz = -1, hint_food = -1;
     if (valid) {
-        if (p.action_bytes == 8) a_in = ((const long long*)p.actions)[e];
-        else if (p.action_bytes == 4) a_in = ((const int*)p.actions)[e];
-        else a_in = ((const short*)p.actions)[e];
+        a_in = load_action(p.actions, p.action_bytes, (size_t)e);
         const short4 h = *reinterpret_cast<const short4*>(p.hints + 4 * (size_t)e);
         hint_head = h.x; hint_sz = h.y; hint_food = h.z;
     }
@@ -711,11 +705,7 @@ __global__ void __launch_bounds__(WURM_BODY_THREADS, WURM_BODY_MINB) single_body
             else if (d == -1 && x2 != 0) k = 3;
         }
         const long long a = (a_in + ((long long)k == a_in ? 2 : 0)) % 4;     // :221-222
-        if (l == 0 && a != a_in) {
-            if (p.action_bytes == 8) ((long long*)p.actions)[e] = a;
-            else if (p.action_bytes == 4) ((int*)p.actions)[e] = (int)a;
-            else ((short*)p.actions)[e] = (short)a;
-        }
+        if (l == 0 && a != a_in) store_action(p.actions, p.action_bytes, (size_t)e, a);
         int ny, nx;
         {
             const int hy = div_S(hp, p.magic_S), hx = hp - hy * S;       // :225-233
@@ -768,6 +758,7 @@ __global__ void __launch_bounds__(WURM_BODY_THREADS, WURM_BODY_MINB) single_body
             p.self_col[e] = sc;
             p.edge_col[e] = !interior;                                   // :290-293
             p.done[e] = sc || !interior;
+            if (p.packed) p.packed[e] = pack_result(sc || !interior, sc, !interior, ov);
             short4 h;
             h.x = (short)np; h.y = (short)((np >= 0) ? (int)(size + ov) : -1); h.z = (short)food_now; h.w = 0;
             *reinterpret_cast<short4*>(p.hints + 4 * (size_t)e) = h;
@@ -1110,13 +1101,14 @@ static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions
                             const int32_t* food_cell_replay, int auto_reset, const int32_t* spawn_replay, uint64_t seed,
                             uint64_t step, const uint64_t* step_dev, float* obs, float* reward, uint8_t* done,
                             uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, int16_t* hints,
-                            void* stream) {
+                            uint8_t* packed, void* stream) {
     SingleParams p = {};
     SingleLaunch L;
     if (int rc = plan_single(cfg, &p, &L)) return rc;
     if (!envs || !actions || !reward || !done || !self_col || !edge_col || !status) return fail(WURM_E_INVALID, "NULL pointer");
-    if (action_bytes != 2 && action_bytes != 4 && action_bytes != 8) return fail(WURM_E_INVALID, "action_bytes must be 2, 4 or 8");
+    if (!valid_action_bytes(action_bytes)) return fail(WURM_E_INVALID, "action_bytes must be 1, 2, 4 or 8");
     if (cfg->obs_mode != WURM_OBS_NONE && !obs) return fail(WURM_E_INVALID, "obs is NULL");
+    p.packed = packed;
     p.envs = envs; p.actions = actions; p.action_bytes = action_bytes; p.food_replay = food_cell_replay;
     p.auto_reset = auto_reset; p.spawn = spawn_replay; p.hints = hints;
     p.seed = seed; p.step = step; p.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
@@ -1133,18 +1125,18 @@ static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions
 extern "C" int wurm_single_step(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                                 const int32_t* food_cell_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                                 float* obs, float* reward, uint8_t* done, uint8_t* self_col, uint8_t* edge_col,
-                                int32_t* status, int64_t* stats, int16_t* hints, void* stream) {
+                                int32_t* status, int64_t* stats, int16_t* hints, uint8_t* packed, void* stream) {
     return single_step_impl(cfg, envs, actions, action_bytes, food_cell_replay, 0, nullptr, seed, step, step_dev, obs, reward,
-                            done, self_col, edge_col, status, stats, hints, stream);
+                            done, self_col, edge_col, status, stats, hints, packed, stream);
 }
 
 extern "C" int wurm_single_step_reset(const WurmSingleCfg* cfg, float* envs, void* actions, int action_bytes,
                                       const int32_t* food_cell_replay, const int32_t* spawn_replay, uint64_t seed,
                                       uint64_t step, const uint64_t* step_dev, float* obs, float* reward, uint8_t* done,
                                       uint8_t* self_col, uint8_t* edge_col, int32_t* status, int64_t* stats, int16_t* hints,
-                                      void* stream) {
+                                      uint8_t* packed, void* stream) {
     return single_step_impl(cfg, envs, actions, action_bytes, food_cell_replay, 1, spawn_replay, seed, step, step_dev, obs,
-                            reward, done, self_col, edge_col, status, stats, hints, stream);
+                            reward, done, self_col, edge_col, status, stats, hints, packed, stream);
 }
 
 extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream) {

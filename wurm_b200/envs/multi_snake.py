@@ -27,7 +27,7 @@ from ..config import DEFAULT_DEVICE, EPS  # noqa: F401
 
 Spec = namedtuple('Spec', ['reward_threshold'])
 
-_ACTION_BYTES = {torch.short: 2, torch.int: 4, torch.long: 8}
+_ACTION_BYTES = {torch.uint8: 1, torch.short: 2, torch.int: 4, torch.long: 8}
 
 
 def _ptr(t):
@@ -305,7 +305,7 @@ class MultiSnake(object):
             raise RuntimeError('Must have a Tensor of actions for each snake')
 
         for agent, act in actions.items():
-            if act.dtype not in (torch.short, torch.int, torch.long):
+            if act.dtype not in _ACTION_BYTES:     # the reference's three integer types, plus uint8 (an extension)
                 raise TypeError('actions Tensor must be an integer type i.e. '
                                 '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
 

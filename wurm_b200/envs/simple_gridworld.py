@@ -19,7 +19,7 @@ from ..config import DEFAULT_DEVICE
 Spec = namedtuple('Spec', ['reward_threshold'])
 
 _OBS_MODES = {'default': _lib.OBS_DEFAULT, 'raw': _lib.OBS_RAW, 'positions': _lib.OBS_POSITIONS}
-_ACTION_BYTES = {torch.short: 2, torch.int: 4, torch.long: 8}
+_ACTION_BYTES = {torch.uint8: 1, torch.short: 2, torch.int: 4, torch.long: 8}
 
 
 def _ptr(t):
@@ -121,7 +121,7 @@ class SimpleGridworld(object):
         return (self._observe('default') * 255).round().short()
 
     def step(self, actions: torch.Tensor, *, food_cell_replay: torch.Tensor = None):
-        if actions.dtype not in (torch.short, torch.int, torch.long):
+        if actions.dtype not in _ACTION_BYTES:     # the reference's three integer types, plus uint8 (an extension)
             raise TypeError('actions Tensor must be an integer type i.e. '
                             '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
 

@@ -26,7 +26,7 @@ Spec = namedtuple('Spec', ['reward_threshold'])
 
 _OBS_MODES = {'default': _lib.OBS_DEFAULT, 'raw': _lib.OBS_RAW, 'one_channel': _lib.OBS_ONE_CHANNEL,
               'positions': _lib.OBS_POSITIONS}
-_ACTION_BYTES = {torch.short: 2, torch.int: 4, torch.long: 8}
+_ACTION_BYTES = {torch.uint8: 1, torch.short: 2, torch.int: 4, torch.long: 8}
 
 
 def _ptr(t):
@@ -207,14 +207,17 @@ class SingleSnake(object):
         return (self._observe('default') * 255).round().short()
 
     def step(self, actions: torch.Tensor, *, food_cell_replay: torch.Tensor = None, auto_reset: bool = False,
-             spawn_replay: torch.Tensor = None, obs_out: torch.Tensor = None):
+             spawn_replay: torch.Tensor = None, obs_out: torch.Tensor = None, packed_out: torch.Tensor = None):
         """reference :197-304.  `auto_reset=True` (an extension) fuses the `reset(done)` the reference's driver
         issues right after every step (experiments/main.py:227) into the same launch: the returned observation,
         reward, done and info are the step's (terminal observation for envs that just ended, as in the
         reference's loop), `envs` holds the re-created environments; bit-identical to the two calls.
         `obs_out` (an extension): a contiguous fp32 CUDA tensor of the observation's shape -- e.g. one time slice of
-        a trajectory buffer or the policy's input buffer -- that the kernel renders into directly."""
-        if actions.dtype not in (torch.short, torch.int, torch.long):
+        a trajectory buffer or the policy's input buffer -- that the kernel renders into directly.
+        `packed_out` (an extension): a (num_envs,) uint8 CUDA tensor that additionally receives the step's results as
+        one byte per env (bit 0 done, bit 1 self collision, bit 2 edge collision, bits 3-4 reward): what `HostStepper`
+        brings back over PCIe.  uint8 actions are accepted besides the reference's three integer types."""
+        if actions.dtype not in _ACTION_BYTES:
             raise TypeError('actions Tensor must be an integer type i.e. '
                             '{torch.ShortTensor, torch.IntTensor, torch.LongTensor}')
 
@@ -243,6 +246,9 @@ class SingleSnake(object):
             food_cell_replay = food_cell_replay.to(device=dev, dtype=torch.int32).contiguous()
         if spawn_replay is not None:
             spawn_replay = spawn_replay.to(device=dev, dtype=torch.int32).contiguous()
+        if packed_out is not None and (packed_out.dtype != torch.uint8 or packed_out.device != dev or
+                                       packed_out.numel() != self.num_envs or not packed_out.is_contiguous()):
+            raise RuntimeError(f'packed_out must be a contiguous uint8 tensor of {self.num_envs} elements on {dev}')
         self._draws += 1
         with torch.cuda.device(dev):
             if auto_reset:
@@ -250,14 +256,14 @@ class SingleSnake(object):
                     ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                     _ptr(spawn_replay), self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
                     _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), _ptr(self._hints),
-                    self._stream()))
+                    _ptr(packed_out), self._stream()))
                 self._draws += 1            # the fused reset consumed the next counter value
             else:
                 _lib.check(self._lib.wurm_single_step(
                     ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                     self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
                     _ptr(self_collision), _ptr(edge_collision), _ptr(self._status), _ptr(self._stats), _ptr(self._hints),
-                    self._stream()))
+                    _ptr(packed_out), self._stream()))
         if host_actions is not None:
             host_actions.copy_(actions, non_blocking=True)      # the sanitised actions (reference :222)
         info = {'self_collision': self_collision, 'edge_collision': edge_collision}
