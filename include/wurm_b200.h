@@ -44,6 +44,7 @@ extern "C" {
                                      (the reference raises a view-shape error: single_snake.py:191) */
 #define WURM_ST_NO_SPAWN 4       /* no available location to create a snake (multi_snake.py:865,947) */
 #define WURM_ST_OVERLAP 8        /* MultiSnake input state with two bodies on one cell at step start */
+#define WURM_ST_NOT_COMPACT 16   /* a state handed to wurm_*_compact that the compact records cannot carry exactly */
 
 /* observation modes (single_snake.py:130-195) */
 #define WURM_OBS_DEFAULT 0     /* (N,3,S,S) rgb/255 */
@@ -195,6 +196,15 @@ typedef struct WurmMultiState {
      * tensors they only cost the scan back.  (What is not re-verified is the absence of a SECOND head of a snake: such
      * states are outside the supported set, as for the reference's own check_consistency.) */
     int16_t* head_hints;
+    /* COMPACT RESIDENT STATE (optional, NULL = the reference's tensors above are the state).  (E, Cp) uint32 records,
+     * Cp = S*S rounded up to a multiple of 4, 16-byte aligned: bits 0-15 body value, bits 16-21 owner snake + 1, bit 29
+     * food, all other bits zero; the snakes' head cells live in head_hints (authoritative in this mode: -1 = no head).
+     * When set, every entry point below reads and writes the records INSTEAD of foods / heads / bodies (which may be
+     * NULL): 16 KB per env at K=16, S=64 instead of 541 KB of fp32 that is 99 % zeros.  wurm_multi_compact /
+     * wurm_multi_expand convert between the two forms; results are bit-identical to the dense path on every state
+     * the records can carry (integral body values < 65536, food / head values 1, one body per cell, heads on their
+     * own bodies), which includes every state the kernels themselves produce from such a state. */
+    uint32_t* cells;
 } WurmMultiState;
 
 /* Replayed random draws of one step, dense per env (NULL struct pointer -> Philox).
@@ -253,6 +263,12 @@ int wurm_multi_step_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, 
 int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* state, const uint8_t* env_done,
                      const WurmMultiResetDraws* draws, uint64_t seed, uint64_t step, const uint64_t* step_dev,
                      int32_t* status, void* stream);
+
+/* fp32 tensors -> compact records (+ head cells); raises WURM_ST_NOT_COMPACT in *status for a state the records cannot
+ * carry.  `state` must hold both forms. */
+int wurm_multi_compact(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* status, void* stream);
+/* compact records (+ head cells) -> the reference's fp32 tensors, dense. */
+int wurm_multi_expand(const WurmMultiCfg* cfg, const WurmMultiState* state, void* stream);
 
 /* Replaces MultiSnake._observe (multi_snake.py:283-334) on the current state. */
 int wurm_multi_observe(const WurmMultiCfg* cfg, const WurmMultiState* state, float* obs, int32_t* status, void* stream);

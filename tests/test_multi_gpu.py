@@ -57,12 +57,16 @@ def check_step_outputs(env, K, obs, rewards, dones, info, expect, tag):
     assert_same(np.stack([np_(obs[f'agent_{k}']) for k in range(K)]), expect['obs'], tag + ': observations')
 
 
+STATES = ['dense', 'compact']     # state='compact': records resident in HBM, fp32 tensors materialised for the comparison
+
+
+@pytest.mark.parametrize('state', STATES)
 @pytest.mark.parametrize('i', range(len(MULTI)))
-def test_golden_replay(i):
+def test_golden_replay(i, state):
     """CUDA path == reference on the recorded trajectories."""
     tr = MULTI[i]
     E, K, S, mode = int(tr['E']), int(tr['K']), int(tr['S']), str(tr['mode'])
-    env = make_env(E, K, S, mode, manual_setup=True, **multi_rules(tr))
+    env = make_env(E, K, S, mode, manual_setup=True, state=state, **multi_rules(tr))
     init = multi_state_arrays(tr, 'init')
     env.agent_colours = torch.from_numpy(init['agent_colours']).to(DEV)
     env._create_all(draws=dict(create=tr['init/create'], respawn=np.full((E, 2), -1, np.int32), colours=init['agent_colours']))
@@ -104,11 +108,12 @@ ROLLOUTS = [
 ]
 
 
+@pytest.mark.parametrize('state', STATES)
 @pytest.mark.parametrize('E,K,S,mode,steps,rules,adtype', ROLLOUTS)
-def test_rollout_matches_oracle(E, K, S, mode, steps, rules, adtype):
+def test_rollout_matches_oracle(E, K, S, mode, steps, rules, adtype, state):
     """Seeded random rollout (actions in [0,8): moves and boosts), Philox draws on both sides."""
     seed = 4321 + E + K + S
-    env = make_env(E, K, S, mode, seed=seed, **rules)
+    env = make_env(E, K, S, mode, seed=seed, state=state, **rules)
     cfg = orc.multi_cfg(E, K, S, **rules)
     st = orc.MultiState(E, K, S)
     assert orc.multi_reset(cfg, st, np.ones(E, np.uint8), None, seed=seed, step=env._draws) == 0
@@ -475,12 +480,13 @@ FUSED_CASES = [
 ]
 
 
+@pytest.mark.parametrize('state', STATES)
 @pytest.mark.parametrize('E,K,S,mode,rules', FUSED_CASES)
-def test_fused_step_reset_equals_step_then_reset(E, K, S, mode, rules):
+def test_fused_step_reset_equals_step_then_reset(E, K, S, mode, rules, state):
     """step(a, auto_reset=True) == step(a); reset(dones['__all__'], return_observations=False): same outputs, same
     state afterwards (re-created envs, recoloured and respawned snakes), same draws."""
     two_calls = make_env(E, K, S, mode, seed=91, **rules)
-    fused = make_env(E, K, S, mode, seed=91, **rules)
+    fused = make_env(E, K, S, mode, seed=91, state=state, **rules)
     fused.agent_colours = two_calls.agent_colours.clone()
     g = torch.Generator().manual_seed(3)
     for t in range(50):
@@ -499,12 +505,13 @@ def test_fused_step_reset_equals_step_then_reset(E, K, S, mode, rules):
     assert fused._draws == two_calls._draws
 
 
+@pytest.mark.parametrize('state', STATES)
 @pytest.mark.parametrize('i', range(len(MULTI)))
-def test_fused_step_reset_golden_replay(i):
+def test_fused_step_reset_golden_replay(i, state):
     """The fused launch against the reference's recorded step+reset trajectories (both tapes replayed)."""
     tr = MULTI[i]
     E, K, S, mode = int(tr['E']), int(tr['K']), int(tr['S']), str(tr['mode'])
-    env = make_env(E, K, S, mode, manual_setup=True, **multi_rules(tr))
+    env = make_env(E, K, S, mode, manual_setup=True, state=state, **multi_rules(tr))
     init = multi_state_arrays(tr, 'init')
     env.agent_colours = torch.from_numpy(init['agent_colours']).to(DEV)
     env._create_all(draws=dict(create=tr['init/create'], respawn=np.full((E, 2), -1, np.int32), colours=init['agent_colours']))
@@ -612,3 +619,41 @@ def test_second_head_written_by_the_caller_is_reported_not_ignored():
     # by hand, for raw-pointer writers
     env.invalidate_hints()
     assert int((env._head_hints != -2).sum()) == 0
+
+
+def test_compact_state_takes_caller_edits_and_refuses_what_it_cannot_carry():
+    """state='compact': the fp32 tensors are materialised on access; in-place writes and replaced tensors are folded back
+    into the records before the next call (the reference's tests build their fixtures exactly like this), and a state the
+    records cannot carry exactly raises instead of being rounded."""
+    E, K, S = 8, 2, 12
+    twin = make_env(E, K, S, 'full', manual_setup=True, seed=3)
+    env = make_env(E, K, S, 'full', manual_setup=True, seed=3, state='compact')
+    env.agent_colours = twin.agent_colours.clone()
+    for e_ in (twin, env):
+        for i in range(E):
+            e_.heads[2 * i, 0, 5, 5] = 1
+            e_.bodies[2 * i, 0, 5, 5] = 4; e_.bodies[2 * i, 0, 4, 5] = 3; e_.bodies[2 * i, 0, 4, 4] = 2; e_.bodies[2 * i, 0, 4, 3] = 1
+            e_.heads[2 * i + 1, 0, 8, 7] = 1
+            e_.bodies[2 * i + 1, 0, 8, 7] = 4; e_.bodies[2 * i + 1, 0, 8, 8] = 3; e_.bodies[2 * i + 1, 0, 8, 9] = 2; e_.bodies[2 * i + 1, 0, 9, 9] = 1
+        e_.foods[:, 0, 1, 1] = 1
+        e_.orientations = torch.tensor([1, 3] * E, device=DEV)
+    g = torch.Generator().manual_seed(1)
+    for t in range(12):
+        acts = torch.randint(0, 8, (K, E), generator=g).to(DEV)
+        o1, r1, d1, _ = twin.step({f'agent_{k}': acts[k] for k in range(K)}, auto_reset=True)
+        o2, r2, d2, _ = env.step({f'agent_{k}': acts[k] for k in range(K)}, auto_reset=True)
+        for k in range(K):
+            assert_same(np_(o2[f'agent_{k}']), np_(o1[f'agent_{k}']), f'step {t}: obs {k}')
+        assert_same(stack_dict(r2, K), stack_dict(r1, K), f'step {t}: rewards')
+        check_state(env, env_state(twin), f'step {t}')
+        if t == 5:                                       # replace a tensor wholesale, and write into another
+            new_foods = twin.foods.clone(); new_foods[:, 0, 6, 6] = 1
+            twin.foods = new_foods.clone(); env.foods = new_foods
+    env.check_consistency()
+    assert env._dense is not None                        # materialised by the checks above ...
+    acts = torch.zeros((K, E), dtype=torch.long, device=DEV)
+    env.step({f'agent_{k}': acts[k] for k in range(K)})
+    assert env._dense is None                            # ... and dropped by the state-changing call
+    env.bodies[0, 0, 2, 2] = 0.5                         # a non-integral body value: not a record
+    with pytest.raises(RuntimeError, match='compact'):
+        env.step({f'agent_{k}': acts[k] for k in range(K)})

@@ -482,7 +482,7 @@ def test_graphed_stepper_with_host_io():
         plain.reset(done2, return_observations=False)
         assert_same(np_(graphed.envs), np_(plain.envs), f'step {t}: state after reset')
     with pytest.raises(RuntimeError):
-        GraphedStepper(plain, a0, warmup=1).step_host()
+        GraphedStepper(plain, static_actions.clone(), warmup=1).step_host()
 
 
 @pytest.mark.parametrize('S', [9, 16])

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
 ABI_VERSION = 5
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
-ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP = 1, 2, 4, 8
+ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP, ST_NOT_COMPACT = 1, 2, 4, 8, 16
 STATS_SLOTS, STATS_FIELDS = 32, 5
 STAT_NAMES = ['env_steps', 'episodes', 'reward', 'self_collisions', 'edge_collisions']
 PACKED_DONE, PACKED_SELF, PACKED_EDGE, PACKED_REWARD_SHIFT = 1, 2, 4, 3
@@ -22,7 +22,7 @@ OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1
 SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_step_reset',
            'wurm_single_reset',
            'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_step_reset', 'wurm_multi_reset', 'wurm_multi_observe',
-           'wurm_multi_env_images', 'wurm_single_check', 'wurm_multi_check', 'wurm_grid_step', 'wurm_grid_reset',
+           'wurm_multi_env_images', 'wurm_multi_compact', 'wurm_multi_expand', 'wurm_single_check', 'wurm_multi_check', 'wurm_grid_step', 'wurm_grid_reset',
            'wurm_grid_observe', 'wurm_a2c_returns']
 CHECK_REPORT = 4
 # WURM_CHK_* bits in the order the reference tests them, with the reference's messages
@@ -62,7 +62,7 @@ class WurmMultiCfg(ctypes.Structure):
 
 class WurmMultiState(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step',
-                                               'agent_colours', 'head_hints')]
+                                               'agent_colours', 'head_hints', 'cells')]
 
 
 class WurmMultiStepDraws(ctypes.Structure):
@@ -126,6 +126,10 @@ def lib():
     L.wurm_multi_observe.argtypes = [mcfg, mst, vp, vp, vp]
     L.wurm_multi_env_images.restype = i32
     L.wurm_multi_env_images.argtypes = [mcfg, mst, vp, vp, vp]
+    L.wurm_multi_compact.restype = i32
+    L.wurm_multi_compact.argtypes = [mcfg, mst, vp, vp]
+    L.wurm_multi_expand.restype = i32
+    L.wurm_multi_expand.argtypes = [mcfg, mst, vp]
     gcfg = ctypes.POINTER(WurmGridCfg)
     L.wurm_grid_step.restype = i32
     L.wurm_grid_step.argtypes = [gcfg, vp, vp, i32, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]

@@ -49,6 +49,8 @@ struct MultiParams {
     uint8_t* boost_this_step;
     short* colours;
     short* head_hints;    // (E*K) nullable: head cell left by the previous call (-1 dead, -2 unknown), verified before use
+    uint32_t* cells;      // compact resident state (E, Cp) or NULL: see WurmMultiState.cells; head_hints is then authoritative
+    int Cp;               // row pitch of `cells`: C rounded up to a multiple of 4 (rows stay 16-byte aligned)
     // step inputs
     const void* actions[kMaxK];
     int action_bytes;
@@ -323,6 +325,51 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
     }
 }
 
+// COMPACT RESIDENT STATE.  Between calls the env may live in HBM in the kernel's own form instead of the reference's
+// fp32 tensors: one 32-bit record per cell -- bits 0-15 body value, 16-21 owner + 1, bit 29 food, everything else zero
+// -- plus each snake's head cell in `head_hints` (authoritative in this mode: -1 = none).  16 KB per env at K=16, S=64
+// instead of the 278 KB of fp32 zeros the dense path streams.  Loading is a copy into shared memory that queues the
+// ~1 % non-zero cells on the live list as it goes; the per-call bits (owner / food when loaded, listed) are derived here.
+__device__ __forceinline__ uint32_t hbm_record(uint32_t rec) { return rec & (kLive | kFood); }
+
+template <bool CHECK = false>
+__device__ __forceinline__ void load_env_compact(const MultiParams& p, const MultiSmem& s, int e) {
+    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t* g = p.cells + (size_t)e * p.Cp;
+    if (tid < K) {
+        const int h = p.head_hints[(size_t)e * K + tid];
+        s.hp[tid] = (h >= 0 && h < C) ? h : -1;
+        s.hcnt[tid] = (h >= 0 && h < C) ? 1 : 0;
+    }
+    auto take = [&](int q, uint32_t v) {
+        uint32_t rec = 0u;
+        if (v != 0u) {
+            rec = hbm_record(v) | kListed;
+            rec |= ((rec >> 16) & 63u) << 22;                        // owner when loaded
+            if (rec & kFood) { rec |= kFood0; atomicAdd(&s.misc[0], 1); }
+            if (rec & kLive) {
+                const int k = rec_owner(rec), val = rec_value(rec);
+                atomicMax(&s.size[k], val);
+                if (CHECK) atomicAdd(&s.sum[k], val);
+            }
+            list_push(s, q);
+        }
+        return rec;
+    };
+    const uint4* g4 = reinterpret_cast<const uint4*>(g);
+    uint4* c4 = reinterpret_cast<uint4*>(s.cell);
+    const int nvec = C >> 2;
+    for (int j = tid; j < nvec; j += nthr) {
+        uint4 v;
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g4 + j));
+        if ((v.x | v.y | v.z | v.w) != 0u) {
+            v.x = take(4 * j, v.x); v.y = take(4 * j + 1, v.y); v.z = take(4 * j + 2, v.z); v.w = take(4 * j + 3, v.w);
+        }
+        c4[j] = v;
+    }
+    if (tid < (C & 3)) { const int q = (C & ~3) + tid; s.cell[q] = take(q, g[q]); }
+}
+
 // multi_snake.py:197-206: int16 colour of a body (or, is_head, head) cell of snake o
 __device__ __forceinline__ void snake_rgb(const MultiSmem& s, int o, bool is_head, int rgb[3]) {
     float inten = 1.0f * 1.0f / 3.0f + (is_head ? 1.0f : 0.0f) * 1.0f / 3.0f;                  // :197
@@ -579,18 +626,26 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
 // caller has zeroed (or is zeroing, to the same values) whatever else the tensors held.
 __device__ __forceinline__ void write_recreated(const MultiParams& p, int e, const ResetScratch& sc, int fcell) {
     const int C = p.C, K = p.K, tid = threadIdx.x;
-    if (tid == 0 && fcell >= 0) p.foods[(size_t)e * C + fcell] = 1.0f;
+    uint32_t* gc = p.cells ? p.cells + (size_t)e * p.Cp : nullptr;  // compact resident state: records instead of floats
+    if (tid == 0 && fcell >= 0) {
+        if (gc) gc[fcell] = kFood;
+        else p.foods[(size_t)e * C + fcell] = 1.0f;
+    }
     if (tid < K) {
         const size_t n = (size_t)e * K + tid;
         if (sc.snake_cell[tid] >= 0) {
             int tl, hd;
             snake_cells(p, sc.snake_cell[tid], sc.snake_dir[tid], tl, hd);
-            p.heads[n * C + hd] = 1.0f;
-            p.bodies[n * C + hd] = 3.0f; p.bodies[n * C + sc.snake_cell[tid]] = 2.0f; p.bodies[n * C + tl] = 1.0f;
+            if (gc) {
+                gc[hd] = make_rec(tid, 3); gc[sc.snake_cell[tid]] = make_rec(tid, 2); gc[tl] = make_rec(tid, 1);
+            } else {
+                p.heads[n * C + hd] = 1.0f;
+                p.bodies[n * C + hd] = 3.0f; p.bodies[n * C + sc.snake_cell[tid]] = 2.0f; p.bodies[n * C + tl] = 1.0f;
+            }
             p.orientations[n] = sc.snake_dir[tid];                    // :793
             if (p.head_hints) p.head_hints[n] = (short)hd;
         } else if (p.head_hints) {
-            p.head_hints[n] = -2;
+            p.head_hints[n] = gc ? -1 : -2;
         }
         p.dones[n] = 0;                                               // :798
     }
@@ -620,8 +675,13 @@ __device__ __forceinline__ void write_respawned(const MultiParams& p, int e, int
     if (cell >= 0) {
         int tl, hd;
         snake_cells(p, cell, d, tl, hd);
-        p.heads[n * p.C + hd] = 1.0f;
-        p.bodies[n * p.C + hd] = 3.0f; p.bodies[n * p.C + cell] = 2.0f; p.bodies[n * p.C + tl] = 1.0f;
+        if (p.cells) {                                                // compact resident state
+            uint32_t* gc = p.cells + (size_t)e * p.Cp;
+            gc[hd] = make_rec(k, 3); gc[cell] = make_rec(k, 2); gc[tl] = make_rec(k, 1);
+        } else {
+            p.heads[n * p.C + hd] = 1.0f;
+            p.bodies[n * p.C + hd] = 3.0f; p.bodies[n * p.C + cell] = 2.0f; p.bodies[n * p.C + tl] = 1.0f;
+        }
     }
     p.orientations[n] = d;                                            // :828 even when the spawn failed
     p.dones[n] = cell < 0;                                            // :829
@@ -651,7 +711,7 @@ __device__ __forceinline__ void recolour(const MultiParams& p, int e, int k, uin
 // lane-per-snake logic runs and 32 envs stay resident per SM (K=4, S=25: 0.466 ms per launch against 0.489 /
 // 0.533 ms with 64 / 128 threads; staging the raw env through shared memory with TMA was tried and lost to the
 // occupancy it costs); 256 threads for S=64, where streaming 540 KB per env wants the loads of many threads in flight.
-template <bool STEP, int THREADS>
+template <bool STEP, int THREADS, bool COMPACT = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? 12 : THREADS == 64 ? 20 : 32)
 multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -667,7 +727,7 @@ multi_env_kernel(const MultiParams p) {
     // dependent look-up into the heads tensor can be issued ahead of the scans
     int hint_h = -1;
     bool hint_dead = false;
-    const bool use_hints = p.head_hints != nullptr;
+    const bool use_hints = !COMPACT && p.head_hints != nullptr;
     if (use_hints && tid < K) {
         hint_h = p.head_hints[(size_t)e * K + tid];
         hint_dead = p.dones[(size_t)e * K + tid] != 0;
@@ -681,7 +741,7 @@ multi_env_kernel(const MultiParams p) {
         pre_orient = p.orientations[n];
         if (p.replay && p.u_cost) pre_cost = p.u_cost[n];
     }
-    {
+    if (!COMPACT) {                                                   // (the compact load writes every record itself)
         uint4* c4 = reinterpret_cast<uint4*>(s.cell);                 // 16-byte aligned: the start of the dynamic shared memory
         for (int j = tid; j < (C >> 2); j += nthr) c4[j] = make_uint4(0u, 0u, 0u, 0u);
         if (tid < (C & 3)) s.cell[(C & ~3) + tid] = 0u;
@@ -697,7 +757,8 @@ multi_env_kernel(const MultiParams p) {
     float hint_val = 0.0f;
     if (use_hints && tid < K && hint_h >= 0 && hint_h < C) hint_val = p.heads[((size_t)e * K + tid) * C + hint_h];
     __syncthreads();
-    load_env<false, (THREADS >= 256 ? 8 : 4)>(p, s, e, use_hints, hint_h, hint_val, hint_dead);
+    if (COMPACT) load_env_compact<false>(p, s, e);
+    else load_env<false, (THREADS >= 256 ? 8 : 4)>(p, s, e, use_hints, hint_h, hint_val, hint_dead);
     __syncthreads();
 
     if (STEP) {
@@ -900,7 +961,16 @@ multi_env_kernel(const MultiParams p) {
         __syncthreads();
 
         // ---- write the new state back ----
-        if (s.misc[3]) {
+        if (COMPACT) {
+            // compact resident state: the records that changed go back as records (4 bytes each); the head cells
+            // already went into head_hints with the per-agent outputs
+            uint32_t* gc = p.cells + (size_t)e * p.Cp;
+            for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {
+                const int q = s.list[n];
+                const uint32_t rec = s.cell[q];
+                if ((rec & kDirty) || (((rec >> 29) ^ (rec >> 30)) & 1u)) gc[q] = hbm_record(rec);
+            }
+        } else if (s.misc[3]) {
             // non-canonical input: expand the whole compact form into the reference's tensors
             store_floats(p.foods + (size_t)e * C, C, [&](int i) { return (s.cell[i] & kFood) ? 1.0f : 0.0f; });
             store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
@@ -953,7 +1023,10 @@ multi_env_kernel(const MultiParams p) {
             const int fcell = decide_recreate(p, e, ctr, sc);
             // all snakes are dead, so their tensors are already zero (the step deleted them); only food is left
             for (int q = tid; q < C; q += nthr)
-                if (s.cell[q] & kFood) p.foods[(size_t)e * C + q] = 0.0f;
+                if (s.cell[q] & kFood) {
+                    if (COMPACT) p.cells[(size_t)e * p.Cp + q] = 0u;
+                    else p.foods[(size_t)e * C + q] = 0.0f;
+                }
             __syncthreads();
             write_recreated(p, e, sc, fcell);
         } else if (first_dead >= 0) {
@@ -984,7 +1057,8 @@ __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, i
     __syncthreads();
     MultiParams q = p;
     q.status = &s.misc[4];                      // overlap / multi-head of THIS env, not the env object's status word
-    load_env<true>(q, s, e);
+    if (p.cells) load_env_compact<true>(q, s, e);
+    else load_env<true>(q, s, e);
     __syncthreads();
     if (tid < K) {
         const int k = tid;
@@ -1007,6 +1081,53 @@ __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, i
     }
 }
 
+// Conversions between the reference's fp32 tensors and the compact resident state (see load_env_compact), one CTA per
+// env.  TO_COMPACT folds the tensors exactly as a dense step would and stores every record; a state the records cannot
+// carry exactly (food / head values other than 1, non-integral or oversized body values, two bodies on one cell, a
+// head that does not sit on its own body, two heads of one snake) raises WURM_ST_NOT_COMPACT.  !TO_COMPACT expands the
+// records into the three tensors with dense 128-bit stores.
+template <bool TO_COMPACT>
+__global__ void __launch_bounds__(256) multi_convert_kernel(const MultiParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const MultiSmem s = carve(smem_raw, p.C, p.K);
+    const int C = p.C, K = p.K, e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    if (TO_COMPACT)
+        for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
+    if (tid < K) { s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.sum[tid] = 0; s.done[tid] = 0; }
+    if (tid < 8) s.misc[tid] = 0;
+    __syncthreads();
+    if (TO_COMPACT) {
+        load_env<false>(p, s, e);                                     // no hints: the heads tensor is scanned
+        __syncthreads();
+        uint32_t* gc = p.cells + (size_t)e * p.Cp;
+        for (int q = tid; q < p.Cp; q += nthr) gc[q] = q < C ? hbm_record(s.cell[q]) : 0u;
+        if (tid < K) {
+            const int hp = s.hp[tid], hc = s.hcnt[tid];
+            bool bad = hc > 1;
+            if (hc == 1) {
+                const uint32_t rec = s.cell[hp];
+                bad = !(rec_body(rec) && rec_owner(rec) == tid);      // a head must sit on its own body to be a record
+            }
+            p.head_hints[(size_t)e * K + tid] = (short)((hc == 1 && !bad) ? hp : -1);
+            if (bad) atomicOr(p.status, WURM_ST_NOT_COMPACT);
+        }
+        if (tid == 0 && s.misc[3]) atomicOr(p.status, WURM_ST_NOT_COMPACT);
+    } else {
+        load_env_compact<false>(p, s, e);
+        __syncthreads();
+        store_floats(p.foods + (size_t)e * C, C, [&](int i) { return (s.cell[i] & kFood) ? 1.0f : 0.0f; });
+        store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv_C(i, C, p.magic_C);
+            return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
+        });
+        store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv_C(i, C, p.magic_C);
+            const uint32_t rec = s.cell[i - kk * C];
+            return (rec_body(rec) && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
+        });
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // reset (multi_snake.py:771-831)
 // ---------------------------------------------------------------------------------------------
@@ -1022,6 +1143,27 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         if (p.dones[(size_t)e * K + k]) { first_dead = k; ++ndead; }
     if (!recreate && (ndead == 0 || !p.respawn_any)) return;          // nothing to do for this env
 
+    if (p.cells) {                                                    // compact resident state: the same on records
+        uint32_t* gc = p.cells + (size_t)e * p.Cp;
+        if (recreate) {
+            const int fcell = decide_recreate(p, e, ctr, sc);
+            for (int q = tid; q < C; q += nthr)
+                if (gc[q] != 0u) gc[q] = 0u;
+            __syncthreads();
+            write_recreated(p, e, sc, fcell);
+            return;
+        }
+        for (int q = tid; q < C; q += nthr) {
+            const uint32_t rec = gc[q];
+            sc.occ[q] = rec != 0u;                                    // (leftovers count as occupied, as in the dense path)
+            if (rec_body(rec) && rec_owner(rec) == first_dead) gc[q] = rec & ~kLive;            // leftovers of the dead snake
+        }
+        __syncthreads();
+        int d;
+        const int cell = decide_respawn(p, e, ctr, sc, d);
+        if (tid == 0) write_respawned(p, e, first_dead, cell, d);
+        return;
+    }
     float* gfood = p.foods + (size_t)e * C;
     float* ghead = p.heads + (size_t)e * K * C;
     float* gbody = p.bodies + (size_t)e * K * C;
@@ -1104,12 +1246,18 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     if (cfg->obs_mode < WURM_MOBS_NONE || cfg->obs_mode > WURM_MOBS_PARTIAL) return fail(WURM_E_INVALID, "bad obs_mode");
     if (cfg->obs_mode == WURM_MOBS_PARTIAL && (cfg->obs_n < 0 || cfg->obs_n > 127)) return fail(WURM_E_INVALID, "bad obs_n");
     if (cfg->food_mode != 0 && cfg->food_mode != 1) return fail(WURM_E_INVALID, "bad food_mode");
-    if (!st->foods || !st->heads || !st->bodies || !st->dones || !st->orientations || !st->boost_this_step || !st->agent_colours)
+    if (!st->dones || !st->orientations || !st->boost_this_step || !st->agent_colours) return fail(WURM_E_INVALID, "NULL state pointer");
+    if (st->cells) {
+        if (!st->head_hints) return fail(WURM_E_INVALID, "compact state needs head_hints (the snakes' head cells)");
+        if (reinterpret_cast<uintptr_t>(st->cells) & 15u) return fail(WURM_E_INVALID, "cells must be 16-byte aligned");
+    } else if (!st->foods || !st->heads || !st->bodies) {
         return fail(WURM_E_INVALID, "NULL state pointer");
+    }
     p->foods = st->foods; p->heads = st->heads; p->bodies = st->bodies; p->dones = st->dones;
     p->orientations = reinterpret_cast<long long*>(st->orientations); p->boost_this_step = st->boost_this_step;
     p->colours = st->agent_colours;
     p->head_hints = (cfg->size * cfg->size <= 32767) ? st->head_hints : nullptr;
+    p->cells = st->cells; p->Cp = (cfg->size * cfg->size + 3) & ~3;
     p->E = cfg->num_envs; p->K = cfg->num_snakes; p->S = cfg->size; p->C = cfg->size * cfg->size;
     p->boost = cfg->boost; p->food_on_death = cfg->food_on_death; p->food_mode = cfg->food_mode;
     p->respawn_any = cfg->respawn_any; p->colour_random = cfg->colour_random;
@@ -1122,9 +1270,9 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     return WURM_OK;
 }
 
-template <bool STEP, int THREADS>
+template <bool STEP, int THREADS, bool COMPACT = false>
 static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
-    auto kern = multi_env_kernel<STEP, THREADS>;
+    auto kern = multi_env_kernel<STEP, THREADS, COMPACT>;
     const size_t smem = multi_smem_bytes(p.C, p.K);
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
     static SmemOptIn opt_in;                           // per instantiation, per device inside
@@ -1139,6 +1287,18 @@ static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
     int threads = 32;
     while (threads < 256 && p.C > 24 * threads) threads <<= 1;
     if (const char* v = getenv("WURM_MULTI_THREADS")) threads = atoi(v);       // tuning override: 32, 64, 128, 256
+    if (p.cells) {
+        // compact resident state: nothing to stream, so the CTA is sized by the per-cell passes alone
+        threads = 32;
+        while (threads < 256 && p.C > 48 * threads) threads <<= 1;
+        if (const char* v = getenv("WURM_MULTI_COMPACT_THREADS")) threads = atoi(v);
+        switch (threads) {
+            case 32: return launch_multi_env_t<STEP, 32, true>(p, stream);
+            case 64: return launch_multi_env_t<STEP, 64, true>(p, stream);
+            case 128: return launch_multi_env_t<STEP, 128, true>(p, stream);
+            default: return launch_multi_env_t<STEP, 256, true>(p, stream);
+        }
+    }
     switch (threads) {
         case 32: return launch_multi_env_t<STEP, 32>(p, stream);
         case 64: return launch_multi_env_t<STEP, 64>(p, stream);
@@ -1249,6 +1409,30 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
     const size_t smem = reset_scratch_bytes(p.C) + 16;
     multi_reset_kernel<<<(p.E + 31) / 32, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
+}
+
+static int multi_convert(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* status, void* stream, bool to_compact) {
+    MultiParams p = {};
+    if (int rc = plan_multi(cfg, state, &p)) return rc;
+    if (!state->cells || !state->foods || !state->heads || !state->bodies) return fail(WURM_E_INVALID, "conversion needs both forms of the state");
+    if (to_compact && !status) return fail(WURM_E_INVALID, "NULL pointer");
+    p.status = status;
+    const size_t smem = multi_smem_bytes(p.C, p.K);
+    if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
+    static SmemOptIn opt_in[2];
+    const void* kern = to_compact ? reinterpret_cast<const void*>(multi_convert_kernel<true>) : reinterpret_cast<const void*>(multi_convert_kernel<false>);
+    if (int rc = ensure_dynamic_smem(kern, &opt_in[to_compact ? 1 : 0], (int)smem, false, "cudaFuncSetAttribute(multi_convert_kernel)")) return rc;
+    if (to_compact) multi_convert_kernel<true><<<p.E, 256, smem, (cudaStream_t)stream>>>(p);
+    else multi_convert_kernel<false><<<p.E, 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("multi_convert_kernel");
+}
+
+extern "C" int wurm_multi_compact(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* status, void* stream) {
+    return multi_convert(cfg, state, status, stream, true);
+}
+
+extern "C" int wurm_multi_expand(const WurmMultiCfg* cfg, const WurmMultiState* state, void* stream) {
+    return multi_convert(cfg, state, nullptr, stream, false);
 }
 
 extern "C" int wurm_multi_check(const WurmMultiCfg* cfg, const WurmMultiState* state, int32_t* report, void* stream) {

@@ -64,7 +64,8 @@ class MultiSnake(object):
                  verbose: int = 0,
                  render_args: dict = None,
                  agent_colours: str = 'random',
-                 seed: int = None):
+                 seed: int = None,
+                 state: str = 'dense'):
         self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
         self.num_envs = num_envs
         self.num_snakes = num_snakes
@@ -80,6 +81,12 @@ class MultiSnake(object):
                                "the CPU implementation of this path is the reference itself")
         if dtype != torch.float:
             raise NotImplementedError('wurm_b200.MultiSnake keeps the state in float32 only')
+        if state not in ('dense', 'compact'):
+            raise ValueError("state must be 'dense' (the reference's fp32 tensors are the state) or 'compact'")
+        # state='compact' (an extension): between calls the env lives in HBM as one 32-bit record per cell (include/
+        # wurm_b200.h, WurmMultiState.cells) instead of the reference's (1+2K) fp32 grids that are ~99 % zeros; `foods`,
+        # `heads` and `bodies` are then materialised on attribute access and folded back in if the caller wrote to them.
+        self._compact = state == 'compact'
         if num_snakes > _lib.MULTI_MAX_SNAKES:
             raise NotImplementedError(f'at most {_lib.MULTI_MAX_SNAKES} snakes per environment')
         if observation_mode.startswith('partial_'):
@@ -104,10 +111,18 @@ class MultiSnake(object):
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_FIELDS), dtype=torch.int64, device=self.device)
 
         E, K, S = num_envs, num_snakes, size
-        self.foods = torch.zeros((E, 1, S, S), dtype=self.dtype, device=self.device)
-        self.heads = torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device)
-        self.bodies = torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device)
         self.dones = torch.zeros(E * K, dtype=torch.bool, device=self.device)
+        self._dev = self.dones.device
+        self._dense_key = None
+        if self._compact:
+            self._cells = torch.zeros((E, (S * S + 3) & ~3), dtype=torch.int32, device=self.device)
+            self._head_hints.fill_(-1)               # authoritative in this mode: no heads yet
+            self._dense = None                       # fp32 tensors exist only while a caller looks at them
+        else:
+            self._cells = None
+            self._dense = {'foods': torch.zeros((E, 1, S, S), dtype=self.dtype, device=self.device),
+                           'heads': torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device),
+                           'bodies': torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device)}
         self.boost_this_step = torch.zeros(E * K, dtype=torch.bool, device=self.device)
         self.rewards = torch.zeros(E * K, dtype=torch.float, device=self.device)
         self.env_lifetimes = torch.zeros(E, dtype=torch.long, device=self.device)
@@ -199,11 +214,70 @@ class MultiSnake(object):
             raise RuntimeError(f'{name} has shape {tuple(t.shape)}, expected {shape}')
         return t
 
+    # ---- the reference's state tensors: plain tensors in dense mode, materialised on access in compact mode ----
+    def _get_dense(self, name):
+        if self._dense is None:
+            self._materialise()
+        return self._dense[name]
+
+    def _set_dense(self, name, value):
+        if self._dense is None:
+            self._materialise()
+        self._dense[name] = value
+
+    foods = property(lambda self: self._get_dense('foods'), lambda self, v: self._set_dense('foods', v))
+    heads = property(lambda self: self._get_dense('heads'), lambda self, v: self._set_dense('heads', v))
+    bodies = property(lambda self: self._get_dense('bodies'), lambda self, v: self._set_dense('bodies', v))
+
+    def _dense_identity(self):
+        return tuple((t.data_ptr(), t._version) for t in self._dense.values())
+
+    def _compact_struct(self, dense):
+        return _lib.WurmMultiState(
+            _ptr(dense['foods']) if dense else None, _ptr(dense['heads']) if dense else None,
+            _ptr(dense['bodies']) if dense else None, _ptr(self.dones), _ptr(self.orientations), _ptr(self.boost_this_step),
+            _ptr(self.agent_colours), _ptr(self._head_hints), _ptr(self._cells))
+
+    def _materialise(self):
+        """compact records -> the reference's three fp32 tensors (one launch), remembered until the next state-changing
+        call so that repeated reads cost nothing."""
+        E, K, S = self.num_envs, self.num_snakes, self.size
+        dense = {'foods': torch.empty((E, 1, S, S), dtype=torch.float32, device=self._dev),
+                 'heads': torch.empty((E * K, 1, S, S), dtype=torch.float32, device=self._dev),
+                 'bodies': torch.empty((E * K, 1, S, S), dtype=torch.float32, device=self._dev)}
+        cfg = self._cfg(None)
+        st = self._compact_struct(dense)
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wurm_multi_expand(ctypes.byref(cfg), ctypes.byref(st), self._stream()))
+        self._dense = dense
+        self._dense_key = self._dense_identity()
+
+    def _compress(self):
+        """the (caller-edited) fp32 tensors -> compact records; raises if the records cannot carry the state."""
+        cfg = self._cfg(None)
+        st = self._compact_struct(self._dense)
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wurm_multi_compact(ctypes.byref(cfg), ctypes.byref(st), _ptr(self._status), self._stream()))
+        self._dense_key = self._dense_identity()
+        st_word = int(self._status.item())
+        if st_word & _lib.ST_NOT_COMPACT:
+            self._status.zero_()
+            raise RuntimeError("state='compact' cannot carry this state exactly (food / head values other than 1, non-integral "
+                               "body values, two bodies on one cell, or a head off its own body); use state='dense'")
+
+    def _snapshot_names(self):
+        """Attributes that make up the env's state in compact mode (GraphedStepper snapshots them around its warm-up)."""
+        return ('_cells', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards', '_head_hints', '_stats', '_status')
+
     def _hint_identity(self):
         return tuple((t.data_ptr(), t._version) for t in (self.heads, self.bodies, self.foods, self.dones))
 
     def _adopt_state(self):
         """Records the identity of the state tensors as what the head hints describe (after this env's own kernels)."""
+        if self._compact:
+            if self._dense is not None:
+                self._dense_key = self._dense_identity()
+            return
         self._hint_key = self._hint_identity()
 
     def invalidate_hints(self):
@@ -211,26 +285,37 @@ class MultiSnake(object):
         when a state tensor was replaced or written through torch since this env's last own call (the kernels verify
         that a hinted cell still holds a head, not that it is the snake's ONLY head cell); call it by hand after
         writing the state through a raw pointer, which torch's version counter cannot see."""
+        if self._compact:
+            return                                   # the head cells are state in this mode, not hints
         self._head_hints.fill_(-2)
         self._adopt_state()
 
-    def _state(self):
+    def _state(self, mutates=False):
         """The state attributes may have been replaced by the caller (tests assign them): normalise.  Also where the
-        head hints are dropped if the caller touched a state tensor since this env's last own call."""
+        head hints are dropped if the caller touched a state tensor since this env's last own call.  `mutates`: the
+        call about to be made changes the state (compact mode: materialised fp32 tensors go stale)."""
         E, K, S = self.num_envs, self.num_snakes, self.size
+        dones = self._norm('dones', torch.bool, (E * K,))
+        small = (_ptr(dones), _ptr(self._norm('orientations', torch.long, (E * K,))),
+                 _ptr(self._norm('boost_this_step', torch.bool, (E * K,))), _ptr(self._norm('agent_colours', torch.short, (E * K, 3))))
+        if self._compact:
+            if self._dense is not None:
+                for name, shape in (('foods', (E, 1, S, S)), ('heads', (E * K, 1, S, S)), ('bodies', (E * K, 1, S, S))):
+                    self._norm(name, torch.float32, shape)
+                if self._dense_identity() != self._dense_key:
+                    self._compress()                 # the caller wrote to (or replaced) a materialised tensor
+                if mutates:
+                    self._dense = None
+            return _lib.WurmMultiState(None, None, None, *small, _ptr(self._head_hints), _ptr(self._cells))
         foods = self._norm('foods', torch.float32, (E, 1, S, S))
         heads = self._norm('heads', torch.float32, (E * K, 1, S, S))
         bodies = self._norm('bodies', torch.float32, (E * K, 1, S, S))
-        dones = self._norm('dones', torch.bool, (E * K,))
         if self._hint_identity() != self._hint_key:
             self.invalidate_hints()
-        return _lib.WurmMultiState(
-            _ptr(foods), _ptr(heads), _ptr(bodies), _ptr(dones),
-            _ptr(self._norm('orientations', torch.long, (E * K,))), _ptr(self._norm('boost_this_step', torch.bool, (E * K,))),
-            _ptr(self._norm('agent_colours', torch.short, (E * K, 3))), _ptr(self._head_hints))
+        return _lib.WurmMultiState(_ptr(foods), _ptr(heads), _ptr(bodies), *small, _ptr(self._head_hints), None)
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.foods.device).cuda_stream)
+        return ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
 
     def _obs_shape(self, cfg):
         E, K, S = self.num_envs, self.num_snakes, self.size
@@ -267,8 +352,8 @@ class MultiSnake(object):
     def _observe_tensor(self, mode):
         cfg = self._cfg(mode)
         st = self._state()
-        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=self.foods.device)
-        with torch.cuda.device(self.foods.device):
+        obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=self._dev)
+        with torch.cuda.device(self._dev):
             _lib.check(self._lib.wurm_multi_observe(ctypes.byref(cfg), ctypes.byref(st), _ptr(obs), _ptr(self._status),
                                                     self._stream()))
         return obs
@@ -286,8 +371,8 @@ class MultiSnake(object):
         """int16 (E,3,S,S) image of every env (reference :194-227)."""
         cfg = self._cfg(None)
         st = self._state()
-        img = torch.empty((self.num_envs, 3, self.size, self.size), dtype=torch.short, device=self.foods.device)
-        with torch.cuda.device(self.foods.device):
+        img = torch.empty((self.num_envs, 3, self.size, self.size), dtype=torch.short, device=self._dev)
+        with torch.cuda.device(self._dev):
             _lib.check(self._lib.wurm_multi_env_images(ctypes.byref(cfg), ctypes.byref(st), _ptr(img), _ptr(self._status),
                                                        self._stream()))
         return img
@@ -314,8 +399,8 @@ class MultiSnake(object):
 
         t0 = time()
         E, K = self.num_envs, self.num_snakes
-        st = self._state()
-        dev = self.foods.device
+        st = self._state(mutates=True)
+        dev = self._dev
         acts = list(actions.values())                     # dict order, key names are never parsed (reference :482)
         dtype = acts[0].dtype
         if any(a.dtype != dtype for a in acts):
@@ -393,8 +478,8 @@ class MultiSnake(object):
     # ------------------------------------------------------------------------------------------
     def _reset_mask(self, env_done, draws=None):
         cfg = self._cfg(None)
-        st = self._state()
-        dev = self.foods.device
+        st = self._state(mutates=True)
+        dev = self._dev
         dr, keep = None, []
         if draws is not None:
             def dev_t(key, dt):
@@ -425,7 +510,7 @@ class MultiSnake(object):
         done = done.view((done.shape[0]))
         if done.shape[0] != self.num_envs:
             raise RuntimeError('Must have one done flag per environment.')
-        dev = self.foods.device
+        dev = self._dev
         if not (done.dtype == torch.bool and done.device == dev and done.is_contiguous()):
             done = (done != 0).to(device=dev).contiguous()
         self._reset_mask(done, draws)
@@ -445,7 +530,7 @@ class MultiSnake(object):
         living snakes), as one fused kernel and one host sync."""
         cfg = self._cfg(None)
         st = self._state()
-        dev = self.foods.device
+        dev = self._dev
         report = torch.tensor([0, 0, 2 ** 31 - 1, 0], dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self._lib.wurm_multi_check(ctypes.byref(cfg), ctypes.byref(st), _ptr(report), self._stream()))

@@ -62,8 +62,13 @@ class GraphedStepper(object):
         # Warm-up outside the capture (first-launch work: function attributes, allocator pools) runs REAL steps, so the
         # env's state, statistics, hints and call counter are snapshotted before and restored after: constructing a
         # GraphedStepper leaves the env exactly as it found it.
-        names = ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards',
-                 '_head_hints', '_stats', '_status') if self.multi else ('envs', 'done', '_hints', '_stats', '_status')
+        if getattr(env, '_compact', False):          # compact resident state: the records ARE the state
+            names = env._snapshot_names()
+        elif self.multi:
+            names = ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards',
+                     '_head_hints', '_stats', '_status')
+        else:
+            names = ('envs', 'done', '_hints', '_stats', '_status')
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
