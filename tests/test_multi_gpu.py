@@ -657,3 +657,29 @@ def test_compact_state_takes_caller_edits_and_refuses_what_it_cannot_carry():
     env.bodies[0, 0, 2, 2] = 0.5                         # a non-integral body value: not a record
     with pytest.raises(RuntimeError, match='compact'):
         env.step({f'agent_{k}': acts[k] for k in range(K)})
+
+
+@pytest.mark.parametrize('E,K,S,mode', [(24, 4, 25, 'partial_4'), (6, 8, 40, 'partial_2'), (4, 16, 64, 'partial_4')])
+def test_compact_state_with_more_live_cells_than_the_live_list_holds(E, K, S, mode):
+    """state='compact' keeps its live list only as large as the fused reset's scratch (shared memory per CTA is what
+    limits residency); a board flooded with food overflows it and the per-cell passes walk the whole grid instead.
+    Results must not change: compared with the dense twin, whose list can hold every cell."""
+    rules = dict(food_mode='random_rate', food_rate=0.97, respawn_mode='any', food_on_death_prob=1.0)
+    dense = make_env(E, K, S, mode, seed=7, **rules)
+    compact = make_env(E, K, S, mode, seed=7, state='compact', **rules)
+    compact.agent_colours = dense.agent_colours.clone()
+    g = torch.Generator().manual_seed(4)
+    for t in range(16):
+        acts = torch.randint(0, 8, (K, E), generator=g).to(DEV)
+        o1, r1, d1, _ = dense.step({f'agent_{k}': acts[k] for k in range(K)}, auto_reset=True)
+        o2, r2, d2, _ = compact.step({f'agent_{k}': acts[k] for k in range(K)}, auto_reset=True)
+        for k in range(K):
+            assert_same(np_(o2[f'agent_{k}']), np_(o1[f'agent_{k}']), f'step {t}: obs {k}')
+        assert_same(stack_dict(r2, K), stack_dict(r1, K), f'step {t}: rewards')
+        check_state(compact, env_state(dense), f'step {t}')
+        if t == 0:
+            assert float(dense.foods.sum()) > 0.6 * E * (S - 2) ** 2     # the flood happened
+        if t == 8:                                      # back to sparse boards: the list is used again
+            dense.food_rate = compact.food_rate = 1e-3
+            dense.foods = torch.zeros_like(dense.foods); compact.foods = torch.zeros_like(dense.foods)
+    compact.check_consistency()

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'libwurm_b200.so')
+# WURM_B200_LIB: a tuning variant of the library built by scripts/build_variant.sh (A/B experiments only)
+LIB_PATH = os.environ.get('WURM_B200_LIB') or os.path.join(_HERE, '_C', 'libwurm_b200.so')
 
 ABI_VERSION = 5
 

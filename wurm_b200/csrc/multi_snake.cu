@@ -193,7 +193,9 @@ struct MultiSmem {
     int* cost;
     int* boost;
     int* sum;         // sum of body values per snake (invariant check)
-    int* misc;        // [0] food cells, [1] live-list length, [2] run_boost, [3] force full write-back, [6] queued hits
+    int* misc;        // [0] food cells, [1] live-list length, [2] run_boost, [3] force full write-back, [6] queued hits,
+                      // [8] the live list overflowed its capacity: the per-cell passes visit every cell instead
+    int lcap;         // capacity of the live list
     int2* queue;      // non-zero elements found by the load scan: (tensor << 30 | index, value bits), see load_env
     int qcap;
     short* col;       // K*3
@@ -208,35 +210,62 @@ struct MultiSmem {
 // per-snake arrays are sized by K (rounded up to 4), not by the 32-snake maximum.
 __host__ __device__ __forceinline__ int snakes_padded(int K) { return (K + 3) & ~3; }
 __host__ __device__ __forceinline__ int queue_capacity(int K) { return 12 * K + 32; }
+// Bytes of the region that serves, in turn, the live list, the colour table (768) and the fused reset's scratch
+// (occupancy bytes + picks).  Dense layout: the list can hold every cell.  Compact layout (multi_env_kernel<.,.,true>):
+// the region is only as large as the reset scratch needs -- the list holds what fits (a few times the typical ~1 % of the
+// grid) and an env with more live cells than that is walked cell by cell instead (misc[8]); no load queue either.
+// Shared memory per CTA is what limits the number of resident envs, and the kernel is latency-bound.
+__host__ __device__ __forceinline__ int scratch_bytes(int C, bool compact) {
+    int scratch = ((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;
+    if (scratch < 768) scratch = 768;
+    if (!compact && scratch < 2 * C) scratch = 2 * C;
+    return scratch;
+}
 
-__device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C, int K) {
+__device__ __forceinline__ MultiSmem carve(unsigned char* smem, int C, int K, bool compact = false) {
     MultiSmem s;
     const int KP = snakes_padded(K);
     s.cell = reinterpret_cast<uint32_t*>(smem);
     s.queue = reinterpret_cast<int2*>(s.cell + ((C + 1) & ~1));        // 8-byte aligned
-    s.qcap = queue_capacity(K);
+    s.qcap = compact ? 0 : queue_capacity(K);
+    s.lcap = compact ? min(C, scratch_bytes(C, true) / 2) : C;
     s.hp = reinterpret_cast<int*>(s.queue + s.qcap);
     s.size = s.hp + KP; s.hcnt = s.size + KP; s.done = s.hcnt + KP; s.decay = s.done + KP; s.cost = s.decay + KP;
     s.boost = s.cost + KP; s.sum = s.boost + KP; s.misc = s.sum + KP;
-    s.col = reinterpret_cast<short*>(s.misc + 8);
+    s.col = reinterpret_cast<short*>(s.misc + 12);
     s.reset = reinterpret_cast<unsigned char*>(s.col + 3 * KP);
     s.tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15);
     s.list = reinterpret_cast<unsigned short*>(s.tab);
     return s;
 }
 
-static size_t multi_smem_bytes(int C, int K) {
-    // records + per-snake arrays + misc + colours + the fused reset's scratch (occupancy bytes, picks)
-    // one region serves, in turn, the live list (2C bytes), the colour table (768) and the fused reset's scratch
-    size_t scratch = (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;
-    if (scratch < 768) scratch = 768;
-    if (scratch < 2 * (size_t)C) scratch = 2 * (size_t)C;
+static size_t multi_smem_bytes(int C, int K, bool compact = false) {
+    // records + load queue + per-snake arrays + misc + colours + the shared scratch region
     const size_t KP = (size_t)snakes_padded(K);
-    return (size_t)((C + 1) & ~1) * 4 + (size_t)queue_capacity(K) * 8 + 8 * KP * 4 + 8 * 4 + 3 * KP * 2 + scratch + 32;
+    return (size_t)((C + 1) & ~1) * 4 + (size_t)(compact ? 0 : queue_capacity(K)) * 8 + 8 * KP * 4 + 12 * 4 + 3 * KP * 2 +
+           (size_t)scratch_bytes(C, compact) + 32;
 }
 
 // Food transitions keep the env's food-cell count (misc[0]) current, so _add_food needs no counting pass.
-__device__ __forceinline__ void list_push(const MultiSmem& s, int q) { s.list[atomicAdd(&s.misc[1], 1)] = (unsigned short)q; }
+__device__ __forceinline__ void list_push(const MultiSmem& s, int q) {
+    const int n = atomicAdd(&s.misc[1], 1);
+    if (n < s.lcap) s.list[n] = (unsigned short)q;
+    else s.misc[8] = 1;
+}
+// The per-cell passes walk the live list, or every cell of the grid once the list has overflowed.  The choice is taken
+// ONCE per pass (a push that overflows while a pass is running must not change what its loop indices mean); cells that
+// become live during a pass are for the next one, as with the list.
+struct LiveWalk {
+    int cnt;
+    bool all;
+};
+__device__ __forceinline__ LiveWalk live_walk(const MultiSmem& s, int C) {
+    LiveWalk w;
+    w.all = s.misc[8] != 0;
+    w.cnt = w.all ? C : min(s.misc[1], s.lcap);
+    return w;
+}
+__device__ __forceinline__ int live_at(const MultiSmem& s, const LiveWalk& w, int n) { return w.all ? n : (int)s.list[n]; }
 __device__ __forceinline__ void set_food(const MultiSmem& s, int q) {
     const uint32_t old = atomicOr(&s.cell[q], kFood | kListed);
     if (!(old & kFood)) atomicAdd(&s.misc[0], 1);
@@ -334,40 +363,66 @@ __device__ __forceinline__ uint32_t hbm_record(uint32_t rec) { return rec & (kLi
 
 template <bool CHECK = false>
 __device__ __forceinline__ void load_env_compact(const MultiParams& p, const MultiSmem& s, int e) {
-    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
+    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const uint32_t* g = p.cells + (size_t)e * p.Cp;
     if (tid < K) {
         const int h = p.head_hints[(size_t)e * K + tid];
         s.hp[tid] = (h >= 0 && h < C) ? h : -1;
         s.hcnt[tid] = (h >= 0 && h < C) ? 1 : 0;
     }
-    auto take = [&](int q, uint32_t v) {
-        uint32_t rec = 0u;
-        if (v != 0u) {
-            rec = hbm_record(v) | kListed;
-            rec |= ((rec >> 16) & 63u) << 22;                        // owner when loaded
-            if (rec & kFood) { rec |= kFood0; atomicAdd(&s.misc[0], 1); }
-            if (rec & kLive) {
-                const int k = rec_owner(rec), val = rec_value(rec);
-                atomicMax(&s.size[k], val);
-                if (CHECK) atomicAdd(&s.sum[k], val);
-            }
-            list_push(s, q);
-        }
-        return rec;
-    };
+    // Pass 1: copy the records into shared memory as they are and put the cells that hold anything on the live list.
+    // ~99 % of the 128-bit vectors are zero (one ballot tells); for the others the list slots are claimed with ONE
+    // shared-memory atomic per warp and component (ballot + popc ranking), not one per cell.
     const uint4* g4 = reinterpret_cast<const uint4*>(g);
     uint4* c4 = reinterpret_cast<uint4*>(s.cell);
     const int nvec = C >> 2;
-    for (int j = tid; j < nvec; j += nthr) {
-        uint4 v;
-        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g4 + j));
-        if ((v.x | v.y | v.z | v.w) != 0u) {
-            v.x = take(4 * j, v.x); v.y = take(4 * j + 1, v.y); v.z = take(4 * j + 2, v.z); v.w = take(4 * j + 3, v.w);
+    for (int j0 = tid - lane; j0 < nvec; j0 += nthr) {               // warp-uniform trip count
+        const int j = j0 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (j < nvec) {
+            asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g4 + j));
+            c4[j] = v;
         }
-        c4[j] = v;
+        if (__ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u) == 0u) continue;
+        const uint32_t comp[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool nz = comp[c] != 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, nz);
+            if (m == 0u) continue;
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&s.misc[1], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (nz) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < s.lcap) s.list[slot] = (unsigned short)(4 * j + c);
+                else s.misc[8] = 1;
+            }
+        }
     }
-    if (tid < (C & 3)) { const int q = (C & ~3) + tid; s.cell[q] = take(q, g[q]); }
+    if (tid < (C & 3)) {
+        const int q = (C & ~3) + tid;
+        const uint32_t v = g[q];
+        s.cell[q] = v;
+        if (v != 0u) list_push(s, q);
+    }
+    __syncthreads();
+    // Pass 2, every lane busy: the per-call bits of the listed records (owner / food when loaded, listed), the env's food
+    // count and each snake's size.
+    const LiveWalk lw = live_walk(s, C);
+    for (int n = tid; n < lw.cnt; n += nthr) {
+        const int q = live_at(s, lw, n);
+        if (s.cell[q] == 0u) continue;                               // (only met when walking the whole grid)
+        uint32_t rec = hbm_record(s.cell[q]) | kListed;
+        rec |= ((rec >> 16) & 63u) << 22;                            // owner when loaded
+        if (rec & kFood) { rec |= kFood0; atomicAdd(&s.misc[0], 1); }
+        if (rec & kLive) {
+            const int k = rec_owner(rec), val = rec_value(rec);
+            atomicMax(&s.size[k], val);
+            if (CHECK) atomicAdd(&s.sum[k], val);
+        }
+        s.cell[q] = rec;
+    }
 }
 
 // multi_snake.py:197-206: int16 colour of a body (or, is_head, head) cell of snake o
@@ -413,36 +468,43 @@ __device__ __forceinline__ void write_multi_obs(const MultiParams& p, const Mult
         __syncthreads();                                              // the live list (same memory) is dead from here on
         build_colour_table(p, s);
         __syncthreads();
+        // colour of window cell (y, x); zero padding :301-302, black border :225
+        auto pixel = [&](int y, int x, float& v0, float& v1, float& v2) {
+            v0 = v1 = v2 = 0.0f;
+            if ((unsigned)(y - 1) < (unsigned)(S - 2) && (unsigned)(x - 1) < (unsigned)(S - 2)) {
+                const int q = y * S + x;
+                const uint32_t rec = s.cell[q];
+                if (!(rec & kFood)) {
+                    v0 = v1 = v2 = 1.0f;                              // empty: white (255 / 255)
+                    if (rec_body(rec)) {
+                        const int ow = rec_owner(rec);
+                        const float* t = s.tab + 3 * (2 * ow + (s.hp[ow] == q ? 1 : 0));
+                        v0 = t[0]; v1 = t[1]; v2 = t[2];
+                    }
+                } else if (!rec_body(rec)) {
+                    v0 = 1.0f;                                        // food: (255, 0, 0)
+                } else {                                              // food under a body: the general expression
+                    int rgb[3];
+                    env_pixel(p, s, q, y, x, rgb);
+                    v0 = div255(rgb[0]); v1 = div255(rgb[1]); v2 = div255(rgb[2]);            // :296
+                }
+            }
+        };
+        // (Unrolling the per-lane window cells so that the channel stores get constant offsets was tried and LOST on
+        // B200 -- C4 0.340 -> 0.376 ms: the one-warp-per-env shape is bound by instruction fetch, and four inlined copies
+        // of the cell colouring cost more than the address arithmetic they save.)
         for (int k = warp; k < K; k += nwarps) {
             float* o = p.obs + ((size_t)k * p.E + e) * 3 * WW;
             const int hp = s.hp[k];
-            if (s.done[k] || hp < 0 || s.hcnt[k] > 1) {               // :320-323 zeros for dead agents
+            if (s.done[k] || hp < 0 || s.hcnt[k] > 1) {           // :320-323 zeros for dead agents
                 for (int r = lane; r < 3 * WW; r += 32) o[r] = 0.0f;
                 continue;
             }
             const int hy = fdiv(hp, p.magic_S), hx = hp - hy * S;
-            for (int ij = lane; ij < WW; ij += 32) {                  // one window cell per lane, three channel rows
+            for (int ij = lane; ij < WW; ij += 32) {              // one window cell per lane, three channel rows
                 const int i = fdiv(ij, p.magic_W), j = ij - i * W;
-                const int y = hy - n + i, x = hx - n + j;
-                float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;                // zero padding :301-302, black border :225
-                if ((unsigned)(y - 1) < (unsigned)(S - 2) && (unsigned)(x - 1) < (unsigned)(S - 2)) {
-                    const int q = y * S + x;
-                    const uint32_t rec = s.cell[q];
-                    if (!(rec & kFood)) {
-                        v0 = v1 = v2 = 1.0f;                          // empty: white (255 / 255)
-                        if (rec_body(rec)) {
-                            const int ow = rec_owner(rec);
-                            const float* t = s.tab + 3 * (2 * ow + (s.hp[ow] == q ? 1 : 0));
-                            v0 = t[0]; v1 = t[1]; v2 = t[2];
-                        }
-                    } else if (!rec_body(rec)) {
-                        v0 = 1.0f;                                    // food: (255, 0, 0)
-                    } else {                                          // food under a body: the general expression
-                        int rgb[3];
-                        env_pixel(p, s, q, y, x, rgb);
-                        v0 = div255(rgb[0]); v1 = div255(rgb[1]); v2 = div255(rgb[2]);        // :296
-                    }
-                }
+                float v0, v1, v2;
+                pixel(hy - n + i, hx - n + j, v0, v1, v2);
                 o[ij] = v0; o[WW + ij] = v1; o[2 * WW + ij] = v2;
             }
         }
@@ -712,10 +774,11 @@ __device__ __forceinline__ void recolour(const MultiParams& p, int e, int k, uin
 // 0.533 ms with 64 / 128 threads; staging the raw env through shared memory with TMA was tried and lost to the
 // occupancy it costs); 256 threads for S=64, where streaming 540 KB per env wants the loads of many threads in flight.
 template <bool STEP, int THREADS, bool COMPACT = false>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? 12 : THREADS == 64 ? 20 : 32)
+// (the compact 128-thread shape serves grids from 56 x 56 up, where shared memory allows ~10 CTAs per SM anyway)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? (COMPACT ? 10 : 12) : THREADS == 64 ? 20 : 32)
 multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const MultiSmem s = carve(smem_raw, p.C, p.K);
+    const MultiSmem s = carve(smem_raw, p.C, p.K, COMPACT);
     const int C = p.C, K = p.K, S = p.S;
     const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
 
@@ -732,7 +795,10 @@ multi_env_kernel(const MultiParams p) {
         hint_h = p.head_hints[(size_t)e * K + tid];
         hint_dead = p.dones[(size_t)e * K + tid] != 0;
     }
-    constexpr bool kPrefetch = THREADS == 256;
+    // the call counter is read where a draw needs it (rare: something died or was eaten); hoisting the load to the top
+    // of the kernel was measured and lost (a register held across the whole step)
+#define ctr_now call_counter(p)
+    constexpr bool kPrefetch = THREADS == 256 || (COMPACT && THREADS >= 64);
     long long pre_action = 0, pre_orient = 0;
     float pre_cost = 0.0f;
     if (STEP && kPrefetch && tid < K) {
@@ -751,7 +817,7 @@ multi_env_kernel(const MultiParams p) {
         s.done[tid] = p.dones[(size_t)e * K + tid] != 0;
         s.boost[tid] = !STEP ? (p.boost_this_step[(size_t)e * K + tid] != 0) : 0;
     }
-    if (tid < 8) s.misc[tid] = 0;
+    if (tid < 12) s.misc[tid] = 0;
     for (int t = tid; t < 3 * K; t += nthr) s.col[t] = p.colours[(size_t)e * K * 3 + t];
     // Head hints: the heads tensor's value at this thread's snake's hinted cell (the hint itself was fetched first thing)
     float hint_val = 0.0f;
@@ -814,8 +880,9 @@ multi_env_kernel(const MultiParams p) {
                 if (active && ov) { a_reward += 1.0f; a_foodc += 1.0f; }   // :527-529 / :629-631
             }
             __syncthreads();
-            for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {  // _decay_bodies :362-363
-                const int q = s.list[n];
+            const LiveWalk lw = live_walk(s, C);
+            for (int n = tid; n < lw.cnt; n += nthr) {  // _decay_bodies :362-363
+                const int q = live_at(s, lw, n);
                 const uint32_t rec = s.cell[q];
                 if (rec_body(rec) && s.decay[rec_owner(rec)])
                     s.cell[q] = ((rec_value(rec) == 1) ? (rec & ~kLive) : rec - 1u) | kDirty;
@@ -849,7 +916,7 @@ multi_env_kernel(const MultiParams p) {
                     bool cost = false;
                     if (valid && a_boosted) {
                         const float u = p.replay ? (kPrefetch ? pre_cost : p.u_cost[(size_t)e * K + k])
-                                                 : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiBoostCost, (uint32_t)k));
+                                                 : unit_float(draw_i(p.seed, ctr_now, (uint32_t)e, kStreamMultiBoostCost, (uint32_t)k));
                         cost = u < p.boost_cost_prob;
                     }
                     if (valid) s.cost[k] = cost;
@@ -860,8 +927,9 @@ multi_env_kernel(const MultiParams p) {
             {   // food from dead bodies (:416-428), boost cost on the bodies (:583-589), deletion (:595 / :676)
                 const float* U = p.replay ? (boost_phase ? p.u_boost : p.u_reg) : nullptr;
                 const uint32_t stream = boost_phase ? kStreamMultiDeathBoost : kStreamMultiDeathRegular;
-                for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {
-                    const int q = s.list[n];
+                const LiveWalk lw = live_walk(s, C);
+                for (int n = tid; n < lw.cnt; n += nthr) {
+                    const int q = live_at(s, lw, n);
                     uint32_t rec = s.cell[q];
                     if (!rec_body(rec)) continue;
                     const int o = rec_owner(rec);
@@ -870,7 +938,7 @@ multi_env_kernel(const MultiParams p) {
                         const int y = fdiv(q, p.magic_S), x = q - y * S;
                         if (!(y == 1 || x == 0 || y == S - 1 || x == S - 1)) {   // sic: row 1 (:418)
                             const float u = p.replay ? (U ? U[(size_t)e * C + q] : 0.0f)
-                                                     : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, stream, (uint32_t)q));
+                                                     : unit_float(draw_i(p.seed, ctr_now, (uint32_t)e, stream, (uint32_t)q));
                             food = u > p.death_thr;
                         }
                     }
@@ -898,7 +966,7 @@ multi_env_kernel(const MultiParams p) {
                     else {
                         const int I = S - 2;
                         for (uint32_t t = 0; t < kRejectionTries && cell < 0; ++t) {
-                            const int cand = (int)bounded(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodOne, t), (uint32_t)(I * I));
+                            const int cand = (int)bounded(draw_i(p.seed, ctr_now, (uint32_t)e, kStreamMultiFoodOne, t), (uint32_t)(I * I));
                             const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
                             if (cell_free(q)) cell = q;
                         }
@@ -907,7 +975,7 @@ multi_env_kernel(const MultiParams p) {
                             for (int y = 1; y < S - 1; ++y)
                                 for (int x = 1; x < S - 1; ++x) nfree += cell_free(y * S + x);
                             if (nfree > 0) {
-                                int r = (int)bounded(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodOne, kRejectionTries), (uint32_t)nfree);
+                                int r = (int)bounded(draw_i(p.seed, ctr_now, (uint32_t)e, kStreamMultiFoodOne, kRejectionTries), (uint32_t)nfree);
                                 for (int y = 1; y < S - 1 && cell < 0; ++y)
                                     for (int x = 1; x < S - 1; ++x)
                                         if (cell_free(y * S + x) && r-- == 0) { cell = y * S + x; break; }
@@ -921,7 +989,7 @@ multi_env_kernel(const MultiParams p) {
                     const int y = fdiv(q, p.magic_S), x = q - y * S;
                     if (y < 1 || y > S - 2 || x < 1 || x > S - 2 || !cell_free(q)) continue;
                     const float u = p.replay ? p.u_rate[(size_t)e * C + q]
-                                             : unit_float(draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamMultiFoodRate, (uint32_t)q));
+                                             : unit_float(draw_i(p.seed, ctr_now, (uint32_t)e, kStreamMultiFoodRate, (uint32_t)q));
                     if (u < p.food_rate) set_food(s, q);
                 }
             }
@@ -947,6 +1015,7 @@ multi_env_kernel(const MultiParams p) {
             const unsigned ecols = __ballot_sync(0xffffffffu, valid && a_ecol);
             const int eaten = group_sum<32>(valid ? (int)a_foodc : 0, 0xffffffffu);
             if (lane == 0) {
+                s.misc[4] = (int)alive;                               // for the fused reset below
                 p.all_done[e] = alive == 0u;                          // :703
                 if (p.stats) {
                     unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
@@ -965,8 +1034,9 @@ multi_env_kernel(const MultiParams p) {
             // compact resident state: the records that changed go back as records (4 bytes each); the head cells
             // already went into head_hints with the per-agent outputs
             uint32_t* gc = p.cells + (size_t)e * p.Cp;
-            for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {
-                const int q = s.list[n];
+            const LiveWalk lw = live_walk(s, C);
+            for (int n = tid; n < lw.cnt; n += nthr) {
+                const int q = live_at(s, lw, n);
                 const uint32_t rec = s.cell[q];
                 if ((rec & kDirty) || (((rec >> 29) ^ (rec >> 30)) & 1u)) gc[q] = hbm_record(rec);
             }
@@ -988,8 +1058,9 @@ multi_env_kernel(const MultiParams p) {
             // touches O(snake length) cells of an S*S grid: write traffic drops from the full state
             // to a few sectors per snake.
             float* bodies = p.bodies + (size_t)e * K * C;
-            for (int n = tid, cnt = s.misc[1]; n < cnt; n += nthr) {
-                const int q = s.list[n];
+            const LiveWalk lw = live_walk(s, C);
+            for (int n = tid; n < lw.cnt; n += nthr) {
+                const int q = live_at(s, lw, n);
                 const uint32_t rec = s.cell[q];
                 if (rec & kDirty) {
                     const int ko = rec_owner0(rec), kn = rec_body(rec) ? rec_owner(rec) : -1;
@@ -1013,12 +1084,11 @@ multi_env_kernel(const MultiParams p) {
         // kernel has to scan the tensors for: which cells are occupied, which snakes are dead.
         __syncthreads();                                              // the observation is done with the records
         const ResetScratch sc = carve_reset(reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15), C);
-        const uint64_t ctr = call_counter(p) + 1;
-        int first_dead = -1;
-        for (int kk = K - 1; kk >= 0; --kk)
-            if (s.done[kk]) first_dead = kk;
-        bool all_dead = true;
-        for (int kk = 0; kk < K; ++kk) all_dead &= s.done[kk] != 0;
+        const uint64_t ctr = ctr_now + 1;
+        const unsigned alive_mask = (unsigned)s.misc[4];              // snakes alive after this step (ballot of warp 0)
+        const unsigned dead_mask = ~alive_mask & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u));
+        const int first_dead = dead_mask ? __ffs(dead_mask) - 1 : -1;
+        const bool all_dead = alive_mask == 0u;
         if (all_dead) {                                               // :787-798 re-create the env
             const int fcell = decide_recreate(p, e, ctr, sc);
             // all snakes are dead, so their tensors are already zero (the step deleted them); only food is left
@@ -1053,7 +1123,7 @@ __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, i
         s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.sum[tid] = 0;
         s.done[tid] = p.dones[(size_t)e * K + tid] != 0;
     }
-    if (tid < 8) s.misc[tid] = 0;
+    if (tid < 12) s.misc[tid] = 0;
     __syncthreads();
     MultiParams q = p;
     q.status = &s.misc[4];                      // overlap / multi-head of THIS env, not the env object's status word
@@ -1094,7 +1164,7 @@ __global__ void __launch_bounds__(256) multi_convert_kernel(const MultiParams p)
     if (TO_COMPACT)
         for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
     if (tid < K) { s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.sum[tid] = 0; s.done[tid] = 0; }
-    if (tid < 8) s.misc[tid] = 0;
+    if (tid < 12) s.misc[tid] = 0;
     __syncthreads();
     if (TO_COMPACT) {
         load_env<false>(p, s, e);                                     // no hints: the heads tensor is scanned
@@ -1273,7 +1343,8 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
 template <bool STEP, int THREADS, bool COMPACT = false>
 static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
     auto kern = multi_env_kernel<STEP, THREADS, COMPACT>;
-    const size_t smem = multi_smem_bytes(p.C, p.K);
+    size_t smem = multi_smem_bytes(p.C, p.K, COMPACT);
+    if (const char* v = getenv("WURM_MULTI_SMEM_PAD")) smem += (size_t)atoi(v);     // occupancy experiments
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
     static SmemOptIn opt_in;                           // per instantiation, per device inside
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, (int)smem, false, "cudaFuncSetAttribute(multi_env_kernel)")) return rc;
