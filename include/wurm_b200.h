@@ -131,6 +131,27 @@ int wurm_single_reset(const WurmSingleCfg* cfg, float* envs, const uint8_t* done
 /* Replaces SingleSnake._observe (single_snake.py:130-195) on the current state. */
 int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, float* obs, int32_t* status, void* stream);
 
+/* ---- SingleSnake with a COMPACT RESIDENT STATE (optional; wurm_b200/csrc/single_compact.cu) ----
+ * Instead of the reference's (N,3,S,S) fp32 tensor the env lives in HBM as
+ *   cells (N, Cp) uint16, Cp = S*S rounded up to a multiple of 8, 16-byte aligned: bits 0-13 body value, bit 14 head,
+ *         bit 15 food;
+ *   aux   (N, 4) int16, 8-byte aligned: head cell (-1 none), snake size, neck cell, flags -- derived data the kernels
+ *         maintain (wurm_single_compact computes it from scratch);
+ * 176 bytes per env at size 9 instead of 972.  Same semantics, same draws, same outputs as the entry points above
+ * (bit-identical on every state the records can carry: integral body values < 16384, food / head values 0 or 1; size
+ * <= 90); wurm_single_compact / wurm_single_expand convert, the former raising WURM_ST_NOT_COMPACT for anything else. */
+int wurm_single_compact_step(const WurmSingleCfg* cfg, uint16_t* cells, int16_t* aux, void* actions, int action_bytes,
+                             const int32_t* food_cell_replay, int auto_reset /* fuse reset(done) into the launch */,
+                             const int32_t* spawn_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev, float* obs,
+                             float* reward, uint8_t* done, uint8_t* self_col, uint8_t* edge_col, int32_t* status,
+                             int64_t* stats /* nullable */, uint8_t* packed /* nullable */, void* stream);
+int wurm_single_compact_reset(const WurmSingleCfg* cfg, uint16_t* cells, int16_t* aux, const uint8_t* done_mask,
+                              const int32_t* spawn_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream);
+int wurm_single_compact_observe(const WurmSingleCfg* cfg, const uint16_t* cells, const int16_t* aux, float* obs,
+                                int32_t* status, void* stream);
+int wurm_single_compact(const WurmSingleCfg* cfg, const float* envs, uint16_t* cells, int16_t* aux, int32_t* status, void* stream);
+int wurm_single_expand(const WurmSingleCfg* cfg, const uint16_t* cells, const int16_t* aux, float* envs, void* stream);
+
 /* Invariant checks (wurm/utils.py:113-178 snake_consistency + env_consistency, and
  * MultiSnake.check_consistency multi_snake.py:733-769) fused into ONE reduction kernel per call.  The
  * reference's drivers run these every step (experiments/main.py:215, experiments/multiagent.py:378)

@@ -27,12 +27,16 @@ def np_(t):
     return t.detach().cpu().numpy()
 
 
+STATES = ['dense', 'compact']     # state='compact': records resident in HBM, `envs` materialised for the comparison
+
+
+@pytest.mark.parametrize('state', STATES)
 @pytest.mark.parametrize('i', range(len(SINGLE)))
-def test_golden_replay(i):
+def test_golden_replay(i, state):
     """CUDA path == reference on the recorded trajectories (states, actions, rewards, dones, info, obs)."""
     tr = SINGLE[i]
     N, S, mode = tr.N, tr.S, tr.mode
-    env = make_env(N, S, mode, manual_setup=True)
+    env = make_env(N, S, mode, manual_setup=True, state=state)
     if 'init_spawn' in tr:
         env.envs = env._create_envs(N, spawn_replay=torch.from_numpy(tr['init_spawn']))
         assert_same(np_(env.envs), tr['init_envs'].astype(np.float32), 'created envs')
@@ -77,11 +81,14 @@ ROLLOUTS = [
 ]
 
 
+@pytest.mark.parametrize('state', STATES)
 @pytest.mark.parametrize('N,S,mode,steps,reset_every,adtype', ROLLOUTS)
-def test_rollout_matches_oracle(N, S, mode, steps, reset_every, adtype):
+def test_rollout_matches_oracle(N, S, mode, steps, reset_every, adtype, state):
     """Seeded random rollout, draws derived from Philox on both sides: every tensor identical."""
+    if state == 'compact' and S > 90:
+        pytest.skip('compact records carry sizes up to 90')
     seed = 1234 + N + S
-    env = make_env(N, S, mode, seed=seed)
+    env = make_env(N, S, mode, seed=seed, state=state)
     state = np.zeros((N, 3, S, S), np.float32)
     orc.single_reset(state, np.ones(N, np.uint8), None, seed=seed, step=env._draws)
     assert_same(np_(env.envs), state, 'created envs')
@@ -363,10 +370,11 @@ def test_graphed_stepper_is_bit_identical_to_call_by_call_stepping():
 
 @pytest.mark.parametrize('N,S,mode', [(1000, 9, 'partial_2'), (300, 12, 'default'), (130, 36, 'one_channel'), (257, 16, 'partial_3'),
                                       (65, 36, 'default'), (40, 20, 'positions')])
-def test_fused_step_reset_equals_step_then_reset(N, S, mode):
+@pytest.mark.parametrize('state', STATES)
+def test_fused_step_reset_equals_step_then_reset(N, S, mode, state):
     """step(a, auto_reset=True) == step(a); reset(done): same outputs, same state afterwards, same draws."""
     two_calls = make_env(N, S, mode, seed=55)
-    fused = make_env(N, S, mode, seed=55)
+    fused = make_env(N, S, mode, seed=55, state=state)
     g = torch.Generator().manual_seed(8)
     for t in range(30):
         a = torch.randint(0, 4, (N,), generator=g).to(DEV)
@@ -587,3 +595,31 @@ def test_raw_pointer_writers_can_invalidate_hints_by_hand():
     assert env._hint_key == key                          # the env's own launches do not look like caller edits
     env.envs[0, 0, 1, 1] = 0.0                           # a torch write does
     assert (env.envs.data_ptr(), env.envs._version) != env._hint_key
+
+
+def test_compact_state_takes_caller_edits_and_refuses_what_it_cannot_carry():
+    """state='compact': `envs` is materialised on access; an assigned tensor (how the reference's tests install their
+    fixtures) or an in-place write is folded back into the records before the next call, and a state the records cannot
+    carry exactly raises instead of being rounded."""
+    from wurm_b200.utils import get_test_env
+    S = 12
+    twin = make_env(1, S, 'default', manual_setup=True, seed=3)
+    env = make_env(1, S, 'default', manual_setup=True, seed=3, state='compact')
+    twin.envs = get_test_env(S, 'up').to(DEV)
+    env.envs = get_test_env(S, 'up').to(DEV)
+    for t, a in enumerate([0, 3, 3, 0, 0]):                 # the reference's test_eat_food sequence
+        act = torch.tensor([a], device=DEV)
+        o1, r1, d1, _ = twin.step(act.clone())
+        o2, r2, d2, _ = env.step(act.clone())
+        assert_same(np_(o2), np_(o1), f'step {t}: obs')
+        assert_same(np_(r2), np_(r1), f'step {t}: reward')
+        assert_same(np_(env.envs), np_(twin.envs), f'step {t}: state')
+    env.check_consistency()
+    twin.envs[0, 0, 1, 1] = 1.0; env.envs[0, 0, 1, 1] = 1.0  # an in-place write through the materialised tensor
+    act = torch.tensor([1], device=DEV)
+    twin.step(act.clone()); env.step(act.clone())
+    assert env._dense is None                                # dropped by the state-changing call
+    assert_same(np_(env.envs), np_(twin.envs), 'state after the edit')
+    env.envs[0, 2, 3, 3] = 0.5                               # a non-integral body value: not a record
+    with pytest.raises(RuntimeError, match='compact'):
+        env.step(act.clone())

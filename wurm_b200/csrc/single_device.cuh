@@ -150,7 +150,9 @@ __device__ __forceinline__ float new_env_value(int i, int C, int tail, int mid, 
 }
 
 // single_snake.py:197-300 for one environment held in shared memory, executed by a group of G lanes.
-template <int G>
+// WT (write-through): mirror every update of `env` into the fp32 state in HBM (p.envs); the compact-state kernels run
+// the same code on a scratch expansion of their records and pass false.
+template <int G, bool WT = true>
 __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e, int l, int* cnt_s, long long a_in,
                                         int hint_head, int hint_sz, bool& ended) {
     const unsigned gm = group_mask<G>();
@@ -252,7 +254,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
 #pragma unroll 4
         for (int q = l; q < C; q += G) {
             const float v = body[q], nv = fmaxf(v - 1.0f, 0.0f);
-            if (nv != v) { body[q] = nv; gbody[q] = nv; }
+            if (nv != v) { body[q] = nv; if (WT) gbody[q] = nv; }
         }
     }
     __syncwarp(gm);
@@ -260,12 +262,12 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
     const bool interior = (np >= 0) && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
     __syncwarp(gm);
     if (l == 0 && hp >= 0) {
-        head[hp] = 0.0f; ghead[hp] = 0.0f;
+        head[hp] = 0.0f; if (WT) ghead[hp] = 0.0f;
         if (np >= 0) {
-            head[np] = 1.0f; ghead[np] = 1.0f;
+            head[np] = 1.0f; if (WT) ghead[np] = 1.0f;
             const float grown = body[np] + (size + ov);              // :258-262 growth
-            body[np] = grown; gbody[np] = grown;
-            if (ov != 0.0f) { const float left = food[np] + ov * -1.0f; food[np] = left; gfood[np] = left; }   // :270-272
+            body[np] = grown; if (WT) gbody[np] = grown;
+            if (ov != 0.0f) { const float left = food[np] + ov * -1.0f; food[np] = left; if (WT) gfood[np] = left; }   // :270-272
         }
     }
     __syncwarp(gm);
@@ -286,7 +288,7 @@ __device__ __forceinline__ int step_env(const SingleParams& p, float* env, int e
                 cell = pick_free_cell<G>(env, S, C, p.magic_S,
                                          draw_i(p.seed, call_counter(p), (uint32_t)e, kStreamSingleStepFood, kRejectionTries), l, gm);
         }
-        if (l == 0 && cell >= 0) { const float f = food[cell] + 1.0f; food[cell] = f; gfood[cell] = f; }
+        if (l == 0 && cell >= 0) { const float f = food[cell] + 1.0f; food[cell] = f; if (WT) gfood[cell] = f; }
         if (l == 0 && p.hints) p.hints[4 * (size_t)e + 2] = (short)cell;
     }
     if (l == 0) {

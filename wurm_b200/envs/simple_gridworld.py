@@ -63,6 +63,7 @@ class SimpleGridworld(object):
             self.envs = self._create_envs(self.num_envs)
 
         self.done = torch.zeros(num_envs, dtype=torch.bool, device=self.device)
+        self._dev = self.done.device
         self.viewer = None
         self.head_colour = torch.tensor((0, 255, 0), dtype=torch.short, device=self.device)
         self.food_colour = torch.tensor((255, 0, 0), dtype=torch.short, device=self.device)

@@ -57,8 +57,15 @@ class SingleSnake(object):
                  manual_setup: bool = False,
                  verbose: int = 0,
                  render_args: dict = None,
-                 seed: int = None):
+                 seed: int = None,
+                 state: str = 'dense'):
         self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
+        if state not in ('dense', 'compact'):
+            raise ValueError("state must be 'dense' (the reference's fp32 tensor is the state) or 'compact'")
+        # state='compact' (an extension): between calls the env lives in HBM as one uint16 record per cell (include/
+        # wurm_b200.h, wurm_single_compact_step) instead of the reference's (3,S,S) fp32 grids; `envs` is then materialised
+        # on attribute access and folded back in if the caller wrote to it.
+        self._compact = state == 'compact'
         self.num_envs = num_envs
         self.size = size
         self.max_timesteps = max_timesteps
@@ -89,13 +96,27 @@ class SingleSnake(object):
         # kernel skip two of its scans; never trusted, so editing `envs` behind the env's back stays safe
         self._hints = torch.full((num_envs, 4), -1, dtype=torch.short, device=self.device)
 
-        self.envs = torch.zeros((num_envs, 3, size, size), device=self.device)
         self.t = 0
-
-        if not manual_setup:
-            self.envs = self._create_envs(self.num_envs)
         self._hint_key = None
-        self._adopt_state()
+        self._dev = self._hints.device
+        if self._compact:
+            self._cells = torch.zeros((num_envs, (size * size + 7) & ~7), dtype=torch.int16, device=self.device)
+            self._hints.zero_()
+            self._hints[:, 0] = -1                   # aux vectors: no head, size 0, no neck, not canonical
+            self._hints[:, 2] = -1
+            self._dense = None                       # the fp32 tensor exists only while a caller looks at it
+            self._dense_key = None
+            if not manual_setup:
+                if self.size <= 8:
+                    raise NotImplementedError('Cannot make an env this small without making this code more clever')
+                if self.initial_snake_length != 3:
+                    raise NotImplementedError('Only initial snake length = 3 has been implemented.')
+                self._reset_mask(None, torch.ones(num_envs, dtype=torch.bool, device=self.device))
+        else:
+            self._dense = torch.zeros((num_envs, 3, size, size), device=self.device)
+            if not manual_setup:
+                self._dense = self._create_envs(self.num_envs)
+            self._adopt_state()
 
         self.done = torch.zeros(num_envs, dtype=torch.bool, device=self.device)
 
@@ -127,6 +148,55 @@ class SingleSnake(object):
         return {_lib.OBS_DEFAULT: (n, 3, s, s), _lib.OBS_RAW: (n, 3, s, s), _lib.OBS_ONE_CHANNEL: (n, 1, s, s),
                 _lib.OBS_POSITIONS: (n, 4), _lib.OBS_PARTIAL: (n, 3 * w * w)}[cfg.obs_mode]
 
+    # ---- `envs`: a plain tensor in dense mode, materialised on access in compact mode ----
+    @property
+    def envs(self):
+        if self._dense is None:
+            self._materialise()
+        return self._dense
+
+    @envs.setter
+    def envs(self, value):
+        self._dense = value
+
+    def _materialise(self):
+        """compact records -> the reference's (N,3,S,S) fp32 tensor (one launch), kept until the next state-changing call."""
+        dense = torch.empty((self.num_envs, 3, self.size, self.size), dtype=torch.float32, device=self._dev)
+        cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wurm_single_expand(ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(dense),
+                                                    self._stream()))
+        self._dense = dense
+        self._dense_key = (dense.data_ptr(), dense._version)
+
+    def _compact_state(self, mutates):
+        """Compact mode: folds a caller-edited materialised tensor back into the records (raises if they cannot carry it)
+        and drops the materialised tensor when the call about to be made changes the state."""
+        if self._dense is not None:
+            e = self._dense
+            if e.dtype != torch.float32 or not e.is_contiguous() or e.device != self._dev:
+                e = e.to(device=self._dev, dtype=torch.float32).contiguous()
+                self._dense = e
+            if tuple(e.shape) != (self.num_envs, 3, self.size, self.size):
+                raise RuntimeError(f'envs has shape {tuple(e.shape)}, expected {(self.num_envs, 3, self.size, self.size)}')
+            if (e.data_ptr(), e._version) != self._dense_key:
+                cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
+                with torch.cuda.device(self._dev):
+                    _lib.check(self._lib.wurm_single_compact(ctypes.byref(cfg), _ptr(e), _ptr(self._cells), _ptr(self._hints),
+                                                             _ptr(self._status), self._stream()))
+                self._dense_key = (e.data_ptr(), e._version)
+                st = int(self._status.item())
+                if st & _lib.ST_NOT_COMPACT:
+                    self._status.zero_()
+                    raise RuntimeError("state='compact' cannot carry this state exactly (food / head values other than 0 or 1, "
+                                       "non-integral, negative or oversized body values); use state='dense'")
+            if mutates:
+                self._dense = None
+
+    def _snapshot_names(self):
+        """Attributes that make up the env's state in compact mode (GraphedStepper snapshots them around its warm-up)."""
+        return ('_cells', 'done', '_hints', '_stats', '_status')
+
     def _state(self):
         """`envs` may have been replaced or sliced by the caller (tests assign it): normalise.  Also where the hints
         are dropped if the caller touched the tensor since this env's last own call: the kernels verify that the
@@ -146,17 +216,23 @@ class SingleSnake(object):
 
     def _adopt_state(self):
         """Records the identity of `envs` as the state the hints describe (after this env's own kernels wrote it)."""
+        if self._compact:
+            if self._dense is not None:
+                self._dense_key = (self._dense.data_ptr(), self._dense._version)
+            return
         self._hint_key = (self.envs.data_ptr(), self.envs._version)
 
     def invalidate_hints(self):
         """Drops the per-env (head cell, size, food cell) hints: the next step re-derives everything from `envs`.
         Called automatically when `envs` was replaced or written through torch; call it by hand after writing the
         state through a raw pointer (a custom kernel, `.data_ptr()`), which torch's version counter cannot see."""
+        if self._compact:
+            return                                   # the aux vectors are derived state in this mode, not hints
         self._hints.fill_(-1)
         self._adopt_state()
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.envs.device).cuda_stream)
+        return ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
 
     def stats(self, reduce_group=None):
         """Episode statistics accumulated on the device since construction: a dict of int counters
@@ -195,6 +271,13 @@ class SingleSnake(object):
     # ------------------------------------------------------------------------------------------
     def _observe(self, observation_mode: str = 'default'):
         cfg = self._cfg(observation_mode)
+        if self._compact:
+            self._compact_state(mutates=False)
+            obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=self._dev)
+            with torch.cuda.device(self._dev):
+                _lib.check(self._lib.wurm_single_compact_observe(ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(obs),
+                                                                 _ptr(self._status), self._stream()))
+            return obs
         envs = self._state()
         obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=envs.device)
         with torch.cuda.device(envs.device):
@@ -225,8 +308,12 @@ class SingleSnake(object):
             raise RuntimeError('Must have the same number of actions as environments.')
 
         t0 = time()
-        envs = self._state()
-        dev = envs.device
+        if self._compact:
+            self._compact_state(mutates=True)
+            envs, dev = None, self._dev
+        else:
+            envs = self._state()
+            dev = envs.device
         host_actions = None
         if actions.device != dev or not actions.is_contiguous():
             host_actions, actions = actions, actions.to(dev, non_blocking=True).contiguous()
@@ -251,7 +338,15 @@ class SingleSnake(object):
             raise RuntimeError(f'packed_out must be a contiguous uint8 tensor of {self.num_envs} elements on {dev}')
         self._draws += 1
         with torch.cuda.device(dev):
-            if auto_reset:
+            if self._compact:
+                _lib.check(self._lib.wurm_single_compact_step(
+                    ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(actions), _ACTION_BYTES[actions.dtype],
+                    _ptr(food_cell_replay), int(bool(auto_reset)), _ptr(spawn_replay), self.seed, self._draws,
+                    _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done), _ptr(self_collision), _ptr(edge_collision),
+                    _ptr(self._status), _ptr(self._stats), _ptr(packed_out), self._stream()))
+                if auto_reset:
+                    self._draws += 1        # the fused reset consumed the next counter value
+            elif auto_reset:
                 _lib.check(self._lib.wurm_single_step_reset(
                     ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                     _ptr(spawn_replay), self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done),
@@ -288,11 +383,15 @@ class SingleSnake(object):
             raise RuntimeError('Must have one done flag per environment.')
 
         t0 = time()
-        envs = self._state()
-        if done.dtype == torch.bool and done.device == envs.device and done.is_contiguous():
+        if self._compact:
+            self._compact_state(mutates=True)
+            envs = None
+        else:
+            envs = self._state()
+        if done.dtype == torch.bool and done.device == self._dev and done.is_contiguous():
             mask = done                     # the step's own flags: no conversion kernel on the hot loop
         else:
-            mask = (done != 0).to(device=envs.device).contiguous()
+            mask = (done != 0).to(device=self._dev).contiguous()
         self._reset_mask(envs, mask, spawn_replay)
 
         if self.verbose:
@@ -302,14 +401,21 @@ class SingleSnake(object):
             return self._observe(self.observation_mode)
 
     def _reset_mask(self, envs, mask, spawn_replay=None):
-        cfg = _lib.WurmSingleCfg(envs.shape[0], self.size, _lib.OBS_NONE, 0)
         if spawn_replay is not None:
-            spawn_replay = spawn_replay.to(device=envs.device, dtype=torch.int32).contiguous()
+            spawn_replay = spawn_replay.to(device=self._dev, dtype=torch.int32).contiguous()
         self._draws += 1
+        if envs is None:                    # compact resident state
+            cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
+            with torch.cuda.device(self._dev):
+                _lib.check(self._lib.wurm_single_compact_reset(ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(mask),
+                                                               _ptr(spawn_replay), self.seed, self._draws, _ptr(self._draws_dev),
+                                                               self._stream()))
+            return
+        cfg = _lib.WurmSingleCfg(envs.shape[0], self.size, _lib.OBS_NONE, 0)
         with torch.cuda.device(envs.device):
             _lib.check(self._lib.wurm_single_reset(ctypes.byref(cfg), _ptr(envs), _ptr(mask), _ptr(spawn_replay),
                                                    self.seed, self._draws, _ptr(self._draws_dev),
-                                                   _ptr(self._hints) if envs.shape[0] == self.num_envs else None,
+                                                   _ptr(self._hints) if (envs.shape[0] == self.num_envs and not self._compact) else None,
                                                    self._stream()))
 
     def _create_envs(self, num_envs: int, *, spawn_replay: torch.Tensor = None):

@@ -41,7 +41,7 @@ class GraphedStepper(object):
         self.multi = hasattr(env, 'num_snakes')
         self.auto_reset = auto_reset
         self.host_io = host_io
-        dev = env.envs.device if not self.multi else env.foods.device
+        dev = env._dev
         self._dev = dev
         if host_io:
             pin = dict(pin_memory=True)
