@@ -37,6 +37,9 @@ N-rank weak-scaling figure, so C5 is BASELINE configs[4] itself: 32 768 envs per
              under ~1 s; CPU throughput is flat in num_envs), rank 0, N=1 only.  `cpu_baseline_port` is the C/OpenMP
              restatement (oracle/wurm_oracle.c) on the same cores; `reference_cuda` the same unmodified reference
              code with device='cuda' (stock ATen kernels on this B200).
+  compact_state  the same workload on an env built with state='compact' (an opt-in extension: the env lives in HBM as
+             one small record per cell instead of the reference's dense fp32 tensors, which are materialised on
+             attribute access; bit-identical results) -- the headline `value` stays on the reference layout
 
 `--impl reference` times the reference's own PyTorch CPU implementation alone and prints the same line shape.
 """
@@ -96,13 +99,15 @@ class SingleAdapter(object):
     """Uniform loop interface over the env classes (GPU arm)."""
     kernel = 'single_tile_kernel<G,STEP=true>'
 
-    def __init__(self, key, dev, seed, rank):
+    def __init__(self, key, dev, seed, rank, state='dense'):
         import torch
         from wurm_b200.envs import SingleSnake
         _, S, N, mode, _ = WORKLOADS[key]
         self.N, self.torch = N, torch
-        self.env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=seed)
-        if S % 2 == 0 and S >= 16 and (mode in ('default', 'one_channel') or not 20 < S < 32):
+        self.env = SingleSnake(num_envs=N, size=S, observation_mode=mode, device=dev, seed=seed, state=state)
+        if state == 'compact':
+            self.kernel = 'single_compact_kernel<G,STEP=true>'
+        elif S % 2 == 0 and S >= 16 and (mode in ('default', 'one_channel') or not 20 < S < 32):
             self.kernel = 'single_body_kernel<G>'       # even sizes from 16 up step on body-only tiles (DESIGN.md 4.1b)
         g = torch.Generator(device=dev).manual_seed(4321 + rank)
         self.pool = [torch.randint(0, 4, (N,), device=dev, generator=g) for _ in range(ACTION_POOL)]
@@ -130,7 +135,7 @@ class SingleAdapter(object):
 class GridAdapter(SingleAdapter):
     kernel = 'grid_small_kernel<STEP=true>'    # grids up to 64 cells; larger: grid_env_kernel<32,true>
 
-    def __init__(self, key, dev, seed, rank):
+    def __init__(self, key, dev, seed, rank, state='dense'):
         import torch
         from wurm_b200.envs import SimpleGridworld
         _, S, N, mode, _ = WORKLOADS[key]
@@ -148,12 +153,14 @@ class GridAdapter(SingleAdapter):
 class MultiAdapter(object):
     kernel = 'multi_env_kernel<STEP=true>'
 
-    def __init__(self, key, dev, seed, rank):
+    def __init__(self, key, dev, seed, rank, state='dense'):
         import torch
         from wurm_b200.envs import MultiSnake
         _, S, N, mode, K = WORKLOADS[key]
         self.N, self.K, self.torch = N, K, torch
-        self.env = MultiSnake(num_envs=N, num_snakes=K, size=S, observation_mode=mode, device=dev, seed=seed)
+        self.env = MultiSnake(num_envs=N, num_snakes=K, size=S, observation_mode=mode, device=dev, seed=seed, state=state)
+        if state == 'compact':
+            self.kernel = 'multi_env_kernel<STEP=true,COMPACT=true>'
         g = torch.Generator(device=dev).manual_seed(4321 + rank)
         self.pool = [{f'agent_{k}': torch.randint(0, 8, (N,), device=dev, generator=g) for k in range(K)}
                      for _ in range(ACTION_POOL)]
@@ -178,9 +185,112 @@ class MultiAdapter(object):
         return [{a: t.to(self.torch.uint8).cpu().pin_memory() for a, t in d.items()} for d in self.pool]
 
 
-def make_adapter(key, dev, seed, rank):
+def make_adapter(key, dev, seed, rank, state='dense'):
     cls = {'MultiSnake': MultiAdapter, 'SimpleGridworld': GridAdapter}.get(WORKLOADS[key][0], SingleAdapter)
-    return cls(key, dev, seed, rank)
+    return cls(key, dev, seed, rank, state)
+
+
+def compact_bytes_per_env(key):
+    """Bytes of the compact resident state per env (records + per-env / per-snake side vectors)."""
+    env, S, _, _, K = WORKLOADS[key]
+    if env == 'MultiSnake':
+        return ((S * S + 3) & ~3) * 4 + K * (2 + 1 + 8 + 1 + 6)
+    return ((S * S + 7) & ~7) * 2 + 8
+
+
+def measure_compact(ctx, key, K, W, obs_elems):
+    """The same workload with state='compact' (records resident in HBM instead of the reference's fp32 tensors; opt-in,
+    bit-identical results, tensors materialised on attribute access).  Returns the sub-record on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from wurm_b200 import HostStepper
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    _, S, N, mode, _ = WORKLOADS[key]
+    ad = make_adapter(key, dev, 1234 + rank, rank, state='compact')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for t in range(W):
+        obs, reward, done = ad.step(t)
+        ad.reset(done)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    a.record()
+    for t in range(K):
+        ev[t][0].record()
+        obs, reward, done = ad.step(t)
+        ev[t][1].record()
+        ad.reset(done)
+    b.record()
+    barrier()
+    two_ms = a.elapsed_time(b)
+    kernel_ms = statistics.mean(x.elapsed_time(y) for x, y in ev)
+    for t in range(W):
+        ad.fused_step(t)
+    barrier()
+    a.record()
+    for t in range(K):
+        ad.fused_step(t)
+    b.record()
+    barrier()
+    fused_ms = a.elapsed_time(b)
+    host_pool = ad.host_pool()
+    stepper = HostStepper(ad.env, depth=2)
+    Ke = max(10, K // 2)
+    tickets = []
+    for t in range(4):
+        tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
+    while tickets:
+        tickets.pop(0).wait()
+    barrier()
+    a.record()
+    for t in range(Ke):
+        tickets.append(stepper.submit(host_pool[t % ACTION_POOL]))
+        if len(tickets) > stepper.depth:
+            tickets.pop(0).wait()
+    while tickets:
+        tickets.pop(0).wait()
+    b.record(stepper.d2h)
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    h2d, d2h, api = stepper.h2d_bytes_per_step, stepper.d2h_bytes_per_step, stepper.describe()
+    ad.env.check_status()
+    t = torch.tensor([two_ms, fused_ms, kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    two_ms, fused_ms, kernel_ms, e2e_ms = t.tolist()
+    kernel_name = ad.kernel
+    del ad, stepper, host_pool
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, _ = measured_peak_gbs()
+    traffic, traffic_src = profiled_traffic(key, 'compact')
+    algorithmic = algorithmic_bytes_per_env_step(key, obs_elems) * N
+    moved = (2 * compact_bytes_per_env(key) + obs_elems * 4 + 16) * N      # records read + written (upper bound) + obs + vectors
+    return {'value': world * N * K / (two_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': two_ms / K, 'steps': K,
+            'loop': 'env.step(a); env.reset(done, return_observations=False) on an env built with state=\'compact\'',
+            'fused_step_reset': {'value': world * N * K / (fused_ms * 1e-3), 'ms_per_step': fused_ms / K,
+                                 'loop': 'env.step(a, auto_reset=True)'},
+            'e2e': {'value': world * N * Ke / (e2e_ms * 1e-3), 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / Ke, 'api': api},
+            'resident_state_bytes_per_env': compact_bytes_per_env(key),
+            'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'kernel_ms': kernel_ms,
+                         'achieved': algorithmic / (kernel_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': algorithmic / (kernel_ms * 1e-3) / 1e9 / peak, 'bytes_per_launch': algorithmic,
+                         'compact_bytes_per_launch': moved, 'traffic': traffic, 'traffic_source': traffic_src,
+                         'physical_frac': (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         'compact_gbs': moved / (kernel_ms * 1e-3) / 1e9, 'compact_frac': moved / (kernel_ms * 1e-3) / 1e9 / peak,
+                         'note': 'frac keeps the SURVEY 8(d) denominator (the reference\'s dense fp32 layout) over the step '
+                                 'kernel\'s launch time; compact_* count the bytes this layout has to move (records in + out, '
+                                 'observation, per-env vectors)'}}
+
 
 
 class ClockSampler(object):
@@ -254,13 +364,13 @@ def csrc_hash():
     return h.hexdigest()[:16]
 
 
-def profiled_traffic(key):
+def profiled_traffic(key, state='dense'):
     """dram bytes per launch of the step kernel from the last `ncu --set full` capture (profiles/traffic.json), and
     where it came from.  Refused (None + reason) when the kernel sources changed since that capture."""
     path = os.path.join(ROOT, 'profiles', 'traffic.json')
     if not os.path.exists(path):
         return None, 'profiles/traffic.json missing'
-    rec = json.load(open(path)).get(key)
+    rec = json.load(open(path)).get(key if state == 'dense' else key + ':compact')
     if not isinstance(rec, dict):
         return None, 'no capture recorded for this workload'
     if rec.get('csrc_hash') != csrc_hash():
@@ -679,6 +789,9 @@ def measure_config(ctx, key, K, W, min_seconds, exact_steps):
     import gc
     gc.collect()
     torch.cuda.empty_cache()
+    compact = None
+    if ctx.compact and WORKLOADS[key][0] in ('SingleSnake', 'MultiSnake'):
+        compact = measure_compact(ctx, key, K, W, obs_elems)
     if rank != 0:
         return None
 
@@ -715,6 +828,8 @@ def measure_config(ctx, key, K, W, min_seconds, exact_steps):
                      'physical_frac': (traffic / (step_kernel_ms * 1e-3) / 1e9 / peak) if traffic else None},
         'episode_stats': stats,
     }
+    if compact is not None:
+        rec['compact_state'] = compact
     if sustained is not None:
         rec['sustained'] = {'value': world * N * sustained[0] / (sustained[1] * 1e-3), 'unit': 'env-steps/s', 'steps': sustained[0],
                             'seconds': sustained[1] * 1e-3}
@@ -759,6 +874,7 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=ctx.dev)
+    ctx.compact = not args.no_compact
     ctx.sampler = ClockSampler(local_rank)
     ctx.sampler.start()                     # nvidia-smi takes a moment to produce its first row: start before the warm-up
 
@@ -822,6 +938,7 @@ def main():
     ap.add_argument('--configs', default='auto', help="sub-records: 'auto' (C1,C3,C4,C5 beside the default headline), 'none', or a comma list")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-cuda', action='store_true')
+    ap.add_argument('--no-compact', action='store_true', help="skip the state='compact' sub-records")
     ap.add_argument('--reference-child', default=None, help=argparse.SUPPRESS)
     ap.add_argument('--ref-device', default='cpu', help=argparse.SUPPRESS)
     ap.add_argument('--ref-envs', default=None, help=argparse.SUPPRESS)

@@ -200,12 +200,18 @@ __device__ __forceinline__ int fast_step(const SingleParams& p, uint16_t* row, i
         if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
     }
     const int ov = (np >= 0 && (row[np] & kFoodBit)) ? 1 : 0;        // :242
-    if (!ov) {                                                       // :246-249 every body cell - 1, two cells per word
-        uint32_t* w32 = reinterpret_cast<uint32_t*>(row);
-        for (int j = l; j < (Cp >> 1); j += G) {
-            const uint32_t w = w32[j];
+    if (!ov) {                                                       // :246-249 every body cell - 1: two cells per word, eight per load
+        uint4* r4 = reinterpret_cast<uint4*>(row);
+        auto dec = [](uint32_t w) {                                  // per 16-bit half: body field - 1 where it is non-zero
             const uint32_t x = w & 0x3fff3fffu;
-            if (x) w32[j] = w - (((x + 0x3fff3fffu) >> 14) & 0x00010001u);
+            return w - (((x + 0x3fff3fffu) >> 14) & 0x00010001u);
+        };
+        for (int j = l; j < (Cp >> 3); j += G) {
+            uint4 v = r4[j];
+            if ((v.x | v.y | v.z | v.w) & 0x3fff3fffu) {
+                v.x = dec(v.x); v.y = dec(v.y); v.z = dec(v.z); v.w = dec(v.w);
+                r4[j] = v;
+            }
         }
     }
     __syncwarp(gm);
@@ -352,8 +358,8 @@ __global__ void __launch_bounds__(256) single_compact_kernel(const CompactParams
             __syncwarp(gm);
             int tail = 0, mid = 0, hd = 0, cell = -1;
             if (l == 0) new_env_layout(p, p.spawn, call_counter(p) + 1, e, tail, mid, hd, cell);
-            uint32_t* w32 = reinterpret_cast<uint32_t*>(row);
-            for (int j = l; j < (Cp >> 1); j += G) w32[j] = 0u;
+            uint4* r4 = reinterpret_cast<uint4*>(row);
+            for (int j = l; j < (Cp >> 3); j += G) r4[j] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp(gm);
             if (l == 0) aux = stamp_new_env(row, tail, mid, hd, cell);
         }
@@ -470,13 +476,15 @@ static int plan_compact(const WurmSingleCfg* cfg, uint16_t* cells, int16_t* aux,
     p.obs_mode = cfg->obs_mode; p.obs_n = cfg->obs_n; p.W = W;
     p.magic_S = (uint32_t)((0x100000000ull + (uint64_t)S - 1) / (uint64_t)S);
     p.magic_W = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
+    // lanes per env: ~64 cells each (measured on B200 at size 9, profiles/r02_sweep_single_compact.txt: 2 lanes 0.137 ms,
+    // 4 lanes 0.172, 8 lanes 0.293 -- the serial parts of a step idle the other lanes of the group)
     int G = 1;
-    while (G < 32 && G * 32 < C) G <<= 1;               // ~32 cells (16 words) per lane
+    while (G < 32 && G * 64 < C) G <<= 1;
     if (const char* v = getenv("WURM_COMPACT_G")) {
         const int g = atoi(v);
         if (g >= 1 && g <= 32 && (g & (g - 1)) == 0) G = g;
     }
-    int threads = 64;
+    int threads = (cfg->obs_mode == WURM_OBS_PARTIAL && C <= 1024) ? 32 : 64;    // one-warp CTAs for small staged tiles (same sweep)
     if (const char* v = getenv("WURM_COMPACT_THREADS")) threads = atoi(v);
     if (threads < 32) threads = 32;
     if (threads > 256) threads = 256;
