@@ -15,6 +15,11 @@ Call sequence kept from the reference:  state = env.reset();  loop:  probs, valu
 action ~ Categorical(probs);  state, reward, done, info = env.step(action);
 env_consistency(env.envs[~done]);  env.reset(done)  -- whose observation is discarded (main.py:227), so
 `return_observations=False` is passed here.
+
+Multi-GPU: launched under `torch.distributed.run --nproc-per-node N` every rank owns an
+independent slice of the `--num-envs` environments (`env_slice`), its own Philox seed (`rank_seed`) and its own copy of
+the policy; there is no data-path collective.  Every LOG_INTERVAL steps the episode counters the step kernels keep are
+summed over ranks with one small all-reduce (`env.stats(reduce_group=True)`) and rank 0 prints the job-wide line.
 """
 import argparse
 from itertools import count
@@ -24,6 +29,7 @@ import torch
 from torch import nn
 from torch.distributions import Categorical
 
+from wurm_b200.distributed import env_slice, finish, init_from_env, rank_seed
 from wurm_b200.envs import SingleSnake, SimpleGridworld
 from wurm_b200.rl import A2C
 from wurm_b200.trajectory_store import TrajectoryStore
@@ -93,6 +99,12 @@ def main(argv=None):
     if args.train and args.agent == 'random':
         raise ValueError('--train true needs a trainable agent')
 
+    ranks = init_from_env(args.device)
+    args.device = ranks.device
+    total_envs = args.num_envs
+    _, args.num_envs = env_slice(total_envs, ranks.rank, ranks.world_size)       # this rank's slice of the environments
+    if args.seed is not None:
+        args.seed = rank_seed(args.seed, ranks.rank) if ranks.world_size > 1 else args.seed
     render_args = {'size': args.render_window_size, 'num_rows': args.render_rows, 'num_cols': args.render_cols}
     if args.env == 'gridworld':                          # reference main.py:166-168
         env = SimpleGridworld(num_envs=args.num_envs, size=args.size, start_location=(args.size // 2, args.size // 2),
@@ -154,20 +166,26 @@ def main(argv=None):
             trajectories.clear()
             losses = dict(value_loss=value_loss.item(), policy_loss=policy_loss.item())
 
-        num_steps += args.num_envs
+        num_steps += total_envs                       # job-wide: every rank steps its slice in lockstep
         if i_step % LOG_INTERVAL == 0 or num_steps >= args.total_steps:
-            stats = env.stats()                       # device counters kept by the step kernel: one tiny D2H read
+            # device counters kept by the step kernel, summed over ranks: one tiny all-reduce + D2H read
+            stats = env.stats(reduce_group=True if ranks.world_size > 1 else None)
             num_episodes = stats['episodes']
             dt = time() - t0
+            sizes = env.envs[:, -1].reshape(args.num_envs, -1).max(dim=-1)[0].sum().reshape(1)
+            if ranks.world_size > 1:
+                torch.distributed.all_reduce(sizes)
             summary = dict(steps=num_steps, episodes=num_episodes, reward_rate=stats['reward'] / max(stats['env_steps'], 1),
                            edge_collisions=stats['edge_collisions'], self_collisions=stats['self_collisions'],
-                           avg_size=env.envs[:, -1].reshape(args.num_envs, -1).max(dim=-1)[0].mean().item(),
-                           steps_per_second=num_steps / dt, **losses)
-            print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
+                           avg_size=sizes.item() / total_envs, steps_per_second=num_steps / dt, ranks=ranks.world_size,
+                           env_steps=stats['env_steps'], **losses)
+            if ranks.is_main:
+                print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
 
         if num_steps >= args.total_steps or num_episodes >= args.total_episodes:
             break
     env.check_status()
+    finish(ranks)
     return summary
 
 

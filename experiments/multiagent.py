@@ -12,6 +12,10 @@ device (`wurm_b200.rl.A2C`); species, shared backbones, recurrent agents and DIA
 repository's scope.
 
     python -m experiments.multiagent --n-envs 4096 --n-agents 4 --size 25 --obs partial_4 --total-steps 1e6
+
+Multi-GPU (BASELINE config 5 is 32 768 envs per GPU across 8 GPUs): under `torch.distributed.run
+--nproc-per-node N` every rank owns an independent slice of the `--n-envs` environments, its own Philox seed and its own
+policy copy; the only collective is the all-reduce of the episode counters every LOG_INTERVAL steps, printed by rank 0.
 """
 import argparse
 from itertools import count
@@ -22,6 +26,7 @@ from torch import nn
 from torch.distributions import Categorical
 
 from experiments.main import FeedforwardAgent
+from wurm_b200.distributed import env_slice, finish, init_from_env, rank_seed
 from wurm_b200.envs import MultiSnake
 from wurm_b200.rl import A2C
 from wurm_b200.trajectory_store import TrajectoryStore
@@ -72,6 +77,13 @@ def main(argv=None):
         raise ValueError('Unrecognised agent (this driver covers random and feedforward)')
     train = bool(args.train) and agent_type != 'random'
 
+    ranks = init_from_env(args.device)
+    args.device = ranks.device
+    total_envs = args.n_envs
+    _, args.n_envs = env_slice(total_envs, ranks.rank, ranks.world_size)         # this rank's slice of the environments
+    if args.seed is not None and ranks.world_size > 1:
+        args.seed = rank_seed(args.seed, ranks.rank)
+
     env = MultiSnake(num_envs=args.n_envs, num_snakes=args.n_agents, size=args.size, device=args.device,
                      observation_mode=args.obs, boost=args.boost, boost_cost_prob=args.boost_cost,
                      food_on_death_prob=args.food_on_death, reward_on_death=args.reward_on_death, food_mode=args.food_mode,
@@ -99,9 +111,9 @@ def main(argv=None):
     for i_step in count(1):
         # hyper-parameter annealing: the reference mutates the env's attributes between steps (:337-345)
         if args.food_rate_min is not None:
-            env.food_rate -= (args.food_rate - args.food_rate_min) / args.total_steps * args.n_envs
+            env.food_rate -= (args.food_rate - args.food_rate_min) / args.total_steps * total_envs
         if args.food_on_death_min is not None:
-            env.food_on_death_prob -= (args.food_on_death - args.food_on_death_min) / args.total_steps * args.n_envs
+            env.food_on_death_prob -= (args.food_on_death - args.food_on_death_min) / args.total_steps * total_envs
 
         if model is None:
             dist = Categorical(uniform)
@@ -135,17 +147,19 @@ def main(argv=None):
             trajectories.clear()
             losses = dict(value_loss=value_loss.item(), policy_loss=policy_loss.item())
 
-        num_steps += args.n_envs
+        num_steps += total_envs                       # job-wide: every rank steps its slice in lockstep
         if i_step % LOG_INTERVAL == 0 or num_steps >= args.total_steps:
-            stats = env.stats()
+            stats = env.stats(reduce_group=True if ranks.world_size > 1 else None)      # summed over ranks (one all-reduce)
             summary = dict(steps=num_steps, episodes=stats['episodes'], food=stats['reward'],
                            snake_collisions=stats['self_collisions'], edge_collisions=stats['edge_collisions'],
                            food_rate=env.food_rate, food_on_death_prob=env.food_on_death_prob,
-                           fps=num_steps / (time() - t0), **losses)
-            print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
+                           fps=num_steps / (time() - t0), ranks=ranks.world_size, env_steps=stats['env_steps'], **losses)
+            if ranks.is_main:
+                print('\t'.join(f'{k}={v:.4g}' if isinstance(v, float) else f'{k}={v}' for k, v in summary.items()))
         if num_steps >= args.total_steps or summary.get('episodes', 0) >= args.total_episodes:
             break
     env.check_status()
+    finish(ranks)
     return summary
 
 

@@ -64,3 +64,30 @@ def test_bench_reference_arm_under_torchrun():
     # the arm times the reference ITSELF (PyTorch, under the loader's shims); the C port rides along as a second figure
     assert line['cpu_baseline']['kind'] == 'reference' and line['cpu_baseline_port']['kind'] == 'port'
     assert line['e2e']['h2d_bytes_per_step'] == 0
+
+
+_RANK_SCRIPT = '''
+import sys, torch
+sys.path.insert(0, %r)
+from wurm_b200.distributed import init_from_env, env_slice, rank_seed, all_reduce_stats, finish
+ranks = init_from_env('cpu')                          # gloo: the same plumbing the drivers use on GPUs with NCCL
+start, count = env_slice(1001, ranks.rank, ranks.world_size)
+totals = torch.tensor([count, ranks.rank, 1, 0, 0], dtype=torch.int64)
+all_reduce_stats(totals)
+if ranks.is_main:
+    print('TOTALS', totals.tolist(), ranks.world_size, rank_seed(3, 0) != rank_seed(3, 1))
+finish(ranks)
+'''
+
+
+def test_driver_rank_plumbing_under_torchrun_gloo(tmp_path):
+    """init_from_env + env_slice + all_reduce_stats + finish as experiments/main.py uses them, two ranks over gloo."""
+    script = tmp_path / 'ranks.py'
+    script.write_text(_RANK_SCRIPT % ROOT)
+    port = 33000 + os.getpid() % 2000
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith('TOTALS')]
+    assert lines == ['TOTALS [1001, 1, 2, 0, 0] 2 True']

@@ -3,6 +3,8 @@
 Environments never interact, so the data path has NO collective; the only
 exchange is the all-reduce of the episode-statistics counters the step kernels accumulate.
 """
+import os
+
 import torch
 
 
@@ -26,3 +28,41 @@ def all_reduce_stats(totals: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
     return totals
+
+
+class Ranks(object):
+    """What a driver needs to know about its place in a one-process-per-GPU job."""
+
+    def __init__(self, rank, world_size, local_rank, device):
+        self.rank, self.world_size, self.local_rank, self.device = rank, world_size, local_rank, device
+
+    @property
+    def is_main(self):
+        return self.rank == 0
+
+
+def init_from_env(device: str = 'cuda') -> Ranks:
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK (set by `torch.distributed.run`); with more than one rank binds this process
+    to its GPU (`cuda:LOCAL_RANK`) and initialises the default process group (NCCL for CUDA, gloo otherwise).  A plain
+    `python -m experiments.main` run has no such variables and gets Ranks(0, 1, 0, device) without any group."""
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if torch.device(device).type == 'cuda':
+            torch.cuda.set_device(local)
+            device = f'cuda:{local}'
+            if not dist.is_initialized():
+                dist.init_process_group('nccl', device_id=torch.device(device))
+        elif not dist.is_initialized():
+            dist.init_process_group('gloo')
+    return Ranks(rank, world, local, device)
+
+
+def finish(ranks: Ranks):
+    import torch.distributed as dist
+    if ranks.world_size > 1 and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
