@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 for w in ${WORKLOADS:-C2 C3 C4 C5}; do
   for st in dense compact; do
-    case $w in C2|C3|C1) k='regex:single_(tile|body|compact)_kernel<[0-9]+(, 1)?>' ;; *) k='regex:multi_env_kernel<1' ;; esac
+    case $w in C2|C3|C1) k='regex:single_tile_kernel|single_body_kernel|single_compact_kernel' ;; *) k='regex:multi_env_kernel' ;; esac
     ncu --set full --clock-control none --import-source on -k "$k" -s 11 -c 1 -f -o gpurun_out/r02_ncu_${w}_${st} \
         python scripts/profile_step.py $w $st 14 2>&1 | tail -1
   done

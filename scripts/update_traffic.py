@@ -27,7 +27,8 @@ for w in ('C1', 'C2', 'C3', 'C4', 'C5'):
         total = mbytes('dram__bytes_read.sum') + mbytes('dram__bytes_write.sum')
         key = w if st == 'dense' else w + ':compact'
         out[key] = {'dram_bytes_per_launch': int(total), 'kernel': d['Kernel Name'], 'csrc_hash': bench.csrc_hash(),
-                    'source': f'profiles/{tag}_ncu_{w}_{st}.txt', 'gpu_time_us': float(d['gpu__time_duration.sum'])}
+                    'source': f'profiles/{tag}_ncu_{w}_{st}.txt',
+                    'gpu_time_us': float(d['gpu__time_duration.sum']) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}[u['gpu__time_duration.sum']]}
         summary = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_summary.py'), rep,
                                   f'{w} {st} state, step kernel of the bench loop (12th launch), csrc {bench.csrc_hash()}'],
                                  capture_output=True, text=True).stdout

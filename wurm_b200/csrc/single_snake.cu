@@ -200,6 +200,105 @@ __global__ void __launch_bounds__(256) single_tile_kernel(const SingleParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// EXPERIMENT (WURM_SINGLE_RING=stages): persistent one-warp CTAs with a multi-stage TMA ring
+// ---------------------------------------------------------------------------------------------
+// single_tile_kernel overlaps load, compute and store by oversubscription: ~20 one-warp CTAs per SM, each doing
+// load -> wait -> step -> store once.  This variant makes the overlap explicit instead: grid = a few CTAs per SM, each
+// walking tiles blockIdx, blockIdx + gridDim, ... with a ring of STAGES tile buffers -- the bulk load of tile i+STAGES is
+// issued (cp.async.bulk + mbarrier expect_tx) as soon as tile i has been stepped, so every warp always has STAGES-1
+// loads in flight while it computes -- and two observation staging buffers so that the bulk store of tile i drains while
+// tile i+1 is rendered.  Partial observations, full tiles and 16-byte-aligned bases only (the C2 shape); selected by the
+// environment variable for the measurement recorded in profiles/r02_c2_ring_experiment.txt.
+template <int G, int STAGES>
+__global__ void __launch_bounds__(32) single_ring_kernel(const SingleParams p, int ntiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int KC = p.C, n3 = 3 * KC;
+    const int E = 3 * p.W * p.W;
+    float* tiles = reinterpret_cast<float*>(smem);
+    float* stages = reinterpret_cast<float*>(smem + (size_t)STAGES * p.tile_bytes_padded);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * p.tile_bytes_padded + 2 * (size_t)p.stage_bytes);
+    int* cnt_s = reinterpret_cast<int*>(bars + STAGES);
+    const int lane = threadIdx.x, t = lane / G, l = lane % G;
+    const uint32_t bytes = (uint32_t)(p.T * n3) * 4u;
+    if (lane < 4) cnt_s[lane] = 0;
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+        for (int s = 0; s < STAGES; ++s) {
+            const int tile = blockIdx.x + s * gridDim.x;
+            if (tile < ntiles) {
+                mbar_arrive_expect_tx(bars + s, bytes);
+                bulk_load(reinterpret_cast<unsigned char*>(tiles) + (size_t)s * p.tile_bytes_padded, p.envs + (size_t)tile * p.T * n3, bytes, bars + s);
+            }
+        }
+    }
+    __syncwarp();
+    int done_tiles = 0;
+    for (int tile = blockIdx.x, it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        float* tbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tiles) + (size_t)s * p.tile_bytes_padded);
+        float* stage = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stages) + (size_t)(it & 1) * p.stage_bytes);
+        const int env0 = tile * p.T;
+        const size_t e = (size_t)(env0 + t);
+        const long long a_in = load_action(p.actions, p.action_bytes, e);       // per-env scalars while the tile is in flight
+        int hint_head = -1, hint_sz = -1;
+        if (p.hints) { hint_head = p.hints[4 * e]; hint_sz = p.hints[4 * e + 1]; }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this staging buffer's last store has read it
+        __syncwarp();
+        mbar_wait(bars + s, parity);
+        float* env = tbuf + (size_t)t * n3;
+        bool ended = false;
+        const int hp = step_env<G>(p, env, env0 + t, l, cnt_s, a_in, hint_head, hint_sz, ended);
+        render_partial<G>(p, env, hp, stage + (size_t)t * E, l);
+        if (p.auto_reset) {                                         // fused reset, as in single_tile_kernel
+            int my_tail = 0, my_mid = 0, my_hd = 0, my_cell = -1;
+            const bool mine = ended && l == 0;
+            __syncwarp();
+            if (mine) new_env_layout(p, p.spawn, call_counter(p) + 1, env0 + t, my_tail, my_mid, my_hd, my_cell);
+            unsigned todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int tail = __shfl_sync(0xffffffffu, my_tail, src), mid = __shfl_sync(0xffffffffu, my_mid, src);
+                const int hd = __shfl_sync(0xffffffffu, my_hd, src), cell = __shfl_sync(0xffffffffu, my_cell, src);
+                const int ts = src / G;
+                const float* old = tbuf + (size_t)ts * n3;
+                float* g = p.envs + (size_t)(env0 + ts) * n3;
+                for (int i = lane; i < n3; i += 32)
+                    if (old[i] != 0.0f) g[i] = 0.0f;
+                __syncwarp();
+                if (lane < 5) {
+                    const int idx = lane == 0 ? cell : lane == 1 ? KC + hd : lane == 2 ? 2 * KC + tail : lane == 3 ? 2 * KC + mid : 2 * KC + hd;
+                    const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
+                    if (idx >= 0) g[idx] = val;
+                }
+                if (lane == 0 && p.hints) { short* h = p.hints + 4 * (size_t)(env0 + ts); h[0] = (short)hd; h[1] = 3; h[2] = (short)cell; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();                                    // the warp's generic reads / writes of tile and stage come first
+            bulk_store(p.obs + (size_t)env0 * E, stage, (uint32_t)(p.T * E) * 4u);
+            bulk_commit();
+            const int next = tile + STAGES * gridDim.x;             // refill this ring slot
+            if (next < ntiles) {
+                mbar_arrive_expect_tx(bars + s, bytes);
+                bulk_load(tbuf, p.envs + (size_t)next * p.T * n3, bytes, bars + s);
+            }
+        }
+        ++done_tiles;
+    }
+    __syncwarp();
+    if (p.stats && lane < WURM_STATS_FIELDS) {
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        const int v = lane == 0 ? done_tiles * p.T : cnt_s[lane - 1];
+        if (v) atomicAdd(slot + lane, (unsigned long long)v);
+    }
+    if (lane == 0) bulk_wait_read_all();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Body-only tiles: the steady-state path for larger grids
 // ---------------------------------------------------------------------------------------------
 // In steady state the previous call left every env's head cell, snake size and food cell.  If the head cell still
@@ -255,7 +354,7 @@ __device__ __noinline__ int3 slow_step_on_global(const SingleParams p, int e, in
     fc = group_sum<G>(fc, gm);
     fq = group_max<G>(fq, gm);
     const int food_now = fc == 1 ? fq : -1;
-    if (l == 0) p.hints[4 * (size_t)e + 2] = (short)food_now;
+    if (l == 0 && p.hints) p.hints[4 * (size_t)e + 2] = (short)food_now;
     // the observation of this env is rendered here, before a fused reset can overwrite the terminal state in HBM
     if (p.obs_mode == WURM_OBS_PARTIAL) render_partial<G>(p, genv, np, partial_out, l);
     if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
@@ -278,6 +377,95 @@ __device__ __noinline__ int3 slow_step_on_global(const SingleParams p, int e, in
         }
     }
     return make_int3(np, food_now, ended ? 1 : 0);
+}
+
+// Envs too large for a shared-memory tile (grid sides above 128: 3*S*S floats no longer fit next to anything else):
+// one warp per env, the general step straight on global memory -- slow_step_on_global, the code the body-only kernel
+// runs for envs whose hints do not verify -- so that the reference's "any size" holds here too.  Not a tuned path.
+template <bool STEP>
+__global__ void __launch_bounds__(128) single_global_kernel(const SingleParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int C = p.C, S = p.S, E = 3 * p.W * p.W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)warp * (p.obs_mode == WURM_OBS_PARTIAL ? E : 0);
+    int* cnt_s = reinterpret_cast<int*>(smem + p.stage_bytes);
+    if (threadIdx.x < 4) cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    const int e = blockIdx.x * nwarps + warp;
+    if (e < p.N) {
+        float* genv = p.envs + (size_t)e * 3 * C;
+        int np = -1;
+        bool ended = false;
+        if (STEP) {
+            const long long a_in = load_action(p.actions, p.action_bytes, (size_t)e);
+            int hint_head = -1, hint_sz = -1;
+            if (p.hints) { hint_head = p.hints[4 * (size_t)e]; hint_sz = p.hints[4 * (size_t)e + 1]; }
+            const int3 res = slow_step_on_global<32>(p, e, lane, cnt_s, a_in, hint_head, hint_sz, stage);
+            np = res.x; ended = res.z != 0;
+        } else {
+            if (p.obs_mode == WURM_OBS_PARTIAL) {
+                np = find_head<32>(p, genv, lane);
+                render_partial<32>(p, genv, np, stage, lane);
+            } else if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_ONE_CHANNEL) {
+                for (int q = lane; q < C; q += 32) {
+                    const int y = div_S(q, p.magic_S), x = q - y * S;
+                    const bool border = y == 0 || x == 0 || y == S - 1 || x == S - 1;
+                    const float f = genv[q], h = genv[C + q], b = genv[2 * C + q];
+                    if (p.obs_mode == WURM_OBS_DEFAULT) {
+                        float* o = p.obs + (size_t)e * 3 * C;
+                        o[q] = rgb_channel(f, h, b, border, 0); o[C + q] = rgb_channel(f, h, b, border, 1); o[2 * C + q] = rgb_channel(f, h, b, border, 2);
+                    } else {
+                        float v = (b > kEps ? 1.0f : 0.0f) * 0.5f;
+                        v += h * 0.5f;
+                        v += f * 1.5f;
+                        p.obs[(size_t)e * C + q] = border ? -1.0f : v;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (p.obs_mode == WURM_OBS_PARTIAL) {
+            for (int r = lane; r < E; r += 32) p.obs[(size_t)e * E + r] = stage[r];
+        } else if (p.obs_mode == WURM_OBS_RAW) {                     // :139-141
+            for (int i = lane; i < 3 * C; i += 32) p.obs[(size_t)e * 3 * C + i] = genv[i];
+        } else if (p.obs_mode == WURM_OBS_POSITIONS) {               // :152-165 first argmax of head / food
+            int idx[2];
+            for (int ch = 0; ch < 2; ++ch) {
+                const float* v = genv + (ch == 0 ? C : 0);
+                float bv = -INFINITY;
+                int bq = 0;
+                for (int q = lane; q < C; q += 32)
+                    if (v[q] > bv) { bv = v[q]; bq = q; }
+                const float gv = group_max<32>(bv, 0xffffffffu);
+                idx[ch] = -group_max<32>(bv == gv ? -bq : -(1 << 30), 0xffffffffu);
+            }
+            if (lane == 0) {
+                float* o = p.obs + (size_t)e * 4;
+                const int hy = div_S(idx[0], p.magic_S), fy = div_S(idx[1], p.magic_S);
+                o[0] = (float)hy; o[1] = (float)(idx[0] - hy * S); o[2] = (float)fy; o[3] = (float)(idx[1] - fy * S);
+            }
+        }
+        if (STEP && p.auto_reset && ended) {                         // fused reset (:322-337), see single_tile_kernel
+            __syncwarp();
+            int tail = 0, mid = 0, hd = 0, cell = -1;
+            new_env_layout(p, p.spawn, call_counter(p) + 1, e, tail, mid, hd, cell);
+            for (int i = lane; i < 3 * C; i += 32)
+                if (genv[i] != 0.0f) genv[i] = 0.0f;
+            __syncwarp();
+            if (lane < 5) {
+                const int idx = lane == 0 ? cell : lane == 1 ? C + hd : lane == 2 ? 2 * C + tail : lane == 3 ? 2 * C + mid : 2 * C + hd;
+                const float val = lane == 3 ? 2.0f : lane == 4 ? 3.0f : 1.0f;
+                if (idx >= 0) genv[idx] = val;
+            }
+            if (lane == 0 && p.hints) { short* h = p.hints + 4 * (size_t)e; h[0] = (short)hd; h[1] = 3; h[2] = (short)cell; }
+        }
+    }
+    __syncthreads();
+    if (STEP && p.stats && threadIdx.x < WURM_STATS_FIELDS) {
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        const int v = threadIdx.x == 0 ? min(nwarps, p.N - (int)blockIdx.x * nwarps) : cnt_s[threadIdx.x - 1];
+        if (v) atomicAdd(slot + threadIdx.x, (unsigned long long)v);
+    }
 }
 
 // 64 threads (two size-36 envs) and >= 12 CTAs per SM measured best on B200 (profiles/r01_sweep_single_body.txt)
@@ -621,14 +809,28 @@ __global__ void __launch_bounds__(256) single_check_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 struct SingleLaunch {
     int G, T, threads, blocks, smem;
+    bool global;          // the env does not fit a shared-memory tile: single_global_kernel
 };
+
+template <bool STEP>
+static int launch_global(SingleParams p, cudaStream_t stream) {
+    if (p.S > 181) p.hints = nullptr;                   // cell indices no longer fit the int16 hints
+    const int warps = 4, E = p.obs_mode == WURM_OBS_PARTIAL ? 3 * p.W * p.W : 0;
+    p.stage_bytes = (warps * E * 4 + 15) & ~15;
+    const int smem = p.stage_bytes + 16;
+    auto kern = single_global_kernel<STEP>;
+    static SmemOptIn opt_in;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, smem, false, "cudaFuncSetAttribute(single_global_kernel)")) return rc;
+    kern<<<(p.N + warps - 1) / warps, 32 * warps, smem, stream>>>(p);
+    return check_launch("single_global_kernel");
+}
 
 static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* L) {
     if (!cfg) return fail(WURM_E_INVALID, "cfg is NULL");
     const int N = cfg->num_envs, S = cfg->size;
     if (N <= 0) return fail(WURM_E_INVALID, "num_envs must be positive");
     if (S < 9) return fail(WURM_E_INVALID, "size must be >= 9 (reference single_snake.py:346)");
-    if (S > 128) return fail(WURM_E_UNSUPPORTED, "size > 128: one env no longer fits a shared-memory tile");
+    if (S > 255) return fail(WURM_E_UNSUPPORTED, "size > 255: cell indices no longer fit the 16-bit index arithmetic");
     if (cfg->obs_mode < WURM_OBS_NONE || cfg->obs_mode > WURM_OBS_PARTIAL) return fail(WURM_E_INVALID, "bad obs_mode");
     if (cfg->obs_mode == WURM_OBS_PARTIAL && (cfg->obs_n < 0 || cfg->obs_n > 127)) return fail(WURM_E_INVALID, "bad obs_n");
     const int C = S * S;
@@ -660,7 +862,7 @@ static int plan_single(const WurmSingleCfg* cfg, SingleParams* p, SingleLaunch* 
     const int tile_bytes_padded = (T * env_bytes + 15) & ~15;
     const int stage_bytes = (T * stage_env_bytes + 15) & ~15;
     const int smem = tile_bytes_padded + stage_bytes + 8 + 16;
-    if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "tile does not fit shared memory");
+    L->global = smem > 200 * 1024 || S > 128;             // one env no longer fits a tile: step it on global memory
     p->N = N; p->S = S; p->C = C; p->T = T;
     p->obs_mode = cfg->obs_mode; p->obs_n = cfg->obs_n; p->W = W;
     p->magic_S = (uint32_t)((0x100000000ull + (uint64_t)S - 1) / (uint64_t)S);
@@ -741,6 +943,36 @@ static int try_launch_body(SingleParams p, int G, cudaStream_t stream) {
     }
 }
 
+template <int G, int STAGES>
+static int launch_ring_t(const SingleParams& p, int ntiles, int ctas, int smem, cudaStream_t stream) {
+    auto kern = single_ring_kernel<G, STAGES>;
+    static SmemOptIn opt_in;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, smem, true, "cudaFuncSetAttribute(single_ring_kernel)")) return rc;
+    kern<<<ctas, 32, smem, stream>>>(p, ntiles);
+    return check_launch("single_ring_kernel");
+}
+
+// -1 if the experiment is not selected or does not apply to this call
+static int try_launch_ring(const SingleParams& p, const SingleLaunch& L, cudaStream_t stream) {
+    const char* v = getenv("WURM_SINGLE_RING");
+    if (!v || p.obs_mode != WURM_OBS_PARTIAL || !p.bulk_ok || L.threads != 32 || L.G != 4 || (p.N % p.T) != 0) return -1;
+    if ((reinterpret_cast<uintptr_t>(p.obs) & 15u) || ((size_t)p.T * 3 * p.W * p.W * 4) % 16) return -1;
+    const int stages = atoi(v);
+    const int per_sm = getenv("WURM_SINGLE_RING_CTAS") ? atoi(getenv("WURM_SINGLE_RING_CTAS")) : 12;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = p.N / p.T;
+    const int ctas = min(ntiles, sms * per_sm);
+    const int smem = stages * p.tile_bytes_padded + 2 * p.stage_bytes + 8 * stages + 16 + 16;
+    switch (stages) {
+        case 2: return launch_ring_t<4, 2>(p, ntiles, ctas, smem, stream);
+        case 3: return launch_ring_t<4, 3>(p, ntiles, ctas, smem, stream);
+        case 4: return launch_ring_t<4, 4>(p, ntiles, ctas, smem, stream);
+        default: return -1;
+    }
+}
+
 }  // namespace wurm
 
 using namespace wurm;
@@ -776,8 +1008,13 @@ static int single_step_impl(const WurmSingleCfg* cfg, float* envs, void* actions
     p.obs = obs; p.reward = reward; p.done = done; p.self_col = self_col;
     p.edge_col = edge_col; p.status = status; p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
+    if (L.global) return launch_global<true>(p, (cudaStream_t)stream);
     {
         const int rc = try_launch_body(p, L.G, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
+    {
+        const int rc = try_launch_ring(p, L, (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
     return dispatch_tile<true>(p, L, (cudaStream_t)stream);
@@ -808,6 +1045,7 @@ extern "C" int wurm_single_observe(const WurmSingleCfg* cfg, const float* envs, 
     if (cfg->obs_mode == WURM_OBS_NONE) return WURM_OK;
     p.envs = const_cast<float*>(envs); p.obs = obs; p.status = status;
     p.bulk_ok = aligned16(envs) && ((size_t)p.T * 3 * p.C * 4) % 16 == 0 && (cfg->obs_mode != WURM_OBS_RAW || aligned16(obs));
+    if (L.global) return launch_global<false>(p, (cudaStream_t)stream);
     return dispatch_tile<false>(p, L, (cudaStream_t)stream);
 }
 
