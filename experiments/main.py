@@ -125,7 +125,7 @@ def main(argv=None):
     if train:
         optimizer = torch.optim.Adam(model.parameters(), lr=args.lr)
         a2c = A2C(gamma=args.gamma)
-        trajectories = TrajectoryStore()
+        trajectories = TrajectoryStore(capacity=args.update_steps)       # rewards / dones / actions in a device ring
 
     num_steps = num_episodes = 0
     t0 = time()

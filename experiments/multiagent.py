@@ -100,7 +100,7 @@ def main(argv=None):
     if train:
         optimizer = torch.optim.Adam(model.parameters(), lr=args.lr)
         a2c = A2C(gamma=args.gamma)
-        trajectories = TrajectoryStore()
+        trajectories = TrajectoryStore(capacity=args.update_steps)       # rewards / dones / actions in a device ring
     losses = {}
 
     def flat(d):                                     # the reference's flatten_dict: agent-major (K*E, 1)

@@ -55,3 +55,31 @@ def test_a2c_loss_and_gradients_n_step():
     assert_same(policy_loss.detach().cpu().numpy(), pl.detach().cpu().numpy(), 'policy loss')
     assert_same(values_a.grad.cpu().numpy(), values_b.grad.cpu().numpy(), 'd loss / d values')
     assert_same(logp_a.grad.cpu().numpy(), logp_b.grad.cpu().numpy(), 'd loss / d log_probs')
+
+
+def test_trajectory_ring_receives_observations_straight_from_the_step_kernel():
+    """TrajectoryStore(capacity=T): the no-gradient fields live in preallocated (T, N, ...) rings; with state_slot() the
+    step kernel renders the observation into the ring itself (obs_out=), and the properties are views, not stacks."""
+    from wurm_b200.envs import SingleSnake
+    from wurm_b200.trajectory_store import TrajectoryStore
+    N, S, T = 300, 9, 6
+    ringed = SingleSnake(num_envs=N, size=S, observation_mode='partial_2', device='cuda', seed=9)
+    listed = SingleSnake(num_envs=N, size=S, observation_mode='partial_2', device='cuda', seed=9)
+    ring, plain = TrajectoryStore(capacity=T), TrajectoryStore()
+    g = torch.Generator().manual_seed(2)
+    for update in range(2):
+        for t in range(T):
+            a = torch.randint(0, 4, (N,), generator=g).to('cuda')
+            slot = ring.state_slot((N, 75))
+            obs, reward, done, _ = ringed.step(a.clone(), auto_reset=True, obs_out=slot)
+            assert obs.data_ptr() == slot.data_ptr()
+            ring.append(state=obs, action=a, reward=reward, done=done)
+            obs2, reward2, done2, _ = listed.step(a.clone(), auto_reset=True)
+            plain.append(state=obs2, action=a, reward=reward2, done=done2)
+        assert len(ring) == T and ring.states.data_ptr() == ring._ring['state'].data_ptr()      # a view of the ring
+        for name in ('states', 'actions', 'rewards', 'dones'):
+            assert torch.equal(getattr(ring, name), getattr(plain, name)), name
+        ring.clear(); plain.clear()
+    with pytest.raises(RuntimeError):
+        for t in range(T + 1):
+            ring.append(reward=reward)

@@ -78,6 +78,10 @@ ROLLOUTS = [
     (333, 16, 'partial_2', 40, 1, torch.long),      # body-only tiles (even sizes from 16 up), ragged last tile
     (200, 18, 'default', 30, 7, torch.int),         # ... with dead envs stepped again (general step on global memory)
     (77, 24, 'one_channel', 30, 3, torch.long),
+    (5, 150, 'partial_3', 10, 1, torch.long),       # sides above 128: no shared-memory tile, the general step on global memory
+    (3, 200, 'default', 6, 1, torch.int),           # ... above 181 also without hints (cell indices exceed int16)
+    (4, 140, 'positions', 9, 3, torch.long),
+    (3, 130, 'raw', 6, 1, torch.long),
 ]
 
 
