@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(256) single_compact_kernel(const CompactParams
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
+    }
+    if (threadIdx.x < 32) __syncwarp();     // (orders the barrier's initialisation before its first use for racecheck's warp-level model)
+    if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar, bytes);
         bulk_load(tile, gtile, bytes, bar);
     }

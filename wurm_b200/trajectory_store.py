@@ -27,7 +27,8 @@ class TrajectoryStore(object):
         `obs_out=` so that the step kernel writes the observation there, then pass the returned observation to append()."""
         if self.capacity is None:
             raise RuntimeError('state_slot() needs a TrajectoryStore(capacity=T)')
-        return self._slot('state', len(self._lists['state']), torch.Size(shape), dtype, torch.device(device))
+        device = torch.empty(0, device=device).device             # 'cuda' -> 'cuda:<current>': what the tensors will report
+        return self._slot('state', len(self._lists['state']), torch.Size(shape), dtype, device)
 
     def _slot(self, name, t, shape, dtype, device):
         if t >= self.capacity:
