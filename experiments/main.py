@@ -92,6 +92,8 @@ def main(argv=None):
     parser.add_argument('--gamma', default=0.99, type=float)
     parser.add_argument('--update-steps', default=20, type=int)
     parser.add_argument('--entropy', default=0.0, type=float)
+    parser.add_argument('--state', default='dense', type=str, choices=['dense', 'compact'],
+                        help="'compact': the env lives in HBM as small records instead of the reference's dense fp32 tensors")
     args = parser.parse_args(argv)
 
     if args.env not in ('snake', 'gridworld'):
@@ -111,7 +113,7 @@ def main(argv=None):
                               observation_mode=args.observation, device=args.device, seed=args.seed)
     else:
         env = SingleSnake(num_envs=args.num_envs, size=args.size, device=args.device, observation_mode=args.observation,
-                          render_args=render_args, seed=args.seed)
+                          render_args=render_args, seed=args.seed, state=args.state)
 
     state = env.reset()
     if args.agent == 'random':

@@ -68,6 +68,8 @@ def main(argv=None):
     parser.add_argument('--gamma', default=0.99, type=float)
     parser.add_argument('--update-steps', default=5, type=int)
     parser.add_argument('--entropy', default=0.0, type=float)
+    parser.add_argument('--state', default='dense', type=str, choices=['dense', 'compact'],
+                        help="'compact': the env lives in HBM as small records instead of the reference's dense fp32 tensors")
     args = parser.parse_args(argv)
 
     if args.env != 'snake':
@@ -87,7 +89,8 @@ def main(argv=None):
     env = MultiSnake(num_envs=args.n_envs, num_snakes=args.n_agents, size=args.size, device=args.device,
                      observation_mode=args.obs, boost=args.boost, boost_cost_prob=args.boost_cost,
                      food_on_death_prob=args.food_on_death, reward_on_death=args.reward_on_death, food_mode=args.food_mode,
-                     food_rate=args.food_rate, respawn_mode=args.respawn_mode, agent_colours=args.colour_mode, seed=args.seed)
+                     food_rate=args.food_rate, respawn_mode=args.respawn_mode, agent_colours=args.colour_mode, seed=args.seed,
+                     state=args.state)
 
     num_actions = 8 if args.boost else 4
     K, E = args.n_agents, args.n_envs

@@ -149,6 +149,9 @@ int wurm_single_compact_reset(const WurmSingleCfg* cfg, uint16_t* cells, int16_t
                               const int32_t* spawn_replay, uint64_t seed, uint64_t step, const uint64_t* step_dev, void* stream);
 int wurm_single_compact_observe(const WurmSingleCfg* cfg, const uint16_t* cells, const int16_t* aux, float* obs,
                                 int32_t* status, void* stream);
+/* wurm_single_check (env_consistency, wurm/utils.py:113-178) on records: same report, same WURM_CHK_* bits. */
+int wurm_single_compact_check(const WurmSingleCfg* cfg, const uint16_t* cells, const uint8_t* skip /* nullable */, int32_t* report,
+                              void* stream);
 int wurm_single_compact(const WurmSingleCfg* cfg, const float* envs, uint16_t* cells, int16_t* aux, int32_t* status, void* stream);
 int wurm_single_expand(const WurmSingleCfg* cfg, const uint16_t* cells, const int16_t* aux, float* envs, void* stream);
 

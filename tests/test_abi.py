@@ -40,7 +40,7 @@ def test_obs_elems():
     ((0, 9, 0, 0), _lib.E_INVALID),          # no envs
     ((4, 8, 0, 0), _lib.E_INVALID),          # size <= 8 (reference single_snake.py:346)
     ((4, 9, 7, 0), _lib.E_INVALID),          # unknown observation mode
-    ((4, 200, 0, 0), _lib.E_UNSUPPORTED),    # one env no longer fits a shared-memory tile
+    ((4, 300, 0, 0), _lib.E_UNSUPPORTED),    # cell indices no longer fit the 16-bit index arithmetic (sides up to 255 run)
 ])
 def test_bad_config_is_rejected_on_the_host(cfg, code):
     L = _lib.lib()

@@ -127,3 +127,29 @@ def test_multi_checker():
     env5.heads[a, 0, y, x] = 1
     with pytest.raises(RuntimeError, match='num_heads'):
         env5.check_consistency()
+
+
+def test_compact_single_checker_works_on_the_records():
+    """state='compact': check_consistency runs on the records (no fp32 materialisation), honours `skip`, and reports
+    corruptions folded in from a caller-edited tensor with the reference's messages."""
+    from wurm_b200.envs import SingleSnake
+    n, S = 64, 12
+    env = SingleSnake(num_envs=n, size=S, observation_mode='one_channel', device=DEV, seed=5, state='compact')
+    g = torch.Generator().manual_seed(5)
+    for _ in range(10):
+        _, _, done, _ = env.step(torch.randint(0, 4, (n,), generator=g).to(DEV))
+        env.check_consistency(skip=done)                     # the driver's per-step call: terminal envs skipped
+        assert env._dense is None                            # nothing was materialised for it
+        env.reset(done, return_observations=False)
+    env.check_consistency()
+    for needle, corrupt in [('multiple num_heads', lambda e: e.__setitem__((3, 1, 1, 1), 1.0)),
+                            ('exactly one food', lambda e: e[3, 0].zero_()),
+                            ('head not at the end', lambda e: (e[3, 1].zero_(), e[3, 1].__setitem__((1, 1), 1.0)))]:
+        saved = env.envs.clone()
+        corrupt(env.envs)                                    # through the materialised tensor: folded back on the next call
+        with pytest.raises(RuntimeError, match=needle):
+            env.check_consistency()
+        skip = torch.zeros(n, dtype=torch.bool, device=DEV); skip[3] = True
+        env.check_consistency(skip=skip)
+        env.envs = saved
+        env.check_consistency()

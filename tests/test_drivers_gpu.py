@@ -17,6 +17,18 @@ def test_rollout_driver(agent, observation):
     assert 3.0 <= summary['avg_size'] < 6.0
 
 
+def test_drivers_on_the_compact_state():
+    """`--state compact`: both drivers run their reference loops (consistency checked every step, on the records)."""
+    from experiments.main import main
+    summary = main(['--env', 'snake', '--num-envs', '512', '--size', '9', '--agent', 'feedforward', '--observation', 'partial_2',
+                    '--total-steps', str(512 * 150), '--seed', '3', '--state', 'compact'])
+    assert summary['steps'] == 512 * 150 and summary['episodes'] > 0 and 3.0 <= summary['avg_size'] < 6.0
+    from experiments.multiagent import main as multi_main
+    summary = multi_main(['--n-envs', '256', '--n-agents', '4', '--size', '25', '--obs', 'partial_4', '--total-steps',
+                          str(256 * 120), '--seed', '2', '--state', 'compact'])
+    assert summary['steps'] == 256 * 120 and summary['edge_collisions'] > 0 and summary['food'] > 0
+
+
 def test_multisnake_speed_sweep():
     from experiments.speeds import sweep
     fps = sweep(num_agents=4, size=20, min_log2=4, max_log2=8, num_steps=5, check=True, verbose=False)

@@ -22,7 +22,7 @@ OBS_NONE, OBS_DEFAULT, OBS_RAW, OBS_ONE_CHANNEL, OBS_POSITIONS, OBS_PARTIAL = -1
 # every symbol include/wurm_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = ['wurm_abi_version', 'wurm_last_error', 'wurm_single_obs_elems', 'wurm_single_step', 'wurm_single_step_reset',
            'wurm_single_reset', 'wurm_single_compact_step', 'wurm_single_compact_reset', 'wurm_single_compact_observe',
-           'wurm_single_compact', 'wurm_single_expand',
+           'wurm_single_compact_check', 'wurm_single_compact', 'wurm_single_expand',
            'wurm_single_observe', 'wurm_multi_obs_elems', 'wurm_multi_step', 'wurm_multi_step_reset', 'wurm_multi_reset', 'wurm_multi_observe',
            'wurm_multi_env_images', 'wurm_multi_compact', 'wurm_multi_expand', 'wurm_single_check', 'wurm_multi_check', 'wurm_grid_step', 'wurm_grid_reset',
            'wurm_grid_observe', 'wurm_a2c_returns']
@@ -118,6 +118,8 @@ def lib():
     L.wurm_single_compact_reset.argtypes = [cfg, vp, vp, vp, vp, u64, u64, vp, vp]
     L.wurm_single_compact_observe.restype = i32
     L.wurm_single_compact_observe.argtypes = [cfg, vp, vp, vp, vp, vp]
+    L.wurm_single_compact_check.restype = i32
+    L.wurm_single_compact_check.argtypes = [cfg, vp, vp, vp, vp]
     L.wurm_single_compact.restype = i32
     L.wurm_single_compact.argtypes = [cfg, vp, vp, vp, vp, vp]
     L.wurm_single_expand.restype = i32

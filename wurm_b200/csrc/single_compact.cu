@@ -454,6 +454,41 @@ __global__ void __launch_bounds__(256) single_convert_kernel(const CompactParams
     }
 }
 
+// wurm/utils.py:113-178 (snake_consistency + env_consistency) on records: one warp per env, the same seven sums as
+// single_check_kernel (single_snake.cu) taken from the decoded cells, the same verdict bits in the same report.
+__global__ void __launch_bounds__(256) single_compact_check_kernel(const uint16_t* __restrict__ cells, const uint8_t* __restrict__ skip,
+                                                                   int N, int C, int Cp, int* report) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= N || (skip && skip[e])) return;
+    const uint16_t* row = cells + (size_t)e * Cp;
+    float sum_food = 0.0f, sum_head = 0.0f, sum_body = 0.0f, max_body = -INFINITY, head_body = 0.0f, head_food = 0.0f;
+    for (int q = lane; q < C; q += 32) {
+        const uint32_t v = row[q];
+        const float f = cell_food(v), h = cell_head(v), b = cell_body(v);
+        sum_food += f; sum_head += h; sum_body += b;
+        max_body = fmaxf(max_body, b);
+        head_body += h * b; head_food += h * f;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_food += __shfl_xor_sync(0xffffffffu, sum_food, o); sum_head += __shfl_xor_sync(0xffffffffu, sum_head, o);
+        sum_body += __shfl_xor_sync(0xffffffffu, sum_body, o); head_body += __shfl_xor_sync(0xffffffffu, head_body, o);
+        head_food += __shfl_xor_sync(0xffffffffu, head_food, o);
+        max_body = fmaxf(max_body, __shfl_xor_sync(0xffffffffu, max_body, o));
+    }
+    if (lane == 0) {
+        int bits = 0;                                                // (a food pixel is 0 or 1 by construction: no WURM_CHK_FOOD_VALUE)
+        if (sum_head != 1.0f) bits |= WURM_CHK_HEAD_COUNT;
+        if (!(sum_body > 0.0f)) bits |= WURM_CHK_NO_SNAKE;
+        if (head_body != max_body) bits |= WURM_CHK_HEAD_NOT_AT_END;
+        if ((sqrtf(8.0f * sum_body + 1.0f) - 1.0f) / 2.0f != max_body) bits |= WURM_CHK_BODY_VALUES;
+        if (sum_body < 6.0f) bits |= WURM_CHK_TOO_SHORT;
+        if (head_food != 0.0f) bits |= WURM_CHK_HEAD_ON_FOOD;
+        if (sum_food != 1.0f) bits |= WURM_CHK_FOOD_COUNT;
+        if (bits) { atomicOr(report, bits); atomicAdd(report + 1, 1); atomicMin(report + 2, e); }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -591,6 +626,15 @@ static int single_convert(const WurmSingleCfg* cfg, float* envs, uint16_t* cells
     if (to_compact) single_convert_kernel<true><<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(cp, envs);
     else single_convert_kernel<false><<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(cp, envs);
     return check_launch("single_convert_kernel");
+}
+
+extern "C" int wurm_single_compact_check(const WurmSingleCfg* cfg, const uint16_t* cells, const uint8_t* skip, int32_t* report,
+                                         void* stream) {
+    if (!cfg || !cells || !report) return fail(WURM_E_INVALID, "NULL pointer");
+    if (cfg->num_envs <= 0 || cfg->size < 1) return fail(WURM_E_INVALID, "bad num_envs / size");
+    const int C = cfg->size * cfg->size, warps = 8, blocks = (cfg->num_envs + warps - 1) / warps;
+    single_compact_check_kernel<<<blocks, 32 * warps, 0, (cudaStream_t)stream>>>(cells, skip, cfg->num_envs, C, (C + 7) & ~7, report);
+    return check_launch("single_compact_check_kernel");
 }
 
 extern "C" int wurm_single_compact(const WurmSingleCfg* cfg, const float* envs, uint16_t* cells, int16_t* aux, int32_t* status,

@@ -249,6 +249,20 @@ class SingleSnake(object):
         """env_consistency (reference wurm/utils.py:167-178) of every env whose `skip` flag is not set, in one
         fused kernel -- what the reference driver does with `env_consistency(env.envs[~done])` (main.py:215),
         without the boolean-mask gather.  Raises the reference's RuntimeError messages."""
+        if self._compact:                    # on the records: no materialisation of the fp32 tensor
+            self._compact_state(mutates=False)
+            report = torch.tensor([0, 0, 2 ** 31 - 1, 0], dtype=torch.int32, device=self._dev)
+            cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
+            if skip is not None:
+                skip = skip.reshape(-1)
+                if skip.dtype != torch.bool or skip.device != self._dev or not skip.is_contiguous():
+                    skip = (skip != 0).to(self._dev).contiguous()
+            with torch.cuda.device(self._dev):
+                _lib.check(self._lib.wurm_single_compact_check(ctypes.byref(cfg), _ptr(self._cells), _ptr(skip), _ptr(report),
+                                                               self._stream()))
+            _lib.raise_on_report(report.tolist())
+            self.check_status()
+            return
         from ..utils import _fused_check
         _lib.raise_on_report(_fused_check(self._state(), skip))
         self.check_status()
