@@ -54,3 +54,27 @@ def test_ranks_get_different_draws():
     from wurm_b200.distributed import env_slice, rank_seed
     assert [env_slice(257, r, 2) for r in range(2)] == [(0, 129), (129, 128)]
     assert len({rank_seed(7, r) for r in range(8)}) == 8
+
+
+@needs_two
+def test_two_devices_in_one_process():
+    """The dynamic shared-memory opt-in of a kernel is a PER-DEVICE attribute: an env stepped on cuda:0 and
+    then another on cuda:1 in the same process must both launch -- with tiles above the 48 KB default (size 9 `default`
+    observations: 62 KB; MultiSnake size 64: > 48 KB of records) -- and agree with each other."""
+    from wurm_b200.envs import SingleSnake, MultiSnake
+    outs = []
+    for dev in ('cuda:0', 'cuda:1'):
+        env = SingleSnake(num_envs=300, size=9, observation_mode='default', device=dev, seed=4)
+        g = torch.Generator().manual_seed(1)
+        for _ in range(5):
+            obs, reward, done, _ = env.step(torch.randint(0, 4, (300,), generator=g).to(dev), auto_reset=True)
+        env.check_status()
+        outs.append((obs.cpu(), env.envs.cpu()))
+        menv = MultiSnake(num_envs=8, num_snakes=16, size=64, observation_mode='partial_4', device=dev, seed=4)
+        acts = {f'agent_{k}': torch.zeros(8, dtype=torch.long, device=dev) for k in range(16)}
+        menv.step(acts, auto_reset=True)
+        menv.check_consistency()
+        cenv = SingleSnake(num_envs=300, size=36, observation_mode='default', device=dev, seed=4, state='compact')
+        cenv.step(torch.zeros(300, dtype=torch.long, device=dev), auto_reset=True)
+        cenv.check_consistency()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
