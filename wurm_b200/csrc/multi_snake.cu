@@ -798,6 +798,8 @@ multi_env_kernel(const MultiParams p) {
     // the call counter is read where a draw needs it (rare: something died or was eaten); hoisting the load to the top
     // of the kernel was measured and lost (a register held across the whole step)
 #define ctr_now call_counter(p)
+    // (An L2 prefetch of the env's foods / bodies lines ahead of the load scan was measured for the small-CTA shapes:
+    // C4 0.3397 -> 0.3357 ms, within noise of not being worth the code; profiles/r02_multi_compact_experiments.txt.)
     constexpr bool kPrefetch = THREADS == 256 || (COMPACT && THREADS >= 64);
     long long pre_action = 0, pre_orient = 0;
     float pre_cost = 0.0f;

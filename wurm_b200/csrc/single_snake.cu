@@ -384,7 +384,7 @@ __device__ __noinline__ int3 slow_step_on_global(const SingleParams p, int e, in
 // runs for envs whose hints do not verify -- so that the reference's "any size" holds here too.  Not a tuned path.
 template <bool STEP>
 __global__ void __launch_bounds__(128) single_global_kernel(const SingleParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int C = p.C, S = p.S, E = 3 * p.W * p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float* stage = reinterpret_cast<float*>(smem) + (size_t)warp * (p.obs_mode == WURM_OBS_PARTIAL ? E : 0);
