@@ -683,3 +683,26 @@ def test_compact_state_with_more_live_cells_than_the_live_list_holds(E, K, S, mo
             dense.food_rate = compact.food_rate = 1e-3
             dense.foods = torch.zeros_like(dense.foods); compact.foods = torch.zeros_like(dense.foods)
     compact.check_consistency()
+
+
+def test_graphed_stepper_on_the_compact_state():
+    from wurm_b200 import GraphedStepper
+    E, K, S, steps = 64, 4, 25, 15
+    dense = make_env(E, K, S, 'partial_4', seed=31, respawn_mode='any')
+    compact = make_env(E, K, S, 'partial_4', seed=31, respawn_mode='any', state='compact')
+    compact.agent_colours = dense.agent_colours.clone()
+    acts = torch.randint(0, 8, (steps, K, E), generator=torch.Generator().manual_seed(2)).to(DEV)
+    static = {f'agent_{k}': acts[0, k].clone() for k in range(K)}
+    stepper = GraphedStepper(compact, static, warmup=2)
+    check_state(compact, env_state(dense), 'state after construction')        # (materialises the tensors ...)
+    for t in range(steps):
+        for k in range(K):
+            static[f'agent_{k}'].copy_(acts[t, k])
+        obs, rewards, dones, info = stepper.step()                          # (... which the replay must drop again)
+        obs2, rewards2, dones2, info2 = dense.step({f'agent_{k}': acts[t, k] for k in range(K)}, auto_reset=True)
+        for k in range(K):
+            assert_same(np_(obs[f'agent_{k}']), np_(obs2[f'agent_{k}']), f'step {t}: obs {k}')
+        assert_same(stack_dict(rewards, K), stack_dict(rewards2, K), f'step {t}: rewards')
+        if t % 5 == 0:
+            check_state(compact, env_state(dense), f'step {t}')
+    check_state(compact, env_state(dense), 'final state')

@@ -627,3 +627,32 @@ def test_compact_state_takes_caller_edits_and_refuses_what_it_cannot_carry():
     env.envs[0, 2, 3, 3] = 0.5                               # a non-integral body value: not a record
     with pytest.raises(RuntimeError, match='compact'):
         env.step(act.clone())
+
+
+def test_graphed_and_host_steppers_on_the_compact_state():
+    """GraphedStepper and HostStepper drive a state='compact' env exactly like a dense one (same draws, same results)."""
+    from wurm_b200 import GraphedStepper, HostStepper
+    N, S, steps = 512, 9, 20
+    dense = make_env(N, S, 'partial_2', seed=21)
+    graphed = make_env(N, S, 'partial_2', seed=21, state='compact')
+    piped = make_env(N, S, 'partial_2', seed=21, state='compact')
+    acts = torch.randint(0, 4, (steps, N), generator=torch.Generator().manual_seed(6))
+    static = acts[0].to(DEV)
+    gs = GraphedStepper(graphed, static, warmup=2)
+    hs = HostStepper(piped, depth=2)
+    assert_same(np_(graphed.envs), np_(dense.envs), 'state after constructing the graphed stepper')
+    for t in range(steps):
+        o1, r1, d1, _ = dense.step(acts[t].to(DEV), auto_reset=True)
+        static.copy_(acts[t])
+        o2, r2, d2, _ = gs.step()
+        ticket = hs.submit(acts[t].to(torch.uint8).pin_memory()).wait()
+        assert_same(np_(o2), np_(o1), f'step {t}: graphed obs')
+        assert_same(np_(r2), np_(r1), f'step {t}: graphed reward')
+        assert_same(np_(ticket.obs), np_(o1), f'step {t}: piped obs')
+        assert_same(ticket.reward.numpy(), np_(r1), f'step {t}: piped reward')
+        assert_same(ticket.done.numpy(), np_(d1), f'step {t}: piped done')
+    assert_same(np_(graphed.envs), np_(dense.envs), 'final state (graphed)')
+    assert_same(np_(piped.envs), np_(dense.envs), 'final state (piped)')
+    out = torch.empty((N, 75), device=DEV)
+    o3, _, _, _ = piped.step(acts[0].to(DEV), obs_out=out)
+    assert o3.data_ptr() == out.data_ptr()

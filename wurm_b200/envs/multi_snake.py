@@ -265,6 +265,10 @@ class MultiSnake(object):
             raise RuntimeError("state='compact' cannot carry this state exactly (food / head values other than 1, non-integral "
                                "body values, two bodies on one cell, or a head off its own body); use state='dense'")
 
+    def _before_replay(self):
+        """GraphedStepper hook (compact mode): what step() does to the materialised tensors before launching."""
+        self._state(mutates=True)
+
     def _snapshot_names(self):
         """Attributes that make up the env's state in compact mode (GraphedStepper snapshots them around its warm-up)."""
         return ('_cells', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards', '_head_hints', '_stats', '_status')

@@ -193,6 +193,10 @@ class SingleSnake(object):
             if mutates:
                 self._dense = None
 
+    def _before_replay(self):
+        """GraphedStepper hook (compact mode): what step() does to the materialised tensor before launching."""
+        self._compact_state(mutates=True)
+
     def _snapshot_names(self):
         """Attributes that make up the env's state in compact mode (GraphedStepper snapshots them around its warm-up)."""
         return ('_cells', 'done', '_hints', '_stats', '_status')

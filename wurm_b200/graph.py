@@ -137,6 +137,8 @@ class GraphedStepper(object):
 
     def _replay(self):
         env = self.env
+        if getattr(env, '_compact', False):         # a replay changes the state behind the Python wrapper's back:
+            env._before_replay()                    # fold caller edits of materialised tensors in, then drop them
         want = env._draws + 1 - self._base          # the captured step must run with the env's next counter value
         if want != self._mirror:                    # direct env.step()/reset() calls were made since the last replay
             self._addend.fill_(want)
