@@ -681,6 +681,29 @@ def measure_config(ctx, key, K, W, min_seconds, exact_steps):
         barrier()
         fused_ms = f_start.elapsed_time(f_stop)
 
+    # ---- C3 as BASELINE.json words it: "RGB obs + feedforward A2C rollout"  ----
+    # the env's observation feeds a 2 x 64 MLP (experiments.main.FeedforwardAgent, plain torch: the policy is outside the hot
+    # path) whose sampled actions drive the next step: obs -> policy -> Categorical.sample -> env.step(auto_reset=True)
+    policy_ms = 0.0
+    if key == 'C3':
+        from torch.distributions import Categorical
+        from experiments.main import FeedforwardAgent
+        model = FeedforwardAgent(num_actions=4, num_layers=2, hidden_units=64, num_inputs=obs_elems).to(dev)
+        state = obs
+        with torch.no_grad():
+            for t in range(W + K):
+                if t == W:
+                    p_start, p_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    barrier()
+                    p_start.record()
+                probs, _ = model(state)
+                action = Categorical(probs).sample()
+                state, _, _, _ = env.step(action, auto_reset=True)
+            p_stop.record()
+            barrier()
+        policy_ms = p_start.elapsed_time(p_stop)
+        del model, state
+
     # ---- end to end through the public API with host buffers ----
     from wurm_b200 import HostStepper, GraphedStepper
     host_pool = ad.host_pool()
@@ -770,8 +793,8 @@ def measure_config(ctx, key, K, W, min_seconds, exact_steps):
             e2e_obs_bytes = stepper.d2h_bytes_per_step
             del stepper
 
-    ms_total, e2e_ms, step_kernel_ms, fused_ms, graphed_ms, e2e_obs_ms = reduce_max(
-        [ms_total, e2e_ms, step_kernel_ms, fused_ms, graphed_ms, e2e_obs_ms])
+    ms_total, e2e_ms, step_kernel_ms, fused_ms, graphed_ms, e2e_obs_ms, policy_ms = reduce_max(
+        [ms_total, e2e_ms, step_kernel_ms, fused_ms, graphed_ms, e2e_obs_ms, policy_ms])
     if sustained is not None:
         sustained = (sustained[0], reduce_max([sustained[1]])[0])
     stats = env.stats(reduce_group=True if world > 1 else None)
@@ -828,6 +851,10 @@ def measure_config(ctx, key, K, W, min_seconds, exact_steps):
                      'physical_frac': (traffic / (step_kernel_ms * 1e-3) / 1e9 / peak) if traffic else None},
         'episode_stats': stats,
     }
+    if policy_ms:
+        rec['rollout_with_policy'] = {'value': world * N * K / (policy_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': policy_ms / K,
+                                      'loop': 'probs, value = FeedforwardAgent(2 x 64)(obs); a = Categorical(probs).sample(); '
+                                              'obs, r, d, info = env.step(a, auto_reset=True)   (policy in plain torch, no grad)'}
     if compact is not None:
         rec['compact_state'] = compact
     if sustained is not None:
