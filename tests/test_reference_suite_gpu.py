@@ -30,17 +30,22 @@ REFERENCE_TESTS = [
 ]
 
 
-def run_suite(target):
+def run_suite(target, state=None):
+    env = dict(os.environ)
+    if state:
+        env['WURM_B200_STATE'] = state          # the constructors' default: the reference's tests never pass `state=`
     out = subprocess.run([sys.executable, os.path.join(HERE, 'reference_suite.py'), '--target', target],
-                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
     assert lines, f'reference_suite.py produced no result (rc {out.returncode}): {out.stderr[-2000:]}'
     return json.loads(lines[-1])
 
 
-@pytest.fixture(scope='module')
-def results():
-    res = run_suite('dropin')
+@pytest.fixture(scope='module', params=['dense', 'compact'])
+def results(request):
+    """One run of the whole reference suite per state mode (state='compact': every env the reference's tests construct
+    keeps its state as records; their reads and writes of env.envs / env.heads / ... go through the materialised tensors)."""
+    res = run_suite('dropin', request.param)
     if 'error' in res:
         pytest.skip(res['error'])
     return res

@@ -18,6 +18,7 @@ from collections import namedtuple, OrderedDict
 from time import time
 from typing import Dict, Optional
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -65,7 +66,7 @@ class MultiSnake(object):
                  render_args: dict = None,
                  agent_colours: str = 'random',
                  seed: int = None,
-                 state: str = 'dense'):
+                 state: str = None):
         self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
         self.num_envs = num_envs
         self.num_snakes = num_snakes
@@ -81,6 +82,9 @@ class MultiSnake(object):
                                "the CPU implementation of this path is the reference itself")
         if dtype != torch.float:
             raise NotImplementedError('wurm_b200.MultiSnake keeps the state in float32 only')
+        if state is None:
+            state = os.environ.get('WURM_B200_STATE', 'dense')     # process-wide default (how the reference's own tests are
+                                                                   # run against the compact state without touching them)
         if state not in ('dense', 'compact'):
             raise ValueError("state must be 'dense' (the reference's fp32 tensors are the state) or 'compact'")
         # state='compact' (an extension): between calls the env lives in HBM as one 32-bit record per cell (include/

@@ -16,6 +16,7 @@ randperm, wurm/utils.py:188,224, and cannot be regenerated).
 from collections import namedtuple
 from time import time
 import ctypes
+import os
 
 import torch
 
@@ -58,8 +59,11 @@ class SingleSnake(object):
                  verbose: int = 0,
                  render_args: dict = None,
                  seed: int = None,
-                 state: str = 'dense'):
+                 state: str = None):
         self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
+        if state is None:
+            state = os.environ.get('WURM_B200_STATE', 'dense')     # process-wide default (how the reference's own tests are
+                                                                   # run against the compact state without touching them)
         if state not in ('dense', 'compact'):
             raise ValueError("state must be 'dense' (the reference's fp32 tensor is the state) or 'compact'")
         # state='compact' (an extension): between calls the env lives in HBM as one uint16 record per cell (include/
