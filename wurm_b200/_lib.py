@@ -163,6 +163,26 @@ def lib():
     return L
 
 
+class _NoGuard(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(dev):
+    """`with device_guard(dev):` makes `dev` the current CUDA device for a launch, like `torch.cuda.device(dev)`, but costs
+    nothing when it already is (the common case: a few microseconds matter at launch-bound batch sizes)."""
+    import torch
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NO_GUARD
+    return torch.cuda.device(dev)
+
+
 def check(rc):
     if rc != OK:
         raise WurmError(rc, lib().wurm_last_error().decode())

@@ -251,7 +251,7 @@ class MultiSnake(object):
                  'bodies': torch.empty((E * K, 1, S, S), dtype=torch.float32, device=self._dev)}
         cfg = self._cfg(None)
         st = self._compact_struct(dense)
-        with torch.cuda.device(self._dev):
+        with _lib.device_guard(self._dev):
             _lib.check(self._lib.wurm_multi_expand(ctypes.byref(cfg), ctypes.byref(st), self._stream()))
         self._dense = dense
         self._dense_key = self._dense_identity()
@@ -260,7 +260,7 @@ class MultiSnake(object):
         """the (caller-edited) fp32 tensors -> compact records; raises if the records cannot carry the state."""
         cfg = self._cfg(None)
         st = self._compact_struct(self._dense)
-        with torch.cuda.device(self._dev):
+        with _lib.device_guard(self._dev):
             _lib.check(self._lib.wurm_multi_compact(ctypes.byref(cfg), ctypes.byref(st), _ptr(self._status), self._stream()))
         self._dense_key = self._dense_identity()
         st_word = int(self._status.item())
@@ -361,7 +361,7 @@ class MultiSnake(object):
         cfg = self._cfg(mode)
         st = self._state()
         obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=self._dev)
-        with torch.cuda.device(self._dev):
+        with _lib.device_guard(self._dev):
             _lib.check(self._lib.wurm_multi_observe(ctypes.byref(cfg), ctypes.byref(st), _ptr(obs), _ptr(self._status),
                                                     self._stream()))
         return obs
@@ -380,7 +380,7 @@ class MultiSnake(object):
         cfg = self._cfg(None)
         st = self._state()
         img = torch.empty((self.num_envs, 3, self.size, self.size), dtype=torch.short, device=self._dev)
-        with torch.cuda.device(self._dev):
+        with _lib.device_guard(self._dev):
             _lib.check(self._lib.wurm_multi_env_images(ctypes.byref(cfg), ctypes.byref(st), _ptr(img), _ptr(self._status),
                                                        self._stream()))
         return img
@@ -447,7 +447,7 @@ class MultiSnake(object):
             rdr = _lib.WurmMultiResetDraws(dev_r('create', torch.int32), dev_r('respawn', torch.int32),
                                            dev_r('colours', torch.short))
         self._draws += 1
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if auto_reset:
                 _lib.check(self._lib.wurm_multi_step_reset(
                     ctypes.byref(cfg), ctypes.byref(st), act_ptrs, _ACTION_BYTES[dtype],
@@ -497,7 +497,7 @@ class MultiSnake(object):
             dr = _lib.WurmMultiResetDraws(dev_t('create', torch.int32), dev_t('respawn', torch.int32),
                                           dev_t('colours', torch.short))
         self._draws += 1
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(self._lib.wurm_multi_reset(ctypes.byref(cfg), ctypes.byref(st), _ptr(env_done),
                                                   ctypes.byref(dr) if dr is not None else None, self.seed, self._draws,
                                                   _ptr(self._draws_dev), _ptr(self._status), self._stream()))
@@ -540,7 +540,7 @@ class MultiSnake(object):
         st = self._state()
         dev = self._dev
         report = torch.tensor([0, 0, 2 ** 31 - 1, 0], dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(self._lib.wurm_multi_check(ctypes.byref(cfg), ctypes.byref(st), _ptr(report), self._stream()))
         _lib.raise_on_report(report.tolist())
         self.check_status()

@@ -114,7 +114,7 @@ class SimpleGridworld(object):
         cfg = self._cfg(observation_mode)
         envs = self._state()
         obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=envs.device)
-        with torch.cuda.device(envs.device):
+        with _lib.device_guard(envs.device):
             _lib.check(self._lib.wurm_grid_observe(ctypes.byref(cfg), _ptr(envs), _ptr(obs), self._stream()))
         return obs
 
@@ -140,7 +140,7 @@ class SimpleGridworld(object):
         if food_cell_replay is not None:
             food_cell_replay = food_cell_replay.to(device=dev, dtype=torch.int32).contiguous()
         self._draws += 1
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(self._lib.wurm_grid_step(
                 ctypes.byref(cfg), _ptr(envs), _ptr(actions), _ACTION_BYTES[actions.dtype], _ptr(food_cell_replay),
                 self.seed, self._draws, _ptr(self._draws_dev), _ptr(obs), _ptr(reward), _ptr(done), _ptr(self._status),
@@ -155,7 +155,7 @@ class SimpleGridworld(object):
         if food_cell_replay is not None:
             food_cell_replay = food_cell_replay.to(device=envs.device, dtype=torch.int32).contiguous()
         self._draws += 1
-        with torch.cuda.device(envs.device):
+        with _lib.device_guard(envs.device):
             _lib.check(self._lib.wurm_grid_reset(ctypes.byref(cfg), _ptr(envs), _ptr(mask), _ptr(food_cell_replay), self.seed,
                                                  self._draws, _ptr(self._draws_dev), self._stream()))
 

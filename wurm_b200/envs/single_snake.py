@@ -61,6 +61,7 @@ class SingleSnake(object):
                  seed: int = None,
                  state: str = None):
         self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
+        self._cfg_cache = {}
         if state is None:
             state = os.environ.get('WURM_B200_STATE', 'dense')     # process-wide default (how the reference's own tests are
                                                                    # run against the compact state without touching them)
@@ -135,6 +136,13 @@ class SingleSnake(object):
     # plumbing
     # ------------------------------------------------------------------------------------------
     def _cfg(self, observation_mode, num_envs=None):
+        key = (observation_mode, self.observation_mode, num_envs, self.num_envs, self.size)
+        cached = self._cfg_cache.get(key)
+        if cached is None:
+            cached = self._cfg_cache[key] = self._make_cfg(observation_mode, num_envs)
+        return cached
+
+    def _make_cfg(self, observation_mode, num_envs=None):
         if observation_mode is None:
             mode, n = _lib.OBS_NONE, 0
         elif observation_mode.startswith('partial_'):
@@ -167,7 +175,7 @@ class SingleSnake(object):
         """compact records -> the reference's (N,3,S,S) fp32 tensor (one launch), kept until the next state-changing call."""
         dense = torch.empty((self.num_envs, 3, self.size, self.size), dtype=torch.float32, device=self._dev)
         cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
-        with torch.cuda.device(self._dev):
+        with _lib.device_guard(self._dev):
             _lib.check(self._lib.wurm_single_expand(ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(dense),
                                                     self._stream()))
         self._dense = dense
@@ -185,7 +193,7 @@ class SingleSnake(object):
                 raise RuntimeError(f'envs has shape {tuple(e.shape)}, expected {(self.num_envs, 3, self.size, self.size)}')
             if (e.data_ptr(), e._version) != self._dense_key:
                 cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
-                with torch.cuda.device(self._dev):
+                with _lib.device_guard(self._dev):
                     _lib.check(self._lib.wurm_single_compact(ctypes.byref(cfg), _ptr(e), _ptr(self._cells), _ptr(self._hints),
                                                              _ptr(self._status), self._stream()))
                 self._dense_key = (e.data_ptr(), e._version)
@@ -265,7 +273,7 @@ class SingleSnake(object):
                 skip = skip.reshape(-1)
                 if skip.dtype != torch.bool or skip.device != self._dev or not skip.is_contiguous():
                     skip = (skip != 0).to(self._dev).contiguous()
-            with torch.cuda.device(self._dev):
+            with _lib.device_guard(self._dev):
                 _lib.check(self._lib.wurm_single_compact_check(ctypes.byref(cfg), _ptr(self._cells), _ptr(skip), _ptr(report),
                                                                self._stream()))
             _lib.raise_on_report(report.tolist())
@@ -296,13 +304,13 @@ class SingleSnake(object):
         if self._compact:
             self._compact_state(mutates=False)
             obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=self._dev)
-            with torch.cuda.device(self._dev):
+            with _lib.device_guard(self._dev):
                 _lib.check(self._lib.wurm_single_compact_observe(ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(obs),
                                                                  _ptr(self._status), self._stream()))
             return obs
         envs = self._state()
         obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=envs.device)
-        with torch.cuda.device(envs.device):
+        with _lib.device_guard(envs.device):
             _lib.check(self._lib.wurm_single_observe(ctypes.byref(cfg), _ptr(envs), _ptr(obs), _ptr(self._status),
                                                      self._stream()))
         return obs
@@ -348,9 +356,8 @@ class SingleSnake(object):
                     or not obs.is_contiguous()):
                 raise RuntimeError(f'obs_out must be a contiguous float32 tensor of shape {self._obs_shape(cfg)} on {dev}')
         reward = torch.empty(self.num_envs, dtype=torch.float32, device=dev)
-        done = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
-        self_collision = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
-        edge_collision = torch.empty(self.num_envs, dtype=torch.bool, device=dev)
+        flags = torch.empty((3, self.num_envs), dtype=torch.bool, device=dev)        # one allocation for the three flag vectors
+        done, self_collision, edge_collision = flags[0], flags[1], flags[2]
         if food_cell_replay is not None:
             food_cell_replay = food_cell_replay.to(device=dev, dtype=torch.int32).contiguous()
         if spawn_replay is not None:
@@ -359,7 +366,7 @@ class SingleSnake(object):
                                        packed_out.numel() != self.num_envs or not packed_out.is_contiguous()):
             raise RuntimeError(f'packed_out must be a contiguous uint8 tensor of {self.num_envs} elements on {dev}')
         self._draws += 1
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if self._compact:
                 _lib.check(self._lib.wurm_single_compact_step(
                     ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(actions), _ACTION_BYTES[actions.dtype],
@@ -428,13 +435,13 @@ class SingleSnake(object):
         self._draws += 1
         if envs is None:                    # compact resident state
             cfg = _lib.WurmSingleCfg(self.num_envs, self.size, _lib.OBS_NONE, 0)
-            with torch.cuda.device(self._dev):
+            with _lib.device_guard(self._dev):
                 _lib.check(self._lib.wurm_single_compact_reset(ctypes.byref(cfg), _ptr(self._cells), _ptr(self._hints), _ptr(mask),
                                                                _ptr(spawn_replay), self.seed, self._draws, _ptr(self._draws_dev),
                                                                self._stream()))
             return
         cfg = _lib.WurmSingleCfg(envs.shape[0], self.size, _lib.OBS_NONE, 0)
-        with torch.cuda.device(envs.device):
+        with _lib.device_guard(envs.device):
             _lib.check(self._lib.wurm_single_reset(ctypes.byref(cfg), _ptr(envs), _ptr(mask), _ptr(spawn_replay),
                                                    self.seed, self._draws, _ptr(self._draws_dev),
                                                    _ptr(self._hints) if (envs.shape[0] == self.num_envs and not self._compact) else None,
