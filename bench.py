@@ -133,7 +133,7 @@ class SingleAdapter(object):
 
 
 class GridAdapter(SingleAdapter):
-    kernel = 'grid_small_kernel<STEP=true>'    # grids up to 64 cells; larger: grid_env_kernel<32,true>
+    kernel = 'grid_tile_kernel<4,STEP=true>'    # grids up to 64 cells (size 8: grid_small_kernel); larger: grid_env_kernel<32,true>
 
     def __init__(self, key, dev, seed, rank, state='dense'):
         import torch

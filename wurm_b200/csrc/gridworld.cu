@@ -1,10 +1,12 @@
 // SimpleGridworld (wurm/envs/simple_gridworld.py) for B200 (sm_100a): the reference's two-channel debug
 // env -- an agent pixel and one food pixel, the same move / eat / respawn / edge machinery as SingleSnake
-// without a body.  An env is 2*S*S floats (392 B at the reference's size 7), far too small to stage: a lane
-// group per env works straight on global memory.  Up to 64 cells (grid_small_kernel): 8 lanes per env with the
-// env held in registers; larger grids (grid_env_kernel): 32 lanes per env, strided loads, the agent found with
-// shuffles.  Either way only the two or three cells a step changes are stored.
+// without a body.  An env is 2*S*S floats (392 B at the reference's size 7).  Up to 64 cells: tiles of eight envs moved
+// by TMA bulk copies and stepped in shared memory (grid_tile_kernel, round 2), or -- where the env stride would line
+// the tile up on one shared-memory bank -- 8 lanes per env with the env held in registers (grid_small_kernel); larger
+// grids (grid_env_kernel): 32 lanes per env, strided loads, the agent found with shuffles.  Either way only the two or
+// three cells a step changes are stored.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/wurm_b200.h"
 #include "common.cuh"
@@ -303,8 +305,185 @@ __global__ void __launch_bounds__(WURM_GRID_THREADS, WURM_GRID_MINB) grid_small_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small grids as TILES (round 2): the SingleSnake tile design applied to the gridworld.  One one-warp CTA = T = 32 / G
+// consecutive envs; the tile's (T,2,S,S) floats arrive by ONE bulk copy (TMA), are stepped in shared memory with the two
+// or three changed cells mirrored to HBM, and the observation is rendered into a shared staging area that leaves by one
+// bulk store -- instead of 8 lanes per env pulling 32-byte pieces of four different envs per load instruction and
+// scattering 32-byte pieces of the observation.  Same arithmetic, same draws.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_pick_free_tile(const GridParams& p, const float* env, uint64_t ctr, int e) {
+    const int S = p.S, C = p.C, I = S - 2;
+    auto is_free = [&](int q) { return env[q] + env[C + q] < kEps; };
+    for (uint32_t t = 0; t < kRejectionTries; ++t) {
+        const int cand = (int)bounded(draw_i(p.seed, ctr, (uint32_t)e, kStreamGridStepFood, t), (uint32_t)(I * I));
+        const int cy = cand / I, q = (1 + cy) * S + 1 + (cand - cy * I);
+        if (is_free(q)) return q;
+    }
+    int nfree = 0;
+    for (int y = 1; y < S - 1; ++y)
+        for (int x = 1; x < S - 1; ++x) nfree += is_free(y * S + x);
+    if (nfree == 0) return -1;
+    int r = (int)bounded(draw_i(p.seed, ctr, (uint32_t)e, kStreamGridStepFood, kRejectionTries), (uint32_t)nfree);
+    for (int y = 1; y < S - 1; ++y)
+        for (int x = 1; x < S - 1; ++x)
+            if (is_free(y * S + x) && r-- == 0) return y * S + x;
+    return -1;
+}
+
+template <int G, bool STEP>
+__global__ void __launch_bounds__(32) grid_tile_kernel(const GridParams p, int tile_bytes_padded, int stage_env_floats) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int T = 32 / G;
+    const int S = p.S, C = p.C, n2 = 2 * C;
+    float* tile = reinterpret_cast<float*>(smem);
+    float* stage = reinterpret_cast<float*>(smem + tile_bytes_padded);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes_padded + ((T * stage_env_floats * 4 + 15) & ~15));
+    int* cnt_s = reinterpret_cast<int*>(bar + 1);
+    const unsigned gm = group_mask<G>();
+    const int lane = threadIdx.x, t = lane / G, l = lane % G;
+    const int env0 = blockIdx.x * T, nvalid = min(T, p.N - env0);
+    const size_t goff = (size_t)env0 * n2;
+    const uint32_t bytes = (uint32_t)(nvalid * n2) * 4u;
+    const bool bulk = (bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(p.envs + goff) & 15u) == 0);
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_load(tile, p.envs + goff, bytes, bar);
+        }
+    } else {
+        for (int i = lane; i < nvalid * n2; i += 32) tile[i] = p.envs[goff + i];
+    }
+    if (lane < 4) cnt_s[lane] = 0;
+    const bool valid = t < nvalid;
+    const int e = env0 + (valid ? t : 0);
+    long long a = 0;
+    if (STEP && valid) a = load_action(p.actions, p.action_bytes, (size_t)e);
+    __syncwarp();
+    if (bulk) mbar_wait(bar, 0);
+    float* food = tile + (size_t)t * n2;
+    float* head = food + C;
+    float* gfood = p.envs + (size_t)e * n2;
+    float* ghead = gfood + C;
+    if (STEP && valid) {
+        int hp = -1, hc = 0;
+        for (int q = l; q < C; q += G)
+            if (head[q] != 0.0f) { hp = q; ++hc; }
+        hp = group_max<G>(hp, gm);
+        hc = group_sum<G>(hc, gm);
+        int np = -1, ny = -1, nx = -1;                                // :149-158 the conv2d translates the agent by -OFF[a]
+        if (hp >= 0) {
+            const int hy = (int)__umulhi((uint32_t)hp, p.magic_S), hx = hp - hy * S;
+            ny = hy - off_y((int)a); nx = hx - off_x((int)a);
+            if (ny >= 0 && ny < S && nx >= 0 && nx < S) np = ny * S + nx;
+        }
+        const float ov = np >= 0 ? food[np] : 0.0f;                   // :169 agent-food overlap
+        __syncwarp(gm);
+        if (l == 0 && hp >= 0) {
+            head[hp] = 0.0f; ghead[hp] = 0.0f;
+            if (np >= 0) {
+                head[np] = 1.0f; ghead[np] = 1.0f;
+                if (ov != 0.0f) { const float left = ov + ov * -1.0f; food[np] = left; gfood[np] = left; }   // :171
+            }
+        }
+        __syncwarp(gm);
+        if (ov != 0.0f) {                                             // :176-181 respawn
+            const int cell = p.food_replay ? p.food_replay[e] : grid_pick_free_tile(p, food, call_counter(p), e);
+            __syncwarp(gm);
+            if (l == 0 && cell >= 0) { const float f = food[cell] + 1.0f; food[cell] = f; gfood[cell] = f; }
+        }
+        const bool interior = np >= 0 && ny >= 1 && ny <= S - 2 && nx >= 1 && nx <= S - 2;
+        if (l == 0) {
+            p.reward[e] = 0.0f - ov * -1.0f;
+            p.done[e] = !interior;                                    // :189-194 edge collision is the only way to end
+            if (hc > 1) atomicOr(p.status, WURM_ST_MULTI_HEAD);
+            if (p.stats) {
+                atomicAdd(&cnt_s[0], 1);
+                if (!interior) atomicAdd(&cnt_s[1], 1);
+                if (ov != 0.0f) atomicAdd(&cnt_s[2], 1);
+            }
+        }
+        __syncwarp(gm);
+    }
+    // ---- observation (:88-133), rendered from the tile into the staging area ----
+    if (valid && p.obs_mode == WURM_OBS_DEFAULT) {                    // black background (:90), agent green, food red
+        float* o = stage + (size_t)t * 3 * C;
+        for (int q = l; q < C; q += G) {
+            const int y = (int)__umulhi((uint32_t)q, p.magic_S), x = q - y * S;
+            float r = 0.0f, g = 0.0f;
+            if (head[q] > kEps) { r = 0.0f; g = 1.0f; }
+            if (food[q] > kEps) { r = 1.0f; g = 0.0f; }
+            if (y == 0 || x == 0 || y == S - 1 || x == S - 1) r = g = 0.0f;
+            o[q] = r; o[C + q] = g; o[2 * C + q] = 0.0f;
+        }
+    } else if (valid && p.obs_mode == WURM_OBS_POSITIONS) {           // first argmax of agent / food (:119-130)
+        int idx[2];
+        for (int ch = 0; ch < 2; ++ch) {
+            const float* v = ch == 0 ? head : food;
+            float bv = -INFINITY;
+            int bq = 0;
+            for (int q = l; q < C; q += G)
+                if (v[q] > bv) { bv = v[q]; bq = q; }
+            const float gv = group_max<G>(bv, gm);
+            idx[ch] = -group_max<G>(bv == gv ? -bq : -(1 << 30), gm);
+        }
+        if (l == 0) {
+            float* o = p.obs + (size_t)e * 4;
+            o[0] = (float)(idx[0] / S); o[1] = (float)(idx[0] % S); o[2] = (float)(idx[1] / S); o[3] = (float)(idx[1] % S);
+        }
+    }
+    fence_proxy_async();                    // generic-proxy writes -> visible to the bulk stores
+    __syncwarp();
+    if (STEP && p.stats && lane < 3 && cnt_s[lane]) {
+        unsigned long long* slot = p.stats + (blockIdx.x % WURM_STATS_SLOTS) * WURM_STATS_FIELDS;
+        if (lane == 0) atomicAdd(slot + WURM_STAT_ENV_STEPS, (unsigned long long)cnt_s[0]);
+        if (lane == 1) {
+            atomicAdd(slot + WURM_STAT_EPISODES, (unsigned long long)cnt_s[1]);
+            atomicAdd(slot + WURM_STAT_EDGE_COLLISIONS, (unsigned long long)cnt_s[1]);
+        }
+        if (lane == 2) atomicAdd(slot + WURM_STAT_REWARD, (unsigned long long)cnt_s[2]);
+    }
+    if (p.obs_mode == WURM_OBS_DEFAULT || p.obs_mode == WURM_OBS_RAW) {
+        const int per_env = p.obs_mode == WURM_OBS_DEFAULT ? 3 * C : n2;
+        const float* src = p.obs_mode == WURM_OBS_DEFAULT ? stage : tile;   // raw: a copy of the (updated) tile
+        float* dst = p.obs + (size_t)env0 * per_env;
+        const uint32_t obytes = (uint32_t)(nvalid * per_env) * 4u;
+        if ((obytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+            if (lane == 0) { bulk_store(dst, src, obytes); bulk_commit(); bulk_wait_read_all(); }
+        } else {
+            for (int i = lane; i < nvalid * per_env; i += 32) dst[i] = src[i];
+        }
+    }
+}
+
+// -1: the tile kernel does not apply.  Grids above 64 cells keep the lane-group kernels, and so does size 8: an env of 128
+// floats puts the same cell of all eight envs of a tile on one shared-memory bank (measured on B200, 2^20 envs, `default`
+// observations, step kernel: size 5 0.190 ms tile / 0.207 lanes, size 6 0.196 / 0.213, size 7 0.204 / 0.266, size 8 0.400 / 0.261).
+template <bool STEP>
+static int try_launch_grid_tile(const GridParams& p, cudaStream_t stream) {
+    if (p.C > 64 || (2 * p.C) % 32 == 0 || getenv("WURM_GRID_NO_TILE")) return -1;
+    constexpr int G = 4, T = 32 / G;
+    const int tile_bytes_padded = (T * 2 * p.C * 4 + 15) & ~15;
+    const int stage_env_floats = p.obs_mode == WURM_OBS_DEFAULT ? 3 * p.C : 0;
+    const int smem = tile_bytes_padded + ((T * stage_env_floats * 4 + 15) & ~15) + 8 + 16 + 16;
+    auto kern = grid_tile_kernel<G, STEP>;
+    static SmemOptIn opt_in;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), &opt_in, smem, true, "cudaFuncSetAttribute(grid_tile_kernel)")) return rc;
+    kern<<<(p.N + T - 1) / T, 32, smem, stream>>>(p, tile_bytes_padded, stage_env_floats);
+    return check_launch("grid_tile_kernel");
+}
+
 template <bool STEP>
 static int launch_grid_env(const GridParams& p, cudaStream_t stream) {
+    {
+        const int rc = try_launch_grid_tile<STEP>(p, stream);
+        if (rc >= 0) return rc;
+    }
     const long long threads_g8 = (long long)p.N * 8, threads_g32 = (long long)p.N * 32;
     if (p.C <= 64) grid_small_kernel<STEP><<<(unsigned)((threads_g8 + WURM_GRID_THREADS - 1) / WURM_GRID_THREADS), WURM_GRID_THREADS, 0, stream>>>(p);
     else grid_env_kernel<32, STEP><<<(unsigned)((threads_g32 + 255) / 256), 256, 0, stream>>>(p);
