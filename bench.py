@@ -353,14 +353,26 @@ def measured_peak_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def csrc_hash():
-    """Content hash of the kernel sources: what a profiled traffic figure is valid for."""
+KERNEL_SOURCES = {
+    # the files a workload's step kernel is compiled from: what a profiled traffic figure is valid for
+    'single': ('common.cuh', 'host_util.h', 'single_device.cuh', 'single_snake.cu', 'single_compact.cu'),
+    'multi': ('common.cuh', 'host_util.h', 'multi_snake.cu'),
+    'grid': ('common.cuh', 'host_util.h', 'gridworld.cu'),
+}
+
+
+def kernel_family(key):
+    return {'SingleSnake': 'single', 'MultiSnake': 'multi', 'SimpleGridworld': 'grid'}[WORKLOADS[key][0]]
+
+
+def csrc_hash(family=None):
+    """Content hash of kernel sources: all of wurm_b200/csrc, or the files one kernel family is compiled from."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'wurm_b200', 'csrc')
-    for name in sorted(os.listdir(d)):
-        if name.endswith(('.cu', '.cuh', '.h')):
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), 'rb').read())
+    names = KERNEL_SOURCES[family] if family else sorted(n for n in os.listdir(d) if n.endswith(('.cu', '.cuh', '.h')))
+    for name in names:
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), 'rb').read())
     return h.hexdigest()[:16]
 
 
@@ -373,9 +385,10 @@ def profiled_traffic(key, state='dense'):
     rec = json.load(open(path)).get(key if state == 'dense' else key + ':compact')
     if not isinstance(rec, dict):
         return None, 'no capture recorded for this workload'
-    if rec.get('csrc_hash') != csrc_hash():
-        return None, (f"stale: captured from csrc {rec.get('csrc_hash')} ({rec.get('source')}), "
-                      f'the library is built from csrc {csrc_hash()}')
+    now = csrc_hash(kernel_family(key))
+    if rec.get('csrc_hash') != now:
+        return None, (f"stale: captured from kernel sources {rec.get('csrc_hash')} ({rec.get('source')}), "
+                      f'the library is built from {now}')
     return rec['dram_bytes_per_launch'], f"{rec.get('source')} (csrc {rec.get('csrc_hash')})"
 
 

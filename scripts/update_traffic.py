@@ -11,9 +11,9 @@ path = os.path.join(ROOT, 'profiles', 'traffic.json')
 out = json.load(open(path)) if os.path.exists(path) else {}
 out = {k: v for k, v in out.items() if isinstance(v, dict) or k.startswith('_')}
 out['_comment'] = ('dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel (env.step of the bench loop, 12th '
-                   'launch) from `ncu --set full` captures; csrc_hash = bench.csrc_hash() of the kernel sources the capture was '
-                   'taken from; read by bench.py for roofline.traffic')
-for w in ('C1', 'C2', 'C3', 'C4', 'C5'):
+                   'launch) from `ncu --set full` captures; csrc_hash = bench.csrc_hash(family) of the source files that kernel is compiled from (`sources`) at '
+                   'capture time; read by bench.py for roofline.traffic')
+for w in ('C1', 'C2', 'C3', 'C4', 'C5', 'G1'):
     for st in ('dense', 'compact'):
         rep = os.path.join(ROOT, 'gpurun_out', f'{tag}_ncu_{w}_{st}.ncu-rep')
         if not os.path.exists(rep):
@@ -26,11 +26,11 @@ for w in ('C1', 'C2', 'C3', 'C4', 'C5'):
             return v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}[unit]
         total = mbytes('dram__bytes_read.sum') + mbytes('dram__bytes_write.sum')
         key = w if st == 'dense' else w + ':compact'
-        out[key] = {'dram_bytes_per_launch': int(total), 'kernel': d['Kernel Name'], 'csrc_hash': bench.csrc_hash(),
+        out[key] = {'dram_bytes_per_launch': int(total), 'kernel': d['Kernel Name'], 'csrc_hash': bench.csrc_hash(bench.kernel_family(w)), 'sources': list(bench.KERNEL_SOURCES[bench.kernel_family(w)]),
                     'source': f'profiles/{tag}_ncu_{w}_{st}.txt',
                     'gpu_time_us': float(d['gpu__time_duration.sum']) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}[u['gpu__time_duration.sum']]}
         summary = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_summary.py'), rep,
-                                  f'{w} {st} state, step kernel of the bench loop (12th launch), csrc {bench.csrc_hash()}'],
+                                  f'{w} {st} state, step kernel of the bench loop (12th launch), kernel sources {bench.csrc_hash(bench.kernel_family(w))}'],
                                  capture_output=True, text=True).stdout
         open(os.path.join(ROOT, 'profiles', f'{tag}_ncu_{w}_{st}.txt'), 'w').write(summary)
         print(key, out[key])
