@@ -624,6 +624,10 @@ def test_compact_state_takes_caller_edits_and_refuses_what_it_cannot_carry():
     twin.step(act.clone()); env.step(act.clone())
     assert env._dense is None                                # dropped by the state-changing call
     assert_same(np_(env.envs), np_(twin.envs), 'state after the edit')
+    env.envs.data[0, 0, 2, 2] = 1.0; twin.envs[0, 0, 2, 2] = 1.0   # a write torch's version counter cannot see (`.data`) ...
+    env.invalidate_hints()                                   # ... needs the manual form: the tensor is folded back in
+    twin.step(act.clone()); env.step(act.clone())
+    assert_same(np_(env.envs), np_(twin.envs), 'state after the invisible edit + invalidate_hints()')
     env.envs[0, 2, 3, 3] = 0.5                               # a non-integral body value: not a record
     with pytest.raises(RuntimeError, match='compact'):
         env.step(act.clone())

@@ -228,6 +228,7 @@ class MultiSnake(object):
         if self._dense is None:
             self._materialise()
         self._dense[name] = value
+        self._dense_key = None               # compact mode: an assigned tensor is always folded back in before the next call
 
     foods = property(lambda self: self._get_dense('foods'), lambda self, v: self._set_dense('foods', v))
     heads = property(lambda self: self._get_dense('heads'), lambda self, v: self._set_dense('heads', v))
@@ -293,8 +294,9 @@ class MultiSnake(object):
         when a state tensor was replaced or written through torch since this env's last own call (the kernels verify
         that a hinted cell still holds a head, not that it is the snake's ONLY head cell); call it by hand after
         writing the state through a raw pointer, which torch's version counter cannot see."""
-        if self._compact:
-            return                                   # the head cells are state in this mode, not hints
+        if self._compact:                            # the head cells are state in this mode, not hints: "forget what you
+            self._dense_key = None                   # assumed" means "fold the materialised tensors back in"
+            return
         self._head_hints.fill_(-2)
         self._adopt_state()
 

@@ -170,6 +170,7 @@ class SingleSnake(object):
     @envs.setter
     def envs(self, value):
         self._dense = value
+        self._dense_key = None               # compact mode: an assigned tensor is always folded back in before the next call
 
     def _materialise(self):
         """compact records -> the reference's (N,3,S,S) fp32 tensor (one launch), kept until the next state-changing call."""
@@ -242,8 +243,9 @@ class SingleSnake(object):
         """Drops the per-env (head cell, size, food cell) hints: the next step re-derives everything from `envs`.
         Called automatically when `envs` was replaced or written through torch; call it by hand after writing the
         state through a raw pointer (a custom kernel, `.data_ptr()`), which torch's version counter cannot see."""
-        if self._compact:
-            return                                   # the aux vectors are derived state in this mode, not hints
+        if self._compact:                            # the aux vectors are derived state in this mode, not hints: what "forget
+            self._dense_key = None                   # what you assumed" means here is "fold the materialised tensor back in"
+            return
         self._hints.fill_(-1)
         self._adopt_state()
 
