@@ -229,6 +229,13 @@ typedef struct WurmMultiState {
      * the records can carry (integral body values < 65536, food / head values 1, one body per cell, heads on their
      * own bodies), which includes every state the kernels themselves produce from such a state. */
     uint32_t* cells;
+    /* With BOTH forms present (tensors and cells): cells_valid != 0 says the records describe the tensors' current content
+     * and nothing else was written into the tensors since the library last wrote them -- a step then loads the records,
+     * VERIFIES that every cell they name still holds that value in the tensors (and every head cell its head; a mismatch
+     * re-loads the env from the tensors), and writes its changes to both forms: the dense state at close to the compact
+     * state's cost.  cells_valid == 0: the step loads the tensors as usual and EMITS the records, after which the caller
+     * may pass 1.  Ignored (taken as 1) when the tensors are NULL. */
+    int32_t cells_valid;
 } WurmMultiState;
 
 /* Replayed random draws of one step, dense per env (NULL struct pointer -> Philox).

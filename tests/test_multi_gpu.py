@@ -57,7 +57,10 @@ def check_step_outputs(env, K, obs, rewards, dones, info, expect, tag):
     assert_same(np.stack([np_(obs[f'agent_{k}']) for k in range(K)]), expect['obs'], tag + ': observations')
 
 
-STATES = ['dense', 'compact']     # state='compact': records resident in HBM, fp32 tensors materialised for the comparison
+# state='dense': the reference's tensors, shadowed by the kernels' records (loaded instead of the tensors while nobody else wrote
+# to them); 'dense_scan': the tensors alone, streamed by every call; 'compact': records resident in HBM, fp32 tensors
+# materialised for the comparison
+STATES = ['dense', 'dense_scan', 'compact']
 
 
 @pytest.mark.parametrize('state', STATES)
@@ -528,16 +531,18 @@ def test_fused_step_reset_golden_replay(i, state):
     env.check_status()
 
 
+@pytest.mark.parametrize('state', ['dense', 'dense_scan'])
 @pytest.mark.parametrize('E,K,S,mode', [(96, 4, 25, 'partial_4'), (24, 16, 64, 'partial_4'), (48, 3, 12, 'full')])
-def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mode):
+def test_state_edited_between_calls_makes_head_hints_stale_not_wrong(E, K, S, mode, state):
     """The kernels keep each snake's head cell from one call to the next and skip streaming the heads tensor when every
     hint still verifies.  Rolling the envs along the batch (every env now sits under its neighbour's hints), replacing
     the tensors wholesale and killing snakes by hand must only cost the scan back, never the result.  The Python class
     drops the hints by itself when it sees such edits (tensor identity / version); `_adopt_state()` after every edit
-    hides them from it -- as a raw-pointer writer would -- so that what is tested is the KERNEL's own verification."""
+    hides them from it -- as a raw-pointer writer would -- so that what is tested is the KERNEL's own verification.
+    state='dense': the same for the shadow records (every cell they name must still hold that value in the tensors)."""
     seed = 99 + E
     rules = dict(respawn_mode='any')
-    env = make_env(E, K, S, mode, seed=seed, **rules)
+    env = make_env(E, K, S, mode, seed=seed, state=state, **rules)
     cfg = orc.multi_cfg(E, K, S, **rules)
     st = orc.MultiState(E, K, S)
     assert orc.multi_reset(cfg, st, np.ones(E, np.uint8), None, seed=seed, step=env._draws) == 0
@@ -706,3 +711,140 @@ def test_graphed_stepper_on_the_compact_state():
         if t % 5 == 0:
             check_state(compact, env_state(dense), f'step {t}')
     check_state(compact, env_state(dense), 'final state')
+
+
+SHADOW_CASES = [
+    (96, 4, 25, 'partial_4', dict(respawn_mode='any')),
+    (64, 3, 12, 'full', dict(food_mode='random_rate', food_rate=5e-3, food_on_death_prob=1.0)),
+    (16, 16, 64, 'partial_4', dict(respawn_mode='any', food_on_death_prob=0.33)),
+    (8, 32, 40, 'partial_2', dict()),
+]
+
+
+@pytest.mark.parametrize('E,K,S,mode,rules', SHADOW_CASES)
+def test_shadow_records_track_the_tensors(E, K, S, mode, rules):
+    """state='dense' (the default): the reference's tensors are the state and the library keeps its records beside them.
+    Stepped next to a 'dense_scan' env (tensors only) with the same seed and actions -- fused and two-call steps, observes and
+    consistency checks in between -- every output and every state tensor must be identical after every call, and the records
+    must always equal what a fresh conversion of the tensors gives."""
+    shadow = make_env(E, K, S, mode, seed=17, state='dense', **rules)
+    scan = make_env(E, K, S, mode, seed=17, state='dense_scan', **rules)
+    scan.agent_colours = shadow.agent_colours.clone()
+    probe = make_env(E, K, S, mode, seed=1, state='compact', manual_setup=True)
+    g = torch.Generator().manual_seed(8)
+    assert shadow._cells is not None and scan._cells is None
+    for t in range(40):
+        acts = torch.randint(0, 8, (K, E), generator=g).to(DEV)
+        fused = t % 3 == 1
+        outs = []
+        for env in (shadow, scan):
+            obs, rewards, dones, info = env.step({f'agent_{k}': acts[k] for k in range(K)}, auto_reset=fused)
+            if not fused:
+                env.reset(dones['__all__'], return_observations=False)
+            outs.append((obs, rewards, dones, info))
+        tag = f'step {t}: '
+        assert shadow._shadow_ok
+        for k in range(K):
+            assert_same(np_(outs[0][0][f'agent_{k}']), np_(outs[1][0][f'agent_{k}']), tag + f'obs {k}')
+        for i, name in ((1, 'rewards'), (2, 'dones')):
+            assert_same(stack_dict(outs[0][i], K), stack_dict(outs[1][i], K), tag + name)
+        assert_same(np_(outs[0][2]['__all__']), np_(outs[1][2]['__all__']), tag + '__all__')
+        for name in ('snake_collision', 'edge_collision', 'boost', 'food', 'size'):
+            assert_same(stack_dict(outs[0][3], K, name + '_'), stack_dict(outs[1][3], K, name + '_'), tag + name)
+        check_state(shadow, env_state(scan), tag + 'state')
+        if t % 4 == 3:
+            o1, o2 = shadow._observe('full'), scan._observe('full')
+            for k in range(K):
+                assert_same(np_(o1[f'agent_{k}']), np_(o2[f'agent_{k}']), tag + f'full observation {k}')
+            assert_same(np_(shadow._get_env_images()), np_(scan._get_env_images()), tag + 'env images')
+            shadow.check_consistency()
+            # the records against a fresh conversion of the tensors
+            probe.foods, probe.heads, probe.bodies = shadow.foods.clone(), shadow.heads.clone(), shadow.bodies.clone()
+            probe.dones = shadow.dones.clone()
+            probe._state()
+            assert_same(np_(shadow._cells), np_(probe._cells), tag + 'records')
+            assert_same(np_(shadow._head_hints), np_(probe._head_hints), tag + 'head cells')
+    shadow.check_status()
+    scan.check_status()
+
+
+def test_shadow_records_are_dropped_when_the_caller_writes_to_the_tensors():
+    """A write through torch (in place, or a replaced tensor) is seen by the version counters: the records are not trusted
+    for the next call, which streams the tensors and re-emits them.  Adding a food cell and a whole extra snake body
+    segment -- things the records' presence check alone could not notice -- must change the trajectory exactly as it does
+    for the tensors-only env and the oracle."""
+    E, K, S, mode = 48, 4, 25, 'partial_4'
+    rules = dict(food_mode='random_rate', food_rate=1e-3)
+    env = make_env(E, K, S, mode, seed=23, **rules)
+    cfg = orc.multi_cfg(E, K, S, **rules)
+    st = orc.MultiState(E, K, S)
+    assert orc.multi_reset(cfg, st, np.ones(E, np.uint8), None, seed=23, step=env._draws) == 0
+    st.agent_colours[:] = np_(env.agent_colours)
+    g = torch.Generator().manual_seed(4)
+
+    def run(steps, tag):
+        for t in range(steps):
+            acts = torch.randint(0, 8, (E, K), generator=g)
+            obs, rewards, dones, info = env.step({f'agent_{k}': acts[:, k].contiguous().to(DEV) for k in range(K)})
+            out = orc.multi_step(cfg, st, acts.numpy(), None, seed=23, step=env._draws)
+            check_state(env, st, f'{tag} step {t}')
+            o, _ = orc.multi_observe(cfg, st, mode)
+            assert_same(np.stack([np_(obs[f'agent_{k}']) for k in range(K)]), o, f'{tag} step {t}: obs')
+            assert_same(stack_dict(rewards, K), out['rewards'], f'{tag} step {t}: rewards')
+            env.reset(dones['__all__'], return_observations=False)
+            orc.multi_reset(cfg, st, out['all_done'], None, seed=23, step=env._draws)
+
+    run(5, 'warm')
+    assert env._shadow_ok
+    # food in front of every living snake's head (in place: version bump)
+    heads = env.heads.view(E, K, S, S)
+    for e in range(E):
+        for k in range(K):
+            if not bool(env.dones[e * K + k]):
+                y, x = divmod(int(heads[e, k].flatten().argmax()), S)
+                for yy, xx in ((y - 1, x), (y + 1, x), (y, x - 1), (y, x + 1)):
+                    if 0 < yy < S - 1 and 0 < xx < S - 1 and float(env.bodies.view(E, K, S, S)[e, :, yy, xx].sum()) == 0:
+                        env.foods[e, 0, yy, xx] = 1.0
+                        st.foods[e, 0, yy, xx] = 1.0
+    run(5, 'food added')
+    assert env._shadow_ok
+    # replaced tensors (new objects, same content but one more food cell in env 0)
+    f = env.foods.clone()
+    free = ((env.bodies.view(E, K, S, S)[0].sum(0) + f[0, 0]) == 0).nonzero()
+    y, x = [int(v) for v in free[(free[:, 0] > 0) & (free[:, 0] < S - 1) & (free[:, 1] > 0) & (free[:, 1] < S - 1)][0]]
+    f[0, 0, y, x] = 1.0
+    st.foods[0, 0, y, x] = 1.0
+    env.foods = f
+    run(5, 'foods replaced')
+    env.check_status()
+
+
+def test_graphed_stepper_on_the_shadowed_state_sees_caller_edits():
+    """The captured launch is the record-loading one; an edit of the tensors between replays is noticed on the host (version
+    counters) and handed to the captured kernel as 'unknown' head hints, which makes it re-load those envs from the tensors."""
+    from wurm_b200 import GraphedStepper
+    E, K, S, steps = 64, 4, 25, 18
+    plain = make_env(E, K, S, 'partial_4', seed=31, state='dense_scan', respawn_mode='any')
+    graphed = make_env(E, K, S, 'partial_4', seed=31, state='dense', respawn_mode='any')
+    graphed.agent_colours = plain.agent_colours.clone()
+    acts = torch.randint(0, 8, (steps + 1, K, E), generator=torch.Generator().manual_seed(2)).to(DEV)
+    static = {f'agent_{k}': acts[0, k].clone() for k in range(K)}
+    stepper = GraphedStepper(graphed, static, warmup=2)
+    assert graphed._shadow_ok                                   # derived at construction: the capture loads records
+    check_state(graphed, env_state(plain), 'state after construction')
+    for t in range(1, steps + 1):
+        if t % 5 == 0:                                          # the caller drops food onto a free cell of every env
+            for env in (graphed, plain):
+                occ = env.bodies.view(E, K, S, S).sum(1) + env.foods.view(E, S, S)
+                occ[:, 0, :] = 1; occ[:, -1, :] = 1; occ[:, :, 0] = 1; occ[:, :, -1] = 1
+                cell = (occ == 0).view(E, -1).float().argmax(dim=1)
+                env.foods.view(E, -1)[torch.arange(E, device=DEV), cell] = 1.0
+        for k in range(K):
+            static[f'agent_{k}'].copy_(acts[t, k])
+        obs, rewards, dones, info = stepper.step()
+        obs2, rewards2, dones2, info2 = plain.step({f'agent_{k}': acts[t, k] for k in range(K)}, auto_reset=True)
+        for k in range(K):
+            assert_same(np_(obs[f'agent_{k}']), np_(obs2[f'agent_{k}']), f'step {t}: obs {k}')
+        assert_same(stack_dict(rewards, K), stack_dict(rewards2, K), f'step {t}: rewards')
+        check_state(graphed, env_state(plain), f'step {t}: state')
+    graphed.check_status()

@@ -64,7 +64,7 @@ class WurmMultiCfg(ctypes.Structure):
 
 class WurmMultiState(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step',
-                                               'agent_colours', 'head_hints', 'cells')]
+                                               'agent_colours', 'head_hints', 'cells')] + [('cells_valid', ctypes.c_int32)]
 
 
 class WurmMultiStepDraws(ctypes.Structure):

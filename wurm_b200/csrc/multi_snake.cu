@@ -51,6 +51,7 @@ struct MultiParams {
     short* head_hints;    // (E*K) nullable: head cell left by the previous call (-1 dead, -2 unknown), verified before use
     uint32_t* cells;      // compact resident state (E, Cp) or NULL: see WurmMultiState.cells; head_hints is then authoritative
     int Cp;               // row pitch of `cells`: C rounded up to a multiple of 4 (rows stay 16-byte aligned)
+    int cells_valid;      // the records describe the current state (load from them); 0: load the dense tensors, emit the records
     // step inputs
     const void* actions[kMaxK];
     int action_bytes;
@@ -307,8 +308,8 @@ __device__ __forceinline__ void fold_nonzero(const MultiSmem& s, int C, uint32_t
 // (plain arguments: a reference to the kernel's parameter struct would force a copy of it onto the stack)
 template <bool CHECK>
 __device__ __noinline__ void fold_nonzero_overflow(unsigned char* smem, int C, int K, uint32_t magic_C, int32_t* status, int what,
-                                                   int i, float v) {
-    fold_nonzero<CHECK>(carve(smem, C, K), C, magic_C, status, what, i, v);
+                                                   int i, float v, bool compact_layout) {
+    fold_nonzero<CHECK>(carve(smem, C, K, compact_layout), C, magic_C, status, what, i, v);
 }
 
 // Streams env e's tensors from HBM into the compact shared-memory form.  ONE copy of the scan loop runs over the
@@ -343,7 +344,7 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
         scan_nonzero<U>(base, what == 0 ? C : K * C, [&](int i, float v) {
             const int n = atomicAdd(&s.misc[6], 1);
             if (n < s.qcap) s.queue[n] = make_int2((int)((unsigned)i | ((unsigned)what << 30)), __float_as_int(v));
-            else fold_nonzero_overflow<CHECK>(reinterpret_cast<unsigned char*>(s.cell), C, K, p.magic_C, p.status, what, i, v);
+            else fold_nonzero_overflow<CHECK>(reinterpret_cast<unsigned char*>(s.cell), C, K, p.magic_C, p.status, what, i, v, s.qcap == 0);
         });
     }
     __syncthreads();
@@ -369,6 +370,7 @@ __device__ __forceinline__ void load_env_compact(const MultiParams& p, const Mul
         const int h = p.head_hints[(size_t)e * K + tid];
         s.hp[tid] = (h >= 0 && h < C) ? h : -1;
         s.hcnt[tid] = (h >= 0 && h < C) ? 1 : 0;
+        if (h == -2 && p.foods) s.misc[9] = 1;                       // shadowed dense state: "unknown" = the records of this env are stale
     }
     // Pass 1: copy the records into shared memory as they are and put the cells that hold anything on the live list.
     // ~99 % of the 128-bit vectors are zero (one ballot tells); for the others the list slots are claimed with ONE
@@ -423,6 +425,40 @@ __device__ __forceinline__ void load_env_compact(const MultiParams& p, const Mul
         }
         s.cell[q] = rec;
     }
+}
+
+// SHADOWED DENSE STATE.  A caller who keeps the reference's fp32 tensors may let the library keep the records beside them
+// (WurmMultiState.cells with cells_valid): a step then loads the records, checks that every cell they name still holds that
+// food / body value in the tensors and every head cell its head -- PRESENCE is verified, a few scattered 4-byte loads; that
+// nothing ELSE appeared in the tensors is the caller's word (the Python class gives it only while torch's version counters say
+// the tensors were not written to) -- and writes its changes to both forms.  A mismatch re-loads the env from the tensors.
+__device__ __forceinline__ bool records_match_tensors(const MultiParams& p, const MultiSmem& s, int e) {
+    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
+    bool ok = true;
+    const LiveWalk lw = live_walk(s, C);
+    for (int n = tid; n < lw.cnt; n += nthr) {
+        const int q = live_at(s, lw, n);
+        const uint32_t rec = s.cell[q];
+        if (rec & kFood) ok &= p.foods[(size_t)e * C + q] == 1.0f;
+        if (rec_body(rec)) ok &= p.bodies[((size_t)e * K + rec_owner(rec)) * C + q] == (float)rec_value(rec);
+    }
+    if (tid < K) {
+        const int h = s.hp[tid];
+        ok &= h >= 0 ? (s.done[tid] == 0 && p.heads[((size_t)e * K + tid) * C + h] == 1.0f) : (s.done[tid] != 0);
+    }
+    return ok;
+}
+
+// (out of line, parameters by value: the cold path must not weigh on the kernel's code or pin its parameter struct)
+__device__ __noinline__ void reload_from_tensors(const MultiParams p, unsigned char* smem_raw, int e) {
+    const MultiSmem s = carve(smem_raw, p.C, p.K, true);
+    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
+    for (int q = tid; q < C; q += nthr) s.cell[q] = 0u;
+    if (tid < K) { s.hp[tid] = -1; s.size[tid] = 0; s.hcnt[tid] = 0; s.sum[tid] = 0; }
+    if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; s.misc[3] = 0; s.misc[6] = 0; s.misc[8] = 0; s.misc[10] = 1; }
+    __syncthreads();
+    load_env<false, 4>(p, s, e);                                     // no hints: the heads tensor is scanned too
+    __syncthreads();
 }
 
 // multi_snake.py:197-206: int16 colour of a body (or, is_head, head) cell of snake o
@@ -688,19 +724,19 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
 // caller has zeroed (or is zeroing, to the same values) whatever else the tensors held.
 __device__ __forceinline__ void write_recreated(const MultiParams& p, int e, const ResetScratch& sc, int fcell) {
     const int C = p.C, K = p.K, tid = threadIdx.x;
-    uint32_t* gc = p.cells ? p.cells + (size_t)e * p.Cp : nullptr;  // compact resident state: records instead of floats
+    uint32_t* gc = p.cells ? p.cells + (size_t)e * p.Cp : nullptr;  // records and / or the reference's tensors: whichever the caller keeps
+    const bool dense = p.foods != nullptr;
     if (tid == 0 && fcell >= 0) {
         if (gc) gc[fcell] = kFood;
-        else p.foods[(size_t)e * C + fcell] = 1.0f;
+        if (dense) p.foods[(size_t)e * C + fcell] = 1.0f;
     }
     if (tid < K) {
         const size_t n = (size_t)e * K + tid;
         if (sc.snake_cell[tid] >= 0) {
             int tl, hd;
             snake_cells(p, sc.snake_cell[tid], sc.snake_dir[tid], tl, hd);
-            if (gc) {
-                gc[hd] = make_rec(tid, 3); gc[sc.snake_cell[tid]] = make_rec(tid, 2); gc[tl] = make_rec(tid, 1);
-            } else {
+            if (gc) { gc[hd] = make_rec(tid, 3); gc[sc.snake_cell[tid]] = make_rec(tid, 2); gc[tl] = make_rec(tid, 1); }
+            if (dense) {
                 p.heads[n * C + hd] = 1.0f;
                 p.bodies[n * C + hd] = 3.0f; p.bodies[n * C + sc.snake_cell[tid]] = 2.0f; p.bodies[n * C + tl] = 1.0f;
             }
@@ -737,10 +773,11 @@ __device__ __forceinline__ void write_respawned(const MultiParams& p, int e, int
     if (cell >= 0) {
         int tl, hd;
         snake_cells(p, cell, d, tl, hd);
-        if (p.cells) {                                                // compact resident state
+        if (p.cells) {                                                // records and / or the reference's tensors
             uint32_t* gc = p.cells + (size_t)e * p.Cp;
             gc[hd] = make_rec(k, 3); gc[cell] = make_rec(k, 2); gc[tl] = make_rec(k, 1);
-        } else {
+        }
+        if (p.foods) {
             p.heads[n * p.C + hd] = 1.0f;
             p.bodies[n * p.C + hd] = 3.0f; p.bodies[n * p.C + cell] = 2.0f; p.bodies[n * p.C + tl] = 1.0f;
         }
@@ -764,6 +801,60 @@ __device__ __forceinline__ void recolour(const MultiParams& p, int e, int k, uin
         const float c0 = unit_float(r.x) / 1.5f, c1 = unit_float(r.y), c2 = unit_float(r.z);
         const float norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
         col[0] = (short)(c0 / norm * 192.0f); col[1] = (short)(c1 / norm * 192.0f); col[2] = (short)(c2 / norm * 192.0f);
+    }
+}
+
+// The new state of env e goes back as records: the listed records that changed (4 bytes each; `all`: every record, after a
+// load from the dense tensors); the head cells go into head_hints with the per-agent outputs.
+__device__ __forceinline__ void records_writeback(const MultiParams& p, const MultiSmem& s, int e, bool all) {
+    const int C = p.C, tid = threadIdx.x, nthr = blockDim.x;
+    uint32_t* gc = p.cells + (size_t)e * p.Cp;
+    if (all) {
+        for (int q = tid; q < p.Cp; q += nthr) gc[q] = q < C ? hbm_record(s.cell[q]) : 0u;
+        return;
+    }
+    const LiveWalk lw = live_walk(s, C);
+    for (int n = tid; n < lw.cnt; n += nthr) {
+        const int q = live_at(s, lw, n);
+        const uint32_t rec = s.cell[q];
+        if ((rec & kDirty) || (((rec >> 29) ^ (rec >> 30)) & 1u)) gc[q] = hbm_record(rec);
+    }
+}
+
+// ... and / or into the reference's fp32 tensors.  The compact form knows exactly which cells changed: only those are stored
+// (a step touches O(snake length) cells of an S*S grid: a few sectors per snake instead of the full state); an input the
+// records could not carry exactly (misc[3]) is expanded densely instead, which normalises it.
+__device__ __forceinline__ void dense_writeback(const MultiParams& p, const MultiSmem& s, int e, bool valid, int k, int a_hp0, int a_hp) {
+    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
+    if (s.misc[3]) {
+        store_floats(p.foods + (size_t)e * C, C, [&](int i) { return (s.cell[i] & kFood) ? 1.0f : 0.0f; });
+        store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv_C(i, C, p.magic_C);
+            return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
+        });
+        store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
+            const int kk = fdiv_C(i, C, p.magic_C);
+            const uint32_t rec = s.cell[i - kk * C];
+            return (rec_body(rec) && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
+        });
+        return;
+    }
+    float* bodies = p.bodies + (size_t)e * K * C;
+    const LiveWalk lw = live_walk(s, C);
+    for (int n = tid; n < lw.cnt; n += nthr) {
+        const int q = live_at(s, lw, n);
+        const uint32_t rec = s.cell[q];
+        if (rec & kDirty) {
+            const int ko = rec_owner0(rec), kn = rec_body(rec) ? rec_owner(rec) : -1;
+            if (ko >= 0 && ko != kn) bodies[(size_t)ko * C + q] = 0.0f;
+            if (kn >= 0) bodies[(size_t)kn * C + q] = (float)rec_value(rec);
+        }
+        if (((rec >> 29) ^ (rec >> 30)) & 1u) p.foods[(size_t)e * C + q] = (rec & kFood) ? 1.0f : 0.0f;
+    }
+    if (valid && a_hp0 != a_hp) {
+        float* head = p.heads + ((size_t)e * K + k) * C;
+        if (a_hp0 >= 0) head[a_hp0] = 0.0f;
+        if (a_hp >= 0) head[a_hp] = 1.0f;
     }
 }
 
@@ -825,8 +916,17 @@ multi_env_kernel(const MultiParams p) {
     float hint_val = 0.0f;
     if (use_hints && tid < K && hint_h >= 0 && hint_h < C) hint_val = p.heads[((size_t)e * K + tid) * C + hint_h];
     __syncthreads();
-    if (COMPACT) load_env_compact<false>(p, s, e);
-    else load_env<false, (THREADS >= 256 ? 8 : 4)>(p, s, e, use_hints, hint_h, hint_val, hint_dead);
+    if (COMPACT) {
+        load_env_compact<false>(p, s, e);
+        if (p.foods) {                                                // shadowed dense state: the records must still match the tensors
+            __syncthreads();
+            if (!records_match_tensors(p, s, e)) s.misc[9] = 1;
+            __syncthreads();
+            if (s.misc[9]) reload_from_tensors(p, smem_raw, e);
+        }
+    } else {
+        load_env<false, (THREADS >= 256 ? 8 : 4)>(p, s, e, use_hints, hint_h, hint_val, hint_dead);
+    }
     __syncthreads();
 
     if (STEP) {
@@ -1009,7 +1109,8 @@ multi_env_kernel(const MultiParams p) {
                 p.sizes[n] = (float)a_size;
                 p.dones[n] = a_done;
                 p.dones_out[n] = a_done;
-                if (p.head_hints) p.head_hints[n] = (short)(a_done ? -1 : a_hp);
+                // (a snake with several head cells is not something a hint or a record can stand for: "unknown")
+                if (p.head_hints) p.head_hints[n] = (short)(s.hcnt[k] > 1 ? -2 : a_done ? -1 : a_hp);
                 p.boost_out[n] = a_boosted;
             }
             const unsigned alive = __ballot_sync(0xffffffffu, valid && !a_done);
@@ -1031,52 +1132,10 @@ multi_env_kernel(const MultiParams p) {
         }
         __syncthreads();
 
-        // ---- write the new state back ----
-        if (COMPACT) {
-            // compact resident state: the records that changed go back as records (4 bytes each); the head cells
-            // already went into head_hints with the per-agent outputs
-            uint32_t* gc = p.cells + (size_t)e * p.Cp;
-            const LiveWalk lw = live_walk(s, C);
-            for (int n = tid; n < lw.cnt; n += nthr) {
-                const int q = live_at(s, lw, n);
-                const uint32_t rec = s.cell[q];
-                if ((rec & kDirty) || (((rec >> 29) ^ (rec >> 30)) & 1u)) gc[q] = hbm_record(rec);
-            }
-        } else if (s.misc[3]) {
-            // non-canonical input: expand the whole compact form into the reference's tensors
-            store_floats(p.foods + (size_t)e * C, C, [&](int i) { return (s.cell[i] & kFood) ? 1.0f : 0.0f; });
-            store_floats(p.heads + (size_t)e * K * C, K * C, [&](int i) {
-                const int kk = fdiv_C(i, C, p.magic_C);
-                return s.hp[kk] == i - kk * C ? 1.0f : 0.0f;
-            });
-            store_floats(p.bodies + (size_t)e * K * C, K * C, [&](int i) {
-                const int kk = fdiv_C(i, C, p.magic_C);
-                const uint32_t rec = s.cell[i - kk * C];
-                return (rec_body(rec) && rec_owner(rec) == kk) ? (float)rec_value(rec) : 0.0f;
-            });
-        } else {
-            // The compact form knows exactly which cells changed: only those are stored (the sectors
-            // were read by this CTA microseconds ago, so the partial writes merge in L2).  A step
-            // touches O(snake length) cells of an S*S grid: write traffic drops from the full state
-            // to a few sectors per snake.
-            float* bodies = p.bodies + (size_t)e * K * C;
-            const LiveWalk lw = live_walk(s, C);
-            for (int n = tid; n < lw.cnt; n += nthr) {
-                const int q = live_at(s, lw, n);
-                const uint32_t rec = s.cell[q];
-                if (rec & kDirty) {
-                    const int ko = rec_owner0(rec), kn = rec_body(rec) ? rec_owner(rec) : -1;
-                    if (ko >= 0 && ko != kn) bodies[(size_t)ko * C + q] = 0.0f;
-                    if (kn >= 0) bodies[(size_t)kn * C + q] = (float)rec_value(rec);
-                }
-                if (((rec >> 29) ^ (rec >> 30)) & 1u) p.foods[(size_t)e * C + q] = (rec & kFood) ? 1.0f : 0.0f;
-            }
-            if (valid && a_hp0 != a_hp) {
-                float* head = p.heads + ((size_t)e * K + k) * C;
-                if (a_hp0 >= 0) head[a_hp0] = 0.0f;
-                if (a_hp >= 0) head[a_hp] = 1.0f;
-            }
-        }
+        // ---- write the new state back: into the records, the reference's tensors, or both (whichever the caller keeps) ----
+        const bool resync = !COMPACT || s.misc[10] != 0;             // the records do not describe the loaded state: emit them all
+        if (p.cells) records_writeback(p, s, e, resync);
+        if (p.foods) dense_writeback(p, s, e, valid, k, a_hp0, a_hp);
     }
     write_multi_obs(p, s, e);
 
@@ -1096,8 +1155,8 @@ multi_env_kernel(const MultiParams p) {
             // all snakes are dead, so their tensors are already zero (the step deleted them); only food is left
             for (int q = tid; q < C; q += nthr)
                 if (s.cell[q] & kFood) {
-                    if (COMPACT) p.cells[(size_t)e * p.Cp + q] = 0u;
-                    else p.foods[(size_t)e * C + q] = 0.0f;
+                    if (p.cells) p.cells[(size_t)e * p.Cp + q] = 0u;
+                    if (p.foods) p.foods[(size_t)e * C + q] = 0.0f;
                 }
             __syncthreads();
             write_recreated(p, e, sc, fcell);
@@ -1129,7 +1188,7 @@ __global__ void __launch_bounds__(256) multi_check_kernel(const MultiParams p, i
     __syncthreads();
     MultiParams q = p;
     q.status = &s.misc[4];                      // overlap / multi-head of THIS env, not the env object's status word
-    if (p.cells) load_env_compact<true>(q, s, e);
+    if (p.cells && p.cells_valid) load_env_compact<true>(q, s, e);
     else load_env<true>(q, s, e);
     __syncthreads();
     if (tid < K) {
@@ -1215,12 +1274,25 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         if (p.dones[(size_t)e * K + k]) { first_dead = k; ++ndead; }
     if (!recreate && (ndead == 0 || !p.respawn_any)) return;          // nothing to do for this env
 
-    if (p.cells) {                                                    // compact resident state: the same on records
+    if (p.cells && p.cells_valid) {
+        // the records are the state, or a valid shadow of the tensors: decide on the records, write to whichever forms exist
         uint32_t* gc = p.cells + (size_t)e * p.Cp;
+        const bool dense = p.foods != nullptr;
         if (recreate) {
             const int fcell = decide_recreate(p, e, ctr, sc);
-            for (int q = tid; q < C; q += nthr)
-                if (gc[q] != 0u) gc[q] = 0u;
+            for (int q = tid; q < C; q += nthr) {
+                const uint32_t rec = gc[q];
+                if (rec == 0u) continue;
+                gc[q] = 0u;
+                if (dense) {
+                    if (rec & kFood) p.foods[(size_t)e * C + q] = 0.0f;
+                    if (rec_body(rec)) p.bodies[((size_t)e * K + rec_owner(rec)) * C + q] = 0.0f;     // (none on a consistent state)
+                }
+            }
+            if (dense && tid < K) {
+                const int h = p.head_hints[(size_t)e * K + tid];
+                if (h >= 0 && h < C) p.heads[((size_t)e * K + tid) * C + h] = 0.0f;                   // (none on a consistent state)
+            }
             __syncthreads();
             write_recreated(p, e, sc, fcell);
             return;
@@ -1228,7 +1300,10 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         for (int q = tid; q < C; q += nthr) {
             const uint32_t rec = gc[q];
             sc.occ[q] = rec != 0u;                                    // (leftovers count as occupied, as in the dense path)
-            if (rec_body(rec) && rec_owner(rec) == first_dead) gc[q] = rec & ~kLive;            // leftovers of the dead snake
+            if (rec_body(rec) && rec_owner(rec) == first_dead) {      // leftovers of the dead snake
+                gc[q] = rec & ~kLive;
+                if (dense) p.bodies[((size_t)e * K + first_dead) * C + q] = 0.0f;
+            }
         }
         __syncthreads();
         int d;
@@ -1330,6 +1405,7 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     p->colours = st->agent_colours;
     p->head_hints = (cfg->size * cfg->size <= 32767) ? st->head_hints : nullptr;
     p->cells = st->cells; p->Cp = (cfg->size * cfg->size + 3) & ~3;
+    p->cells_valid = st->cells ? (st->cells_valid != 0 || !st->foods) : 0;      // records without tensors are the state by definition
     p->E = cfg->num_envs; p->K = cfg->num_snakes; p->S = cfg->size; p->C = cfg->size * cfg->size;
     p->boost = cfg->boost; p->food_on_death = cfg->food_on_death; p->food_mode = cfg->food_mode;
     p->respawn_any = cfg->respawn_any; p->colour_random = cfg->colour_random;
@@ -1360,8 +1436,8 @@ static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
     int threads = 32;
     while (threads < 256 && p.C > 24 * threads) threads <<= 1;
     if (const char* v = getenv("WURM_MULTI_THREADS")) threads = atoi(v);       // tuning override: 32, 64, 128, 256
-    if (p.cells) {
-        // compact resident state: nothing to stream, so the CTA is sized by the per-cell passes alone
+    if (p.cells && p.cells_valid) {
+        // the records are the state (or a valid shadow of it): nothing to stream, so the CTA is sized by the per-cell passes alone
         threads = 32;
         while (threads < 256 && p.C > 48 * threads) threads <<= 1;
         if (const char* v = getenv("WURM_MULTI_COMPACT_THREADS")) threads = atoi(v);

@@ -85,8 +85,11 @@ class MultiSnake(object):
         if state is None:
             state = os.environ.get('WURM_B200_STATE', 'dense')     # process-wide default (how the reference's own tests are
                                                                    # run against the compact state without touching them)
-        if state not in ('dense', 'compact'):
-            raise ValueError("state must be 'dense' (the reference's fp32 tensors are the state) or 'compact'")
+        if state == 'dense' and os.environ.get('WURM_B200_SHADOW', '1') == '0':
+            state = 'dense_scan'
+        if state not in ('dense', 'dense_scan', 'compact'):
+            raise ValueError("state must be 'dense' (the reference's fp32 tensors are the state; the library shadows them with "
+                             "its own records), 'dense_scan' (the same without the shadow: every call streams the tensors) or 'compact'")
         # state='compact' (an extension): between calls the env lives in HBM as one 32-bit record per cell (include/
         # wurm_b200.h, WurmMultiState.cells) instead of the reference's (1+2K) fp32 grids that are ~99 % zeros; `foods`,
         # `heads` and `bodies` are then materialised on attribute access and folded back in if the caller wrote to them.
@@ -123,7 +126,13 @@ class MultiSnake(object):
             self._head_hints.fill_(-1)               # authoritative in this mode: no heads yet
             self._dense = None                       # fp32 tensors exist only while a caller looks at them
         else:
-            self._cells = None
+            # The reference's tensors stay the state; the library keeps the kernel's own records BESIDE them (4 B per cell, 1 / (1+2K)
+            # of the tensors' size) so that a step need not stream ~99 % zeros to find the snakes: it loads the records, verifies
+            # them against the tensors and writes its changes to both (include/wurm_b200.h, WurmMultiState.cells_valid).  The
+            # records are only trusted while torch's version counters say nobody wrote to the tensors (_state()).
+            # state='dense_scan' (or WURM_B200_SHADOW=0) switches this off: every call then streams the tensors.
+            shadow = state == 'dense'
+            self._cells = torch.zeros((E, (S * S + 3) & ~3), dtype=torch.int32, device=self.device) if shadow else None
             self._dense = {'foods': torch.zeros((E, 1, S, S), dtype=self.dtype, device=self.device),
                            'heads': torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device),
                            'bodies': torch.zeros((E * K, 1, S, S), dtype=self.dtype, device=self.device)}
@@ -172,6 +181,7 @@ class MultiSnake(object):
         self.edge_locations_mask[:, :, :, -1:] = 1
 
         self._hint_key = None
+        self._shadow_ok = False                      # dense mode: the records describe the tensors' current content
         if not manual_setup:
             self._create_all()
         self._adopt_state()
@@ -241,7 +251,7 @@ class MultiSnake(object):
         return _lib.WurmMultiState(
             _ptr(dense['foods']) if dense else None, _ptr(dense['heads']) if dense else None,
             _ptr(dense['bodies']) if dense else None, _ptr(self.dones), _ptr(self.orientations), _ptr(self.boost_this_step),
-            _ptr(self.agent_colours), _ptr(self._head_hints), _ptr(self._cells))
+            _ptr(self.agent_colours), _ptr(self._head_hints), _ptr(self._cells), 0)
 
     def _materialise(self):
         """compact records -> the reference's three fp32 tensors (one launch), remembered until the next state-changing
@@ -271,12 +281,38 @@ class MultiSnake(object):
                                "body values, two bodies on one cell, or a head off its own body); use state='dense'")
 
     def _before_replay(self):
-        """GraphedStepper hook (compact mode): what step() does to the materialised tensors before launching."""
+        """GraphedStepper hook: what step() does before launching -- compact mode: fold caller edits of the materialised
+        tensors in, then drop them; dense mode: if the caller wrote to a state tensor, mark every hint 'unknown' on the device,
+        which is what makes the captured launch re-load those envs from the tensors."""
         self._state(mutates=True)
+        if not self._compact:
+            self._shadow_ok = self._cells is not None
 
     def _snapshot_names(self):
-        """Attributes that make up the env's state in compact mode (GraphedStepper snapshots them around its warm-up)."""
-        return ('_cells', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards', '_head_hints', '_stats', '_status')
+        """Attributes that make up the env's state (GraphedStepper snapshots them around its warm-up)."""
+        small = ('dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards', '_head_hints', '_stats', '_status')
+        if self._compact:
+            return ('_cells',) + small
+        return ('foods', 'heads', 'bodies') + small       # (the shadow records are re-derived: _sync_shadow)
+
+    def _sync_shadow(self):
+        """dense mode: derives the shadow records from the tensors now (one conversion launch and one host sync) instead of
+        letting the next step emit them.  GraphedStepper calls it before capturing, so that the captured launch is the
+        record-loading one.  A state the records cannot carry leaves the shadow off until the next step."""
+        if self._compact or self._cells is None:
+            return
+        st = self._state()
+        if self._shadow_ok:
+            return
+        cfg = self._cfg(None)
+        with _lib.device_guard(self._dev):
+            _lib.check(self._lib.wurm_multi_compact(ctypes.byref(cfg), ctypes.byref(st), _ptr(self._status), self._stream()))
+        st_word = int(self._status.item())
+        if st_word & _lib.ST_NOT_COMPACT:
+            self._status.fill_(st_word & ~_lib.ST_NOT_COMPACT)
+            self._head_hints.fill_(-2)
+        else:
+            self._shadow_ok = True
 
     def _hint_identity(self):
         return tuple((t.data_ptr(), t._version) for t in (self.heads, self.bodies, self.foods, self.dones))
@@ -297,7 +333,8 @@ class MultiSnake(object):
         if self._compact:                            # the head cells are state in this mode, not hints: "forget what you
             self._dense_key = None                   # assumed" means "fold the materialised tensors back in"
             return
-        self._head_hints.fill_(-2)
+        self._head_hints.fill_(-2)                   # (also what tells a captured record-loading launch to re-load from the tensors)
+        self._shadow_ok = False
         self._adopt_state()
 
     def _state(self, mutates=False):
@@ -316,13 +353,14 @@ class MultiSnake(object):
                     self._compress()                 # the caller wrote to (or replaced) a materialised tensor
                 if mutates:
                     self._dense = None
-            return _lib.WurmMultiState(None, None, None, *small, _ptr(self._head_hints), _ptr(self._cells))
+            return _lib.WurmMultiState(None, None, None, *small, _ptr(self._head_hints), _ptr(self._cells), 1)
         foods = self._norm('foods', torch.float32, (E, 1, S, S))
         heads = self._norm('heads', torch.float32, (E * K, 1, S, S))
         bodies = self._norm('bodies', torch.float32, (E * K, 1, S, S))
         if self._hint_identity() != self._hint_key:
             self.invalidate_hints()
-        return _lib.WurmMultiState(_ptr(foods), _ptr(heads), _ptr(bodies), *small, _ptr(self._head_hints), None)
+        return _lib.WurmMultiState(_ptr(foods), _ptr(heads), _ptr(bodies), *small, _ptr(self._head_hints), _ptr(self._cells),
+                                   int(self._shadow_ok))
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
@@ -463,6 +501,8 @@ class MultiSnake(object):
                     ctypes.byref(dr) if dr is not None else None, self.seed, self._draws, _ptr(self._draws_dev),
                     ctypes.byref(out), _ptr(self._status), _ptr(self._stats), self._stream()))
 
+        if not self._compact:
+            self._shadow_ok = self._cells is not None      # every step leaves the records describing the new state
         self.rewards = rewards.view(E * K)
         self._step_dones = flags[2]          # (E,K) copy of the done flags owned by this step's outputs
         observations = OrderedDict([(f'agent_{i}', obs[i]) for i in range(K)])

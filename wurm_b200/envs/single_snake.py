@@ -207,12 +207,16 @@ class SingleSnake(object):
                 self._dense = None
 
     def _before_replay(self):
-        """GraphedStepper hook (compact mode): what step() does to the materialised tensor before launching."""
-        self._compact_state(mutates=True)
+        """GraphedStepper hook: what step() does before launching -- compact mode: fold caller edits of the materialised
+        tensor in, then drop it; dense mode: drop the hints (on the device) if the caller wrote to `envs`."""
+        if self._compact:
+            self._compact_state(mutates=True)
+        else:
+            self._state()
 
     def _snapshot_names(self):
-        """Attributes that make up the env's state in compact mode (GraphedStepper snapshots them around its warm-up)."""
-        return ('_cells', 'done', '_hints', '_stats', '_status')
+        """Attributes that make up the env's state (GraphedStepper snapshots them around its warm-up)."""
+        return ('_cells' if self._compact else 'envs', 'done', '_hints', '_stats', '_status')
 
     def _state(self):
         """`envs` may have been replaced or sliced by the caller (tests assign it): normalise.  Also where the hints

@@ -62,11 +62,8 @@ class GraphedStepper(object):
         # Warm-up outside the capture (first-launch work: function attributes, allocator pools) runs REAL steps, so the
         # env's state, statistics, hints and call counter are snapshotted before and restored after: constructing a
         # GraphedStepper leaves the env exactly as it found it.
-        if getattr(env, '_compact', False):          # compact resident state: the records ARE the state
+        if hasattr(env, '_snapshot_names'):          # (compact resident state: the records ARE the state)
             names = env._snapshot_names()
-        elif self.multi:
-            names = ('foods', 'heads', 'bodies', 'dones', 'orientations', 'boost_this_step', 'agent_colours', 'rewards',
-                     '_head_hints', '_stats', '_status')
         else:
             names = ('envs', 'done', '_hints', '_stats', '_status')
         side = torch.cuda.Stream(dev)
@@ -82,7 +79,11 @@ class GraphedStepper(object):
                 env._draws = saved_draws
                 if hasattr(env, '_adopt_state'):
                     env._adopt_state()              # the restored hints describe the restored state
+                if hasattr(env, '_sync_shadow'):
+                    env._shadow_ok = False          # ... the shadow records (dense MultiSnake) describe the warm-up's
                 del saved
+            if hasattr(env, '_sync_shadow'):
+                env._sync_shadow()                  # records derived now: the captured launch is the record-loading one
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # Call counters.  The captured launches carry the host counter of the capture moment baked in (`_base`) and add
@@ -137,8 +138,8 @@ class GraphedStepper(object):
 
     def _replay(self):
         env = self.env
-        if getattr(env, '_compact', False):         # a replay changes the state behind the Python wrapper's back:
-            env._before_replay()                    # fold caller edits of materialised tensors in, then drop them
+        if hasattr(env, '_before_replay'):          # a replay changes the state behind the Python wrapper's back: fold caller
+            env._before_replay()                    # edits in (compact state) / drop hints and shadow records the caller outdated
         want = env._draws + 1 - self._base          # the captured step must run with the env's next counter value
         if want != self._mirror:                    # direct env.step()/reset() calls were made since the last replay
             self._addend.fill_(want)
