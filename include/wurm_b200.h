@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WURM_ABI_VERSION 5
+#define WURM_ABI_VERSION 6
 
 /* return codes */
 #define WURM_OK 0

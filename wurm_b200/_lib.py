@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # WURM_B200_LIB: a tuning variant of the library built by scripts/build_variant.sh (A/B experiments only)
 LIB_PATH = os.environ.get('WURM_B200_LIB') or os.path.join(_HERE, '_C', 'libwurm_b200.so')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, 1, 2, 3
 ST_MULTI_HEAD, ST_NO_HEAD_PARTIAL, ST_NO_SPAWN, ST_OVERLAP, ST_NOT_COMPACT = 1, 2, 4, 8, 16

@@ -65,6 +65,8 @@ class SingleSnake(object):
         if state is None:
             state = os.environ.get('WURM_B200_STATE', 'dense')     # process-wide default (how the reference's own tests are
                                                                    # run against the compact state without touching them)
+        if state == 'dense_scan':                    # MultiSnake's name for "tensors only, no shadow records": SingleSnake's dense
+            state = 'dense'                          # state never has any (tried and lost, profiles/r02_single_shadow_experiment.txt)
         if state not in ('dense', 'compact'):
             raise ValueError("state must be 'dense' (the reference's fp32 tensor is the state) or 'compact'")
         # state='compact' (an extension): between calls the env lives in HBM as one uint16 record per cell (include/
