@@ -362,15 +362,24 @@ __device__ __forceinline__ void load_env(const MultiParams& p, const MultiSmem& 
 // ~1 % non-zero cells on the live list as it goes; the per-call bits (owner / food when loaded, listed) are derived here.
 __device__ __forceinline__ uint32_t hbm_record(uint32_t rec) { return rec & (kLive | kFood); }
 
-template <bool CHECK = false>
-__device__ __forceinline__ void load_env_compact(const MultiParams& p, const MultiSmem& s, int e) {
+// VERIFY (shadowed dense state, below): the same walk also checks the records against the reference's tensors; returns this
+// thread's verdict (to be combined across the CTA by the caller).
+template <bool CHECK = false, bool VERIFY = false>
+__device__ __forceinline__ bool load_env_compact(const MultiParams& p, const MultiSmem& s, int e) {
     const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const uint32_t* g = p.cells + (size_t)e * p.Cp;
+    bool ok = true;
+    float head_val = 1.0f;
+    int head_cell = -1;
     if (tid < K) {
         const int h = p.head_hints[(size_t)e * K + tid];
-        s.hp[tid] = (h >= 0 && h < C) ? h : -1;
-        s.hcnt[tid] = (h >= 0 && h < C) ? 1 : 0;
-        if (h == -2 && p.foods) s.misc[9] = 1;                       // shadowed dense state: "unknown" = the records of this env are stale
+        head_cell = (h >= 0 && h < C) ? h : -1;
+        s.hp[tid] = head_cell;
+        s.hcnt[tid] = head_cell >= 0 ? 1 : 0;
+        if (VERIFY) {
+            if (h == -2) ok = false;                                 // "unknown": the records of this env are stale
+            if (head_cell >= 0) head_val = p.heads[((size_t)e * K + tid) * C + head_cell];       // (used after the copy below)
+        }
     }
     // Pass 1: copy the records into shared memory as they are and put the cells that hold anything on the live list.
     // ~99 % of the 128-bit vectors are zero (one ballot tells); for the others the list slots are claimed with ONE
@@ -416,6 +425,13 @@ __device__ __forceinline__ void load_env_compact(const MultiParams& p, const Mul
         const int q = live_at(s, lw, n);
         if (s.cell[q] == 0u) continue;                               // (only met when walking the whole grid)
         uint32_t rec = hbm_record(s.cell[q]) | kListed;
+        // shadowed dense state: every cell the records name must still hold that value in the tensors (loads issued first,
+        // compared after the shared-memory work of this iteration)
+        float t_food = 1.0f, t_body = 0.0f;
+        if (VERIFY) {
+            if (rec & kFood) t_food = p.foods[(size_t)e * C + q];
+            if (rec & kLive) t_body = p.bodies[((size_t)e * K + rec_owner(rec)) * C + q];
+        }
         rec |= ((rec >> 16) & 63u) << 22;                            // owner when loaded
         if (rec & kFood) { rec |= kFood0; atomicAdd(&s.misc[0], 1); }
         if (rec & kLive) {
@@ -424,7 +440,11 @@ __device__ __forceinline__ void load_env_compact(const MultiParams& p, const Mul
             if (CHECK) atomicAdd(&s.sum[k], val);
         }
         s.cell[q] = rec;
+        if (VERIFY) ok &= t_food == 1.0f && (!(rec & kLive) || t_body == (float)rec_value(rec));
     }
+    if (VERIFY && tid < K)                                           // a live snake's head cell holds its head; a dead snake is flagged done
+        ok &= head_cell >= 0 ? (s.done[tid] == 0 && head_val == 1.0f) : (s.done[tid] != 0);
+    return ok;
 }
 
 // SHADOWED DENSE STATE.  A caller who keeps the reference's fp32 tensors may let the library keep the records beside them
@@ -432,23 +452,6 @@ __device__ __forceinline__ void load_env_compact(const MultiParams& p, const Mul
 // food / body value in the tensors and every head cell its head -- PRESENCE is verified, a few scattered 4-byte loads; that
 // nothing ELSE appeared in the tensors is the caller's word (the Python class gives it only while torch's version counters say
 // the tensors were not written to) -- and writes its changes to both forms.  A mismatch re-loads the env from the tensors.
-__device__ __forceinline__ bool records_match_tensors(const MultiParams& p, const MultiSmem& s, int e) {
-    const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
-    bool ok = true;
-    const LiveWalk lw = live_walk(s, C);
-    for (int n = tid; n < lw.cnt; n += nthr) {
-        const int q = live_at(s, lw, n);
-        const uint32_t rec = s.cell[q];
-        if (rec & kFood) ok &= p.foods[(size_t)e * C + q] == 1.0f;
-        if (rec_body(rec)) ok &= p.bodies[((size_t)e * K + rec_owner(rec)) * C + q] == (float)rec_value(rec);
-    }
-    if (tid < K) {
-        const int h = s.hp[tid];
-        ok &= h >= 0 ? (s.done[tid] == 0 && p.heads[((size_t)e * K + tid) * C + h] == 1.0f) : (s.done[tid] != 0);
-    }
-    return ok;
-}
-
 // (out of line, parameters by value: the cold path must not weigh on the kernel's code or pin its parameter struct)
 __device__ __noinline__ void reload_from_tensors(const MultiParams p, unsigned char* smem_raw, int e) {
     const MultiSmem s = carve(smem_raw, p.C, p.K, true);
@@ -722,10 +725,10 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
 
 // Stores the cells of the re-created env's snakes and food and revives its agents (:790-798).  Whole CTA; the
 // caller has zeroed (or is zeroing, to the same values) whatever else the tensors held.
-__device__ __forceinline__ void write_recreated(const MultiParams& p, int e, const ResetScratch& sc, int fcell) {
+// (rec_out / dense_out: into the records and / or the reference's tensors -- compile-time constants in the step kernels)
+__device__ __forceinline__ void write_recreated(const MultiParams& p, int e, const ResetScratch& sc, int fcell, bool rec_out, bool dense) {
     const int C = p.C, K = p.K, tid = threadIdx.x;
-    uint32_t* gc = p.cells ? p.cells + (size_t)e * p.Cp : nullptr;  // records and / or the reference's tensors: whichever the caller keeps
-    const bool dense = p.foods != nullptr;
+    uint32_t* gc = rec_out ? p.cells + (size_t)e * p.Cp : nullptr;
     if (tid == 0 && fcell >= 0) {
         if (gc) gc[fcell] = kFood;
         if (dense) p.foods[(size_t)e * C + fcell] = 1.0f;
@@ -768,16 +771,16 @@ __device__ __forceinline__ int decide_respawn(const MultiParams& p, int e, uint6
 }
 
 // one thread: the respawned snake's cells, orientation and done flag (:826-829)
-__device__ __forceinline__ void write_respawned(const MultiParams& p, int e, int k, int cell, int d) {
+__device__ __forceinline__ void write_respawned(const MultiParams& p, int e, int k, int cell, int d, bool rec_out, bool dense_out) {
     const size_t n = (size_t)e * p.K + k;
     if (cell >= 0) {
         int tl, hd;
         snake_cells(p, cell, d, tl, hd);
-        if (p.cells) {                                                // records and / or the reference's tensors
+        if (rec_out) {
             uint32_t* gc = p.cells + (size_t)e * p.Cp;
             gc[hd] = make_rec(k, 3); gc[cell] = make_rec(k, 2); gc[tl] = make_rec(k, 1);
         }
-        if (p.foods) {
+        if (dense_out) {
             p.heads[n * p.C + hd] = 1.0f;
             p.bodies[n * p.C + hd] = 3.0f; p.bodies[n * p.C + cell] = 2.0f; p.bodies[n * p.C + tl] = 1.0f;
         }
@@ -864,7 +867,10 @@ __device__ __forceinline__ void dense_writeback(const MultiParams& p, const Mult
 // lane-per-snake logic runs and 32 envs stay resident per SM (K=4, S=25: 0.466 ms per launch against 0.489 /
 // 0.533 ms with 64 / 128 threads; staging the raw env through shared memory with TMA was tried and lost to the
 // occupancy it costs); 256 threads for S=64, where streaming 540 KB per env wants the loads of many threads in flight.
-template <bool STEP, int THREADS, bool COMPACT = false>
+// COMPACT: the records are loaded instead of the tensors; SHADOW (with COMPACT): the tensors exist too -- the records are verified
+// against them and every change goes to both forms (template parameters: the record-only kernel is bound by instruction issue
+// and fetch, and carrying the shadow's code as run-time branches cost it 15 %).
+template <bool STEP, int THREADS, bool COMPACT = false, bool SHADOW = false>
 // (the compact 128-thread shape serves grids from 56 x 56 up, where shared memory allows ~10 CTAs per SM anyway)
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? (COMPACT ? 10 : 12) : THREADS == 64 ? 20 : 32)
 multi_env_kernel(const MultiParams p) {
@@ -917,17 +923,17 @@ multi_env_kernel(const MultiParams p) {
     if (use_hints && tid < K && hint_h >= 0 && hint_h < C) hint_val = p.heads[((size_t)e * K + tid) * C + hint_h];
     __syncthreads();
     if (COMPACT) {
-        load_env_compact<false>(p, s, e);
-        if (p.foods) {                                                // shadowed dense state: the records must still match the tensors
+        if (SHADOW) {                                                 // shadowed dense state: the records must still match the tensors
+            const bool ok = load_env_compact<false, true>(p, s, e);
+            if (__syncthreads_or(!ok)) reload_from_tensors(p, smem_raw, e);     // (both ways end on a barrier)
+        } else {
+            load_env_compact<false>(p, s, e);
             __syncthreads();
-            if (!records_match_tensors(p, s, e)) s.misc[9] = 1;
-            __syncthreads();
-            if (s.misc[9]) reload_from_tensors(p, smem_raw, e);
         }
     } else {
         load_env<false, (THREADS >= 256 ? 8 : 4)>(p, s, e, use_hints, hint_h, hint_val, hint_dead);
+        __syncthreads();
     }
-    __syncthreads();
 
     if (STEP) {
         // ---- per-snake registers, live on lane k of warp 0 ----
@@ -1133,9 +1139,9 @@ multi_env_kernel(const MultiParams p) {
         __syncthreads();
 
         // ---- write the new state back: into the records, the reference's tensors, or both (whichever the caller keeps) ----
-        const bool resync = !COMPACT || s.misc[10] != 0;             // the records do not describe the loaded state: emit them all
-        if (p.cells) records_writeback(p, s, e, resync);
-        if (p.foods) dense_writeback(p, s, e, valid, k, a_hp0, a_hp);
+        const bool resync = !COMPACT || (SHADOW && s.misc[10] != 0);  // the records do not describe the loaded state: emit them all
+        if (COMPACT || p.cells != nullptr) records_writeback(p, s, e, resync);
+        if (!COMPACT || SHADOW) dense_writeback(p, s, e, valid, k, a_hp0, a_hp);
     }
     write_multi_obs(p, s, e);
 
@@ -1150,16 +1156,18 @@ multi_env_kernel(const MultiParams p) {
         const unsigned dead_mask = ~alive_mask & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u));
         const int first_dead = dead_mask ? __ffs(dead_mask) - 1 : -1;
         const bool all_dead = alive_mask == 0u;
+        const bool rec_out = COMPACT || p.cells != nullptr;
+        constexpr bool dense_out = !COMPACT || SHADOW;
         if (all_dead) {                                               // :787-798 re-create the env
             const int fcell = decide_recreate(p, e, ctr, sc);
             // all snakes are dead, so their tensors are already zero (the step deleted them); only food is left
             for (int q = tid; q < C; q += nthr)
                 if (s.cell[q] & kFood) {
-                    if (p.cells) p.cells[(size_t)e * p.Cp + q] = 0u;
-                    if (p.foods) p.foods[(size_t)e * C + q] = 0.0f;
+                    if (rec_out) p.cells[(size_t)e * p.Cp + q] = 0u;
+                    if (dense_out) p.foods[(size_t)e * C + q] = 0.0f;
                 }
             __syncthreads();
-            write_recreated(p, e, sc, fcell);
+            write_recreated(p, e, sc, fcell, rec_out, dense_out);
         } else if (first_dead >= 0) {
             if (p.colour_random && tid < K && s.done[tid]) recolour(p, e, tid, ctr);     // :800-803
             if (p.respawn_any) {                                      // :805-829
@@ -1167,7 +1175,7 @@ multi_env_kernel(const MultiParams p) {
                 __syncthreads();
                 int d;
                 const int cell = decide_respawn(p, e, ctr, sc, d);
-                if (tid == 0) write_respawned(p, e, first_dead, cell, d);
+                if (tid == 0) write_respawned(p, e, first_dead, cell, d, rec_out, dense_out);
             }
         }
     }
@@ -1294,7 +1302,7 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
                 if (h >= 0 && h < C) p.heads[((size_t)e * K + tid) * C + h] = 0.0f;                   // (none on a consistent state)
             }
             __syncthreads();
-            write_recreated(p, e, sc, fcell);
+            write_recreated(p, e, sc, fcell, p.cells != nullptr, p.foods != nullptr);
             return;
         }
         for (int q = tid; q < C; q += nthr) {
@@ -1308,7 +1316,7 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         __syncthreads();
         int d;
         const int cell = decide_respawn(p, e, ctr, sc, d);
-        if (tid == 0) write_respawned(p, e, first_dead, cell, d);
+        if (tid == 0) write_respawned(p, e, first_dead, cell, d, p.cells != nullptr, p.foods != nullptr);
         return;
     }
     float* gfood = p.foods + (size_t)e * C;
@@ -1323,7 +1331,7 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         scan_nonzero(ghead, K * C, [&](int i, float) { ghead[i] = 0.0f; });
         scan_nonzero(gbody, K * C, [&](int i, float) { gbody[i] = 0.0f; });
         __syncthreads();
-        write_recreated(p, e, sc, fcell);
+        write_recreated(p, e, sc, fcell, p.cells != nullptr, p.foods != nullptr);
         return;                                                       // every agent alive: no respawn
     }
 
@@ -1344,7 +1352,7 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
     __syncthreads();
     int d;
     const int cell = decide_respawn(p, e, ctr, sc, d);
-    if (tid == 0) write_respawned(p, e, first_dead, cell, d);
+    if (tid == 0) write_respawned(p, e, first_dead, cell, d, p.cells != nullptr, p.foods != nullptr);
 }
 
 // One CTA looks at 32 consecutive envs: lane i of warp 0 reads env i's flags (coalesced), a ballot gives
@@ -1418,9 +1426,9 @@ static int plan_multi(const WurmMultiCfg* cfg, const WurmMultiState* st, MultiPa
     return WURM_OK;
 }
 
-template <bool STEP, int THREADS, bool COMPACT = false>
+template <bool STEP, int THREADS, bool COMPACT = false, bool SHADOW = false>
 static int launch_multi_env_t(const MultiParams& p, cudaStream_t stream) {
-    auto kern = multi_env_kernel<STEP, THREADS, COMPACT>;
+    auto kern = multi_env_kernel<STEP, THREADS, COMPACT, SHADOW>;
     size_t smem = multi_smem_bytes(p.C, p.K, COMPACT);
     if (const char* v = getenv("WURM_MULTI_SMEM_PAD")) smem += (size_t)atoi(v);     // occupancy experiments
     if (smem > 227 * 1024) return fail(WURM_E_UNSUPPORTED, "env does not fit shared memory");
@@ -1441,6 +1449,14 @@ static int launch_multi_env(const MultiParams& p, cudaStream_t stream) {
         threads = 32;
         while (threads < 256 && p.C > 48 * threads) threads <<= 1;
         if (const char* v = getenv("WURM_MULTI_COMPACT_THREADS")) threads = atoi(v);
+        if (p.foods) {                                                 // shadowed dense state
+            switch (threads) {
+                case 32: return launch_multi_env_t<STEP, 32, true, true>(p, stream);
+                case 64: return launch_multi_env_t<STEP, 64, true, true>(p, stream);
+                case 128: return launch_multi_env_t<STEP, 128, true, true>(p, stream);
+                default: return launch_multi_env_t<STEP, 256, true, true>(p, stream);
+            }
+        }
         switch (threads) {
             case 32: return launch_multi_env_t<STEP, 32, true>(p, stream);
             case 64: return launch_multi_env_t<STEP, 64, true>(p, stream);
