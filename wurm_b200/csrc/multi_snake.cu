@@ -365,21 +365,18 @@ __device__ __forceinline__ uint32_t hbm_record(uint32_t rec) { return rec & (kLi
 // VERIFY (shadowed dense state, below): the same walk also checks the records against the reference's tensors; returns this
 // thread's verdict (to be combined across the CTA by the caller).
 template <bool CHECK = false, bool VERIFY = false>
-__device__ __forceinline__ bool load_env_compact(const MultiParams& p, const MultiSmem& s, int e) {
+// (VERIFY: the caller has fetched this thread's snake's head cell `pre_h` and the heads tensor's value there `head_val` already)
+__device__ __forceinline__ bool load_env_compact(const MultiParams& p, const MultiSmem& s, int e, int pre_h = -1, float head_val = 1.0f) {
     const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const uint32_t* g = p.cells + (size_t)e * p.Cp;
     bool ok = true;
-    float head_val = 1.0f;
     int head_cell = -1;
     if (tid < K) {
-        const int h = p.head_hints[(size_t)e * K + tid];
+        const int h = VERIFY ? pre_h : (int)p.head_hints[(size_t)e * K + tid];
         head_cell = (h >= 0 && h < C) ? h : -1;
         s.hp[tid] = head_cell;
         s.hcnt[tid] = head_cell >= 0 ? 1 : 0;
-        if (VERIFY) {
-            if (h == -2) ok = false;                                 // "unknown": the records of this env are stale
-            if (head_cell >= 0) head_val = p.heads[((size_t)e * K + tid) * C + head_cell];       // (used after the copy below)
-        }
+        if (VERIFY && h == -2) ok = false;                           // "unknown": the records of this env are stale
     }
     // Pass 1: copy the records into shared memory as they are and put the cells that hold anything on the live list.
     // ~99 % of the 128-bit vectors are zero (one ballot tells); for the others the list slots are claimed with ONE
@@ -872,7 +869,10 @@ __device__ __forceinline__ void dense_writeback(const MultiParams& p, const Mult
 // and fetch, and carrying the shadow's code as run-time branches cost it 15 %).
 template <bool STEP, int THREADS, bool COMPACT = false, bool SHADOW = false>
 // (the compact 128-thread shape serves grids from 56 x 56 up, where shared memory allows ~10 CTAs per SM anyway)
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? (COMPACT ? 10 : 12) : THREADS == 64 ? 20 : 32)
+#ifndef WURM_SHADOW_CTAS_128
+#define WURM_SHADOW_CTAS_128 9
+#endif
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : THREADS == 128 ? (SHADOW ? WURM_SHADOW_CTAS_128 : COMPACT ? 10 : 12) : THREADS == 64 ? 20 : 32)
 multi_env_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MultiSmem s = carve(smem_raw, p.C, p.K, COMPACT);
@@ -887,7 +887,7 @@ multi_env_kernel(const MultiParams p) {
     // dependent look-up into the heads tensor can be issued ahead of the scans
     int hint_h = -1;
     bool hint_dead = false;
-    const bool use_hints = !COMPACT && p.head_hints != nullptr;
+    const bool use_hints = (!COMPACT || SHADOW) && p.head_hints != nullptr;     // (SHADOW: always there, and part of the state)
     if (use_hints && tid < K) {
         hint_h = p.head_hints[(size_t)e * K + tid];
         hint_dead = p.dones[(size_t)e * K + tid] != 0;
@@ -924,7 +924,7 @@ multi_env_kernel(const MultiParams p) {
     __syncthreads();
     if (COMPACT) {
         if (SHADOW) {                                                 // shadowed dense state: the records must still match the tensors
-            const bool ok = load_env_compact<false, true>(p, s, e);
+            const bool ok = load_env_compact<false, true>(p, s, e, hint_h, hint_val);
             if (__syncthreads_or(!ok)) reload_from_tensors(p, smem_raw, e);     // (both ways end on a barrier)
         } else {
             load_env_compact<false>(p, s, e);
