@@ -92,7 +92,7 @@ def main(argv=None):
     parser.add_argument('--gamma', default=0.99, type=float)
     parser.add_argument('--update-steps', default=20, type=int)
     parser.add_argument('--entropy', default=0.0, type=float)
-    parser.add_argument('--state', default='dense', type=str, choices=['dense', 'compact'],
+    parser.add_argument('--state', default='dense', type=str, choices=['dense', 'dense_scan', 'compact'],
                         help="'compact': the env lives in HBM as small records instead of the reference's dense fp32 tensors")
     args = parser.parse_args(argv)
 

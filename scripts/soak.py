@@ -14,7 +14,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = random.Random(int(time.time()))
 t0 = time.time(); runs = 0
 while time.time() - t0 < budget:
-    state = rng.choice(['dense', 'compact'])
+    state = rng.choice(['dense', 'dense_scan', 'compact'])
     if rng.random() < 0.5:
         S = rng.choice([9, 10, 11, 12, 13, 16, 18, 20, 22, 24, 30, 36, 40, 64, 90, 130])
         if S > 90:

@@ -14,7 +14,7 @@ out['_comment'] = ('dram__bytes_read.sum + dram__bytes_write.sum per launch of t
                    'launch) from `ncu --set full` captures; csrc_hash = bench.csrc_hash(family) of the source files that kernel is compiled from (`sources`) at '
                    'capture time; read by bench.py for roofline.traffic')
 for w in ('C1', 'C2', 'C3', 'C4', 'C5', 'G1'):
-    for st in ('dense', 'compact'):
+    for st in ('dense', 'compact', 'dense_scan'):
         rep = os.path.join(ROOT, 'gpurun_out', f'{tag}_ncu_{w}_{st}.ncu-rep')
         if not os.path.exists(rep):
             continue
@@ -25,7 +25,7 @@ for w in ('C1', 'C2', 'C3', 'C4', 'C5', 'G1'):
             v = float(d[name]); unit = u[name].lower()
             return v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}[unit]
         total = mbytes('dram__bytes_read.sum') + mbytes('dram__bytes_write.sum')
-        key = w if st == 'dense' else w + ':compact'
+        key = w if st == 'dense' else w + ':' + st
         out[key] = {'dram_bytes_per_launch': int(total), 'kernel': d['Kernel Name'], 'csrc_hash': bench.csrc_hash(bench.kernel_family(w)), 'sources': list(bench.KERNEL_SOURCES[bench.kernel_family(w)]),
                     'source': f'profiles/{tag}_ncu_{w}_{st}.txt',
                     'gpu_time_us': float(d['gpu__time_duration.sum']) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}[u['gpu__time_duration.sum']]}
