@@ -366,7 +366,10 @@ __device__ __forceinline__ uint32_t hbm_record(uint32_t rec) { return rec & (kLi
 // thread's verdict (to be combined across the CTA by the caller).
 template <bool CHECK = false, bool VERIFY = false>
 // (VERIFY: the caller has fetched this thread's snake's head cell `pre_h` and the heads tensor's value there `head_val` already)
-__device__ __forceinline__ bool load_env_compact(const MultiParams& p, const MultiSmem& s, int e, int pre_h = -1, float head_val = 1.0f) {
+// `bar`: the records' 128-bit vectors are already on their way into s.cell by ONE bulk copy (TMA) the caller issued at the top
+// of the kernel, completion on this mbarrier -- instead of every thread pulling its vectors one dependent load after the other.
+__device__ __forceinline__ bool load_env_compact(const MultiParams& p, const MultiSmem& s, int e, int pre_h = -1, float head_val = 1.0f,
+                                                 uint64_t* bar = nullptr) {
     const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const uint32_t* g = p.cells + (size_t)e * p.Cp;
     bool ok = true;
@@ -384,12 +387,17 @@ __device__ __forceinline__ bool load_env_compact(const MultiParams& p, const Mul
     const uint4* g4 = reinterpret_cast<const uint4*>(g);
     uint4* c4 = reinterpret_cast<uint4*>(s.cell);
     const int nvec = C >> 2;
+    if (bar) mbar_wait(bar, 0);
     for (int j0 = tid - lane; j0 < nvec; j0 += nthr) {               // warp-uniform trip count
         const int j = j0 + lane;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (j < nvec) {
-            asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g4 + j));
-            c4[j] = v;
+            if (bar) {
+                v = c4[j];
+            } else {
+                asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g4 + j));
+                c4[j] = v;
+            }
         }
         if (__ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u) == 0u) continue;
         const uint32_t comp[4] = {v.x, v.y, v.z, v.w};
@@ -879,6 +887,19 @@ multi_env_kernel(const MultiParams p) {
     const int C = p.C, K = p.K, S = p.S;
     const int e = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
 
+    // COMPACT: the env's records set off for shared memory first thing, as ONE bulk copy (TMA) straight into s.cell; everything
+    // up to the load's record walk -- hints, flags, colours, the first barrier -- runs under its latency.  (Before: each thread
+    // pulled its C / (4 * THREADS) vectors one after the other, every ballot waiting for its own load: 21 % of the C5 kernel's
+    // stall samples sat on that loop, profiles/r02_ncu_C5_compact.txt.)
+    __shared__ __align__(8) uint64_t rec_bar;
+    if (COMPACT && tid == 0) {
+        mbar_init(&rec_bar, 1);
+        fence_mbar_init();
+        const uint32_t bytes = (uint32_t)(C >> 2) * 16u;
+        mbar_arrive_expect_tx(&rec_bar, bytes);
+        bulk_load(s.cell, p.cells + (size_t)e * p.Cp, bytes, &rec_bar);
+    }
+
     // per-snake scalars (action, orientation, boost-cost draw) are fetched by warp 0 before the env is streamed
     // in, so that their latency hides behind the load instead of heading the serial per-snake logic
     // (measured on B200: +2 % at K=16,S=64 with 256 threads; a loss for the small-grid variant, where the values are
@@ -924,10 +945,10 @@ multi_env_kernel(const MultiParams p) {
     __syncthreads();
     if (COMPACT) {
         if (SHADOW) {                                                 // shadowed dense state: the records must still match the tensors
-            const bool ok = load_env_compact<false, true>(p, s, e, hint_h, hint_val);
+            const bool ok = load_env_compact<false, true>(p, s, e, hint_h, hint_val, &rec_bar);
             if (__syncthreads_or(!ok)) reload_from_tensors(p, smem_raw, e);     // (both ways end on a barrier)
         } else {
-            load_env_compact<false>(p, s, e);
+            load_env_compact<false>(p, s, e, -1, 1.0f, &rec_bar);
             __syncthreads();
         }
     } else {
