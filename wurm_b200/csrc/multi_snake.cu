@@ -644,7 +644,7 @@ __device__ __forceinline__ ResetScratch carve_reset(unsigned char* base, int C) 
 // occupies its 3x3 neighbourhood.  The occupancy bytes carry that test precomputed: bit 0 = the cell is occupied,
 // bit 1 = "no seed here" (too close to the wall, or an occupied cell in the 3x3 neighbourhood), so that the
 // candidate scans of block_pick read one byte per cell instead of nine.
-constexpr uint8_t kOccupied = 1, kNoSeed = 2;
+constexpr uint8_t kOccupied = 1, kNoSeed = 2, kBorder = 4;        // (kBorder: decide_recreate's map only -- no food on the wall)
 __device__ __forceinline__ bool spawnable(const uint8_t* occ, int q) { return !(occ[q] & kNoSeed); }
 __device__ __forceinline__ bool seed_margin(const MultiParams& p, int q) {
     const int S = p.S, y = fdiv(q, p.magic_S), x = q - y * S;
@@ -678,53 +678,100 @@ __device__ __forceinline__ void snake_cells(const MultiParams& p, int cell, int 
     tl = (y - off_y(d)) * S + (x - off_x(d));
 }
 
-// _create_envs (:996-1019): K snakes placed one after the other (_add_snake :911-994) and one food, decided on a
-// fresh occupancy map; results in sc.snake_cell / sc.snake_dir and the returned food cell.  Whole CTA.
-__device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
-    const int C = p.C, K = p.K, S = p.S, tid = threadIdx.x, nthr = blockDim.x;
-    for (int q = tid; q < C; q += nthr) sc.occ[q] = seed_margin(p, q) ? kNoSeed : 0;
-    __syncthreads();
-    for (int k = 0; k < K; ++k) {
-        if (tid == 0) sc.pick[0] = -1;
-        __syncthreads();
-        int d;
-        if (p.create) {
-            if (tid == 0) sc.pick[0] = p.create[((size_t)e * (K + 1) + k) * 2];
-            d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
-            __syncthreads();
-        } else {
-            const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
-            block_pick(C, sc.counts, r.x, sc.pick, [&](int q) { return spawnable(sc.occ, q); });
-            d = (int)(r.y >> 30);
-        }
-        const int cell = sc.pick[0];
-        __syncthreads();
-        if (tid == 0) {
-            sc.snake_cell[k] = cell; sc.snake_dir[k] = d;
-            if (cell < 0) atomicOr(p.status, WURM_ST_NO_SPAWN);       // the reference raises (:947)
-        }
-        if (cell >= 0) {                                              // the new snake's three cells and their surroundings
-            int tl, hd;
-            snake_cells(p, cell, d, tl, hd);
-            for (int j = tid; j < 27; j += nthr) {
-                const int c = j < 9 ? tl : j < 18 ? cell : hd;
-                if (j % 9 == 4) occ_or(sc.occ, c, kOccupied);
-                block_around(p, sc.occ, c, j % 9);
+// block_pick's choice -- the bounded(rnd, total)-th cell, in raster order, whose occupancy byte has none of the bits `mask`
+// (any of bits 0-3) -- made by ONE warp without a block barrier: every lane counts the candidates of its contiguous span with
+// 128-bit shared loads, bit masks and POPC, one shuffle scan ranks the spans, the owning lane finds the byte.  `bytes16`: the
+// map's length rounded up to 16; its padding bytes carry every bit (never candidates).  All 32 lanes must call; all get the
+// cell (or -1).  The K snakes of a re-created env are placed one after the other, each on the map the previous one left:
+// K block-wide picks with ~6 block barriers each were the longest dependent chain of the whole reset (~50 us at 16 snakes
+// on a 64 x 64 grid, and every launch lasts as long as its unluckiest CTA).
+__device__ __forceinline__ int warp_pick(const uint8_t* occ, int bytes16, uint32_t mask, uint32_t rnd) {
+    const int lane = threadIdx.x & 31;
+    const uint4* o4 = reinterpret_cast<const uint4*>(occ);
+    const int nvec = bytes16 >> 4, per_lane = (nvec + 31) >> 5;      // lane l owns vectors [l * per_lane, (l + 1) * per_lane): raster order
+    const int j0 = lane * per_lane, j1 = min(nvec, j0 + per_lane);
+    const uint32_t m4 = mask * 0x01010101u;
+    auto candidates = [&](uint32_t w) {                              // bit 8b = byte b of w is a candidate
+        uint32_t z = w & m4;
+        z |= z >> 1; z |= z >> 2;
+        return ~z & 0x01010101u;
+    };
+    auto count = [&](const uint4& v) {
+        return __popc(candidates(v.x)) + __popc(candidates(v.y)) + __popc(candidates(v.z)) + __popc(candidates(v.w));
+    };
+    int mine = 0;
+    for (int j = j0; j < j1; ++j) mine += count(o4[j]);               // (independent loads: they pipeline)
+    int incl = mine;                                                  // inclusive scan over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return -1;
+    const int r = (int)bounded(rnd, (uint32_t)total);
+    int cell = -1;
+    if (r >= incl - mine && r < incl) {                               // the owner: which vector, which word, which byte
+        int left = r - (incl - mine);
+        for (int j = j0; j < j1 && cell < 0; ++j) {
+            const uint4 v = o4[j];
+            const uint32_t cw[4] = {candidates(v.x), candidates(v.y), candidates(v.z), candidates(v.w)};
+#pragma unroll
+            for (int wd = 0; wd < 4; ++wd) {
+                const int n = __popc(cw[wd]);
+                if (cell < 0 && left < n) cell = 16 * j + 4 * wd + (int)(__fns(cw[wd], 0, left + 1) >> 3);
+                left -= n;
             }
         }
-        __syncthreads();
     }
-    if (tid == 0) sc.pick[0] = -1;
-    __syncthreads();
-    if (p.create) {
-        if (tid == 0) sc.pick[0] = p.create[((size_t)e * (K + 1) + K) * 2];
-        __syncthreads();
-    } else {                                                          // :1016 one food on a free interior cell
-        block_pick(C, sc.counts, draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateFood).x, sc.pick, [&](int q) {
+    const unsigned owner = __ballot_sync(0xffffffffu, cell >= 0);
+    return __shfl_sync(0xffffffffu, cell, __ffs(owner) - 1);
+}
+
+// _create_envs (:996-1019): K snakes placed one after the other (_add_snake :911-994) and one food, decided on a
+// fresh occupancy map; results in sc.snake_cell / sc.snake_dir and the returned food cell.  Whole CTA calls; warp 0 places.
+__device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
+    const int C = p.C, K = p.K, S = p.S, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int bytes16 = (C + 15) & ~15;
+    for (int q = tid; q < bytes16; q += nthr) {
+        uint8_t b = 0xff;                                             // padding: never a candidate
+        if (q < C) {
             const int y = fdiv(q, p.magic_S), x = q - y * S;
-            return y >= 1 && y <= S - 2 && x >= 1 && x <= S - 2 && !(sc.occ[q] & kOccupied);
-        });
+            b = (seed_margin(p, q) ? kNoSeed : 0) | ((y < 1 || y > S - 2 || x < 1 || x > S - 2) ? kBorder : 0);
+        }
+        sc.occ[q] = b;
     }
+    __syncthreads();
+    if (tid < 32) {
+        for (int k = 0; k < K; ++k) {
+            int cell, d;
+            if (p.create) {
+                cell = p.create[((size_t)e * (K + 1) + k) * 2];
+                d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
+            } else {
+                const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
+                cell = warp_pick(sc.occ, bytes16, kNoSeed, r.x);
+                d = (int)(r.y >> 30);
+            }
+            if (lane == 0) {
+                sc.snake_cell[k] = cell; sc.snake_dir[k] = d;
+                if (cell < 0) atomicOr(p.status, WURM_ST_NO_SPAWN);   // the reference raises (:947)
+            }
+            if (cell >= 0 && lane < 27) {                             // the new snake's three cells and their surroundings
+                int tl, hd;
+                snake_cells(p, cell, d, tl, hd);
+                const int c = lane < 9 ? tl : lane < 18 ? cell : hd;
+                if (lane % 9 == 4) occ_or(sc.occ, c, kOccupied);
+                block_around(p, sc.occ, c, lane % 9);
+            }
+            __syncwarp();
+        }
+        int fcell;                                                    // :1016 one food on a free interior cell
+        if (p.create) fcell = p.create[((size_t)e * (K + 1) + K) * 2];
+        else fcell = warp_pick(sc.occ, bytes16, kOccupied | kBorder, draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateFood).x);
+        if (lane == 0) sc.pick[0] = fcell;
+    }
+    __syncthreads();
     return sc.pick[0];
 }
 
@@ -1291,6 +1338,31 @@ __global__ void __launch_bounds__(256) multi_convert_kernel(const MultiParams p)
 // ---------------------------------------------------------------------------------------------
 // reset (multi_snake.py:771-831)
 // ---------------------------------------------------------------------------------------------
+// Calls f(q, record) for every non-zero record of one env's row, whole CTA: 128-bit loads, four in flight per thread before
+// the first is looked at (one dependent 4-byte load per cell was 55 % of the stand-alone reset's stall samples).
+template <typename F>
+__device__ __forceinline__ void walk_records(const uint32_t* row, int Cp, F&& f) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    const int nvec = Cp >> 2, tid = threadIdx.x, nthr = blockDim.x;
+    for (int j0 = tid; j0 < nvec; j0 += 4 * nthr) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * nthr;
+            v[u] = j < nvec ? r4[j] : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0u) continue;
+            const int q = 4 * (j0 + u * nthr);
+            if (v[u].x) f(q, v[u].x);
+            if (v[u].y) f(q + 1, v[u].y);
+            if (v[u].z) f(q + 2, v[u].z);
+            if (v[u].w) f(q + 3, v[u].w);
+        }
+    }
+}
+
 // The CTA-wide part of the stand-alone reset of ONE env (every thread calls it with the same e).
 __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned char* smem_raw, int e) {
     const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
@@ -1309,15 +1381,13 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
         const bool dense = p.foods != nullptr;
         if (recreate) {
             const int fcell = decide_recreate(p, e, ctr, sc);
-            for (int q = tid; q < C; q += nthr) {
-                const uint32_t rec = gc[q];
-                if (rec == 0u) continue;
+            walk_records(gc, p.Cp, [&](int q, uint32_t rec) {
                 gc[q] = 0u;
                 if (dense) {
                     if (rec & kFood) p.foods[(size_t)e * C + q] = 0.0f;
                     if (rec_body(rec)) p.bodies[((size_t)e * K + rec_owner(rec)) * C + q] = 0.0f;     // (none on a consistent state)
                 }
-            }
+            });
             if (dense && tid < K) {
                 const int h = p.head_hints[(size_t)e * K + tid];
                 if (h >= 0 && h < C) p.heads[((size_t)e * K + tid) * C + h] = 0.0f;                   // (none on a consistent state)
@@ -1326,14 +1396,15 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
             write_recreated(p, e, sc, fcell, p.cells != nullptr, p.foods != nullptr);
             return;
         }
-        for (int q = tid; q < C; q += nthr) {
-            const uint32_t rec = gc[q];
-            sc.occ[q] = rec != 0u;                                    // (leftovers count as occupied, as in the dense path)
+        for (int q = tid; q < C; q += nthr) sc.occ[q] = 0;
+        __syncthreads();
+        walk_records(gc, p.Cp, [&](int q, uint32_t rec) {
+            sc.occ[q] = 1;                                            // (leftovers count as occupied, as in the dense path)
             if (rec_body(rec) && rec_owner(rec) == first_dead) {      // leftovers of the dead snake
                 gc[q] = rec & ~kLive;
                 if (dense) p.bodies[((size_t)e * K + first_dead) * C + q] = 0.0f;
             }
-        }
+        });
         __syncthreads();
         int d;
         const int cell = decide_respawn(p, e, ctr, sc, d);
@@ -1379,29 +1450,35 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
 // One CTA looks at 32 consecutive envs: lane i of warp 0 reads env i's flags (coalesced), a ballot gives
 // the envs with work to do, and the CTA handles those one after another.  In the common case (nothing
 // died) an env costs K+1 bytes of traffic and a share of one warp instruction, not a CTA launch.
+// Envs per CTA.  Envs that need CTA-wide work (re-creation, respawn) are handled one after the other, so the kernel lasts as
+// long as its unluckiest CTA; 8 or 16 envs per CTA measured a few per cent better than 4 or 32 (scripts/time_reset.py).
+#ifndef WURM_RESET_ENVS
+#define WURM_RESET_ENVS 8
+#endif
+constexpr int kResetEnvs = WURM_RESET_ENVS;
 __global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned todo_s;
-    const int e0 = blockIdx.x * 32, K = p.K;
+    __shared__ unsigned recreate_s, dead_s;
+    const int e0 = blockIdx.x * kResetEnvs, K = p.K;
     if (threadIdx.x < 32) {
         const int e = e0 + (int)threadIdx.x;
-        bool work = false;
-        if (e < p.E) {
-            const bool recreate = p.env_done[e] != 0;
-            bool any_dead = false;
-            if (!recreate)                                            // a re-created env has every snake alive again
-                for (int k = 0; k < K; ++k) {
-                    if (!p.dones[(size_t)e * K + k]) continue;
-                    any_dead = true;
-                    if (p.colour_random) recolour(p, e, k, call_counter(p));   // :800-803 a new colour for every dead snake
-                }
-            work = recreate || (any_dead && p.respawn_any);          // CTA-wide work: re-creation or a respawn
-        }
-        const unsigned todo = __ballot_sync(0xffffffffu, work);
-        if (threadIdx.x == 0) todo_s = todo;
+        const unsigned rec = __ballot_sync(0xffffffffu, (int)threadIdx.x < kResetEnvs && e < p.E && p.env_done[e] != 0);
+        if (threadIdx.x == 0) { recreate_s = rec; dead_s = 0u; }
     }
     __syncthreads();
-    unsigned todo = todo_s;
+    // one (env, snake) pair per thread and iteration -- the 32 * K done flags of the CTA's envs are one contiguous span -- instead
+    // of one lane per env walking its K flags (and recolouring its dead snakes) one dependent load after the other
+    const unsigned recreate = recreate_s;
+    const int pairs = min(kResetEnvs, p.E - e0) * K;
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+        const int el = i / K, k = i - el * K;
+        if ((recreate >> el) & 1u) continue;                          // a re-created env has every snake alive again
+        if (!p.dones[(size_t)e0 * K + i]) continue;
+        atomicOr(&dead_s, 1u << el);
+        if (p.colour_random) recolour(p, e0 + el, k, call_counter(p));    // :800-803 a new colour for every dead snake
+    }
+    __syncthreads();
+    unsigned todo = recreate | (p.respawn_any ? dead_s : 0u);         // CTA-wide work: re-creation or a respawn
     while (todo) {
         const int e = e0 + __ffs(todo) - 1;
         todo &= todo - 1;
@@ -1593,7 +1670,7 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
     }
     const int threads = p.C <= 1024 ? 128 : 256;
     const size_t smem = reset_scratch_bytes(p.C) + 16;
-    multi_reset_kernel<<<(p.E + 31) / 32, threads, smem, (cudaStream_t)stream>>>(p);
+    multi_reset_kernel<<<(p.E + kResetEnvs - 1) / kResetEnvs, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
 }
 

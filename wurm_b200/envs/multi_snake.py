@@ -68,6 +68,7 @@ class MultiSnake(object):
                  seed: int = None,
                  state: str = None):
         self._lib = _lib.lib()      # raises if the CUDA library is not built: there is no fallback
+        self._cfg_cache = {}
         self.num_envs = num_envs
         self.num_snakes = num_snakes
         self.size = size
@@ -180,6 +181,8 @@ class MultiSnake(object):
         self.edge_locations_mask[:, :, -1:, :] = 1
         self.edge_locations_mask[:, :, :, -1:] = 1
 
+        self._names = {kind: tuple(f'{kind}_{i}' for i in range(K))
+                       for kind in ('agent', 'boost', 'snake_collision', 'edge_collision', 'food', 'size')}
         self._hint_key = None
         self._shadow_ok = False                      # dense mode: the records describe the tensors' current content
         if not manual_setup:
@@ -202,6 +205,17 @@ class MultiSnake(object):
             print(msg)
 
     def _cfg(self, mode=None):
+        # (the rule attributes are mutable and re-read at every call; the struct is rebuilt only when one of them moved)
+        key = (mode, self.food_on_death_prob, self.boost, self.boost_cost_prob, self.food_mode, self.food_rate,
+               self.reward_on_death, self.respawn_mode, self.colour_mode, self.num_envs, self.num_snakes, self.size)
+        hit = self._cfg_cache.get(key)
+        if hit is None:
+            if len(self._cfg_cache) > 64:
+                self._cfg_cache.clear()
+            hit = self._cfg_cache[key] = self._make_cfg(mode)
+        return hit
+
+    def _make_cfg(self, mode=None):
         if mode is None:
             obs_mode, n = _lib.MOBS_NONE, 0
         elif mode == 'full':
@@ -459,9 +473,8 @@ class MultiSnake(object):
 
         cfg = self._cfg(self.observation_mode)
         obs = torch.empty(self._obs_shape(cfg), dtype=torch.float32, device=dev)
-        rewards = torch.empty((E, K), dtype=torch.float32, device=dev)
-        food = torch.empty((E, K), dtype=torch.float32, device=dev)
-        size = torch.empty((E, K), dtype=torch.float32, device=dev)
+        floats = torch.empty((3, E, K), dtype=torch.float32, device=dev)  # one allocation each for the float and the flag outputs
+        rewards, food, size = floats[0], floats[1], floats[2]
         flags = torch.empty((4, E, K), dtype=torch.bool, device=dev)     # snake_collision, edge_collision, dones, boost
         all_done = torch.empty(E, dtype=torch.bool, device=dev)
         out = _lib.WurmMultiStepOut(_ptr(rewards), _ptr(flags[0]), _ptr(flags[1]), _ptr(food), _ptr(size), _ptr(flags[2]),
@@ -505,19 +518,21 @@ class MultiSnake(object):
             self._shadow_ok = self._cells is not None      # every step leaves the records describing the new state
         self.rewards = rewards.view(E * K)
         self._step_dones = flags[2]          # (E,K) copy of the done flags owned by this step's outputs
-        observations = OrderedDict([(f'agent_{i}', obs[i]) for i in range(K)])
-        dones = {f'agent_{i}': flags[2][:, i] for i in range(K)}
+        # The reference's per-agent dicts (:686-731) are views of the (K,E,..) / (E,K) outputs.  One unbind() per tensor makes
+        # the K views in a single call: 8 K Python-level slices cost 0.3 ms per step at 16 snakes -- as long as the kernel.
+        names = self._names
+        observations = OrderedDict(zip(names['agent'], obs.unbind(0)))
+        dones = dict(zip(names['agent'], flags[2].unbind(1)))
         dones['__all__'] = all_done
-        rewards_dict = {f'agent_{i}': rewards[:, i] for i in range(K)}
-        self.info = {}
-        for i in range(K):
-            self.info[f'boost_{i}'] = flags[3][:, i]
-            self.info[f'snake_collision_{i}'] = flags[0][:, i]
-            self.info[f'edge_collision_{i}'] = flags[1][:, i]
-        for i in range(K):
-            self.info[f'food_{i}'] = food[:, i]
-        for i in range(K):
-            self.info[f'size_{i}'] = size[:, i]
+        rewards_dict = dict(zip(names['agent'], rewards.unbind(1)))
+        self.info = info = {}
+        for nb, ns, ne, b, sc, ec in zip(names['boost'], names['snake_collision'], names['edge_collision'],
+                                         flags[3].unbind(1), flags[0].unbind(1), flags[1].unbind(1)):
+            info[nb] = b
+            info[ns] = sc
+            info[ne] = ec
+        info.update(zip(names['food'], food.unbind(1)))
+        info.update(zip(names['size'], size.unbind(1)))
         if self.verbose > 0:
             torch.cuda.synchronize(dev)
             self._log(f'step: {1000 * (time() - t0)}ms')
