@@ -216,8 +216,13 @@ __host__ __device__ __forceinline__ int queue_capacity(int K) { return 12 * K + 
 // the region is only as large as the reset scratch needs -- the list holds what fits (a few times the typical ~1 % of the
 // grid) and an env with more live cells than that is walked cell by cell instead (misc[8]); no load queue either.
 // Shared memory per CTA is what limits the number of resident envs, and the kernel is latency-bound.
+// the fused / stand-alone reset's scratch: occupancy bytes, block_pick's per-warp counts, the pick, K seed cells and directions
+__host__ __device__ __forceinline__ int reset_scratch_size(int C) { return ((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4; }
+// ... and, elsewhere (shared memory per CTA is what the step kernels' occupancy hangs on: the fused reset puts them into the
+// record array, which is dead by then): seed-candidate counts per 16-byte vector of the occupancy bytes and per lane
+__host__ __device__ __forceinline__ int reset_counts_size(int C) { return (((((C + 15) & ~15) >> 4) + 15) & ~15) + 32 * 4; }
 __host__ __device__ __forceinline__ int scratch_bytes(int C, bool compact) {
-    int scratch = ((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4;
+    int scratch = reset_scratch_size(C);
     if (scratch < 768) scratch = 768;
     if (!compact && scratch < 2 * C) scratch = 2 * C;
     return scratch;
@@ -622,18 +627,24 @@ __device__ __forceinline__ int block_pick(int C, int* counts, uint32_t rnd, int*
 // ---- pieces of the reset shared by the stand-alone kernel and the fused step+reset path ----
 struct ResetScratch {
     uint8_t* occ;      // C occupancy bytes
+    uint8_t* vcount;   // seed candidates per 16-byte vector of occ (decide_recreate keeps them current while it places snakes)
+    int* lcount;       // ... and per lane of warp 0 (32)
     int* counts;       // block_pick scratch (one int per warp)
     int* pick;         // [0] chosen cell
     int* snake_cell;   // K seed cells of a re-created env
     int* snake_dir;    // K directions
 };
 
-static size_t reset_scratch_bytes(int C) { return (size_t)((C + 15) & ~15) + (16 + 4 + 32 + 32) * 4; }
+static size_t reset_scratch_bytes(int C) { return (size_t)reset_scratch_size(C); }
 
-__device__ __forceinline__ ResetScratch carve_reset(unsigned char* base, int C) {
+// (`counts_base`: reset_counts_size(C) bytes, 16-byte aligned, for vcount / lcount)
+__device__ __forceinline__ ResetScratch carve_reset(unsigned char* base, int C, unsigned char* counts_base) {
     ResetScratch r;
+    const int bytes16 = (C + 15) & ~15;
     r.occ = base;
-    r.counts = reinterpret_cast<int*>(base + ((C + 15) & ~15));
+    r.vcount = counts_base;
+    r.lcount = reinterpret_cast<int*>(counts_base + (((bytes16 >> 4) + 15) & ~15));
+    r.counts = reinterpret_cast<int*>(base + bytes16);
     r.pick = r.counts + 16;
     r.snake_cell = r.pick + 4;
     r.snake_dir = r.snake_cell + 32;
@@ -652,13 +663,15 @@ __device__ __forceinline__ bool seed_margin(const MultiParams& p, int q) {
 }
 // ORs bits into occupancy byte q; several threads may hit one byte (or its word) at once: a shared-memory atomic on
 // the enclosing 32-bit word (the map starts 16-byte aligned)
-__device__ __forceinline__ void occ_or(uint8_t* occ, int q, uint8_t bits) {
-    atomicOr(reinterpret_cast<unsigned*>(occ + (q & ~3)), (unsigned)bits << (8 * (q & 3)));
+__device__ __forceinline__ uint8_t occ_or(uint8_t* occ, int q, uint8_t bits) {        // returns the byte as it was
+    return (uint8_t)(atomicOr(reinterpret_cast<unsigned*>(occ + (q & ~3)), (unsigned)bits << (8 * (q & 3))) >> (8 * (q & 3)));
 }
 // marks neighbour nb (0..8, row-major 3x3) of occupied cell q
-__device__ __forceinline__ void block_around(const MultiParams& p, uint8_t* occ, int q, int nb) {
+// (returns the neighbour's cell if this call is what took it out of the seed candidates, -1 otherwise)
+__device__ __forceinline__ int block_around(const MultiParams& p, uint8_t* occ, int q, int nb) {
     const int S = p.S, y = fdiv(q, p.magic_S) + nb / 3 - 1, x = q - fdiv(q, p.magic_S) * S + nb % 3 - 1;
-    if (y >= 0 && y < S && x >= 0 && x < S) occ_or(occ, y * S + x, kNoSeed);
+    if (y >= 0 && y < S && x >= 0 && x < S && !(occ_or(occ, y * S + x, kNoSeed) & kNoSeed)) return y * S + x;
+    return -1;
 }
 // completes an occupancy map whose bytes hold bit 0 only: wall margin and 3x3 dilation into bit 1.  Whole CTA.
 __device__ __forceinline__ void finish_occupancy(const MultiParams& p, uint8_t* occ) {
@@ -679,28 +692,33 @@ __device__ __forceinline__ void snake_cells(const MultiParams& p, int cell, int 
 }
 
 // block_pick's choice -- the bounded(rnd, total)-th cell, in raster order, whose occupancy byte has none of the bits `mask`
-// (any of bits 0-3) -- made by ONE warp without a block barrier: every lane counts the candidates of its contiguous span with
-// 128-bit shared loads, bit masks and POPC, one shuffle scan ranks the spans, the owning lane finds the byte.  `bytes16`: the
-// map's length rounded up to 16; its padding bytes carry every bit (never candidates).  All 32 lanes must call; all get the
-// cell (or -1).  The K snakes of a re-created env are placed one after the other, each on the map the previous one left:
-// K block-wide picks with ~6 block barriers each were the longest dependent chain of the whole reset (~50 us at 16 snakes
-// on a 64 x 64 grid, and every launch lasts as long as its unluckiest CTA).
-__device__ __forceinline__ int warp_pick(const uint8_t* occ, int bytes16, uint32_t mask, uint32_t rnd) {
+// (any of bits 0-3) -- made by ONE warp without a block barrier.  Lane l owns the contiguous span of 16-byte vectors
+// [l * per_lane, (l + 1) * per_lane) of the map (`bytes16`: its length rounded up to 16; the padding bytes carry every bit:
+// never candidates).  All 32 lanes must call; all get the cell (or -1).
+// The K snakes of a re-created env are placed one after the other, each on the map the previous one left: as block-wide picks
+// with ~6 block barriers each that was the longest dependent chain of the whole reset (~60 us at 16 snakes on a 64 x 64 grid,
+// and every launch lasts as long as its unluckiest CTA).  COUNTED: the candidates per vector (sc.vcount) and per lane
+// (sc.lcount) are already known -- decide_recreate counts once and then only subtracts what each new snake blocks -- so a pick
+// is one shuffle scan plus the owner's walk over its <= per_lane byte counts.
+__device__ __forceinline__ uint32_t occ_candidates(uint32_t w, uint32_t m4) {      // bit 8b = byte b of w is a candidate
+    uint32_t z = w & m4;
+    z |= z >> 1; z |= z >> 2;
+    return ~z & 0x01010101u;
+}
+__device__ __forceinline__ int occ_count(const uint4& v, uint32_t m4) {
+    return __popc(occ_candidates(v.x, m4)) + __popc(occ_candidates(v.y, m4)) + __popc(occ_candidates(v.z, m4)) +
+           __popc(occ_candidates(v.w, m4));
+}
+template <bool COUNTED>
+__device__ __forceinline__ int warp_pick(const ResetScratch& sc, int bytes16, uint32_t mask, uint32_t rnd) {
     const int lane = threadIdx.x & 31;
-    const uint4* o4 = reinterpret_cast<const uint4*>(occ);
-    const int nvec = bytes16 >> 4, per_lane = (nvec + 31) >> 5;      // lane l owns vectors [l * per_lane, (l + 1) * per_lane): raster order
+    const uint4* o4 = reinterpret_cast<const uint4*>(sc.occ);
+    const int nvec = bytes16 >> 4, per_lane = (nvec + 31) >> 5;
     const int j0 = lane * per_lane, j1 = min(nvec, j0 + per_lane);
     const uint32_t m4 = mask * 0x01010101u;
-    auto candidates = [&](uint32_t w) {                              // bit 8b = byte b of w is a candidate
-        uint32_t z = w & m4;
-        z |= z >> 1; z |= z >> 2;
-        return ~z & 0x01010101u;
-    };
-    auto count = [&](const uint4& v) {
-        return __popc(candidates(v.x)) + __popc(candidates(v.y)) + __popc(candidates(v.z)) + __popc(candidates(v.w));
-    };
     int mine = 0;
-    for (int j = j0; j < j1; ++j) mine += count(o4[j]);               // (independent loads: they pipeline)
+    if (COUNTED) mine = sc.lcount[lane];
+    else for (int j = j0; j < j1; ++j) mine += occ_count(o4[j], m4);     // (independent loads: they pipeline)
     int incl = mine;                                                  // inclusive scan over the lanes
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -714,8 +732,12 @@ __device__ __forceinline__ int warp_pick(const uint8_t* occ, int bytes16, uint32
     if (r >= incl - mine && r < incl) {                               // the owner: which vector, which word, which byte
         int left = r - (incl - mine);
         for (int j = j0; j < j1 && cell < 0; ++j) {
+            if (COUNTED) {
+                const int n = sc.vcount[j];
+                if (left >= n) { left -= n; continue; }
+            }
             const uint4 v = o4[j];
-            const uint32_t cw[4] = {candidates(v.x), candidates(v.y), candidates(v.z), candidates(v.w)};
+            const uint32_t cw[4] = {occ_candidates(v.x, m4), occ_candidates(v.y, m4), occ_candidates(v.z, m4), occ_candidates(v.w, m4)};
 #pragma unroll
             for (int wd = 0; wd < 4; ++wd) {
                 const int n = __popc(cw[wd]);
@@ -730,7 +752,7 @@ __device__ __forceinline__ int warp_pick(const uint8_t* occ, int bytes16, uint32
 
 // _create_envs (:996-1019): K snakes placed one after the other (_add_snake :911-994) and one food, decided on a
 // fresh occupancy map; results in sc.snake_cell / sc.snake_dir and the returned food cell.  Whole CTA calls; warp 0 places.
-__device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
+__device__ __forceinline__ int decide_recreate_inline(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
     const int C = p.C, K = p.K, S = p.S, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int bytes16 = (C + 15) & ~15;
     for (int q = tid; q < bytes16; q += nthr) {
@@ -743,6 +765,18 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
     }
     __syncthreads();
     if (tid < 32) {
+        const int nvec = bytes16 >> 4, per_lane = (nvec + 31) >> 5;
+        if (!p.create) {                                              // seed candidates per vector and per lane, counted once
+            const uint4* o4 = reinterpret_cast<const uint4*>(sc.occ);
+            int mine = 0;
+            for (int j = lane * per_lane; j < min(nvec, (lane + 1) * per_lane); ++j) {
+                const int n = occ_count(o4[j], kNoSeed * 0x01010101u);
+                sc.vcount[j] = (uint8_t)n;
+                mine += n;
+            }
+            sc.lcount[lane] = mine;
+            __syncwarp();
+        }
         for (int k = 0; k < K; ++k) {
             int cell, d;
             if (p.create) {
@@ -750,7 +784,7 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
                 d = p.create[((size_t)e * (K + 1) + k) * 2 + 1];
             } else {
                 const uint4 r = draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateSnake | ((uint32_t)k << 4));
-                cell = warp_pick(sc.occ, bytes16, kNoSeed, r.x);
+                cell = warp_pick<true>(sc, bytes16, kNoSeed, r.x);
                 d = (int)(r.y >> 30);
             }
             if (lane == 0) {
@@ -762,17 +796,34 @@ __device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint
                 snake_cells(p, cell, d, tl, hd);
                 const int c = lane < 9 ? tl : lane < 18 ? cell : hd;
                 if (lane % 9 == 4) occ_or(sc.occ, c, kOccupied);
-                block_around(p, sc.occ, c, lane % 9);
+                const int gone = block_around(p, sc.occ, c, lane % 9);     // a cell this snake takes out of the seed candidates
+                if (gone >= 0 && !p.create) {
+                    const int j = gone >> 4;
+                    atomicSub(reinterpret_cast<unsigned*>(sc.vcount + (j & ~3)), 1u << (8 * (j & 3)));       // (the byte is >= 1: no borrow)
+                    atomicSub(&sc.lcount[j / per_lane], 1);
+                }
             }
             __syncwarp();
         }
         int fcell;                                                    // :1016 one food on a free interior cell
         if (p.create) fcell = p.create[((size_t)e * (K + 1) + K) * 2];
-        else fcell = warp_pick(sc.occ, bytes16, kOccupied | kBorder, draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateFood).x);
+        else fcell = warp_pick<false>(sc, bytes16, kOccupied | kBorder, draw(p.seed, ctr, (uint32_t)e, kStreamMultiCreateFood).x);
         if (lane == 0) sc.pick[0] = fcell;
     }
     __syncthreads();
     return sc.pick[0];
+}
+
+// Out of line, plain arguments (a reference to the kernel's parameter struct would force a copy of it onto the stack): a
+// fraction of a per cent of the envs are re-created per step, and the step kernels are sensitive to the size of their code.
+__device__ __noinline__ int decide_recreate_cold(int C, int K, int S, uint32_t magic_S, const int32_t* create, uint64_t seed, int32_t* status,
+                                                 int e, uint64_t ctr, ResetScratch sc) {
+    MultiParams q = {};
+    q.C = C; q.K = K; q.S = S; q.magic_S = magic_S; q.create = create; q.seed = seed; q.status = status;
+    return decide_recreate_inline(q, e, ctr, sc);
+}
+__device__ __forceinline__ int decide_recreate(const MultiParams& p, int e, uint64_t ctr, const ResetScratch& sc) {
+    return decide_recreate_cold(p.C, p.K, p.S, p.magic_S, p.create, p.seed, p.status, e, ctr, sc);
 }
 
 // Stores the cells of the re-created env's snakes and food and revives its agents (:790-798).  Whole CTA; the
@@ -1218,7 +1269,9 @@ multi_env_kernel(const MultiParams p) {
         // step: same draws (call counter + 1), same result.  The compact form already knows what the stand-alone
         // kernel has to scan the tensors for: which cells are occupied, which snakes are dead.
         __syncthreads();                                              // the observation is done with the records
-        const ResetScratch sc = carve_reset(reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15), C);
+        // (the candidate counts of a re-creation go where the records are: nothing reads those once the old food is cleared)
+        const ResetScratch sc = carve_reset(reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s.reset) + 15) & ~(uintptr_t)15), C,
+                                            reinterpret_cast<unsigned char*>(s.cell));
         const uint64_t ctr = ctr_now + 1;
         const unsigned alive_mask = (unsigned)s.misc[4];              // snakes alive after this step (ballot of warp 0)
         const unsigned dead_mask = ~alive_mask & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u));
@@ -1227,14 +1280,14 @@ multi_env_kernel(const MultiParams p) {
         const bool rec_out = COMPACT || p.cells != nullptr;
         constexpr bool dense_out = !COMPACT || SHADOW;
         if (all_dead) {                                               // :787-798 re-create the env
-            const int fcell = decide_recreate(p, e, ctr, sc);
             // all snakes are dead, so their tensors are already zero (the step deleted them); only food is left
             for (int q = tid; q < C; q += nthr)
                 if (s.cell[q] & kFood) {
                     if (rec_out) p.cells[(size_t)e * p.Cp + q] = 0u;
                     if (dense_out) p.foods[(size_t)e * C + q] = 0.0f;
                 }
-            __syncthreads();
+            __syncthreads();                                          // the records are dead from here on
+            const int fcell = decide_recreate(p, e, ctr, sc);
             write_recreated(p, e, sc, fcell, rec_out, dense_out);
         } else if (first_dead >= 0) {
             if (p.colour_random && tid < K && s.done[tid]) recolour(p, e, tid, ctr);     // :800-803
@@ -1366,7 +1419,7 @@ __device__ __forceinline__ void walk_records(const uint32_t* row, int Cp, F&& f)
 // The CTA-wide part of the stand-alone reset of ONE env (every thread calls it with the same e).
 __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned char* smem_raw, int e) {
     const int C = p.C, K = p.K, tid = threadIdx.x, nthr = blockDim.x;
-    const ResetScratch sc = carve_reset(smem_raw, C);
+    const ResetScratch sc = carve_reset(smem_raw, C, smem_raw + ((reset_scratch_size(C) + 15) & ~15));
     const uint64_t ctr = call_counter(p);
 
     const bool recreate = p.env_done[e] != 0;
@@ -1456,7 +1509,7 @@ __device__ __forceinline__ void reset_one_env(const MultiParams& p, unsigned cha
 #define WURM_RESET_ENVS 8
 #endif
 constexpr int kResetEnvs = WURM_RESET_ENVS;
-__global__ void __launch_bounds__(256) multi_reset_kernel(const MultiParams p) {
+__global__ void __launch_bounds__(256, 4) multi_reset_kernel(const MultiParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned recreate_s, dead_s;
     const int e0 = blockIdx.x * kResetEnvs, K = p.K;
@@ -1669,7 +1722,7 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
             return fail(WURM_E_INVALID, "replay: NULL draw array");
     }
     const int threads = p.C <= 1024 ? 128 : 256;
-    const size_t smem = reset_scratch_bytes(p.C) + 16;
+    const size_t smem = ((reset_scratch_bytes(p.C) + 15) & ~(size_t)15) + reset_counts_size(p.C) + 16;
     multi_reset_kernel<<<(p.E + kResetEnvs - 1) / kResetEnvs, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
 }
