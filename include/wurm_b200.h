@@ -234,7 +234,12 @@ typedef struct WurmMultiState {
      * VERIFIES that every cell they name still holds that value in the tensors (and every head cell its head; a mismatch
      * re-loads the env from the tensors), and writes its changes to both forms: the dense state at close to the compact
      * state's cost.  cells_valid == 0: the step loads the tensors as usual and EMITS the records, after which the caller
-     * may pass 1.  Ignored (taken as 1) when the tensors are NULL. */
+     * may pass 1.  Ignored (taken as 1) when the tensors are NULL.  What the presence check cannot see -- values ADDED to
+     * the tensors since the library last wrote them -- is the caller's word: pass 1 only if nothing else wrote to the tensors.
+     * Per env, a head hint of -2 ("unknown") has the same effect as cells_valid == 0 for that env, so a caller replaying a
+     * captured launch (CUDA graph) can withdraw the records by filling head_hints with -2.  wurm_multi_reset follows the same
+     * flag (records + tensors when valid, tensors only otherwise); wurm_multi_observe / _env_images / _check read the records
+     * when valid. */
     int32_t cells_valid;
 } WurmMultiState;
 
