@@ -19,6 +19,14 @@
 //     those cells are stored back into the reference's fp32 tensors (sparse write-back; a state the
 //     compact form cannot carry exactly is expanded densely instead), and the observations are rendered
 //     from the compact form straight into the policy's per-agent input buffers;
+//   * the same records may also live in HBM between calls (WurmMultiState.cells, 4 bytes per cell): as the state itself
+//     (COMPACT: the fp32 tensors are NULL) or BESIDE the tensors as their shadow (COMPACT + SHADOW, the default of the
+//     Python class: the tensors stay the state, current after every call).  A step then starts with ONE bulk copy (TMA,
+//     cp.async.bulk + mbarrier) of the env's records into the shared record array instead of streaming ~99 % zeros; the
+//     shadow variant checks every record it loaded against the tensors (an env they contradict is re-loaded from them) and
+//     writes its changes to both forms;
+//   * the reset (stand-alone kernel, or fused into the step's launch) decides on the same records; the K sequential snake
+//     placements of a re-created env run on one warp over maintained candidate counts (warp_pick);
 //   * no tensor cores: nothing here is a dense contraction.
 //
 // Supported states: the reference's own invariant (MultiSnake.check_consistency, :733-769) --
@@ -1721,7 +1729,9 @@ extern "C" int wurm_multi_reset(const WurmMultiCfg* cfg, const WurmMultiState* s
         if (!p.create || (p.respawn_any && !p.respawn) || (p.colour_random && !p.colours_replay))
             return fail(WURM_E_INVALID, "replay: NULL draw array");
     }
-    const int threads = p.C <= 1024 ? 128 : 256;
+    // (64 registers: twice as many of these smaller CTAs are resident, and most of them only read their envs' flags;
+    // measured against 128 / 256 threads: 0.040 against 0.045 ms at K=4, S=25 and 0.050 against 0.052 ms at K=16, S=64)
+    const int threads = p.C <= 1024 ? 64 : 128;
     const size_t smem = ((reset_scratch_bytes(p.C) + 15) & ~(size_t)15) + reset_counts_size(p.C) + 16;
     multi_reset_kernel<<<(p.E + kResetEnvs - 1) / kResetEnvs, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("multi_reset_kernel");
