@@ -40,6 +40,8 @@ N-rank weak-scaling figure, so C5 is BASELINE configs[4] itself: 32 768 envs per
   compact_state  the same workload on an env built with state='compact' (an opt-in extension: the env lives in HBM as
              one small record per cell instead of the reference's dense fp32 tensors, which are materialised on
              attribute access; bit-identical results) -- the headline `value` stays on the reference layout
+  dense_scan_state  MultiSnake workloads only: the reference layout WITHOUT the shadow records the default keeps beside the
+             tensors (state='dense_scan': every step streams the fp32 tensors) -- what the shadow buys, in the same line
 
 `--impl reference` times the reference's own PyTorch CPU implementation alone and prints the same line shape.
 """
