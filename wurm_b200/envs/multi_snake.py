@@ -519,7 +519,8 @@ class MultiSnake(object):
         self.rewards = rewards.view(E * K)
         self._step_dones = flags[2]          # (E,K) copy of the done flags owned by this step's outputs
         # The reference's per-agent dicts (:686-731) are views of the (K,E,..) / (E,K) outputs.  One unbind() per tensor makes
-        # the K views in a single call: 8 K Python-level slices cost 0.3 ms per step at 16 snakes -- as long as the kernel.
+        # the K views in a single call: 8 K Python-level slices took three times as long, of the order of the kernel's own
+        # 0.3 ms at 16 snakes (profiles/r02_host_overhead.txt).
         names = self._names
         observations = OrderedDict(zip(names['agent'], obs.unbind(0)))
         dones = dict(zip(names['agent'], flags[2].unbind(1)))
