@@ -99,3 +99,43 @@ def test_a2c_has_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         A2C(gamma=0.99).loss(torch.zeros(N, 1), torch.zeros(T, N, 1), torch.zeros(T, N, 1), torch.zeros(T, N, 1),
                              torch.zeros(T, N, 1, dtype=torch.bool))
+
+
+def test_ctypes_structs_mirror_the_header():
+    """The binding's ctypes structures against include/wurm_b200.h itself: a C program compiled from the header prints
+    sizeof and every member's offset; names, order, offsets and sizes must agree (the header is plain C by contract)."""
+    import re
+    import subprocess
+    import tempfile
+    header = os.path.join(ROOT, 'include', 'wurm_b200.h')
+    text = re.sub(r'/\*.*?\*/', '', open(header).read(), flags=re.S)
+    structs = {}
+    for name, body in re.findall(r'typedef struct (\w+) \{(.*?)\} \1;', text, flags=re.S):
+        members = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if decl:
+                members.append(re.findall(r'(\w+)\s*(?:\[[^\]]*\])?$', decl)[0])
+        structs[name] = members
+    assert set(structs) == {'WurmSingleCfg', 'WurmMultiCfg', 'WurmMultiState', 'WurmMultiStepDraws', 'WurmMultiStepOut',
+                            'WurmMultiResetDraws', 'WurmGridCfg'}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{header}"', 'int main(void) {']
+    for name, members in structs.items():
+        lines.append(f'  printf("{name} sizeof %zu\\n", sizeof({name}));')
+        for m in members:
+            lines.append(f'  printf("{name} {m} %zu\\n", offsetof({name}, {m}));')
+    lines += ['  return 0;', '}']
+    with tempfile.TemporaryDirectory() as tmp:
+        src, exe = os.path.join(tmp, 'layout.c'), os.path.join(tmp, 'layout')
+        open(src, 'w').write('\n'.join(lines))
+        subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-o', exe, src])
+        out = subprocess.check_output([exe], text=True)
+    for line in out.splitlines():
+        name, member, value = line.split()
+        cls = getattr(_lib, name)
+        if member == 'sizeof':
+            assert ctypes.sizeof(cls) == int(value), f'sizeof({name})'
+        else:
+            assert getattr(cls, member).offset == int(value), f'offsetof({name}, {member})'
+    for name, members in structs.items():
+        assert [f[0] for f in getattr(_lib, name)._fields_] == members, f'{name}: member names / order'
